@@ -1,0 +1,284 @@
+"""Query-structure containers: the ``pyjess.Atom`` / ``pyjess.Molecule`` surface EnzyMM uses.
+
+This is the host-side input stage of the hot path.  The reference
+gets these two types from the un-vendored ``pyjess`` wheel (call sites
+``enzymm/jess_run.py:538-548`` for ``Molecule.load`` / ``.conserved``, ``jess_run.py:125-145``
+for the ``Atom`` attribute surface, ``jess_run.py:485-496`` for ``len()`` / iteration).  Here a
+molecule is a set of NumPy columns (SoA) so that a batch of molecules can be packed for upload
+without touching per-atom Python objects; ``Atom`` views are materialised lazily.
+
+Behaviour pinned by the reference's goldens (SURVEY.md §8c rule 1):
+  * ``ATOM`` *and* ``HETATM`` records, in file order, up to the first ``ENDMDL``
+    (3184 + 155 = 3339 atoms for ``1AMY.pdb``, ``tests/test_jess_run.py:75``);
+  * ``conserved(c)`` returns a NEW molecule keeping atoms with ``temperature_factor >= c``
+    (494 residues of the AlphaFold fixture at cutoff 80, ``tests/test_jess_run.py:276,326-329``);
+  * the molecule id defaults to the HEADER idCode (``"1AMY"``, ``tests/test_jess_run.py:62``).
+"""
+from __future__ import annotations
+
+import hashlib
+import io
+import os
+from typing import IO, Iterable, Iterator, List, Optional, Sequence, Union
+
+import numpy as np
+
+__all__ = ["Atom", "Molecule"]
+
+_STR4 = "U4"
+
+
+class Atom:
+    """One query atom (mirror of ``pyjess.Atom``; attribute names as used at
+    ``enzymm/jess_run.py:125-145``)."""
+
+    __slots__ = (
+        "serial", "name", "altloc", "residue_name", "chain_id", "residue_number",
+        "insertion_code", "x", "y", "z", "occupancy", "temperature_factor",
+        "segment", "element", "charge",
+    )
+
+    def __init__(
+        self,
+        *,
+        serial: int,
+        name: str,
+        residue_name: str,
+        chain_id: str,
+        residue_number: int,
+        x: float,
+        y: float,
+        z: float,
+        altloc: str = " ",
+        insertion_code: str = " ",
+        occupancy: float = 0.0,
+        temperature_factor: float = 0.0,
+        segment: str = "",
+        element: str = "",
+        charge: int = 0,
+    ):
+        self.serial = int(serial)
+        self.name = str(name)
+        self.altloc = altloc
+        self.residue_name = str(residue_name)
+        self.chain_id = str(chain_id)
+        self.residue_number = int(residue_number)
+        self.insertion_code = insertion_code
+        self.x = float(x)
+        self.y = float(y)
+        self.z = float(z)
+        self.occupancy = float(occupancy)
+        self.temperature_factor = float(temperature_factor)
+        self.segment = str(segment)
+        self.element = str(element)
+        self.charge = int(charge)
+
+    def _key(self):
+        return tuple(getattr(self, s) for s in self.__slots__)
+
+    def __eq__(self, other):
+        if not isinstance(other, Atom):
+            return NotImplemented
+        return self._key() == other._key()
+
+    def __ne__(self, other):
+        if not isinstance(other, Atom):
+            return NotImplemented
+        return self._key() != other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return (f"Atom(serial={self.serial}, name={self.name!r}, residue_name={self.residue_name!r}, "
+                f"chain_id={self.chain_id!r}, residue_number={self.residue_number}, "
+                f"x={self.x}, y={self.y}, z={self.z})")
+
+
+_COLUMNS = (
+    ("serial", np.int32), ("name", _STR4), ("altloc", "U1"), ("residue_name", _STR4),
+    ("chain_id", "U2"), ("residue_number", np.int32), ("insertion_code", "U1"),
+    ("occupancy", np.float64), ("temperature_factor", np.float64), ("segment", _STR4),
+    ("element", "U2"), ("charge", np.int8),
+)
+
+
+def _parse_pdb_text(lines: Iterable[str]):
+    """Fixed-column PDB reader (ATOM/HETATM up to first ENDMDL)."""
+    cols = {k: [] for k, _ in _COLUMNS}
+    xs: List[float] = []
+    ys: List[float] = []
+    zs: List[float] = []
+    header_id: Optional[str] = None
+    for line in lines:
+        rec = line[:6]
+        if rec == "ATOM  " or rec == "HETATM":
+            line = line.rstrip("\r\n")
+            if len(line) < 54:
+                raise ValueError(f"truncated PDB coordinate record: {line!r}")
+            if len(line) < 80:
+                line = line.ljust(80)
+            try:
+                cols["serial"].append(int(line[6:11]))
+                cols["residue_number"].append(int(line[22:26]))
+                xs.append(float(line[30:38]))
+                ys.append(float(line[38:46]))
+                zs.append(float(line[46:54]))
+            except ValueError as exc:
+                raise ValueError(f"malformed PDB coordinate record: {line!r}") from exc
+            occ = line[54:60].strip()
+            bfac = line[60:66].strip()
+            cols["occupancy"].append(float(occ) if occ else 0.0)
+            cols["temperature_factor"].append(float(bfac) if bfac else 0.0)
+            cols["name"].append(line[12:16].strip())
+            cols["altloc"].append(line[16])
+            cols["residue_name"].append(line[17:20].strip())
+            cols["chain_id"].append(line[20:22].strip())
+            cols["insertion_code"].append(line[26])
+            cols["segment"].append(line[72:76].strip())
+            cols["element"].append(line[76:78].strip())
+            chg = line[78:80].strip()
+            charge = 0
+            if chg and chg[0].isdigit():
+                charge = int(chg[0]) * (-1 if chg.endswith("-") else 1)
+            cols["charge"].append(charge)
+        elif rec == "ENDMDL":
+            break
+        elif rec == "HEADER" and header_id is None:
+            code = line[62:66].strip()
+            header_id = code or None
+    arrays = {k: np.asarray(cols[k], dtype=dt) for k, dt in _COLUMNS}
+    xyz = np.empty((len(xs), 3), dtype=np.float64)
+    xyz[:, 0] = xs
+    xyz[:, 1] = ys
+    xyz[:, 2] = zs
+    return arrays, xyz, header_id
+
+
+class Molecule:
+    """An ordered atom list (mirror of ``pyjess.Molecule``).
+
+    Columns are NumPy arrays of equal length; ``xyz`` is float64 ``[N, 3]`` holding exactly the
+    doubles ``float()`` parses from the PDB text (the oracle and the CUDA path both consume
+    these, so "identical inputs" means these arrays).
+    """
+
+    __slots__ = ("id", "xyz", "_cols", "_digest", "_atoms")
+
+    def __init__(self, atoms: Sequence[Atom] = (), id: Optional[str] = None):
+        self.id = id
+        n = len(atoms)
+        self._cols = {
+            k: np.asarray([getattr(a, k) for a in atoms], dtype=dt) if n else np.zeros(0, dtype=dt)
+            for k, dt in _COLUMNS
+        }
+        self.xyz = np.asarray([(a.x, a.y, a.z) for a in atoms], dtype=np.float64).reshape(n, 3)
+        self._digest = None
+        self._atoms = None
+
+    # -- construction -----------------------------------------------------------------------
+    @classmethod
+    def _from_columns(cls, cols, xyz, id) -> "Molecule":
+        self = cls.__new__(cls)
+        self.id = id
+        self._cols = cols
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._digest = None
+        self._atoms = None
+        return self
+
+    @classmethod
+    def load(cls, file: Union[str, os.PathLike, IO[str]], id: Optional[str] = None) -> "Molecule":
+        """Read a PDB file (path or text file object).  OS errors propagate unchanged
+        (``FileNotFoundError`` / ``IsADirectoryError`` -> CLI errno, ``enzymm/_cli.py:318-328``)."""
+        if isinstance(file, (str, os.PathLike)):
+            with open(os.fspath(file), "r") as handle:
+                cols, xyz, header_id = _parse_pdb_text(handle)
+        else:
+            cols, xyz, header_id = _parse_pdb_text(file)
+        return cls._from_columns(cols, xyz, id if id is not None else header_id)
+
+    @classmethod
+    def loads(cls, text: str, id: Optional[str] = None) -> "Molecule":
+        return cls.load(io.StringIO(text), id=id)
+
+    # -- pyjess surface ---------------------------------------------------------------------
+    def conserved(self, cutoff: float = 0.0) -> "Molecule":
+        """New molecule with the atoms whose ``temperature_factor >= cutoff``."""
+        keep = self._cols["temperature_factor"] >= float(cutoff)
+        return self.select(keep)
+
+    def select(self, keep: np.ndarray) -> "Molecule":
+        cols = {k: v[keep] for k, v in self._cols.items()}
+        return Molecule._from_columns(cols, self.xyz[keep], self.id)
+
+    def copy(self) -> "Molecule":
+        return Molecule._from_columns({k: v.copy() for k, v in self._cols.items()}, self.xyz.copy(), self.id)
+
+    def with_xyz(self, xyz: np.ndarray) -> "Molecule":
+        """Same atoms, other coordinates (used for ``Hit.molecule(transform=True)``)."""
+        return Molecule._from_columns(self._cols, xyz, self.id)
+
+    def column(self, name: str) -> np.ndarray:
+        return self._cols[name]
+
+    def __len__(self) -> int:
+        return self.xyz.shape[0]
+
+    def __bool__(self) -> bool:
+        return self.xyz.shape[0] > 0
+
+    def atom(self, i: int) -> Atom:
+        c = self._cols
+        x, y, z = self.xyz[i]
+        return Atom(
+            serial=c["serial"][i], name=str(c["name"][i]), altloc=str(c["altloc"][i]),
+            residue_name=str(c["residue_name"][i]), chain_id=str(c["chain_id"][i]),
+            residue_number=c["residue_number"][i], insertion_code=str(c["insertion_code"][i]),
+            x=x, y=y, z=z, occupancy=c["occupancy"][i],
+            temperature_factor=c["temperature_factor"][i], segment=str(c["segment"][i]),
+            element=str(c["element"][i]), charge=c["charge"][i],
+        )
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            idx = np.arange(len(self))[i]
+            return self.select(idx)
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        return self.atom(i)
+
+    def __iter__(self) -> Iterator[Atom]:
+        if self._atoms is None:
+            self._atoms = [self.atom(i) for i in range(len(self))]
+        return iter(self._atoms)
+
+    # hashable + comparable: molecules are dict keys in Matcher.run (jess_run.py:915)
+    def _content_digest(self) -> bytes:
+        if self._digest is None:
+            h = hashlib.blake2b(digest_size=16)
+            h.update(repr(self.id).encode())
+            h.update(self.xyz.tobytes())
+            for k, _ in _COLUMNS:
+                h.update(self._cols[k].tobytes())
+            self._digest = h.digest()
+        return self._digest
+
+    def __eq__(self, other):
+        if not isinstance(other, Molecule):
+            return NotImplemented
+        return self is other or self._content_digest() == other._content_digest()
+
+    def __ne__(self, other):
+        if not isinstance(other, Molecule):
+            return NotImplemented
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash(self._content_digest())
+
+    def __repr__(self):
+        return f"Molecule(id={self.id!r}, atoms={len(self)})"

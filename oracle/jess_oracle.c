@@ -1,0 +1,594 @@
+/*
+ * jess_oracle.c -- CPU restatement of the geometric matching hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * build, load or call this file.  The product path (enzymm_b200/) never does: it fails loudly
+ * when its CUDA library is missing.
+ *
+ * What is restated.  `pyjess.Jess(templates).query(molecule, rmsd_threshold, distance_cutoff,
+ * max_dynamic_distance, max_candidates, best_match=True, ignore_chain=...)` as called from
+ * enzymm/jess_run.py:800-811.  The arithmetic lives in the third-party dependency
+ * `pyjess ~=0.5.0` (reference pyproject.toml:30; Cython wrapper of the C library Jess,
+ * README.md:12), which is NOT vendored under /root/reference and not installable offline, so
+ * this file follows the published behaviour as pinned by the reference's own golden vectors
+ * (tests/test_jess_run.py:75-145, 311-357; rule numbers below are SURVEY.md 8(c)):
+ *
+ *   rule 2  residue typing: match_mode < 100 => query residue name must be one of the template
+ *           atom's residue_names; match_mode >= 100 => no residue restriction.
+ *   rule 3  atom-name typing by match_mode % 100 on whitespace-stripped names:
+ *           0 exact name, 3 same first character, 8 same second character,
+ *           1 query atom's first character is N or O  (UNPINNED by any golden; data-driven).
+ *   rule 4  template atoms sharing (chain_id, residue_number) bind query atoms sharing
+ *           (chain_id, residue_number).
+ *   rule 5  injective.
+ *   rule 6  every template pair (i,j): | |q_i-q_j| - |t_i-t_j| | <= delta_ij, delta_ij =
+ *           distance_cutoff when max_dynamic_distance == distance_cutoff, else
+ *           min(distance_cutoff + w_i + w_j, max_dynamic_distance)  (dynamic form UNPINNED).
+ *   rule 7  Kabsch superposition about centroids, proper rotation; rmsd = sqrt(SSD/N);
+ *           accept iff rmsd <= rmsd_threshold.
+ *   rule 8  best_match: minimum-rmsd accepted assignment per template (ties: lexicographically
+ *           smallest atom-index tuple), atoms in template order.
+ *   rule 9  transform q' = R (q - qbar) + tbar.
+ *   rule 11 ignore_chain=0: template atoms on equal chains <=> query atoms on equal chains
+ *           (UNPINNED; EnzyMM always passes ignore_chain=True, jess_run.py:810).
+ *   max_candidates: at most that many complete assignments are examined per template, in
+ *           canonical order (template atom order, ascending query atom index); UNPINNED beyond
+ *           "not reached at defaults on the fixtures".
+ *
+ * Parity status: PINNED at the reference's golden vectors (both RMSDs, both orientations, the
+ * five match vectors, both matched-atom lists, all TestMatcher counts) -- see
+ * tests/test_oracle_golden.py.  Everything marked UNPINNED above has no reference vector.
+ *
+ * All floating point is IEEE double with separately rounded + - * / sqrt (build with
+ * -ffp-contract=off).  The CUDA path evaluates every accept/reject decision with the same
+ * expressions in the same order, so decisions are comparable bit for bit.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <pthread.h>
+
+#define JO_MAX_ATOMS 32
+
+typedef struct {
+    /* molecule */
+    int n;
+    const double *xyz;       /* [n][3] */
+    const char *name;        /* [n][4] stripped, NUL padded */
+    const char *resname;     /* [n][4] */
+    const char *chain;       /* [n][2] */
+    const int32_t *resnum;   /* [n]    */
+    /* derived */
+    int32_t *res_ord;        /* residue ordinal per atom */
+    int32_t *res_start;      /* CSR residue -> atoms */
+    int32_t *res_atoms;
+    int n_res;
+} jo_mol;
+
+typedef struct {
+    int m;
+    const double *xyz;       /* [m][3] */
+    const int32_t *mode;     /* [m] */
+    const char *chain;       /* [m][2] */
+    const int32_t *resnum;   /* [m] */
+    const double *weight;    /* [m] */
+    const int32_t *an_off;   /* [m+1] into an_pool (4-byte names) */
+    const char *an_pool;
+    const int32_t *rn_off;   /* [m+1] into rn_pool */
+    const char *rn_pool;
+} jo_tpl;
+
+typedef struct {
+    int32_t found;
+    int32_t overflow;
+    double rmsd;
+    int32_t atoms[JO_MAX_ATOMS];
+    double rot[9];
+    double qbar[3];
+    double tbar[3];
+    int64_t n_complete;
+    int64_t n_accepted;
+    int64_t nodes;
+    int64_t dist_evals;
+} jo_result;
+
+/* ---------------------------------------------------------------------------------------- */
+/* canonical arithmetic                                                                      */
+
+static double jo_dist(const double *a, const double *b)
+{
+    double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    return sqrt((dx * dx + dy * dy) + dz * dz);
+}
+
+/* Cyclic Jacobi on a symmetric 4x4; eigenvalues on the diagonal of a, vectors in columns of v. */
+static void jo_jacobi4(double a[4][4], double v[4][4])
+{
+    int p, q, k, sweep;
+    for (p = 0; p < 4; ++p)
+        for (q = 0; q < 4; ++q) v[p][q] = (p == q) ? 1.0 : 0.0;
+    for (sweep = 0; sweep < 64; ++sweep) {
+        double off = 0.0;
+        for (p = 0; p < 3; ++p)
+            for (q = p + 1; q < 4; ++q) off = off + fabs(a[p][q]);
+        if (off == 0.0) break;
+        for (p = 0; p < 3; ++p) {
+            for (q = p + 1; q < 4; ++q) {
+                double apq = a[p][q];
+                double g, h, t, c, s, tau, theta;
+                if (apq == 0.0) continue;
+                g = 100.0 * fabs(apq);
+                if (sweep > 3 && fabs(a[p][p]) + g == fabs(a[p][p]) && fabs(a[q][q]) + g == fabs(a[q][q])) {
+                    a[p][q] = 0.0;
+                    a[q][p] = 0.0;
+                    continue;
+                }
+                h = a[q][q] - a[p][p];
+                if (fabs(h) + g == fabs(h)) {
+                    t = apq / h;
+                } else {
+                    theta = (0.5 * h) / apq;
+                    t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+                    if (theta < 0.0) t = -t;
+                }
+                c = 1.0 / sqrt(1.0 + t * t);
+                s = t * c;
+                tau = s / (1.0 + c);
+                h = t * apq;
+                a[p][p] = a[p][p] - h;
+                a[q][q] = a[q][q] + h;
+                a[p][q] = 0.0;
+                a[q][p] = 0.0;
+                for (k = 0; k < 4; ++k) {
+                    if (k != p && k != q) {
+                        double akp = a[k][p], akq = a[k][q];
+                        double nkp = akp - s * (akq + akp * tau);
+                        double nkq = akq + s * (akp - akq * tau);
+                        a[k][p] = nkp; a[p][k] = nkp;
+                        a[k][q] = nkq; a[q][k] = nkq;
+                    }
+                }
+                for (k = 0; k < 4; ++k) {
+                    double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = vkp - s * (vkq + vkp * tau);
+                    v[k][q] = vkq + s * (vkp - vkq * tau);
+                }
+            }
+        }
+    }
+}
+
+/* Optimal proper rotation of query points onto template points (Horn's quaternion form of the
+ * Kabsch problem); returns rmsd, fills rot (row major), qbar, tbar. */
+static double jo_superpose(int m, const double *t, const double *q, double rot[9], double qbar[3],
+                           double tbar[3])
+{
+    double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double N[4][4], V[4][4];
+    double inv_m = 1.0 / (double)m;
+    double best, q0, q1, q2, q3, nrm, ssd;
+    int i, a, b, col;
+    for (a = 0; a < 3; ++a) {
+        double sq = 0.0, st = 0.0;
+        for (i = 0; i < m; ++i) { sq = sq + q[3 * i + a]; st = st + t[3 * i + a]; }
+        qbar[a] = sq * inv_m;
+        tbar[a] = st * inv_m;
+    }
+    for (i = 0; i < m; ++i)
+        for (a = 0; a < 3; ++a)
+            for (b = 0; b < 3; ++b)
+                S[a][b] = S[a][b] + (q[3 * i + a] - qbar[a]) * (t[3 * i + b] - tbar[b]);
+    N[0][0] = (S[0][0] + S[1][1]) + S[2][2];
+    N[1][1] = (S[0][0] - S[1][1]) - S[2][2];
+    N[2][2] = (S[1][1] - S[0][0]) - S[2][2];
+    N[3][3] = (S[2][2] - S[0][0]) - S[1][1];
+    N[0][1] = N[1][0] = S[1][2] - S[2][1];
+    N[0][2] = N[2][0] = S[2][0] - S[0][2];
+    N[0][3] = N[3][0] = S[0][1] - S[1][0];
+    N[1][2] = N[2][1] = S[0][1] + S[1][0];
+    N[1][3] = N[3][1] = S[2][0] + S[0][2];
+    N[2][3] = N[3][2] = S[1][2] + S[2][1];
+    jo_jacobi4(N, V);
+    col = 0;
+    best = N[0][0];
+    for (i = 1; i < 4; ++i)
+        if (N[i][i] > best) { best = N[i][i]; col = i; }
+    q0 = V[0][col]; q1 = V[1][col]; q2 = V[2][col]; q3 = V[3][col];
+    nrm = sqrt(((q0 * q0 + q1 * q1) + q2 * q2) + q3 * q3);
+    q0 = q0 / nrm; q1 = q1 / nrm; q2 = q2 / nrm; q3 = q3 / nrm;
+    rot[0] = ((q0 * q0 + q1 * q1) - q2 * q2) - q3 * q3;
+    rot[1] = 2.0 * (q1 * q2 - q0 * q3);
+    rot[2] = 2.0 * (q1 * q3 + q0 * q2);
+    rot[3] = 2.0 * (q1 * q2 + q0 * q3);
+    rot[4] = ((q0 * q0 - q1 * q1) + q2 * q2) - q3 * q3;
+    rot[5] = 2.0 * (q2 * q3 - q0 * q1);
+    rot[6] = 2.0 * (q1 * q3 - q0 * q2);
+    rot[7] = 2.0 * (q2 * q3 + q0 * q1);
+    rot[8] = ((q0 * q0 - q1 * q1) - q2 * q2) + q3 * q3;
+    ssd = 0.0;
+    for (i = 0; i < m; ++i) {
+        double x = q[3 * i] - qbar[0], y = q[3 * i + 1] - qbar[1], z = q[3 * i + 2] - qbar[2];
+        double rx = ((rot[0] * x + rot[1] * y) + rot[2] * z) - (t[3 * i] - tbar[0]);
+        double ry = ((rot[3] * x + rot[4] * y) + rot[5] * z) - (t[3 * i + 1] - tbar[1]);
+        double rz = ((rot[6] * x + rot[7] * y) + rot[8] * z) - (t[3 * i + 2] - tbar[2]);
+        ssd = ssd + ((rx * rx + ry * ry) + rz * rz);
+    }
+    return sqrt(ssd * inv_m);
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* typing (rules 2-3)                                                                        */
+
+static int jo_name_eq(const char *a, const char *b) { return memcmp(a, b, 4) == 0; }
+
+/* returns 1 match, 0 no match, -1 unknown match mode */
+static int jo_type_match(const jo_tpl *T, int i, const char *qname, const char *qres)
+{
+    int mode = T->mode[i];
+    int k, sub = mode % 100;
+    if (mode < 0) return -1;
+    if (mode < 100) {
+        int ok = 0;
+        for (k = T->rn_off[i]; k < T->rn_off[i + 1]; ++k)
+            if (jo_name_eq(T->rn_pool + 4 * k, qres)) { ok = 1; break; }
+        if (!ok) return 0;
+    }
+    switch (sub) {
+    case 0:
+        for (k = T->an_off[i]; k < T->an_off[i + 1]; ++k)
+            if (jo_name_eq(T->an_pool + 4 * k, qname)) return 1;
+        return 0;
+    case 1:
+        return qname[0] == 'N' || qname[0] == 'O';
+    case 3:
+        for (k = T->an_off[i]; k < T->an_off[i + 1]; ++k)
+            if (T->an_pool[4 * k] == qname[0]) return 1;
+        return 0;
+    case 8:
+        for (k = T->an_off[i]; k < T->an_off[i + 1]; ++k)
+            if (T->an_pool[4 * k + 1] == qname[1]) return 1;
+        return 0;
+    default:
+        return -1;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* molecule residue index (rule 4)                                                           */
+
+typedef struct { uint64_t key; int32_t idx; } jo_keyed;
+
+static int jo_keyed_cmp(const void *a, const void *b)
+{
+    const jo_keyed *x = (const jo_keyed *)a, *y = (const jo_keyed *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+static uint64_t jo_res_key(const char *chain, int32_t resnum)
+{
+    return ((uint64_t)(uint8_t)chain[0] << 40) | ((uint64_t)(uint8_t)chain[1] << 32) | (uint32_t)resnum;
+}
+
+static int jo_mol_index(jo_mol *M)
+{
+    int i, r;
+    jo_keyed *k = (jo_keyed *)malloc(sizeof(jo_keyed) * (size_t)(M->n > 0 ? M->n : 1));
+    M->res_ord = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M->n > 0 ? M->n : 1));
+    M->res_atoms = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M->n > 0 ? M->n : 1));
+    M->res_start = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M->n + 2));
+    if (!k || !M->res_ord || !M->res_atoms || !M->res_start) return -1;
+    for (i = 0; i < M->n; ++i) { k[i].key = jo_res_key(M->chain + 2 * i, M->resnum[i]); k[i].idx = i; }
+    qsort(k, (size_t)M->n, sizeof(jo_keyed), jo_keyed_cmp);
+    r = -1;
+    for (i = 0; i < M->n; ++i) {
+        if (i == 0 || k[i].key != k[i - 1].key) { ++r; M->res_start[r] = i; }
+        M->res_ord[k[i].idx] = r;
+        M->res_atoms[i] = k[i].idx;
+    }
+    M->n_res = r + 1;
+    M->res_start[M->n_res] = M->n;
+    free(k);
+    return 0;
+}
+
+static void jo_mol_free(jo_mol *M)
+{
+    free(M->res_ord); free(M->res_atoms); free(M->res_start);
+    M->res_ord = M->res_atoms = M->res_start = NULL;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* per-molecule typing cache: the string predicate of rules 2-3 is evaluated once per distinct   */
+/* template-atom typing key (tkey), not once per template atom                                   */
+
+typedef struct {
+    int n_keys;
+    uint8_t **compat;   /* [n_keys][n] */
+    int32_t **cand;     /* [n_keys] ascending atom lists */
+    int *n_cand;
+} jo_typing;
+
+static void jo_typing_free(jo_typing *Y)
+{
+    int k;
+    if (Y->compat) for (k = 0; k < Y->n_keys; ++k) free(Y->compat[k]);
+    if (Y->cand) for (k = 0; k < Y->n_keys; ++k) free(Y->cand[k]);
+    free(Y->compat); free(Y->cand); free(Y->n_cand);
+    memset(Y, 0, sizeof *Y);
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* search                                                                                    */
+
+typedef struct {
+    const jo_mol *M;
+    const jo_tpl *T;
+    int m;
+    double dt[JO_MAX_ATOMS][JO_MAX_ATOMS];
+    double delta[JO_MAX_ATOMS][JO_MAX_ATOMS];
+    int leader[JO_MAX_ATOMS];            /* first template atom of the same residue, or -1 */
+    const int32_t *cand[JO_MAX_ATOMS];   /* typing-compatible query atoms, ascending */
+    int n_cand[JO_MAX_ATOMS];
+    const uint8_t *compat[JO_MAX_ATOMS]; /* per query atom flag */
+    uint8_t *used;
+    int32_t assign[JO_MAX_ATOMS];
+    double rmsd_thr;
+    int64_t max_cand;
+    int ignore_chain;
+    int stop;
+    jo_result *out;
+} jo_ctx;
+
+static int jo_chain_ok(const jo_ctx *C)
+{
+    int i, j;
+    for (i = 0; i < C->m; ++i)
+        for (j = i + 1; j < C->m; ++j) {
+            int same_t = memcmp(C->T->chain + 2 * i, C->T->chain + 2 * j, 2) == 0;
+            int same_q = memcmp(C->M->chain + 2 * C->assign[i], C->M->chain + 2 * C->assign[j], 2) == 0;
+            if (same_t != same_q) return 0;
+        }
+    return 1;
+}
+
+static void jo_complete(jo_ctx *C)
+{
+    double q[3 * JO_MAX_ATOMS], rot[9], qbar[3], tbar[3], rmsd;
+    jo_result *R = C->out;
+    int i;
+    if (!C->ignore_chain && !jo_chain_ok(C)) return;
+    R->n_complete++;
+    for (i = 0; i < C->m; ++i) memcpy(q + 3 * i, C->M->xyz + 3 * C->assign[i], 3 * sizeof(double));
+    rmsd = jo_superpose(C->m, C->T->xyz, q, rot, qbar, tbar);
+    if (rmsd <= C->rmsd_thr) {
+        R->n_accepted++;
+        if (!R->found || rmsd < R->rmsd) { /* canonical order => first seen is lexicographically least */
+            R->found = 1;
+            R->rmsd = rmsd;
+            for (i = 0; i < C->m; ++i) R->atoms[i] = C->assign[i];
+            memcpy(R->rot, rot, sizeof rot);
+            memcpy(R->qbar, qbar, sizeof qbar);
+            memcpy(R->tbar, tbar, sizeof tbar);
+        }
+    }
+    if (R->n_complete >= C->max_cand) { R->overflow = 1; C->stop = 1; }
+}
+
+static void jo_dfs(jo_ctx *C, int k)
+{
+    const jo_mol *M = C->M;
+    const int32_t *list;
+    int count, c, j;
+    if (C->leader[k] >= 0) {
+        int r = M->res_ord[C->assign[C->leader[k]]];
+        list = M->res_atoms + M->res_start[r];
+        count = M->res_start[r + 1] - M->res_start[r];
+    } else {
+        list = C->cand[k];
+        count = C->n_cand[k];
+    }
+    for (c = 0; c < count && !C->stop; ++c) {
+        int qa = list[c];
+        int ok = 1;
+        if (!C->compat[k][qa] || C->used[qa]) continue;
+        C->out->nodes++;
+        for (j = 0; j < k; ++j) {
+            double d = jo_dist(M->xyz + 3 * qa, M->xyz + 3 * C->assign[j]);
+            C->out->dist_evals++;
+            if (!(fabs(d - C->dt[k][j]) <= C->delta[k][j])) { ok = 0; break; }
+        }
+        if (!ok) continue;
+        C->assign[k] = qa;
+        if (k + 1 == C->m) {
+            jo_complete(C);
+        } else {
+            C->used[qa] = 1;
+            jo_dfs(C, k + 1);
+            C->used[qa] = 0;
+        }
+    }
+}
+
+/* One (molecule, template) query.  Returns 0, or a negative error code:
+ * -1 allocation, -2 template too large / empty, -3 unknown match mode. */
+static int jo_query_one(const jo_mol *M, const jo_tpl *T, const jo_typing *Y, const int32_t *tkey,
+                        double rmsd_thr, double dist_cut, double max_dyn, int64_t max_cand,
+                        int ignore_chain, jo_result *out)
+{
+    jo_ctx *C;
+    int i, j, rc = 0;
+    memset(out, 0, sizeof *out);
+    if (T->m <= 0 || T->m > JO_MAX_ATOMS) return -2;
+    C = (jo_ctx *)calloc(1, sizeof *C);
+    if (!C) return -1;
+    C->M = M; C->T = T; C->m = T->m; C->out = out;
+    C->rmsd_thr = rmsd_thr; C->max_cand = max_cand > 0 ? max_cand : INT64_MAX; C->ignore_chain = ignore_chain;
+    for (i = 0; i < T->m; ++i) {
+        C->leader[i] = -1;
+        for (j = 0; j < i; ++j)
+            if (memcmp(T->chain + 2 * i, T->chain + 2 * j, 2) == 0 && T->resnum[i] == T->resnum[j]) {
+                C->leader[i] = j;
+                break;
+            }
+        for (j = 0; j < T->m; ++j) {
+            C->dt[i][j] = jo_dist(T->xyz + 3 * i, T->xyz + 3 * j);
+            if (max_dyn == dist_cut) {
+                C->delta[i][j] = dist_cut;
+            } else {
+                double d = (dist_cut + T->weight[i]) + T->weight[j];
+                C->delta[i][j] = d < max_dyn ? d : max_dyn;
+            }
+        }
+    }
+    C->used = (uint8_t *)calloc((size_t)(M->n > 0 ? M->n : 1), 1);
+    if (!C->used) rc = -1;
+    for (i = 0; i < T->m; ++i) {
+        C->compat[i] = Y->compat[tkey[i]];
+        C->cand[i] = Y->cand[tkey[i]];
+        C->n_cand[i] = Y->n_cand[tkey[i]];
+    }
+    if (rc == 0) {
+        int feasible = 1;
+        for (i = 0; i < T->m; ++i)
+            if (C->n_cand[i] == 0) feasible = 0;
+        if (feasible) jo_dfs(C, 0);
+    }
+    free(C->used);
+    free(C);
+    return rc;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* exported entry points (ctypes)                                                            */
+
+/*
+ * Batch: n_mol molecules (CSR by mol_off) x n_tpl templates (CSR by tpl_off); one parameter
+ * triple per template.  results is [n_mol][n_tpl].  Threads over molecules (the reference
+ * parallelises the same way: ThreadPool over molecules, jess_run.py:919-981).
+ */
+typedef struct {
+    int n_mol; const int64_t *mol_off; const double *xyz; const char *name; const char *resname;
+    const char *chain; const int32_t *resnum;
+    int n_tpl; const int32_t *tpl_off; const double *txyz; const int32_t *tmode; const char *tchain;
+    const int32_t *tresnum; const double *tweight; const int32_t *an_off; const char *an_pool;
+    const int32_t *rn_off; const char *rn_pool; int n_keys; const int32_t *tkey; const int32_t *key_rep;
+    const double *rmsd_thr; const double *dist_cut; const double *max_dyn; int64_t max_candidates;
+    int ignore_chain; jo_result *results;
+    int next;      /* work counter (molecule index), guarded by lock */
+    int status;
+    pthread_mutex_t lock;
+} jo_job;
+
+static int jo_run_molecule(const jo_job *J, int mi)
+{
+    jo_mol M;
+    jo_typing Y;
+    int ti, rc;
+    int64_t b = J->mol_off[mi];
+    memset(&M, 0, sizeof M);
+    memset(&Y, 0, sizeof Y);
+    M.n = (int)(J->mol_off[mi + 1] - b);
+    M.xyz = J->xyz + 3 * b; M.name = J->name + 4 * b; M.resname = J->resname + 4 * b;
+    M.chain = J->chain + 2 * b; M.resnum = J->resnum + b;
+    rc = jo_mol_index(&M);
+    if (rc == 0) { /* typing cache: one string-predicate pass per distinct typing key */
+        jo_tpl A; /* all template atoms viewed as one flat template */
+        int k, a;
+        A.m = J->tpl_off[J->n_tpl]; A.xyz = J->txyz; A.mode = J->tmode; A.chain = J->tchain;
+        A.resnum = J->tresnum; A.weight = J->tweight; A.an_off = J->an_off; A.an_pool = J->an_pool;
+        A.rn_off = J->rn_off; A.rn_pool = J->rn_pool;
+        Y.n_keys = J->n_keys;
+        Y.compat = (uint8_t **)calloc((size_t)J->n_keys + 1, sizeof(uint8_t *));
+        Y.cand = (int32_t **)calloc((size_t)J->n_keys + 1, sizeof(int32_t *));
+        Y.n_cand = (int *)calloc((size_t)J->n_keys + 1, sizeof(int));
+        if (!Y.compat || !Y.cand || !Y.n_cand) rc = -1;
+        for (k = 0; k < J->n_keys && rc == 0; ++k) {
+            Y.compat[k] = (uint8_t *)malloc((size_t)(M.n > 0 ? M.n : 1));
+            Y.cand[k] = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M.n > 0 ? M.n : 1));
+            if (!Y.compat[k] || !Y.cand[k]) { rc = -1; break; }
+            for (a = 0; a < M.n; ++a) {
+                int ok = jo_type_match(&A, J->key_rep[k], M.name + 4 * a, M.resname + 4 * a);
+                if (ok < 0) { rc = -3; break; }
+                Y.compat[k][a] = (uint8_t)ok;
+                if (ok) Y.cand[k][Y.n_cand[k]++] = a;
+            }
+        }
+    }
+    for (ti = 0; ti < J->n_tpl && rc == 0; ++ti) {
+        jo_tpl T;
+        int tb = J->tpl_off[ti];
+        T.m = J->tpl_off[ti + 1] - tb;
+        T.xyz = J->txyz + 3 * tb; T.mode = J->tmode + tb; T.chain = J->tchain + 2 * tb;
+        T.resnum = J->tresnum + tb; T.weight = J->tweight + tb;
+        T.an_off = J->an_off + tb; T.an_pool = J->an_pool; T.rn_off = J->rn_off + tb; T.rn_pool = J->rn_pool;
+        rc = jo_query_one(&M, &T, &Y, J->tkey + tb, J->rmsd_thr[ti], J->dist_cut[ti], J->max_dyn[ti],
+                          J->max_candidates, J->ignore_chain,
+                          J->results + (size_t)mi * (size_t)J->n_tpl + ti);
+    }
+    jo_typing_free(&Y);
+    jo_mol_free(&M);
+    return rc;
+}
+
+static void *jo_worker(void *arg)
+{
+    jo_job *J = (jo_job *)arg;
+    for (;;) {
+        int mi, rc;
+        pthread_mutex_lock(&J->lock);
+        mi = J->next++;
+        pthread_mutex_unlock(&J->lock);
+        if (mi >= J->n_mol) break;
+        rc = jo_run_molecule(J, mi);
+        if (rc != 0) {
+            pthread_mutex_lock(&J->lock);
+            J->status = rc;
+            pthread_mutex_unlock(&J->lock);
+        }
+    }
+    return NULL;
+}
+
+int jo_batch_query(int n_mol, const int64_t *mol_off, const double *xyz, const char *name,
+                   const char *resname, const char *chain, const int32_t *resnum,
+                   int n_tpl, const int32_t *tpl_off, const double *txyz, const int32_t *tmode,
+                   const char *tchain, const int32_t *tresnum, const double *tweight,
+                   const int32_t *an_off, const char *an_pool, const int32_t *rn_off,
+                   const char *rn_pool, int n_keys, const int32_t *tkey, const int32_t *key_rep,
+                   const double *rmsd_thr, const double *dist_cut,
+                   const double *max_dyn, int64_t max_candidates, int ignore_chain, int n_threads,
+                   jo_result *results)
+{
+    jo_job J;
+    pthread_t threads[256];
+    int i, started = 0;
+    J.n_mol = n_mol; J.mol_off = mol_off; J.xyz = xyz; J.name = name; J.resname = resname;
+    J.chain = chain; J.resnum = resnum; J.n_tpl = n_tpl; J.tpl_off = tpl_off; J.txyz = txyz;
+    J.tmode = tmode; J.tchain = tchain; J.tresnum = tresnum; J.tweight = tweight; J.an_off = an_off;
+    J.an_pool = an_pool; J.rn_off = rn_off; J.rn_pool = rn_pool; J.n_keys = n_keys; J.tkey = tkey;
+    J.key_rep = key_rep; J.rmsd_thr = rmsd_thr; J.dist_cut = dist_cut; J.max_dyn = max_dyn;
+    J.max_candidates = max_candidates; J.ignore_chain = ignore_chain; J.results = results;
+    J.next = 0; J.status = 0;
+    pthread_mutex_init(&J.lock, NULL);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads > n_mol) n_threads = n_mol > 0 ? n_mol : 1;
+    for (i = 1; i < n_threads; ++i)
+        if (pthread_create(&threads[started], NULL, jo_worker, &J) == 0) ++started;
+    jo_worker(&J);
+    for (i = 0; i < started; ++i) pthread_join(threads[i], NULL);
+    pthread_mutex_destroy(&J.lock);
+    return J.status;
+}
+
+/* Standalone superposition, exported so tests can check it against an SVD Kabsch. */
+double jo_kabsch(int m, const double *t, const double *q, double *rot, double *qbar, double *tbar)
+{
+    return jo_superpose(m, t, q, rot, qbar, tbar);
+}
+
+int jo_result_size(void) { return (int)sizeof(jo_result); }
+int jo_max_atoms(void) { return JO_MAX_ATOMS; }
