@@ -1,0 +1,538 @@
+// emm_api.cu -- host side of the C ABI declared in include/enzymm_b200.h.
+//
+// Owns device memory (plain cudaMalloc, no torch types), lays structure blobs out, launches the
+// prepare and search kernels on the caller's stream and brings hits back sorted.  There is no
+// CPU fallback anywhere: without a CUDA device every entry point fails with EMM_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "emm_device.cuh"
+
+namespace emm {
+void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff,
+                    unsigned long long *stats, unsigned long long *bad, int sm_count, cudaStream_t stream);
+size_t search_smem_bytes(int blob_cap, int levels);
+size_t search_fixed_smem(int levels);
+cudaError_t configure_search(int smem_bytes);
+void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream);
+void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
+                   const unsigned char *skip, bool stats, int grid, size_t smem, cudaStream_t stream);
+}  // namespace emm
+
+using namespace emm;
+
+static thread_local std::string g_error;
+
+static int fail(emm_status st, const std::string &msg)
+{
+    g_error = msg;
+    return (int)st;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(EMM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+struct emm_library {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int compat_version = 0;
+    std::vector<uint16_t> class_leaders;   // per typing class: leader lists it appears in
+    int stats_enabled = 0;
+    DevLibrary d{};
+    std::vector<void *> allocs;
+    std::vector<uint16_t> h_leader_ttype;
+    uint32_t *d_compat = nullptr;
+    double *d_rmsd = nullptr, *d_cut = nullptr, *d_dyn = nullptr, *d_lr_table = nullptr;
+    int32_t *d_lr_index = nullptr;
+    int lr_capacity = 0;
+};
+
+struct emm_session {
+    emm_library *lib = nullptr;
+    int64_t max_atoms = 0;
+    int32_t max_structures = 0;
+    int64_t hit_capacity = 0;
+    // device columns
+    int64_t *d_atom_off = nullptr;
+    double *d_xyz = nullptr;
+    uint16_t *d_klass = nullptr;
+    int32_t *d_residue = nullptr;
+    float *d_bfactor = nullptr;
+    uint16_t *d_chain = nullptr;
+    int32_t *d_atom_id = nullptr;
+    unsigned char *d_blob = nullptr;
+    int64_t blob_capacity = 0;
+    int64_t *d_blob_off = nullptr;
+    emm_hit *d_hits = nullptr;
+    unsigned long long *d_hit_count = nullptr;
+    unsigned int *d_work = nullptr;
+    int *d_any = nullptr, *d_pass = nullptr;
+    unsigned char *d_skip = nullptr;
+    unsigned long long *d_stats = nullptr;
+    // current batch
+    int32_t n_structures = 0;
+    int64_t n_atoms = 0;
+    bool has_bfactor = false, has_chain = false, has_atom_id = false;
+    bool prepared = false;
+    float prepared_cutoff = -1.f;
+    int prepared_version = -1;
+    std::vector<int64_t> h_blob_off;
+    int last_launches = 0;
+};
+
+template <typename T>
+static int dev_copy(emm_library *lib, const T *host, size_t count, T **out)
+{
+    *out = nullptr;
+    if (count == 0) count = 1;
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    lib->allocs.push_back(p);
+    if (host) CUDA_TRY(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    else CUDA_TRY(cudaMemset(p, 0, count * sizeof(T)));
+    *out = reinterpret_cast<T *>(p);
+    return EMM_OK;
+}
+
+static void compute_class_leaders(emm_library *lib, int class_words, const uint32_t *compat)
+{
+    lib->class_leaders.assign((size_t)lib->d.class_words_cap * 32, 0);
+    for (uint16_t tt : lib->h_leader_ttype) {
+        const uint32_t *row = compat + (size_t)tt * class_words;
+        for (int w = 0; w < class_words; ++w) {
+            uint32_t bits = row[w];
+            while (bits) {
+                const int b = __builtin_ctz(bits);
+                lib->class_leaders[(size_t)w * 32 + b]++;
+                bits &= bits - 1;
+            }
+        }
+    }
+    lib->compat_version++;
+}
+
+extern "C" {
+
+int emm_abi_version(void) { return EMM_ABI_VERSION; }
+
+int emm_hit_size(void) { return (int)sizeof(emm_hit); }
+
+const char *emm_last_error(void) { return g_error.c_str(); }
+
+int emm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int emm_library_create(int device, const emm_library_desc *desc, emm_library **out)
+{
+    if (!out) return fail(EMM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!desc) return fail(EMM_ERR_INVALID, "desc is null");
+    int ndev = emm_device_count();
+    if (ndev <= 0) return fail(EMM_ERR_NO_DEVICE, "no CUDA device visible: enzymm_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EMM_ERR_INVALID, "device index out of range");
+    if (desc->n_templates <= 0 || desc->n_atoms <= 0) return fail(EMM_ERR_INVALID, "empty template library");
+    if (desc->n_leader <= 0 || desc->n_leader > 1023) return fail(EMM_ERR_INVALID, "n_leader must be in 1..1023");
+    if (desc->class_words <= 0 || desc->n_ttype <= 0) return fail(EMM_ERR_INVALID, "empty compat matrix");
+
+    // validate the search plans on the host: the kernels trust them
+    int max_m = 0;
+    for (int t = 0; t < desc->n_templates; ++t) {
+        const int a0 = desc->atom_off[t], m = desc->atom_off[t + 1] - a0;
+        if (m <= 0 || m > EMM_MAX_TEMPLATE_ATOMS) return fail(EMM_ERR_INVALID, "template atom count out of range (1..32)");
+        max_m = std::max(max_m, m);
+        if (desc->pair_off[t + 1] - desc->pair_off[t] != (int64_t)m * (m - 1) / 2)
+            return fail(EMM_ERR_INVALID, "pair_off does not match template size");
+        unsigned seen = 0;
+        for (int k = 0; k < m; ++k) {
+            const int src = desc->plan_src[a0 + k];
+            if (k == 0 && src >= 0) return fail(EMM_ERR_INVALID, "plan position 0 must be a leader");
+            if (src >= k) return fail(EMM_ERR_INVALID, "plan_src must refer to an earlier position");
+            if (src < 0 && -1 - src >= desc->n_leader) return fail(EMM_ERR_INVALID, "leader list index out of range");
+            if (desc->plan_ttype[a0 + k] >= desc->n_ttype) return fail(EMM_ERR_INVALID, "plan_ttype out of range");
+            const int pa = desc->plan_atom[a0 + k];
+            if (pa >= m || (seen >> pa) & 1u) return fail(EMM_ERR_INVALID, "plan_atom is not a permutation");
+            seen |= 1u << pa;
+        }
+        if (desc->n_residues[t] < 0 || desc->n_residues[t] > EMM_MAX_RESIDUES || desc->n_residues[t] * 3 > m)
+            return fail(EMM_ERR_INVALID, "n_residues out of range");
+        if (desc->lr_index[t] >= desc->n_lr || desc->lr_index[t] < -2) return fail(EMM_ERR_INVALID, "lr_index out of range");
+    }
+    for (int l = 0; l < desc->n_leader; ++l)
+        if (desc->leader_ttype[l] >= desc->n_ttype) return fail(EMM_ERR_INVALID, "leader_ttype out of range");
+
+    CUDA_TRY(cudaSetDevice(device));
+    emm_library *lib = new emm_library();
+    lib->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    lib->sm_count = prop.multiProcessorCount;
+    lib->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    lib->h_leader_ttype.assign(desc->leader_ttype, desc->leader_ttype + desc->n_leader);
+
+    DevLibrary &d = lib->d;
+    d.n_templates = desc->n_templates;
+    d.n_atoms = desc->n_atoms;
+    d.n_ttype = desc->n_ttype;
+    d.class_words = desc->class_words;
+    d.class_words_cap = std::max(desc->class_words, 32);   // room for 1024 classes without re-allocation
+    d.n_leader = desc->n_leader;
+    d.max_tpl_atoms = max_m;
+    d.n_lr = desc->n_lr;
+    const int T = desc->n_templates, A = desc->n_atoms;
+    const int64_t npairs = desc->pair_off[T];
+    int rc;
+#define COPY(field, src, count) if ((rc = dev_copy(lib, src, (size_t)(count), &field)) != EMM_OK) { emm_library_destroy(lib); return rc; }
+    int32_t *p_i32; double *p_f64; uint16_t *p_u16; uint8_t *p_u8; int16_t *p_i16; int64_t *p_i64; float *p_f32; uint32_t *p_u32;
+    COPY(p_i32, desc->atom_off, T + 1); d.atom_off = p_i32;
+    COPY(p_f64, desc->xyz, 3 * (size_t)A); d.xyz = p_f64;
+    COPY(p_f64, desc->weight, A); d.weight = p_f64;
+    COPY(p_u16, desc->chain, A); d.chain = p_u16;
+    COPY(p_u8, desc->plan_atom, A); d.plan_atom = p_u8;
+    COPY(p_u16, desc->plan_ttype, A); d.plan_ttype = p_u16;
+    COPY(p_i16, desc->plan_src, A); d.plan_src = p_i16;
+    COPY(p_i64, desc->pair_off, T + 1); d.pair_off = p_i64;
+    COPY(p_f64, desc->pair_dist, npairs); d.pair_dist = p_f64;
+    {
+        std::vector<float> p32((size_t)std::max<int64_t>(npairs, 1));
+        for (int64_t i = 0; i < npairs; ++i) p32[(size_t)i] = (float)desc->pair_dist[i];
+        COPY(p_f32, p32.data(), npairs); d.pair_dist32 = p_f32;
+    }
+    {
+        std::vector<uint32_t> wide((size_t)d.n_ttype * d.class_words_cap, 0u);
+        for (int r = 0; r < d.n_ttype; ++r)
+            memcpy(&wide[(size_t)r * d.class_words_cap], desc->compat + (size_t)r * desc->class_words, 4 * (size_t)desc->class_words);
+        COPY(p_u32, wide.data(), wide.size()); d.compat = p_u32; lib->d_compat = p_u32;
+    }
+    COPY(p_u16, desc->leader_ttype, desc->n_leader); d.leader_ttype = p_u16;
+    COPY(p_f64, desc->rmsd_threshold, T); d.rmsd_thr = p_f64; lib->d_rmsd = p_f64;
+    COPY(p_f64, desc->distance_cutoff, T); d.dist_cut = p_f64; lib->d_cut = p_f64;
+    COPY(p_f64, desc->max_dynamic_distance, T); d.max_dyn = p_f64; lib->d_dyn = p_f64;
+    COPY(p_i32, desc->n_residues, T); d.n_residues = p_i32;
+    COPY(p_u8, desc->orient_idx, (size_t)T * EMM_MAX_RESIDUES * 2); d.orient_idx = p_u8;
+    COPY(p_f64, desc->orient_vec, (size_t)T * EMM_MAX_RESIDUES * 3); d.orient_vec = p_f64;
+    COPY(p_i32, desc->lr_index, T); d.lr_index = p_i32; lib->d_lr_index = p_i32;
+    {
+        lib->lr_capacity = std::max(desc->n_lr, 64);
+        std::vector<double> tab((size_t)lib->lr_capacity * EMM_LR_MODELS * 4, 0.0);
+        if (desc->n_lr > 0) memcpy(tab.data(), desc->lr_table, sizeof(double) * (size_t)desc->n_lr * EMM_LR_MODELS * 4);
+        COPY(p_f64, tab.data(), tab.size()); d.lr_table = p_f64; lib->d_lr_table = p_f64;
+    }
+#undef COPY
+    compute_class_leaders(lib, desc->class_words, desc->compat);
+    const char *env = getenv("EMM_STATS");
+    lib->stats_enabled = env && env[0] == '1';
+    *out = lib;
+    return EMM_OK;
+}
+
+int emm_library_set_compat(emm_library *lib, int32_t class_words, const uint32_t *compat)
+{
+    if (!lib || !compat) return fail(EMM_ERR_INVALID, "null argument");
+    if (class_words <= 0 || class_words > lib->d.class_words_cap)
+        return fail(EMM_ERR_INVALID, "class_words exceeds the capacity fixed at library creation (1024 classes)");
+    CUDA_TRY(cudaSetDevice(lib->device));
+    std::vector<uint32_t> wide((size_t)lib->d.n_ttype * lib->d.class_words_cap, 0u);
+    for (int r = 0; r < lib->d.n_ttype; ++r)
+        memcpy(&wide[(size_t)r * lib->d.class_words_cap], compat + (size_t)r * class_words, 4 * (size_t)class_words);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(lib->d_compat, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice));
+    lib->d.class_words = class_words;
+    compute_class_leaders(lib, class_words, compat);
+    return EMM_OK;
+}
+
+int emm_library_set_thresholds(emm_library *lib, const double *rmsd_threshold, const double *distance_cutoff,
+                               const double *max_dynamic_distance)
+{
+    if (!lib || !rmsd_threshold || !distance_cutoff || !max_dynamic_distance) return fail(EMM_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(lib->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t bytes = sizeof(double) * (size_t)lib->d.n_templates;
+    CUDA_TRY(cudaMemcpy(lib->d_rmsd, rmsd_threshold, bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(lib->d_cut, distance_cutoff, bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(lib->d_dyn, max_dynamic_distance, bytes, cudaMemcpyHostToDevice));
+    return EMM_OK;
+}
+
+int emm_library_set_filter(emm_library *lib, const int32_t *lr_index, int32_t n_lr, const double *lr_table)
+{
+    if (!lib || !lr_index || (n_lr > 0 && !lr_table)) return fail(EMM_ERR_INVALID, "null argument");
+    if (n_lr < 0 || n_lr > lib->lr_capacity) return fail(EMM_ERR_INVALID, "n_lr exceeds the capacity fixed at library creation");
+    for (int t = 0; t < lib->d.n_templates; ++t)
+        if (lr_index[t] >= n_lr || lr_index[t] < -2) return fail(EMM_ERR_INVALID, "lr_index out of range");
+    CUDA_TRY(cudaSetDevice(lib->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(lib->d_lr_index, lr_index, sizeof(int32_t) * (size_t)lib->d.n_templates, cudaMemcpyHostToDevice));
+    if (n_lr > 0)
+        CUDA_TRY(cudaMemcpy(lib->d_lr_table, lr_table, sizeof(double) * (size_t)n_lr * EMM_LR_MODELS * 4, cudaMemcpyHostToDevice));
+    lib->d.n_lr = n_lr;
+    return EMM_OK;
+}
+
+void emm_library_destroy(emm_library *lib)
+{
+    if (!lib) return;
+    cudaSetDevice(lib->device);
+    for (void *p : lib->allocs) cudaFree(p);
+    delete lib;
+}
+
+int emm_session_create(emm_library *lib, int64_t max_atoms, int32_t max_structures, int64_t hit_capacity,
+                       emm_session **out)
+{
+    if (!out) return fail(EMM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!lib || max_atoms <= 0 || max_structures <= 0 || hit_capacity <= 0) return fail(EMM_ERR_INVALID, "bad session sizes");
+    CUDA_TRY(cudaSetDevice(lib->device));
+    emm_session *s = new emm_session();
+    s->lib = lib;
+    s->max_atoms = max_atoms;
+    s->max_structures = max_structures;
+    s->hit_capacity = hit_capacity;
+#define ALLOC(ptr, bytes) do { cudaError_t _e = cudaMalloc((void **)&(ptr), (size_t)(bytes)); if (_e != cudaSuccess) { emm_session_destroy(s); return fail(EMM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(_e)); } } while (0)
+    ALLOC(s->d_atom_off, 8 * ((size_t)max_structures + 1));
+    ALLOC(s->d_xyz, 24 * (size_t)max_atoms);
+    ALLOC(s->d_klass, 2 * (size_t)max_atoms);
+    ALLOC(s->d_residue, 4 * (size_t)max_atoms);
+    ALLOC(s->d_bfactor, 4 * (size_t)max_atoms);
+    ALLOC(s->d_chain, 2 * (size_t)max_atoms);
+    ALLOC(s->d_atom_id, 4 * (size_t)max_atoms);
+    ALLOC(s->d_blob_off, 8 * ((size_t)max_structures + 1));
+    ALLOC(s->d_hits, sizeof(emm_hit) * (size_t)hit_capacity);
+    ALLOC(s->d_hit_count, 16);
+    ALLOC(s->d_work, 4);
+    ALLOC(s->d_any, 4 * (size_t)max_structures);
+    ALLOC(s->d_pass, 4 * (size_t)max_structures);
+    ALLOC(s->d_skip, (size_t)max_structures);
+    ALLOC(s->d_stats, 8 * 8);
+    s->blob_capacity = 64 * max_atoms + (1024 + 4 * (int64_t)lib->d.n_leader) * max_structures;   // grown on demand at upload
+    ALLOC(s->d_blob, s->blob_capacity);
+#undef ALLOC
+    cudaMemset(s->d_hit_count, 0, 16);
+    cudaMemset(s->d_stats, 0, 64);
+    cudaMemset(s->d_any, 0, 4 * (size_t)max_structures);
+    cudaMemset(s->d_pass, 0, 4 * (size_t)max_structures);
+    *out = s;
+    return EMM_OK;
+}
+
+void emm_session_destroy(emm_session *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->lib->device);
+    void *ptrs[] = {s->d_atom_off, s->d_xyz, s->d_klass, s->d_residue, s->d_bfactor, s->d_chain, s->d_atom_id,
+                    s->d_blob, s->d_blob_off, s->d_hits, s->d_hit_count, s->d_work, s->d_any, s->d_pass,
+                    s->d_skip, s->d_stats};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete s;
+}
+
+int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
+{
+    if (!s || !b) return fail(EMM_ERR_INVALID, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (b->n_structures < 0 || b->n_structures > s->max_structures) return fail(EMM_ERR_INVALID, "batch has more structures than the session");
+    if (b->n_atoms < 0 || b->n_atoms > s->max_atoms) return fail(EMM_ERR_INVALID, "batch has more atoms than the session");
+    if (b->n_structures > 0 && (!b->atom_off || b->atom_off[0] != 0 || b->atom_off[b->n_structures] != b->n_atoms))
+        return fail(EMM_ERR_INVALID, "atom_off must start at 0 and end at n_atoms");
+    if (b->n_atoms > 0 && (!b->xyz || !b->klass || !b->residue)) return fail(EMM_ERR_INVALID, "xyz, klass and residue are required");
+    emm_library *lib = s->lib;
+    CUDA_TRY(cudaSetDevice(lib->device));
+    const int n = b->n_structures;
+    s->h_blob_off.assign((size_t)n + 1, 0);
+    const uint16_t *cl = lib->class_leaders.data();
+    const size_t n_class = lib->class_leaders.size();
+    for (int i = 0; i < n; ++i) {
+        const int64_t a0 = b->atom_off[i], a1 = b->atom_off[i + 1];
+        if (a1 < a0) return fail(EMM_ERR_INVALID, "atom_off must be non-decreasing");
+        int64_t entries = 0;   // exact size of this structure's leader lists (before masking)
+        for (int64_t a = a0; a < a1; ++a) {
+            const uint16_t k = b->klass[a];
+            if (k >= n_class) return fail(EMM_ERR_INVALID, "typing class out of range");
+            entries += cl[k];
+        }
+        s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + blob_bytes(a1 - a0, lib->d.n_leader, entries);
+    }
+    if (s->h_blob_off[(size_t)n] > s->blob_capacity) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(s->d_blob);
+        s->d_blob = nullptr;
+        s->blob_capacity = s->h_blob_off[(size_t)n] + (s->h_blob_off[(size_t)n] >> 3);
+        cudaError_t e = cudaMalloc((void **)&s->d_blob, (size_t)s->blob_capacity);
+        if (e != cudaSuccess) return fail(EMM_ERR_NOMEM, "cudaMalloc(blob)");
+    }
+    const size_t na = (size_t)b->n_atoms;
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_atom_off, b->atom_off, 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_blob_off, s->h_blob_off.data(), 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
+    }
+    if (na > 0) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_xyz, b->xyz, 24 * na, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_klass, b->klass, 2 * na, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_residue, b->residue, 4 * na, cudaMemcpyHostToDevice, stream));
+        if (b->bfactor) CUDA_TRY(cudaMemcpyAsync(s->d_bfactor, b->bfactor, 4 * na, cudaMemcpyHostToDevice, stream));
+        if (b->chain) CUDA_TRY(cudaMemcpyAsync(s->d_chain, b->chain, 2 * na, cudaMemcpyHostToDevice, stream));
+        if (b->atom_id) CUDA_TRY(cudaMemcpyAsync(s->d_atom_id, b->atom_id, 4 * na, cudaMemcpyHostToDevice, stream));
+    }
+    s->n_structures = n;
+    s->n_atoms = b->n_atoms;
+    s->has_bfactor = b->bfactor != nullptr;
+    s->has_chain = b->chain != nullptr;
+    s->has_atom_id = b->atom_id != nullptr;
+    s->prepared = false;
+    CUDA_TRY(cudaMemsetAsync(s->d_hit_count + 1, 0, 8, stream));   // bad-structure counter
+    return EMM_OK;
+}
+
+int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
+{
+    if (!s || !q) return fail(EMM_ERR_INVALID, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    emm_library *lib = s->lib;
+    CUDA_TRY(cudaSetDevice(lib->device));
+    s->last_launches = 0;
+    const int n = s->n_structures;
+    int tb = q->template_begin, te = q->template_end;
+    if (te <= 0 || te > lib->d.n_templates) te = lib->d.n_templates;
+    if (tb < 0) tb = 0;
+    if (q->reset_structure_state) {
+        CUDA_TRY(cudaMemsetAsync(s->d_hit_count, 0, 8, stream));
+        CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, 64, stream));
+        if (n > 0) {
+            CUDA_TRY(cudaMemsetAsync(s->d_any, 0, 4 * (size_t)n, stream));
+            CUDA_TRY(cudaMemsetAsync(s->d_pass, 0, 4 * (size_t)n, stream));
+        }
+    }
+    if (n == 0 || tb >= te) return EMM_OK;
+    if (!q->ignore_chain && !s->has_chain) return fail(EMM_ERR_INVALID, "ignore_chain=0 needs the chain column");
+
+    DevBatch B{};
+    B.n_structures = n;
+    B.atom_off = s->d_atom_off;
+    B.xyz = s->d_xyz;
+    B.klass = s->d_klass;
+    B.residue = s->d_residue;
+    B.bfactor = s->has_bfactor ? s->d_bfactor : nullptr;
+    B.chain = s->has_chain ? s->d_chain : nullptr;
+    B.atom_id = s->has_atom_id ? s->d_atom_id : nullptr;
+    B.blob = s->d_blob;
+    B.blob_off = s->d_blob_off;
+
+    const float cutoff = q->conservation_cutoff > 0.f ? q->conservation_cutoff : 0.f;
+    if (cutoff > 0.f && !s->has_bfactor) return fail(EMM_ERR_INVALID, "conservation_cutoff needs the bfactor column");
+    unsigned long long *stats = s->d_stats;
+    if (!s->prepared || s->prepared_cutoff != cutoff || s->prepared_version != lib->compat_version) {
+        launch_prepare(lib->d, B, cutoff, stats, s->d_hit_count + 1, lib->sm_count, stream);
+        CUDA_TRY(cudaGetLastError());
+        s->prepared = true;
+        s->prepared_cutoff = cutoff;
+        s->prepared_version = lib->compat_version;
+        s->last_launches++;
+    }
+    const unsigned char *skip = nullptr;
+    if (q->skip_mode == 1 || q->skip_mode == 2) {
+        launch_skip_snapshot(n, q->skip_mode, s->d_any, s->d_pass, s->d_skip, stream);
+        CUDA_TRY(cudaGetLastError());
+        skip = s->d_skip;
+        s->last_launches++;
+    }
+    SearchParams P{};
+    P.max_candidates = q->max_candidates;
+    P.ignore_chain = q->ignore_chain ? 1 : 0;
+    P.template_begin = tb;
+    P.template_end = te;
+    P.skip_mode = q->skip_mode;
+    P.levels = lib->d.max_tpl_atoms + 1;
+    const int grid = lib->sm_count;
+    int chunks = 1;
+    if (n < 2 * grid) chunks = (2 * grid + n - 1) / n;
+    chunks = std::min(chunks, std::max(1, (te - tb) / 8));
+    chunks = std::max(1, std::min(chunks, 256));
+    P.n_chunks = chunks;
+    P.n_items = n * chunks;
+    const int fixed = (int)search_fixed_smem(P.levels);
+    int cap = lib->smem_optin - fixed - 1024;
+    cap &= ~15;
+    if (cap < 0) return fail(EMM_ERR_INVALID, "not enough shared memory for the search queues");
+    P.blob_cap = cap;
+    const size_t smem = search_smem_bytes(cap, P.levels);
+    CUDA_TRY(configure_search((int)smem));
+    SearchOut O{};
+    O.hits = s->d_hits;
+    O.hit_capacity = s->hit_capacity;
+    O.hit_count = s->d_hit_count;
+    O.work_counter = s->d_work;
+    O.struct_any = s->d_any;
+    O.struct_pass = s->d_pass;
+    O.stats = s->d_stats;
+    CUDA_TRY(cudaMemsetAsync(s->d_work, 0, 4, stream));
+    launch_search(lib->d, B, P, O, skip, lib->stats_enabled != 0, std::min(grid, P.n_items), smem, stream);
+    CUDA_TRY(cudaGetLastError());
+    s->last_launches++;
+    return EMM_OK;
+}
+
+int emm_session_last_launches(const emm_session *s) { return s ? s->last_launches : 0; }
+
+int emm_session_download(emm_session *s, emm_hit *hits, int64_t capacity, int64_t *n_hits, emm_stats *stats,
+                         void *stream_)
+{
+    if (!s || !n_hits) return fail(EMM_ERR_INVALID, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CUDA_TRY(cudaSetDevice(s->lib->device));
+    unsigned long long counters[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(counters, s->d_hit_count, 16, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const unsigned long long count = counters[0], bad = counters[1];
+    *n_hits = (int64_t)count;
+    if (stats) {
+        unsigned long long raw[8];
+        CUDA_TRY(cudaMemcpy(raw, s->d_stats, 64, cudaMemcpyDeviceToHost));
+        stats->pairs = raw[0]; stats->sweeps = raw[1]; stats->dist_evals = raw[2]; stats->exact_rechecks = raw[3];
+        stats->complete = raw[4]; stats->kept_atoms = raw[5]; stats->staged_bytes = raw[6]; stats->global_blobs = raw[7];
+    }
+    if ((int64_t)count > s->hit_capacity || (int64_t)count > capacity)
+        return fail(EMM_ERR_CAPACITY, "hit buffer too small: enlarge hit_capacity and run again");
+    if (count > 0) {
+        if (!hits) return fail(EMM_ERR_INVALID, "hits is null");
+        CUDA_TRY(cudaMemcpyAsync(hits, s->d_hits, sizeof(emm_hit) * (size_t)count, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        std::sort(hits, hits + count, [](const emm_hit &a, const emm_hit &b) {
+            return a.structure != b.structure ? a.structure < b.structure : a.template_index < b.template_index;
+        });
+    }
+    if (bad) return fail(EMM_ERR_INPUT, "a structure violates the input contract (residue ordinals must be "
+                                        "non-decreasing and at most 65535 atoms may survive masking)");
+    return EMM_OK;
+}
+
+int emm_query_batch(emm_library *lib, const emm_batch *batch, const emm_query_params *params, emm_hit *hits,
+                    int64_t capacity, int64_t *n_hits, emm_stats *stats)
+{
+    if (!lib || !batch || !params || !n_hits) return fail(EMM_ERR_INVALID, "null argument");
+    emm_session *s = nullptr;
+    int rc = emm_session_create(lib, std::max<int64_t>(batch->n_atoms, 1), std::max(batch->n_structures, 1),
+                                std::max<int64_t>(capacity, 1), &s);
+    if (rc != EMM_OK) return rc;
+    emm_query_params p = *params;
+    p.reset_structure_state = 1;
+    rc = emm_session_upload(s, batch, nullptr);
+    if (rc == EMM_OK) rc = emm_session_run(s, &p, nullptr);
+    if (rc == EMM_OK) rc = emm_session_download(s, hits, capacity, n_hits, stats, nullptr);
+    emm_session_destroy(s);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// emm_device.cuh -- device-side tables shared by the prepare and search kernels (sm_100a).
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   * DevLibrary  : the compiled template library, read-only, ~5 MB for the shipped 6780 active
+//                   templates -> L2 resident, broadcast-read through L1 by every warp.
+//   * DevBatch    : the uploaded query structures as SoA columns.
+//   * structure blob (one per structure, written by emm_prepare_kernel, read by
+//                   emm_search_kernel): header + FP32 centred coordinates + residue CSR + typing
+//                   classes + per-leader-type candidate lists + uniform-grid cell list.  The
+//                   staged part is copied into shared memory once per work item.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/enzymm_b200.h"
+
+namespace emm {
+
+constexpr int kMaxAtoms = EMM_MAX_TEMPLATE_ATOMS;
+constexpr int kSearchThreads = 512;
+constexpr int kSearchWarps = kSearchThreads / 32;
+constexpr int kQueueCap = 64;          // entries per search level per warp
+constexpr int kPrepThreads = 256;
+constexpr float kCellSize = 6.0f;      // uniform grid cell edge (Angstrom)
+constexpr int kMaxCellsPerAxis = 64;
+
+struct DevLibrary {
+    int n_templates, n_atoms, n_ttype, class_words, class_words_cap, n_leader, max_tpl_atoms, n_lr;
+    const int32_t *atom_off;
+    const double *xyz;
+    const double *weight;
+    const uint16_t *chain;
+    const uint8_t *plan_atom;
+    const uint16_t *plan_ttype;
+    const int16_t *plan_src;
+    const int64_t *pair_off;
+    const double *pair_dist;
+    const float *pair_dist32;
+    const uint32_t *compat;
+    const uint16_t *leader_ttype;
+    const double *rmsd_thr;
+    const double *dist_cut;
+    const double *max_dyn;
+    const int32_t *n_residues;
+    const uint8_t *orient_idx;
+    const double *orient_vec;
+    const int32_t *lr_index;
+    const double *lr_table;
+};
+
+struct DevBatch {
+    int n_structures;
+    const int64_t *atom_off;
+    const double *xyz;
+    const uint16_t *klass;
+    const int32_t *residue;
+    const float *bfactor;    // may be null
+    const uint16_t *chain;   // may be null
+    const int32_t *atom_id;  // may be null
+    unsigned char *blob;     // all structure blobs
+    const int64_t *blob_off; // [n_structures+1]
+};
+
+// Blob header (64 bytes).  All off_* are byte offsets from the blob base, 16-byte aligned.
+struct BlobHeader {
+    int32_t n_kept;        // atoms kept (mask + class != 0), local ids 0..n_kept-1 in input order
+    int32_t n_res;         // residues holding at least one kept atom
+    int32_t res_shift;     // log2 of res_stride, res_stride = pow2 >= largest residue
+    int32_t status;        // 0 ok, 1 residue order violated, 2 too many atoms for 16-bit ids
+    float eps;             // FP32 guard band (Angstrom) for this structure
+    int32_t staged_bytes;  // prefix of the blob the search kernel stages into shared memory
+    int32_t off_x, off_y, off_z;   // float[n_kept] centred coordinates
+    int32_t off_res;       // uint16 res_of[n_kept]
+    int32_t off_resstart;  // uint16 res_start[n_res+1]
+    int32_t off_klass;     // uint16 klass[n_kept]
+    int32_t off_leadoff;   // uint32 lead_off[n_leader+1]
+    int32_t off_lead;      // uint16 lead[...]
+    int32_t off_orig;      // int32 orig[n_kept]: position of the atom inside its structure (NOT staged)
+    int32_t pad;
+};
+static_assert(sizeof(BlobHeader) == 64, "blob header is 64 bytes");
+
+struct SearchParams {
+    long long max_candidates;
+    int ignore_chain;
+    int template_begin, template_end;
+    int skip_mode;
+    int n_chunks;          // template chunks per structure (work item = structure x chunk)
+    int n_items;
+    int blob_cap;          // shared-memory bytes available for a staged blob
+    int levels;            // queue levels per warp (max template atoms + 1)
+};
+
+struct SearchOut {
+    emm_hit *hits;
+    long long hit_capacity;
+    unsigned long long *hit_count;
+    unsigned int *work_counter;
+    int *struct_any;       // [n_structures] hits so far
+    int *struct_pass;      // [n_structures] PASSing hits so far
+    unsigned long long *stats;  // emm_stats as 8 counters
+};
+
+inline __host__ __device__ int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
+
+// Size of a structure blob for n input atoms whose leader lists hold lead_entries entries in
+// total (the host computes this exactly at upload, so blobs are laid out without a size pass).
+inline __host__ __device__ int64_t blob_bytes(int64_t n, int n_leader, int64_t lead_entries)
+{
+    int64_t b = sizeof(BlobHeader);
+    b += 3 * align16(4 * n);                 // x y z
+    b += align16(2 * n);                     // res_of
+    b += align16(2 * (n + 1));               // res_start
+    b += align16(2 * n);                     // klass
+    b += align16(4 * (int64_t)(n_leader + 1));
+    b += align16(2 * lead_entries);
+    b += align16(4 * n);                     // orig
+    return b;
+}
+
+}  // namespace emm

@@ -1,0 +1,240 @@
+// emm_prepare.cu -- per-structure preparation kernel (north_star subsystems 1 and 2).
+//
+// One CTA per structure turns the uploaded SoA columns into a compact "structure blob":
+//   * drops masked atoms (bfactor < conservation cutoff, i.e. pyjess Molecule.conserved, call
+//     site enzymm/jess_run.py:541-542) and atoms whose typing class binds no template atom;
+//   * centres coordinates on the bounding-box centre and stores them as FP32 (the search kernel
+//     decides in FP32 inside a rigorous guard band `eps` and re-evaluates in FP64 otherwise);
+//   * builds the residue CSR (same-residue rule, SURVEY.md 8c rule 4) and, per leader type, the
+//     ascending list of atoms that type can bind (this replaces Jess's per-template kd-tree /
+//     annulus candidate search: typing is ~50x more selective than geometry at this scale).
+//
+// Roofline: HBM-bound streaming pass.  Algorithmic bytes per atom: 24 (xyz f64) + 2 (class) +
+// 4 (residue) + 4 (bfactor) read, <= 22 + 2*lists written.
+#include "emm_device.cuh"
+
+namespace emm {
+
+__device__ __forceinline__ int warp_excl_prefix(unsigned ballot, int lane)
+{
+    return __popc(ballot & ((1u << lane) - 1u));
+}
+
+// Exclusive prefix of `flag` over the block (in thread order) + block total.
+__device__ __forceinline__ int block_excl_scan_flag(bool flag, int *warp_tot, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_tot[wid] = __popc(b);
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) {
+        const int c = warp_tot[w];
+        if (w < wid) before += c;
+        tot += c;
+    }
+    __syncthreads();
+    *total = tot;
+    return before + warp_excl_prefix(b, lane);
+}
+
+__device__ __forceinline__ double block_reduce_minmax(double v, bool is_max, double *scratch)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, other) : fmin(v, other);
+    }
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double r = scratch[0];
+#pragma unroll
+    for (int w = 1; w < kPrepThreads / 32; ++w) r = is_max ? fmax(r, scratch[w]) : fmin(r, scratch[w]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
+emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
+                   unsigned long long *stats, unsigned long long *bad)
+{
+    __shared__ int s_warp_tot[kPrepThreads / 32];
+    __shared__ double s_scratch[kPrepThreads / 32];
+    __shared__ int s_bad, s_maxres;
+    __shared__ unsigned s_lead_cnt[1024];   // counts, then offsets (n_leader <= 1023 checked on host)
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool use_mask = (B.bfactor != nullptr) && (cutoff > 0.0f);
+
+    for (int s = blockIdx.x; s < B.n_structures; s += gridDim.x) {
+        const int64_t base = B.atom_off[s];
+        const int N = (int)(B.atom_off[s + 1] - base);
+        unsigned char *blob = B.blob + B.blob_off[s];
+        const int64_t bound = B.blob_off[s + 1] - B.blob_off[s];
+        const int off_orig = (int)(bound - align16(4 * (int64_t)N));
+        int32_t *orig = reinterpret_cast<int32_t *>(blob + off_orig);
+        const uint16_t *klass_in = B.klass + base;
+        const int32_t *res_in = B.residue + base;
+        const double *xyz = B.xyz + 3 * base;
+
+        if (tid == 0) { s_bad = 0; s_maxres = 0; }
+        __syncthreads();
+
+        // ---- pass A: ordered compaction of kept atoms -----------------------------------------
+        int n_kept = 0;
+        for (int chunk = 0; chunk < N; chunk += kPrepThreads) {
+            const int a = chunk + tid;
+            bool keep = false;
+            if (a < N) {
+                keep = klass_in[a] != 0;
+                if (keep && use_mask) keep = B.bfactor[base + a] >= cutoff;
+            }
+            int tot;
+            const int pre = block_excl_scan_flag(keep, s_warp_tot, &tot);
+            if (keep) orig[n_kept + pre] = a;
+            n_kept += tot;
+        }
+        __syncthreads();
+        int status = 0;
+        if (n_kept > 65535) { status = 2; n_kept = 0; }
+
+        // ---- pass B: bounding box -> centre, extent, guard band ---------------------------------
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = tid; i < n_kept; i += kPrepThreads) {
+            const double *p = xyz + 3 * (int64_t)orig[i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], p[c]); hi[c] = fmax(hi[c], p[c]); }
+        }
+        double ctr[3], half = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double mn = block_reduce_minmax(lo[c], false, s_scratch);
+            const double mx = block_reduce_minmax(hi[c], true, s_scratch);
+            ctr[c] = n_kept ? 0.5 * (mn + mx) : 0.0;
+            half = fmax(half, n_kept ? 0.5 * (mx - mn) : 0.0);
+        }
+        // |d_fp32 - d_exact| <= ~36 * 2^-24 * half (DESIGN.md "guard band"); 64 gives ~1.8x margin
+        const float eps = (float)(64.0 * 5.9604644775390625e-08 * fmax(half, 16.0) + 1e-5);
+
+        // ---- layout of the staged part ------------------------------------------------------------
+        const int off_x = (int)sizeof(BlobHeader);
+        const int sz_f = (int)align16(4 * (int64_t)n_kept);
+        const int off_y = off_x + sz_f, off_z = off_y + sz_f;
+        const int off_res = off_z + sz_f;
+        const int off_klass = off_res + (int)align16(2 * (int64_t)n_kept);
+        const int off_resstart = off_klass + (int)align16(2 * (int64_t)n_kept);
+        float *bx = reinterpret_cast<float *>(blob + off_x);
+        float *by = reinterpret_cast<float *>(blob + off_y);
+        float *bz = reinterpret_cast<float *>(blob + off_z);
+        uint16_t *res_of = reinterpret_cast<uint16_t *>(blob + off_res);
+        uint16_t *bklass = reinterpret_cast<uint16_t *>(blob + off_klass);
+        uint16_t *res_start = reinterpret_cast<uint16_t *>(blob + off_resstart);
+
+        // ---- pass C: coordinates, classes, residue CSR ---------------------------------------------
+        int n_res = 0;
+        for (int chunk = 0; chunk < n_kept; chunk += kPrepThreads) {
+            const int i = chunk + tid;
+            bool starts = false;
+            int a = 0;
+            if (i < n_kept) {
+                a = orig[i];
+                const double *p = xyz + 3 * (int64_t)a;
+                bx[i] = (float)(p[0] - ctr[0]);
+                by[i] = (float)(p[1] - ctr[1]);
+                bz[i] = (float)(p[2] - ctr[2]);
+                bklass[i] = klass_in[a];
+                if (i == 0) {
+                    starts = true;
+                } else {
+                    const int rp = res_in[orig[i - 1]], rc = res_in[a];
+                    starts = rc != rp;
+                    if (rc < rp) s_bad = 1;
+                }
+            }
+            int tot;
+            const int pre = block_excl_scan_flag(starts, s_warp_tot, &tot);
+            // residue id of atom i = (#starts at or before i) - 1
+            if (i < n_kept) {
+                const int rid = n_res + pre + (starts ? 1 : 0) - 1;
+                res_of[i] = (uint16_t)rid;
+                if (starts) res_start[rid] = (uint16_t)i;
+            }
+            n_res += tot;
+        }
+        __syncthreads();
+        if (tid == 0) res_start[n_res] = (uint16_t)n_kept;
+        __syncthreads();
+        if (s_bad) status = 1;
+        int local_max = 0;
+        for (int r = tid; r < n_res; r += kPrepThreads)
+            local_max = max(local_max, (int)res_start[r + 1] - (int)res_start[r]);
+        if (local_max) atomicMax(&s_maxres, local_max);
+        __syncthreads();
+        int res_shift = 0;
+        while ((1 << res_shift) < s_maxres) ++res_shift;
+
+        // ---- pass D: leader candidate lists -----------------------------------------------------------
+        const int off_leadoff = off_resstart + (int)align16(2 * (int64_t)(n_res + 1));
+        const int off_lead = off_leadoff + (int)align16(4 * (int64_t)(L.n_leader + 1));
+        uint32_t *lead_off = reinterpret_cast<uint32_t *>(blob + off_leadoff);
+        uint16_t *lead = reinterpret_cast<uint16_t *>(blob + off_lead);
+        const int cw = L.class_words_cap;
+        for (int l = wid; l < L.n_leader; l += kPrepThreads / 32) {
+            const uint32_t *row = L.compat + (size_t)L.leader_ttype[l] * cw;
+            unsigned cnt = 0;
+            for (int i0 = 0; i0 < n_kept; i0 += 32) {
+                const int i = i0 + lane;
+                bool ok = false;
+                if (i < n_kept) { const unsigned k = bklass[i]; ok = (__ldg(row + (k >> 5)) >> (k & 31)) & 1u; }
+                cnt += __popc(__ballot_sync(0xffffffffu, ok));
+            }
+            if (lane == 0) s_lead_cnt[l] = cnt;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned run = 0;
+            for (int l = 0; l < L.n_leader; ++l) { const unsigned c = s_lead_cnt[l]; s_lead_cnt[l] = run; lead_off[l] = run; run += c; }
+            s_lead_cnt[L.n_leader] = run;
+            lead_off[L.n_leader] = run;
+        }
+        __syncthreads();
+        for (int l = wid; l < L.n_leader; l += kPrepThreads / 32) {
+            const uint32_t *row = L.compat + (size_t)L.leader_ttype[l] * cw;
+            unsigned pos = s_lead_cnt[l];
+            for (int i0 = 0; i0 < n_kept; i0 += 32) {
+                const int i = i0 + lane;
+                bool ok = false;
+                if (i < n_kept) { const unsigned k = bklass[i]; ok = (__ldg(row + (k >> 5)) >> (k & 31)) & 1u; }
+                const unsigned b = __ballot_sync(0xffffffffu, ok);
+                if (ok) lead[pos + warp_excl_prefix(b, lane)] = (uint16_t)i;
+                pos += __popc(b);
+            }
+        }
+        __syncthreads();
+
+        if (tid == 0) {
+            BlobHeader h;
+            h.n_kept = n_kept; h.n_res = n_res; h.res_shift = res_shift; h.status = status; h.eps = eps;
+            h.staged_bytes = (int)align16(off_lead + 2 * (int64_t)s_lead_cnt[L.n_leader]);
+            h.off_x = off_x; h.off_y = off_y; h.off_z = off_z; h.off_res = off_res;
+            h.off_resstart = off_resstart; h.off_klass = off_klass; h.off_leadoff = off_leadoff;
+            h.off_lead = off_lead; h.off_orig = off_orig; h.pad = 0;
+            *reinterpret_cast<BlobHeader *>(blob) = h;
+            if (stats) atomicAdd(stats + 5, (unsigned long long)n_kept);
+            if (status != 0 && bad) atomicAdd(bad, 1ull);
+        }
+        __syncthreads();
+    }
+}
+
+void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff,
+                    unsigned long long *stats, unsigned long long *bad, int sm_count, cudaStream_t stream)
+{
+    if (B.n_structures <= 0) return;
+    int grid = B.n_structures < sm_count * 8 ? B.n_structures : sm_count * 8;
+    emm_prepare_kernel<<<grid, kPrepThreads, 0, stream>>>(L, B, cutoff, stats, bad);
+}
+
+}  // namespace emm

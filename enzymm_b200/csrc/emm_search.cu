@@ -1,0 +1,645 @@
+// emm_search.cu -- the (template x structure) candidate search, superposition and filter kernel
+// (north_star subsystems 3, 4 and 5, fused).
+//
+// Replaces pyjess.Jess(templates).query(...) + Match.predicted_correct for a whole batch
+// (reference enzymm/jess_run.py:785-843, 298-346, 425-478).
+//
+// Mapping.  Persistent CTAs (one per SM, 16 warps).  A work item is (structure, template chunk):
+// the CTA stages the structure blob into shared memory once, then each WARP pulls templates off a
+// shared counter and runs a warp-synchronous search:
+//
+//   * level k of the search places plan position k of the template.  Partial assignments live in
+//     per-level shared-memory queues as (parent slot, atom) pairs -- a trie, so a partial costs
+//     4 bytes whatever its depth;
+//   * one SWEEP evaluates 32 (partial, candidate) items, one per lane: candidates come from the
+//     structure's leader list (first atom of a template residue) or from the query residue of an
+//     already placed atom (same-residue rule); the lane walks the partial's chain and tests the
+//     pairwise-distance constraint against every placed atom; survivors are compacted with
+//     ballot/popc into the next level's queue;
+//   * queues are drained depth-first in chunks, so memory is bounded however many candidates a
+//     loose cutoff produces (config 4);
+//   * every accept/reject is decided in FP32 on centred coordinates unless it falls inside the
+//     guard band eps, in which case the lane re-evaluates the constraint in FP64 with separately
+//     rounded operations (__d*_rn) -- the same expressions as the CPU oracle, so the set of
+//     complete assignments is identical bit for bit;
+//   * complete assignments are superposed 32 at a time, one per lane, in FP64 registers (Horn's
+//     quaternion form of Kabsch + cyclic Jacobi), the per-template minimum is kept, and the
+//     winning hit gets EnzyMM's orientation + logistic filter before it is written out.
+//
+// No tensor cores: this is gather/compare-bound FP32 + integer work with a rare FP64 tail.
+#include <math_constants.h>
+
+#include "emm_device.cuh"
+
+namespace emm {
+
+// ---- canonical FP64 arithmetic (no FMA contraction; mirrors oracle/jess_oracle.c) ---------------
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DDIV(a, b) __ddiv_rn((a), (b))
+#define DSQRT(a) __dsqrt_rn((a))
+
+struct WarpState {
+    int n[kMaxAtoms + 1];
+    int cur[kMaxAtoms + 1];
+    double best_rmsd;
+    int best_valid;
+    int overflow;
+    unsigned long long n_complete;
+    uint16_t best_asg[kMaxAtoms];
+};
+
+struct Blob {
+    const float *x, *y, *z;
+    const uint16_t *res_of, *res_start, *klass;
+    const uint32_t *lead_off;
+    const uint16_t *lead;
+    const int32_t *orig;      // global memory
+    const double *xyz64;      // global memory, structure base
+    const uint16_t *chain;    // global, structure base (may be null)
+    const int32_t *atom_id;   // global, structure base (may be null)
+    int res_shift;
+    int n_kept;
+    float eps;
+};
+
+__device__ __forceinline__ float fast_sqrt(float v)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ double exact_dist(const double *xyz, int a, int b)
+{
+    const double *pa = xyz + 3 * (int64_t)a, *pb = xyz + 3 * (int64_t)b;
+    const double dx = DSUB(pa[0], pb[0]), dy = DSUB(pa[1], pb[1]), dz = DSUB(pa[2], pb[2]);
+    return DSQRT(DADD(DADD(DMUL(dx, dx), DMUL(dy, dy)), DMUL(dz, dz)));
+}
+
+// delta_ij of SURVEY 8c rule 6 for plan positions (k, j) -- same operation order as the oracle,
+// which always adds the weight of the LATER template atom first.
+__device__ __forceinline__ double pair_delta(const DevLibrary &L, int a0, int k, int j, double cut,
+                                             double max_dyn)
+{
+    if (max_dyn == cut) return cut;
+    const int ik = L.plan_atom[a0 + k], ij = L.plan_atom[a0 + j];
+    const int hi = ik > ij ? ik : ij, lo = ik > ij ? ij : ik;
+    const double d = DADD(DADD(cut, L.weight[a0 + hi]), L.weight[a0 + lo]);
+    return d < max_dyn ? d : max_dyn;
+}
+
+// Cyclic Jacobi on a symmetric 4x4 (fully unrolled so the matrices stay in registers).
+__device__ __forceinline__ void jacobi4(double (&a)[4][4], double (&v)[4][4])
+{
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[p][q] = (p == q) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) off = DADD(off, fabs(a[p][q]));
+        if (off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = a[p][q];
+                if (apq != 0.0) {
+                    const double g = DMUL(100.0, fabs(apq));
+                    if (sweep > 3 && DADD(fabs(a[p][p]), g) == fabs(a[p][p]) &&
+                        DADD(fabs(a[q][q]), g) == fabs(a[q][q])) {
+                        a[p][q] = 0.0;
+                        a[q][p] = 0.0;
+                    } else {
+                        double h = DSUB(a[q][q], a[p][p]);
+                        double t;
+                        if (DADD(fabs(h), g) == fabs(h)) {
+                            t = DDIV(apq, h);
+                        } else {
+                            const double theta = DDIV(DMUL(0.5, h), apq);
+                            t = DDIV(1.0, DADD(fabs(theta), DSQRT(DADD(1.0, DMUL(theta, theta)))));
+                            if (theta < 0.0) t = -t;
+                        }
+                        const double c = DDIV(1.0, DSQRT(DADD(1.0, DMUL(t, t))));
+                        const double s = DMUL(t, c);
+                        const double tau = DDIV(s, DADD(1.0, c));
+                        h = DMUL(t, apq);
+                        a[p][p] = DSUB(a[p][p], h);
+                        a[q][q] = DADD(a[q][q], h);
+                        a[p][q] = 0.0;
+                        a[q][p] = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k != p && k != q) {
+                                const double akp = a[k][p], akq = a[k][q];
+                                const double nkp = DSUB(akp, DMUL(s, DADD(akq, DMUL(akp, tau))));
+                                const double nkq = DADD(akq, DMUL(s, DSUB(akp, DMUL(akq, tau))));
+                                a[k][p] = nkp; a[p][k] = nkp;
+                                a[k][q] = nkq; a[q][k] = nkq;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const double vkp = v[k][p], vkq = v[k][q];
+                            v[k][p] = DSUB(vkp, DMUL(s, DADD(vkq, DMUL(vkp, tau))));
+                            v[k][q] = DADD(vkq, DMUL(s, DSUB(vkp, DMUL(vkq, tau))));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Optimal proper rotation of the matched query atoms onto the template atoms; returns rmsd.
+// asg[i] = local atom id bound to template atom i (template order).
+__device__ double superpose(int m, const double *__restrict__ txyz, const Blob &S,
+                            const uint16_t *asg, double (&rot)[9], double (&qbar)[3],
+                            double (&tbar)[3])
+{
+    const double inv_m = DDIV(1.0, (double)m);
+    double sq[3] = {0.0, 0.0, 0.0}, st[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < m; ++i) {
+        const double *q = S.xyz64 + 3 * (int64_t)S.orig[asg[i]];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { sq[c] = DADD(sq[c], q[c]); st[c] = DADD(st[c], txyz[3 * i + c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { qbar[c] = DMUL(sq[c], inv_m); tbar[c] = DMUL(st[c], inv_m); }
+    double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < m; ++i) {
+        const double *q = S.xyz64 + 3 * (int64_t)S.orig[asg[i]];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                M[a][b] = DADD(M[a][b], DMUL(DSUB(q[a], qbar[a]), DSUB(txyz[3 * i + b], tbar[b])));
+    }
+    double N[4][4], V[4][4];
+    N[0][0] = DADD(DADD(M[0][0], M[1][1]), M[2][2]);
+    N[1][1] = DSUB(DSUB(M[0][0], M[1][1]), M[2][2]);
+    N[2][2] = DSUB(DSUB(M[1][1], M[0][0]), M[2][2]);
+    N[3][3] = DSUB(DSUB(M[2][2], M[0][0]), M[1][1]);
+    N[0][1] = N[1][0] = DSUB(M[1][2], M[2][1]);
+    N[0][2] = N[2][0] = DSUB(M[2][0], M[0][2]);
+    N[0][3] = N[3][0] = DSUB(M[0][1], M[1][0]);
+    N[1][2] = N[2][1] = DADD(M[0][1], M[1][0]);
+    N[1][3] = N[3][1] = DADD(M[2][0], M[0][2]);
+    N[2][3] = N[3][2] = DADD(M[1][2], M[2][1]);
+    jacobi4(N, V);
+    double best = N[0][0];
+    double q0 = V[0][0], q1 = V[1][0], q2 = V[2][0], q3 = V[3][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (N[i][i] > best) { best = N[i][i]; q0 = V[0][i]; q1 = V[1][i]; q2 = V[2][i]; q3 = V[3][i]; }
+    const double nrm = DSQRT(DADD(DADD(DADD(DMUL(q0, q0), DMUL(q1, q1)), DMUL(q2, q2)), DMUL(q3, q3)));
+    q0 = DDIV(q0, nrm); q1 = DDIV(q1, nrm); q2 = DDIV(q2, nrm); q3 = DDIV(q3, nrm);
+    rot[0] = DSUB(DSUB(DADD(DMUL(q0, q0), DMUL(q1, q1)), DMUL(q2, q2)), DMUL(q3, q3));
+    rot[1] = DMUL(2.0, DSUB(DMUL(q1, q2), DMUL(q0, q3)));
+    rot[2] = DMUL(2.0, DADD(DMUL(q1, q3), DMUL(q0, q2)));
+    rot[3] = DMUL(2.0, DADD(DMUL(q1, q2), DMUL(q0, q3)));
+    rot[4] = DSUB(DADD(DSUB(DMUL(q0, q0), DMUL(q1, q1)), DMUL(q2, q2)), DMUL(q3, q3));
+    rot[5] = DMUL(2.0, DSUB(DMUL(q2, q3), DMUL(q0, q1)));
+    rot[6] = DMUL(2.0, DSUB(DMUL(q1, q3), DMUL(q0, q2)));
+    rot[7] = DMUL(2.0, DADD(DMUL(q2, q3), DMUL(q0, q1)));
+    rot[8] = DADD(DSUB(DSUB(DMUL(q0, q0), DMUL(q1, q1)), DMUL(q2, q2)), DMUL(q3, q3));
+    double ssd = 0.0;
+    for (int i = 0; i < m; ++i) {
+        const double *q = S.xyz64 + 3 * (int64_t)S.orig[asg[i]];
+        const double x = DSUB(q[0], qbar[0]), y = DSUB(q[1], qbar[1]), z = DSUB(q[2], qbar[2]);
+        const double rx = DSUB(DADD(DADD(DMUL(rot[0], x), DMUL(rot[1], y)), DMUL(rot[2], z)), DSUB(txyz[3 * i], tbar[0]));
+        const double ry = DSUB(DADD(DADD(DMUL(rot[3], x), DMUL(rot[4], y)), DMUL(rot[5], z)), DSUB(txyz[3 * i + 1], tbar[1]));
+        const double rz = DSUB(DADD(DADD(DMUL(rot[6], x), DMUL(rot[7], y)), DMUL(rot[8], z)), DSUB(txyz[3 * i + 2], tbar[2]));
+        ssd = DADD(ssd, DADD(DADD(DMUL(rx, rx), DMUL(ry, ry)), DMUL(rz, rz)));
+    }
+    return DSQRT(DMUL(ssd, inv_m));
+}
+
+// Vec3.angle_to (enzymm/template.py:157-181); returns NaN where the reference raises.
+__device__ double angle_between(const double (&u)[3], const double (&v)[3])
+{
+    const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double a[3], b[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { a[c] = nu == 0.0 ? u[c] : u[c] / nu; b[c] = nv == 0.0 ? v[c] : v[c] / nv; }
+    const double dot = DADD(DADD(DMUL(a[0], b[0]), DMUL(a[1], b[1])), DMUL(a[2], b[2]));
+    if (dot >= -1.0 && dot <= 1.0) return acos(dot);
+    if (fabs(dot - 1.0) <= 1e-5 * fmax(fabs(dot), 1.0)) return 0.0;
+    if (fabs(dot + 1.0) <= 1e-5 * fmax(fabs(dot), 1.0)) return CUDART_PI;
+    return CUDART_NAN;
+}
+
+// Write the winning hit of (structure s, template t): superposition, orientation, logistic vote.
+__device__ void emit_hit(const DevLibrary &L, const Blob &S, const SearchOut &O, int s, int t,
+                         const WarpState *ws)
+{
+    const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
+    const double *txyz = L.xyz + 3 * (int64_t)a0;
+    double rot[9], qbar[3], tbar[3];
+    const double rmsd = superpose(m, txyz, S, ws->best_asg, rot, qbar, tbar);
+    unsigned flags = ws->overflow ? EMM_HIT_OVERFLOW : 0u;
+    double orient = CUDART_NAN;
+    const int nres = L.n_residues[t];
+    if (nres > 0) {
+        // Match.match_vector_list / orientation (jess_run.py:425-478) in the template frame
+        double sum = 0.0;
+        for (int r = 0; r < nres; ++r) {
+            double p[3][3];
+            for (int k = 0; k < 3; ++k) {
+                const double *q = S.xyz64 + 3 * (int64_t)S.orig[ws->best_asg[3 * r + k]];
+                const double x = q[0] - qbar[0], y = q[1] - qbar[1], z = q[2] - qbar[2];
+                p[k][0] = rot[0] * x + rot[1] * y + rot[2] * z + tbar[0];
+                p[k][1] = rot[3] * x + rot[4] * y + rot[5] * z + tbar[1];
+                p[k][2] = rot[6] * x + rot[7] * y + rot[8] * z + tbar[2];
+            }
+            const int i0 = L.orient_idx[((size_t)t * EMM_MAX_RESIDUES + r) * 2];
+            const int i1 = L.orient_idx[((size_t)t * EMM_MAX_RESIDUES + r) * 2 + 1];
+            double vec[3];
+            if (i1 == 9) {
+                const int s1 = i0 == 0 ? 1 : 0, s2 = i0 == 2 ? 1 : 2;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) vec[c] = (p[s1][c] + p[s2][c]) / 2.0 - p[i0][c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) vec[c] = p[i1][c] - p[i0][c];
+            }
+            const double *tv = L.orient_vec + ((size_t)t * EMM_MAX_RESIDUES + r) * 3;
+            const double tvec[3] = {tv[0], tv[1], tv[2]};
+            sum += angle_between(tvec, vec);
+        }
+        orient = sum / (double)nres;
+        flags |= EMM_HIT_ORIENTED;
+    }
+    // Match.predicted_correct (jess_run.py:298-346)
+    const int lr = L.lr_index[t];
+    bool pass = true;
+    if (lr == -2) {
+        flags |= EMM_HIT_NO_MODEL;
+        pass = false;
+    } else if (lr >= 0) {
+        int votes = 0;
+        const double *tab = L.lr_table + (size_t)lr * EMM_LR_MODELS * 4;
+        for (int k = 0; k < EMM_LR_MODELS; ++k) {
+            const double z = tab[4 * k + 2] + tab[4 * k] * rmsd + tab[4 * k + 1] * orient;
+            const double value = 1.0 / (1.0 + pow(2.718281828459045, -z));
+            if (value >= tab[4 * k + 3]) ++votes;
+            if (fabs(value - tab[4 * k + 3]) < 1e-9) flags |= EMM_HIT_BORDERLINE;
+        }
+        pass = votes >= 2;  // round(5 / 2, 0) == 2 under banker's rounding
+        if (!(orient == orient)) pass = false;
+    }
+    if (pass) flags |= EMM_HIT_PASS;
+    atomicAdd(O.struct_any + s, 1);
+    if (pass) atomicAdd(O.struct_pass + s, 1);
+    const unsigned long long slot = atomicAdd(O.hit_count, 1ull);
+    if ((long long)slot < O.hit_capacity) {
+        emm_hit *h = O.hits + slot;
+        h->structure = s;
+        h->template_index = t;
+        h->n_complete = (uint32_t)(ws->n_complete > 0xffffffffull ? 0xffffffffull : ws->n_complete);
+        h->n_atoms = (uint16_t)m;
+        h->flags = (uint16_t)flags;
+        h->rmsd = rmsd;
+        h->orientation = orient;
+        for (int i = 0; i < 9; ++i) h->rot[i] = rot[i];
+        for (int i = 0; i < 3; ++i) { h->qbar[i] = qbar[i]; h->tbar[i] = tbar[i]; }
+        for (int i = 0; i < kMaxAtoms; ++i) {
+            int id = -1;
+            if (i < m) { id = S.orig[ws->best_asg[i]]; if (S.atom_id) id = S.atom_id[id]; }
+            h->atoms[i] = id;
+        }
+    }
+}
+
+// Superpose the complete assignments queued at level m (one per lane) and keep the best.
+__device__ void process_complete(const DevLibrary &L, const Blob &S, const SearchParams &P, int t,
+                                 const uint32_t *Q, WarpState *ws, int lane)
+{
+    const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
+    const double *txyz = L.xyz + 3 * (int64_t)a0;
+    const double thr = L.rmsd_thr[t];
+    const int total = ws->n[m];
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        bool have = idx < total;
+        uint16_t asg[kMaxAtoms];
+        if (have) {
+            uint32_t w = Q[m * kQueueCap + idx];
+            for (int pos = m - 1; pos >= 0; --pos) {
+                asg[L.plan_atom[a0 + pos]] = (uint16_t)(w & 0xffffu);
+                if (pos > 0) w = Q[pos * kQueueCap + (w >> 16)];
+            }
+            if (!P.ignore_chain && S.chain) {
+                // template atoms on equal chains <=> query atoms on equal chains (oracle rule 11)
+                for (int i = 0; i < m && have; ++i)
+                    for (int j = i + 1; j < m; ++j) {
+                        const bool st = L.chain[a0 + i] == L.chain[a0 + j];
+                        const bool sq = S.chain[S.orig[asg[i]]] == S.chain[S.orig[asg[j]]];
+                        if (st != sq) { have = false; break; }
+                    }
+            }
+        }
+        const unsigned counted = __ballot_sync(0xffffffffu, have);
+        double rmsd = CUDART_INF;
+        bool accept = false;
+        if (have) {
+            double rot[9], qbar[3], tbar[3];
+            rmsd = superpose(m, txyz, S, asg, rot, qbar, tbar);
+            accept = rmsd <= thr;
+        }
+        double key = accept ? rmsd : CUDART_INF;
+        double mn = key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (mn < CUDART_INF) {
+            unsigned tied = __ballot_sync(0xffffffffu, accept && key == mn);
+            if (__popc(tied) > 1) {  // exact RMSD tie: lexicographically smallest assignment wins
+                for (int i = 0; i < m && __popc(tied) > 1; ++i) {
+                    const unsigned v = ((tied >> lane) & 1u) ? (unsigned)asg[i] : 0xffffffffu;
+                    unsigned mv = v;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mv = min(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+                    tied &= __ballot_sync(0xffffffffu, v == mv);
+                }
+            }
+            const int win = __ffs(tied) - 1;
+            if (lane == win) {
+                bool better = !ws->best_valid || mn < ws->best_rmsd;
+                if (!better && mn == ws->best_rmsd) {
+                    for (int i = 0; i < m; ++i) {
+                        if (asg[i] != ws->best_asg[i]) { better = asg[i] < ws->best_asg[i]; break; }
+                    }
+                }
+                if (better) {
+                    ws->best_valid = 1;
+                    ws->best_rmsd = mn;
+                    for (int i = 0; i < m; ++i) ws->best_asg[i] = asg[i];
+                }
+            }
+        }
+        if (lane == 0) {
+            ws->n_complete += (unsigned long long)__popc(counted);
+            if (P.max_candidates > 0 && ws->n_complete >= (unsigned long long)P.max_candidates) ws->overflow = 1;
+        }
+        __syncwarp();
+        if (ws->overflow) break;
+    }
+}
+
+template <bool kStats>
+__device__ void search_template(const DevLibrary &L, const Blob &S, const SearchParams &P,
+                                const SearchOut &O, int s, int t, uint32_t *Q, WarpState *ws,
+                                int lane, unsigned long long *st_sweeps, unsigned long long *st_evals,
+                                unsigned long long *st_exact)
+{
+    const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
+    const int64_t p0 = L.pair_off[t];
+    const float *pair32 = L.pair_dist32 + p0;
+
+    // a template with an empty leader list cannot match this structure
+    {
+        bool empty = false;
+        if (lane < m) {
+            const int src = L.plan_src[a0 + lane];
+            if (src < 0) empty = S.lead_off[-src] == S.lead_off[-1 - src];
+        }
+        if (__any_sync(0xffffffffu, empty)) return;
+    }
+
+    const double cut64 = L.dist_cut[t], dyn64 = L.max_dyn[t];
+    const bool dynamic = dyn64 != cut64;
+    const float cut32 = (float)cut64;
+    const float eps = S.eps;
+
+    if (lane <= m) { ws->n[lane] = lane == 0 ? 1 : 0; ws->cur[lane] = 0; }
+    if (lane == 0) { ws->best_valid = 0; ws->overflow = 0; ws->n_complete = 0ull; ws->best_rmsd = CUDART_INF; }
+    __syncwarp();
+
+    int k = 0;
+    for (;;) {
+        if (ws->overflow) break;
+        const int src = L.plan_src[a0 + k];
+        int stride, lbase = 0;
+        if (src < 0) {
+            lbase = (int)S.lead_off[-1 - src];
+            stride = (int)S.lead_off[-src] - lbase;
+        } else {
+            stride = 1 << S.res_shift;
+        }
+        const int nk = ws->n[k];
+        const int total = nk * stride;
+        const int cur = ws->cur[k];
+        const int nnext = ws->n[k + 1];
+        if (cur < total && nnext + 32 <= kQueueCap) {
+            // ---------------- one sweep: 32 (partial, candidate) items ----------------
+            const int i = cur + lane;
+            bool alive = i < total;
+            int p = 0, c = 0;
+            if (src < 0) { p = i / stride; c = i - p * stride; }
+            else { p = i >> S.res_shift; c = i & (stride - 1); }
+            uint32_t e = 0;
+            if (k > 0 && alive) e = Q[k * kQueueCap + p];
+            int a = 0;
+            if (src < 0) {
+                if (alive) a = S.lead[lbase + c];
+            } else if (alive) {
+                uint32_t w = e;
+                for (int pos = k - 1; pos > src; --pos) w = Q[pos * kQueueCap + (w >> 16)];
+                const int r = S.res_of[w & 0xffffu];
+                const int rs = S.res_start[r], rl = (int)S.res_start[r + 1] - rs;
+                alive = c < rl;
+                a = rs + c;
+                if (alive) {
+                    const unsigned kl = S.klass[a];
+                    const uint32_t word = __ldg(L.compat + (size_t)L.plan_ttype[a0 + k] * L.class_words_cap + (kl >> 5));
+                    alive = (word >> (kl & 31)) & 1u;
+                }
+            }
+            bool border = false;
+            if (k > 0) {
+                const float xa = alive ? S.x[a] : 0.f, ya = alive ? S.y[a] : 0.f, za = alive ? S.z[a] : 0.f;
+                const float *row = pair32 + (k * (k - 1)) / 2;
+                uint32_t w = e;
+                for (int pos = k - 1; pos >= 0; --pos) {
+                    if (!__any_sync(0xffffffffu, alive)) break;
+                    const int b = (int)(w & 0xffffu);
+                    if (pos > 0) w = Q[pos * kQueueCap + (w >> 16)];
+                    if (alive) {
+                        const float dx = xa - S.x[b], dy = ya - S.y[b], dz = za - S.z[b];
+                        const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                        float delta = cut32;
+                        if (dynamic) delta = (float)pair_delta(L, a0, k, pos, cut64, dyn64);
+                        const float err = fabsf(d - __ldg(row + pos));
+                        if (err > delta + eps || b == a) alive = false;
+                        else if (err >= delta - eps) border = true;
+                        if (kStats) ++(*st_evals);
+                    }
+                }
+                if (alive && border) {
+                    // guard band: decide with the oracle's FP64 expression
+                    if (kStats) ++(*st_exact);
+                    const double *row64 = L.pair_dist + p0 + (k * (k - 1)) / 2;
+                    const int oa = S.orig[a];
+                    uint32_t w2 = e;
+                    for (int pos = k - 1; pos >= 0; --pos) {
+                        const int b = (int)(w2 & 0xffffu);
+                        if (pos > 0) w2 = Q[pos * kQueueCap + (w2 >> 16)];
+                        const double d = exact_dist(S.xyz64, oa, S.orig[b]);
+                        const double delta = pair_delta(L, a0, k, pos, cut64, dyn64);
+                        if (!(fabs(DSUB(d, row64[pos])) <= delta)) { alive = false; break; }
+                    }
+                }
+            }
+            const unsigned surv = __ballot_sync(0xffffffffu, alive);
+            if (alive) Q[(k + 1) * kQueueCap + nnext + __popc(surv & ((1u << lane) - 1u))] = ((uint32_t)p << 16) | (uint32_t)a;
+            if (lane == 0) { ws->cur[k] = cur + 32; ws->n[k + 1] = nnext + __popc(surv); }
+            if (kStats && lane == 0) ++(*st_sweeps);
+            __syncwarp();
+        } else if (nnext > 0) {
+            if (k + 1 == m) {
+                process_complete(L, S, P, t, Q, ws, lane);
+                if (lane == 0) ws->n[m] = 0;
+                __syncwarp();
+            } else {
+                ++k;
+                if (lane == 0) ws->cur[k] = 0;
+                __syncwarp();
+            }
+        } else {
+            if (k == 0) break;
+            if (lane == 0) ws->n[k] = 0;
+            __syncwarp();
+            --k;
+        }
+    }
+    if (kStats && lane == 0 && ws->n_complete) atomicAdd(O.stats + 4, ws->n_complete);
+    if (ws->best_valid && lane == 0) emit_hit(L, S, O, s, t, ws);
+    __syncwarp();
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(kSearchThreads, 1)
+emm_search_kernel(DevLibrary L, DevBatch B, SearchParams P, SearchOut O, const unsigned char *skip)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_item, s_next_tpl;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned char *stage = smem;
+    uint32_t *Q = reinterpret_cast<uint32_t *>(smem + P.blob_cap) + (size_t)wid * P.levels * kQueueCap;
+    WarpState *ws = reinterpret_cast<WarpState *>(smem + P.blob_cap + (size_t)kSearchWarps * P.levels * kQueueCap * 4) + wid;
+
+    unsigned long long st_sweeps = 0, st_evals = 0, st_exact = 0, st_pairs = 0, st_staged = 0, st_global = 0;
+
+    for (;;) {
+        if (tid == 0) s_item = (int)atomicAdd(O.work_counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= P.n_items) break;
+        const int s = item / P.n_chunks, chunk = item - s * P.n_chunks;
+        const unsigned char *gblob = B.blob + B.blob_off[s];
+        const BlobHeader hdr = *reinterpret_cast<const BlobHeader *>(gblob);
+        const int span = P.template_end - P.template_begin;
+        const int per = (span + P.n_chunks - 1) / P.n_chunks;
+        const int tb = P.template_begin + chunk * per;
+        const int te = min(P.template_end, tb + per);
+        const bool run = hdr.status == 0 && hdr.n_kept > 0 && tb < te && !(skip && skip[s]);
+        if (run) {
+            const unsigned char *base = gblob;
+            if (hdr.staged_bytes <= P.blob_cap) {
+                const int4 *src = reinterpret_cast<const int4 *>(gblob);
+                int4 *dst = reinterpret_cast<int4 *>(stage);
+                for (int i = tid; i < hdr.staged_bytes / 16; i += kSearchThreads) dst[i] = __ldg(src + i);
+                base = stage;
+                if (kStats && tid == 0) st_staged += hdr.staged_bytes;
+            } else if (kStats && tid == 0) {
+                ++st_global;
+            }
+            if (tid == 0) s_next_tpl = tb;
+            __syncthreads();
+            Blob S;
+            S.x = reinterpret_cast<const float *>(base + hdr.off_x);
+            S.y = reinterpret_cast<const float *>(base + hdr.off_y);
+            S.z = reinterpret_cast<const float *>(base + hdr.off_z);
+            S.res_of = reinterpret_cast<const uint16_t *>(base + hdr.off_res);
+            S.res_start = reinterpret_cast<const uint16_t *>(base + hdr.off_resstart);
+            S.klass = reinterpret_cast<const uint16_t *>(base + hdr.off_klass);
+            S.lead_off = reinterpret_cast<const uint32_t *>(base + hdr.off_leadoff);
+            S.lead = reinterpret_cast<const uint16_t *>(base + hdr.off_lead);
+            S.orig = reinterpret_cast<const int32_t *>(gblob + hdr.off_orig);
+            const int64_t abase = B.atom_off[s];
+            S.xyz64 = B.xyz + 3 * abase;
+            S.chain = B.chain ? B.chain + abase : nullptr;
+            S.atom_id = B.atom_id ? B.atom_id + abase : nullptr;
+            S.res_shift = hdr.res_shift;
+            S.n_kept = hdr.n_kept;
+            S.eps = hdr.eps;
+            for (;;) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&s_next_tpl, 1);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= te) break;
+                search_template<kStats>(L, S, P, O, s, t, Q, ws, lane, &st_sweeps, &st_evals, &st_exact);
+                if (kStats && lane == 0) ++st_pairs;
+            }
+        }
+        __syncthreads();
+    }
+    if (kStats) {
+        // per-lane counters -> one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_evals += __shfl_xor_sync(0xffffffffu, st_evals, o);
+            st_exact += __shfl_xor_sync(0xffffffffu, st_exact, o);
+        }
+        if (lane == 0) {
+            atomicAdd(O.stats + 0, st_pairs);
+            atomicAdd(O.stats + 1, st_sweeps);
+            atomicAdd(O.stats + 2, st_evals);
+            atomicAdd(O.stats + 3, st_exact);
+            atomicAdd(O.stats + 6, st_staged);
+            atomicAdd(O.stats + 7, st_global);
+        }
+    }
+}
+
+__global__ void emm_skip_snapshot_kernel(int n, int mode, const int *any, const int *pass, unsigned char *skip)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) skip[i] = (mode == 1 ? pass[i] : any[i]) > 0;
+}
+
+size_t search_smem_bytes(int blob_cap, int levels)
+{
+    return (size_t)blob_cap + (size_t)kSearchWarps * levels * kQueueCap * 4 + (size_t)kSearchWarps * sizeof(WarpState);
+}
+
+size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels); }
+
+cudaError_t configure_search(int smem_bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(emm_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(emm_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+
+void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream)
+{
+    if (n > 0) emm_skip_snapshot_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, mode, any, pass, skip);
+}
+
+void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
+                   const unsigned char *skip, bool stats, int grid, size_t smem, cudaStream_t stream)
+{
+    if (P.n_items <= 0) return;
+    if (stats) emm_search_kernel<true><<<grid, kSearchThreads, smem, stream>>>(L, B, P, O, skip);
+    else emm_search_kernel<false><<<grid, kSearchThreads, smem, stream>>>(L, B, P, O, skip);
+}
+
+}  // namespace emm

@@ -1,0 +1,484 @@
+"""``Match`` / ``Matcher`` / ``load_molecules``: EnzyMM's orchestration layer over the CUDA engine.
+
+Same Python-facing API and semantics as ``enzymm/jess_run.py``, but
+``Matcher.run`` hands the whole (molecules x templates) problem to the GPU in one batch instead
+of one ``Jess(templates).query(molecule)`` per (molecule, size group) on a thread pool
+(``jess_run.py:896-988``).  Preserved on purpose (SURVEY.md 5 "quirks"):
+
+* size groups are processed in descending effective size with per-size thresholds
+  (``jess_run.py:564-571, 724-736, 930-947``); sizes below 3 only with ``match_small_templates``;
+* ``_check_completeness`` runs on the raw best hits of one (molecule, size group) BEFORE
+  filtering (``jess_run.py:738-783, 863``);
+* filtering keeps ``Match.predicted_correct`` matches; the result dict is keyed in the order
+  molecules first receive a surviving match, size-major (``jess_run.py:867-894``);
+* ``skip_smaller_hits`` skips a molecule once it holds a surviving match (``jess_run.py:951-958``);
+* the majority vote is ">= round(5/2) == 2 of 5" and a missing distance key is a ``KeyError``
+  (``jess_run.py:298-346``).
+
+The filter verdict used for ``filter_matches`` / ``skip_smaller_hits`` comes from the fused GPU
+filter (``Hit.device_pass``); ``Match.predicted_correct`` is the reference formula in Python and is
+what the parity tests compare it with.
+"""
+from __future__ import annotations
+
+import collections
+import csv
+import io
+import itertools
+import math
+import os
+import sys
+import warnings
+from dataclasses import dataclass, field
+from functools import cached_property
+from pathlib import Path
+from typing import ClassVar, Dict, IO, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import pyjess_api as pyjess
+from .engine import Engine
+from .library import CompiledLibrary, load_lr_models
+from .packing import pack_molecules
+from .pyjess_api import Hit
+from .structures import Molecule
+from .templates import AnnotatedTemplate, Template, Vec3, check_template, rank_order
+
+__all__ = ["LogisticRegressionModel", "Match", "Matcher", "load_molecules"]
+
+PROTEINOGENIC_AMINO_ACIDS = ["ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE",
+                             "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL"]
+SPECIAL_AMINO_ACIDS = ["ASX", "GLX", "SEC", "PYL", "UNK", "MSE", "SEP", "TPO", "PTR", "HYP", "CME",
+                       "CSO", "CSD", "PCA", "MLY", "DAL", "DAR", "DSG", "ORN", "PTM"]
+_COUNTED_RESIDUES = frozenset(PROTEINOGENIC_AMINO_ACIDS + SPECIAL_AMINO_ACIDS)
+
+_ONE_LETTER_ELEMENTS = frozenset("HBCNOFPSKVYIWU")
+
+_TSV_HEADER = [
+    "query_id", "pairwise_distance", "match_index", "template_pdb_id", "template_pdb_chains",
+    "template_cluster_id", "template_cluster_member", "template_cluster_size",
+    "template_effective_size", "template_dimension", "template_mcsa_id", "template_uniprot_id",
+    "template_ec", "template_cath", "template_multimeric", "query_multimeric", "query_atom_count",
+    "query_residue_count", "rmsd", "log_evalue", "orientation", "preserved_order", "completeness",
+    "predicted_correct", "matched_residues", "number_of_mutated_residues",
+    "number_of_side_chain_residues_(template,reference)",
+    "number_of_metal_ligands_(template,reference)", "number_of_ptm_residues_(template, reference)",
+    "total_reference_residues",
+]
+
+
+@dataclass(frozen=True)
+class LogisticRegressionModel:
+    """f(x) = 1 / (1 + e^-(b0 + b1*rmsd + b2*orientation)) with its decision threshold
+    (``jess_run.py:39-56``; the attribute keeps upstream's spelling)."""
+
+    coefficents: List[float]
+    intercept: float
+    threshold: float
+
+
+def _pdb_atom_line(atom) -> str:
+    """Fixed-column ATOM record as the reference writes it (``jess_run.py:125-145``): one-letter
+    elements shift the atom name one column right."""
+    altloc = atom.altloc if atom.altloc is not None else ""
+    name = f"  {atom.name:<3s}" if atom.element in _ONE_LETTER_ELEMENTS else f" {atom.name:<4s}"
+    return (f"ATOM  {atom.serial:>5}{name}{altloc:<1}{atom.residue_name:<3}{atom.chain_id:>2}"
+            f"{atom.residue_number:>4}{atom.insertion_code:1s}   {atom.x:>8.3f}{atom.y:>8.3f}{atom.z:>8.3f}"
+            f"{atom.occupancy:>6.2f}{atom.temperature_factor:>6.2f}      {atom.segment:<4s}{atom.element:>2s} \n")
+
+
+@dataclass
+class Match:
+    """A ``Hit`` plus EnzyMM's derived quantities (``jess_run.py:59-496``)."""
+
+    hit: Hit
+    complete: bool = field(default=False)
+    pairwise_distance: float = field(default=0)
+    index: int = field(default=0)
+    _logistic_regression_models: ClassVar[Dict[str, Dict[str, List[LogisticRegressionModel]]]] = {}
+
+    # ---- geometry ------------------------------------------------------------------------------
+    @cached_property
+    def atom_triplets(self):
+        """Matched atoms (template frame) grouped three by three; every triplet must come from
+        one query residue (``jess_run.py:348-373``)."""
+        atoms = self.hit.atoms(transform=True)
+        triplets = []
+        for start in range(0, len(atoms), 3):
+            triplet = tuple(atoms[start:start + 3])
+            if len(triplet) != 3:
+                raise ValueError(f"Failed to construct residues. Got only {len(triplet)} ATOM lines")
+            owners = {(a.residue_name, a.chain_id, a.residue_number) for a in triplet}
+            if len(owners) != 1:
+                raise ValueError(f"Mixed up atom triplets {owners}. The atoms come from different residues!")
+            triplets.append(triplet)
+        return triplets
+
+    @property
+    def matched_residues(self) -> List[Tuple[str, str, str]]:
+        return [(t[0].residue_name, t[0].chain_id, str(t[0].residue_number)) for t in self.atom_triplets]
+
+    @property
+    def multimeric(self) -> bool:
+        atoms = self.hit.atoms()
+        return any(a.chain_id != atoms[0].chain_id for a in atoms)
+
+    @property
+    def preserved_resid_order(self) -> bool:
+        if self.hit.template.multimeric or self.multimeric:
+            return False
+        return rank_order([t[0].residue_number for t in self.atom_triplets]) == self.hit.template.relative_order
+
+    @cached_property
+    def match_vector_list(self) -> List[Vec3]:
+        """Orientation vector of every matched residue, in the template frame (``jess_run.py:425-452``)."""
+        vectors = []
+        for triplet, residue in zip(self.atom_triplets, self.hit.template.residues):
+            first, second = residue.orientation_vector_indices
+            if second == 9:
+                centre = triplet[first]
+                side_a, side_b = [a for a in triplet if a != centre]
+                vectors.append((Vec3.from_xyz(side_a) + Vec3.from_xyz(side_b)) / 2 - Vec3.from_xyz(centre))
+            else:
+                vectors.append(Vec3.from_xyz(triplet[second]) - Vec3.from_xyz(triplet[first]))
+        return vectors
+
+    @property
+    def template_vector_list(self) -> List[Vec3]:
+        return [r.orientation_vector for r in self.hit.template.residues]
+
+    @property
+    def orientation(self) -> float:
+        """Mean angle (radians) between template and query residue orientations (``jess_run.py:461-478``)."""
+        tv, mv = self.template_vector_list, self.match_vector_list
+        if len(tv) != len(mv):
+            raise ValueError("Vector lists for Template and matching Query structure had different lengths.")
+        angles = [t.angle_to(m) for t, m in zip(tv, mv)]
+        return sum(angles) / len(angles)
+
+    # ---- logistic filter --------------------------------------------------------------------------
+    @property
+    def predicted_correct(self) -> bool:
+        """Majority vote of the logistic models for (effective size, pairwise distance); sizes
+        without models pass (``jess_run.py:298-346``)."""
+        models_by_size = self._logistic_regression_models
+        size_key = str(self.hit.template.effective_size)
+        if size_key not in models_by_size:
+            return True
+        try:
+            models = models_by_size[size_key][str(self.pairwise_distance)]
+            votes = 0
+            for model in models:
+                z = model.intercept + model.coefficents[0] * self.hit.rmsd + model.coefficents[1] * self.orientation
+                votes += (1 / (1 + math.e ** -z)) >= model.threshold
+            return bool(votes >= round(len(models) / 2, 0))
+        except KeyError as exc:
+            raise KeyError(
+                "Missing appropriate model parameters to predict correctness. Encountered either unexpected "
+                f"dictionary structure or no models for the pairwise distance {self.pairwise_distance} were provided"
+            ) from exc
+        except IndexError as exc:
+            raise IndexError("Missing coefficients for both RMSD and Residue Orientation. "
+                             "Expecting models with 2 coeficients.") from exc
+
+    def get_identifying_attributes(self) -> Tuple[int, int, int]:
+        t = self.hit.template
+        return (t.mcsa_id, t.cluster.id, t.dimension)
+
+    # ---- query statistics ---------------------------------------------------------------------------
+    @property
+    def query_atom_count(self) -> int:
+        return len(self.hit.molecule())
+
+    @property
+    def query_residue_count(self) -> int:
+        """Distinct residue NUMBERS among amino-acid residues, chain ignored (``jess_run.py:487-496``)."""
+        mol = self.hit.molecule()
+        names = mol.column("residue_name")
+        keep = np.isin(names, list(_COUNTED_RESIDUES))
+        return int(len(np.unique(mol.column("residue_number")[keep])))
+
+    # ---- writers --------------------------------------------------------------------------------------
+    def dumps(self, header: bool = False) -> str:
+        buffer = io.StringIO()
+        self.dump(buffer, header=header)
+        return buffer.getvalue()
+
+    def dump(self, file: IO[str], header: bool = False, predict_correctness: bool = True):
+        """One TSV row (``jess_run.py:185-284``)."""
+        writer = csv.writer(file, dialect="excel-tab", delimiter="\t", lineterminator="\n")
+        if header:
+            writer.writerow(_TSV_HEADER)
+        t = self.hit.template
+        c = t.cluster
+        row = [
+            str(self.hit.molecule().id), str(self.pairwise_distance), str(self.index),
+            str(t.pdb_id if t.pdb_id else ""), ",".join(set(r.chain_id for r in t.residues)),
+            str(c.id if c else ""), str(c.member if c else ""), str(c.size if c else ""),
+            str(t.effective_size), str(t.dimension), str(t.mcsa_id if t.mcsa_id else ""),
+            str(t.uniprot_id if t.uniprot_id else ""), ",".join(t.ec if t.ec is not None else ""),
+            ",".join(t.cath if t.cath else ""), str(t.multimeric), str(self.multimeric),
+            str(self.query_atom_count), str(self.query_residue_count), str(round(self.hit.rmsd, 5)),
+            str(round(self.hit.log_evalue, 5)), str(round(self.orientation, 5)),
+            str(self.preserved_resid_order), str(self.complete),
+            str(self.predicted_correct) if predict_correctness else "",
+            ",".join("_".join(r) for r in self.matched_residues),
+        ]
+        if isinstance(t, AnnotatedTemplate) and hasattr(t, "number_of_mutated_residues"):
+            row.extend([
+                str(t.number_of_mutated_residues), ",".join(str(i) for i in t.number_of_side_chain_residues),
+                ",".join(str(i) for i in t.number_of_metal_ligands),
+                ",".join(str(i) for i in t.number_of_ptm_residues), str(t.total_reference_residues),
+            ])
+        else:
+            row.extend(["", "", "", "", "", ""])
+        writer.writerow(row)
+
+    def dump2pdb(self, file: IO[str], include_query: bool = False, transform: bool = False):
+        """Matched atoms (optionally preceded by the whole query) as PDB text (``jess_run.py:96-183``)."""
+        mol_id = self.hit.molecule().id
+        if include_query:
+            file.write(f"HEADER MOLECULE_ID {mol_id}\n")
+            for atom in self.hit.molecule(transform=transform):
+                file.write(_pdb_atom_line(atom))
+            file.write("END\n\n")
+        t = self.hit.template
+        file.write(f"HEADER {self.predicted_correct} MATCH {mol_id} {self.index}\n")
+        file.write(f'REMARK TEMPLATE_PDB {t.pdb_id}_{",".join(set(r.chain_id for r in t.residues))}\n')
+        if t.cluster:
+            file.write(f"REMARK TEMPLATE CLUSTER {t.cluster.id}_{t.cluster.member}_{t.cluster.size}\n")
+        if t.represented_sites:
+            file.write(f"REMARK TEMPLATE RESIDUES {t.template_id_string}\n")
+        file.write(f"REMARK MOLECULE_ID {mol_id}\n")
+        file.write(f"REMARK MATCH INDEX {self.index}\n")
+        file.write("REMARK TEMPLATE COORDINATE FRAME\n" if transform else "REMARK QUERY COORDINATE FRAME\n")
+        for atom in self.hit.atoms(transform=transform):
+            file.write(_pdb_atom_line(atom))
+        file.write("END\n\n")
+
+
+def _install_lr_models():
+    Match._logistic_regression_models = {
+        size: {dist: [LogisticRegressionModel([c0, c1], b0, thr) for c0, c1, b0, thr in models]
+               for dist, models in by_dist.items()}
+        for size, by_dist in load_lr_models().items()
+    }
+
+
+_install_lr_models()
+
+
+def load_molecules(molecule_paths: Sequence[Path], conservation_cutoff: float = 0, warn: bool = False) -> List[Molecule]:
+    """Load query structures; repeated file stems get ``_2``, ``_3`` ... ids (``jess_run.py:523-556``).
+
+    As upstream, ``conserved()`` is called and its RESULT DISCARDED (``jess_run.py:541-542``), so
+    the cutoff does not mask anything on this path.  The intended masking
+    is available through ``Matcher(conservation_cutoff=..., apply_conservation_mask=True)``.
+    """
+    molecules: List[Molecule] = []
+    seen: Dict[str, int] = collections.defaultdict(int)
+    for path in molecule_paths:
+        stem = Path(path).stem
+        seen[stem] += 1
+        mol = Molecule.load(str(path), id=stem if seen[stem] == 1 else f"{stem}_{seen[stem]}")
+        if conservation_cutoff:
+            mol.conserved(conservation_cutoff)
+        if mol:
+            molecules.append(mol)
+        elif warn:
+            warnings.warn(f"received an empty molecule from {path}")
+    if not molecules and warn:
+        warnings.warn("received no molecules from input")
+    return molecules
+
+
+def _available_cpus() -> int:
+    return len(os.sched_getaffinity(0)) if sys.platform == "linux" else (os.cpu_count() or 1)
+
+
+class Matcher:
+    """Match a list of templates against query molecules on the GPU (``jess_run.py:559-1000``)."""
+
+    _DEFAULT_JESS_PARAMS = {
+        3: {"rmsd": 2, "distance": 0.9, "max_dynamic_distance": 0.9},
+        4: {"rmsd": 2, "distance": 1.7, "max_dynamic_distance": 1.7},
+        5: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0},
+        6: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0},
+        7: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0},
+        8: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0},
+    }
+
+    def __init__(self, templates: List[Template], jess_params: Optional[Dict[int, Dict[str, float]]] = None,
+                 conservation_cutoff: int = 0, warn: bool = False, verbose: bool = False,
+                 skip_smaller_hits: bool = False, match_small_templates: bool = False,
+                 cpus: Optional[int] = None, filter_matches: bool = True, console=None,
+                 *, device: int = 0, max_candidates: int = 10000, apply_conservation_mask: bool = False):
+        self.templates = templates
+        self.cpus = _available_cpus() if cpus is None else cpus
+        self.conservation_cutoff = conservation_cutoff
+        self.warn = warn
+        self.verbose = verbose
+        self.skip_smaller_hits = skip_smaller_hits
+        self.match_small_templates = match_small_templates
+        self.filter_matches = filter_matches
+        self.jess_params = self._DEFAULT_JESS_PARAMS if jess_params is None else jess_params
+        self.console = console
+        self.device = device
+        self.max_candidates = max_candidates
+        self.apply_conservation_mask = apply_conservation_mask
+
+        if len(set(self.templates)) < len(self.templates):
+            raise ValueError("Duplicate templates were found.")
+        if self.cpus <= 0:
+            self.cpus = max(1, _available_cpus() + self.cpus)
+
+        self.verbose_print(f"PyJess Version: {pyjess.__version__}")
+        self.verbose_print(f"Running on {self.cpus} Thread(s)")
+        self.verbose_print(f"Warnings are set to {self.warn}")
+        self.verbose_print(f"Skip_smaller_hits search is set to {self.skip_smaller_hits}")
+        if self.conservation_cutoff:
+            self.verbose_print(f"Conservation Cutoff set to {self.conservation_cutoff}")
+
+        self.templates_by_effective_size: Dict[int, List[Template]] = collections.defaultdict(list)
+        for template in templates:
+            if check_template(template, warn=self.warn):
+                self.templates_by_effective_size[template.effective_size].append(template)
+        if self.verbose:
+            shown = {s: len(v) for s, v in self.templates_by_effective_size.items()
+                     if self.match_small_templates or s >= 3}
+            print(f"Templates by effective size: {collections.OrderedDict(sorted(shown.items()))}")
+        self.template_effective_sizes = sorted(self.templates_by_effective_size, reverse=True)
+
+        if self.warn:
+            small = [t for s in self.template_effective_sizes if s < 3 for t in self.templates_by_effective_size[s]]
+            if small:
+                tail = ("For small templates Jess parameters for templates of 3 residues will be used."
+                        if self.match_small_templates else
+                        "These will be excluded since these templates are too general.")
+                warnings.warn(f"{len(small)} Templates with an effective size smaller than 3 defined "
+                              f"sidechain residues were supplied.\n{tail}")
+                self.verbose_print("The templates with the following ids are too small:")
+                self.verbose_print([t.id for t in small])
+        self._engine: Optional[Engine] = None
+        self._groups: List[Tuple[int, int, int]] = []
+
+    def verbose_print(self, *args):
+        if self.verbose:
+            print(*args)
+
+    def _get_jess_parameters(self, template_size: int) -> Tuple[float, float, float]:
+        p = self.jess_params[min(max(template_size, 3), 8)]
+        return p["rmsd"], p["distance"], p["max_dynamic_distance"]
+
+    @staticmethod
+    def _check_completeness(matches: List[Match]) -> List[Match]:
+        """A match is complete when every member of its template cluster hit the same molecule
+        in this size group; matches without cluster / M-CSA id are complete (``jess_run.py:738-783``)."""
+        grouped: Dict[tuple, List[Match]] = collections.defaultdict(list)
+        for match in matches:
+            t = match.hit.template
+            if t.mcsa_id is not None and t.cluster is not None:
+                grouped[match.get_identifying_attributes()].append(match)
+            else:
+                match.complete = True
+        for members in grouped.values():
+            want = list(range(1, members[0].hit.template.cluster.size + 1))
+            have = sorted(m.hit.template.cluster.member for m in members)
+            if have == want:
+                for m in members:
+                    m.complete = True
+        return matches
+
+    # ---- engine ---------------------------------------------------------------------------------------
+    def _active_sizes(self) -> List[int]:
+        return [s for s in self.template_effective_sizes if s >= 3 or self.match_small_templates]
+
+    def _ensure_engine(self) -> Engine:
+        """Compile every searched size group into ONE device library (size-descending, caller
+        order inside a group) with per-template thresholds."""
+        if self._engine is None:
+            ordered: List[Template] = []
+            rmsd, dist, dyn = [], [], []
+            self._groups = []
+            for size in self._active_sizes():
+                group = self.templates_by_effective_size[size]
+                r, d, m = self._get_jess_parameters(size)
+                self._groups.append((size, len(ordered), len(ordered) + len(group)))
+                ordered.extend(group)
+                rmsd.extend([r] * len(group))
+                dist.extend([d] * len(group))
+                dyn.extend([m] * len(group))
+            if not ordered:
+                raise ValueError("no templates to search with")
+            self._ordered = ordered
+            self._engine = Engine(CompiledLibrary(ordered, rmsd, dist, dyn), self.device)
+        return self._engine
+
+    def run(self, molecules: List[Molecule]) -> Dict[Molecule, List[Match]]:
+        """Search every molecule against every size group; ``{molecule: [Match, ...]}``."""
+        processed: Dict[Molecule, List[Match]] = collections.defaultdict(list)
+        if not self._active_sizes() or not molecules:
+            return processed
+        engine = self._ensure_engine()
+        batch = pack_molecules(molecules, engine.compiled)
+        cutoff = float(self.conservation_cutoff) if (self.apply_conservation_mask and self.conservation_cutoff) else 0.0
+        session = engine.session_for(batch.n_atoms, batch.n_structures)
+        session.upload(batch)
+        common = dict(max_candidates=self.max_candidates, ignore_chain=True, conservation_cutoff=cutoff)
+        if self.skip_smaller_hits:
+            # one launch per size group; the device skips structures that already hold a surviving hit
+            mode = 1 if self.filter_matches else 2
+            for gi, (_, lo, hi) in enumerate(self._groups):
+                session.run(template_begin=lo, template_end=hi, skip_mode=mode, reset=(gi == 0), **common)
+        else:
+            session.run(template_begin=0, template_end=len(self._ordered), skip_mode=0, reset=True, **common)
+        records = session.download()
+
+        by_cell: Dict[Tuple[int, int], List[np.void]] = collections.defaultdict(list)
+        bounds = np.asarray([hi for _, _, hi in self._groups])
+        for rec in records:
+            gi = int(np.searchsorted(bounds, int(rec["template_index"]), side="right"))
+            by_cell[(gi, int(rec["structure"]))].append(rec)
+
+        for gi, (size, lo, hi) in enumerate(self._groups):
+            rmsd, distance, max_dyn = self._get_jess_parameters(size)
+            self.verbose_print(f"Now matching query structure(s) to template of size {size}")
+            self.verbose_print(f"jess parameters are: {rmsd} {distance} {max_dyn}")
+            total = 0
+            for mi, molecule in enumerate(molecules):
+                recs = by_cell.get((gi, mi))
+                if not recs:
+                    continue
+                matches = [Match(hit=Hit(r, self._ordered[int(r["template_index"])], molecule),
+                                 pairwise_distance=distance) for r in recs]
+                self._check_completeness(matches)
+                if self.filter_matches:
+                    for match in matches:
+                        if match.hit.missing_model:
+                            match.predicted_correct   # raises the reference's KeyError
+                        if match.hit.device_pass:
+                            processed[molecule].append(match)
+                            total += 1
+                else:
+                    processed[molecule].extend(matches)
+                    total += len(matches)
+            self.verbose_print(f"{total} matches found!")
+            self.verbose_print(f"{len(processed)} target structures processed!")
+        return processed
+
+    def run_single(self, molecule: Molecule) -> List[Match]:
+        return self.run([molecule])[molecule]
+
+    # signature-compatible single (molecule, size group) entry point (``jess_run.py:785-843``)
+    @staticmethod
+    def _run_jess(molecule: Molecule, templates: List[Template], rmsd_threshold: float = 2.0,
+                  distance_cutoff: float = 1.5, max_dynamic_distance: float = 1.5,
+                  max_candidates: int = 10000) -> List[Match]:
+        query = pyjess.Jess(templates).query(molecule, rmsd_threshold, distance_cutoff, max_dynamic_distance,
+                                             max_candidates=max_candidates, best_match=True, ignore_chain=True)
+        return [Match(hit=hit, pairwise_distance=distance_cutoff) for hit in query]
+
+    def _single_query_run(self, molecule, templates, rmsd_threshold, distance_cutoff, max_dynamic_distance,
+                          max_candidates: int = 10000) -> List[Match]:
+        return self._check_completeness(self._run_jess(molecule, templates, rmsd_threshold, distance_cutoff,
+                                                       max_dynamic_distance, max_candidates))

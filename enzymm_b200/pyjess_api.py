@@ -1,0 +1,191 @@
+"""The ``pyjess`` names EnzyMM imports, backed by the CUDA engine.
+
+Drop-in surface: ``Jess(templates).query(molecule, rmsd_threshold,
+distance_cutoff, max_dynamic_distance, max_candidates=..., best_match=..., ignore_chain=...)``
+returning an iterator of ``Hit`` (reference call site ``enzymm/jess_run.py:800-811`` and
+``tests/test_jess_run.py:32-39``), with ``Hit.rmsd / .log_evalue / .template / .atoms(transform)
+/ .molecule(transform)`` as consumed at ``jess_run.py:148-182, 243-262, 317, 357, 397, 485``.
+
+There is no CPU path: constructing the engine without the CUDA library or a GPU raises.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Iterator, List, Optional, Sequence
+
+import numpy as np
+
+from . import __version__  # noqa: F401  (pyjess.__version__ is printed at jess_run.py:659)
+from .engine import (Engine, HIT_BORDERLINE, HIT_NO_MODEL, HIT_ORIENTED, HIT_OVERFLOW, HIT_PASS,
+                     PackedBatch)
+from .library import CompiledLibrary
+from .packing import pack_molecules
+from .structures import Atom, Molecule
+from .template_atoms import JessTemplate as Template
+from .template_atoms import TemplateAtom
+
+__all__ = ["Atom", "Molecule", "TemplateAtom", "Template", "Jess", "Query", "Hit"]
+
+
+class Hit:
+    """One template matched onto one molecule (mirror of ``pyjess.Hit``).
+
+    ``log_evalue`` is NaN: its formula lives in the un-vendored Jess C source, only two values
+    are pinned by the reference tests and it feeds no decision (SURVEY.md 8c "parity unpinned").
+    """
+
+    __slots__ = ("rmsd", "log_evalue", "template", "_molecule", "_atom_idx", "_rot", "_qbar", "_tbar",
+                 "orientation", "flags", "n_complete", "template_index", "structure_index")
+
+    def __init__(self, record: np.void, template, molecule: Molecule):
+        n = int(record["n_atoms"])
+        self.rmsd = float(record["rmsd"])
+        self.log_evalue = math.nan
+        self.template = template
+        self._molecule = molecule
+        self._atom_idx = np.asarray(record["atoms"][:n], dtype=np.int64)
+        self._rot = np.asarray(record["rot"], dtype=np.float64).reshape(3, 3).copy()
+        self._qbar = np.asarray(record["qbar"], dtype=np.float64).copy()
+        self._tbar = np.asarray(record["tbar"], dtype=np.float64).copy()
+        self.orientation = float(record["orientation"])
+        self.flags = int(record["flags"])
+        self.n_complete = int(record["n_complete"])
+        self.template_index = int(record["template_index"])
+        self.structure_index = int(record["structure"])
+
+    # device-side verdicts ----------------------------------------------------------------------
+    @property
+    def device_pass(self) -> bool:
+        """``Match.predicted_correct`` as decided by the fused filter on the GPU."""
+        return bool(self.flags & HIT_PASS)
+
+    @property
+    def overflow(self) -> bool:
+        return bool(self.flags & HIT_OVERFLOW)
+
+    @property
+    def borderline(self) -> bool:
+        return bool(self.flags & HIT_BORDERLINE)
+
+    @property
+    def missing_model(self) -> bool:
+        return bool(self.flags & HIT_NO_MODEL)
+
+    @property
+    def atom_indices(self) -> List[int]:
+        """Matched query atom indices in template atom order."""
+        return [int(i) for i in self._atom_idx]
+
+    # pyjess surface -----------------------------------------------------------------------------
+    def _transform(self, xyz: np.ndarray) -> np.ndarray:
+        # q' = R (q - qbar) + tbar : query frame -> template frame (SURVEY 8c rule 9)
+        return (xyz - self._qbar) @ self._rot.T + self._tbar
+
+    def atoms(self, transform: bool = True) -> List[Atom]:
+        """Matched query atoms in template order; ``transform=True`` -> template frame."""
+        mol = self._molecule
+        out = []
+        xyz = mol.xyz[self._atom_idx]
+        if transform:
+            xyz = self._transform(xyz)
+        for row, i in zip(xyz, self._atom_idx):
+            atom = mol.atom(int(i))
+            atom.x, atom.y, atom.z = float(row[0]), float(row[1]), float(row[2])
+            out.append(atom)
+        return out
+
+    def molecule(self, transform: bool = False) -> Molecule:
+        if not transform:
+            return self._molecule
+        return self._molecule.with_xyz(self._transform(self._molecule.xyz))
+
+    def __repr__(self):
+        return f"Hit(template={getattr(self.template, 'id', None)!r}, rmsd={self.rmsd:.4f})"
+
+
+class Query:
+    """Iterator over the hits of one ``Jess.query`` call (mirror of ``pyjess.Query``)."""
+
+    def __init__(self, hits: List[Hit], molecule: Molecule, rmsd_threshold: float, distance_cutoff: float,
+                 max_dynamic_distance: float, max_candidates, best_match: bool, ignore_chain: bool):
+        self._hits = hits
+        self._pos = 0
+        self.molecule = molecule
+        self.rmsd_threshold = rmsd_threshold
+        self.distance_cutoff = distance_cutoff
+        self.max_dynamic_distance = max_dynamic_distance
+        self.max_candidates = max_candidates
+        self.best_match = best_match
+        self.ignore_chain = ignore_chain
+
+    def __iter__(self) -> Iterator[Hit]:
+        return self
+
+    def __next__(self) -> Hit:
+        if self._pos >= len(self._hits):
+            raise StopIteration
+        hit = self._hits[self._pos]
+        self._pos += 1
+        return hit
+
+
+_ENGINE_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_ENGINE_CACHE_SIZE = 4
+
+
+def _engine_for(templates: Sequence[Template], device: int) -> Engine:
+    """EnzyMM rebuilds ``Jess(templates)`` on every call (jess_run.py:800); compiling and
+    uploading a library per call would dominate, so engines are cached by template identity."""
+    key = (device, tuple(id(t) for t in templates))
+    entry = _ENGINE_CACHE.get(key)
+    if entry is not None:
+        _ENGINE_CACHE.move_to_end(key)
+        return entry[0]
+    compiled = CompiledLibrary(templates, 2.0, 2.0, 2.0)
+    engine = Engine(compiled, device)
+    _ENGINE_CACHE[key] = (engine, list(templates))   # keep templates alive so ids stay unique
+    while len(_ENGINE_CACHE) > _ENGINE_CACHE_SIZE:
+        _, (old, _) = _ENGINE_CACHE.popitem(last=False)
+        old.close()
+    return engine
+
+
+class Jess:
+    """A set of templates to query molecules against (mirror of ``pyjess.Jess``)."""
+
+    def __init__(self, templates: Sequence[Template] = (), device: int = 0):
+        self._templates = list(templates)
+        self._device = device
+
+    def __len__(self):
+        return len(self._templates)
+
+    def __iter__(self):
+        return iter(self._templates)
+
+    def __getitem__(self, i):
+        return self._templates[i]
+
+    def query(self, molecule: Molecule, rmsd_threshold: float, distance_cutoff: float,
+              max_dynamic_distance: float, *, max_candidates: Optional[int] = None,
+              ignore_chain: bool = False, best_match: bool = False) -> Query:
+        """Match every template against ``molecule``; yields at most one ``Hit`` per template.
+
+        Only ``best_match=True`` -- the one mode EnzyMM uses (jess_run.py:809) -- is implemented.
+        """
+        if not best_match:
+            raise NotImplementedError(
+                "enzymm_b200 implements best_match=True only (the mode EnzyMM uses, jess_run.py:809)")
+        hits: List[Hit] = []
+        if self._templates and len(molecule):
+            engine = _engine_for(self._templates, self._device)
+            engine.compiled.set_thresholds(rmsd_threshold, distance_cutoff, max_dynamic_distance)
+            engine.device_library.push_thresholds()
+            batch = pack_molecules([molecule], engine.compiled)
+            # pyjess's own default when max_candidates is None is 1000 (comment at jess_run.py:796)
+            cap = 1000 if max_candidates is None else int(max_candidates)
+            records = engine.query(batch, max_candidates=cap, ignore_chain=ignore_chain)
+            hits = [Hit(r, self._templates[int(r["template_index"])], molecule) for r in records]
+        return Query(hits, molecule, rmsd_threshold, distance_cutoff, max_dynamic_distance,
+                     max_candidates, best_match, ignore_chain)

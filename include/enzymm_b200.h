@@ -1,0 +1,206 @@
+/*
+ * enzymm_b200.h -- C ABI of the B200-native geometric matching engine.
+ *
+ * This is the drop-in boundary for ONE path of RayHackett/enzymm: what
+ *     pyjess.Jess(templates).query(molecule, rmsd_threshold, distance_cutoff,
+ *                                  max_dynamic_distance, max_candidates, best_match=True,
+ *                                  ignore_chain=True)
+ * computes inside enzymm.jess_run.Matcher._run_jess (reference enzymm/jess_run.py:785-843), plus
+ * EnzyMM's RMSD/orientation logistic filter (jess_run.py:298-346, 425-478), batched over many
+ * query structures.  The reference has no C plugin ABI for this path -- its boundary is the
+ * Python API of the un-vendored `pyjess` wheel (pyproject.toml:30) -- so each entry point below
+ * names the pyjess / EnzyMM call it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions: plain pointers and sizes only; every function returns EMM_OK (0) or a negative
+ * emm_status; no exceptions cross the boundary; the caller owns all host buffers; the library
+ * owns device memory behind opaque handles; one handle is bound to one CUDA device; calls on one
+ * handle must be serialised by the caller.  `stream` arguments are cudaStream_t passed as void*
+ * (NULL = the legacy default stream).
+ */
+#ifndef ENZYMM_B200_H
+#define ENZYMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMM_ABI_VERSION 1
+#define EMM_MAX_TEMPLATE_ATOMS 32   /* shipped library: 6..24 atoms per template            */
+#define EMM_MAX_RESIDUES 10         /* orientation residues (atom triplets) per template     */
+#define EMM_LR_MODELS 5             /* logistic models per (size, distance) cell             */
+
+typedef enum emm_status {
+    EMM_OK = 0,
+    EMM_ERR_INVALID = -1,       /* bad argument / inconsistent table                          */
+    EMM_ERR_CUDA = -2,          /* CUDA runtime error (see emm_last_error)                    */
+    EMM_ERR_NO_DEVICE = -3,     /* no usable CUDA device: there is NO CPU fallback            */
+    EMM_ERR_CAPACITY = -4,      /* hit buffer too small; *n_hits holds the required count     */
+    EMM_ERR_INPUT = -5,         /* a structure violates the input contract (see emm_batch)    */
+    EMM_ERR_NOMEM = -6
+} emm_status;
+
+/* hit.flags */
+#define EMM_HIT_OVERFLOW   0x01u  /* max_candidates reached: result depends on enumeration order */
+#define EMM_HIT_BORDERLINE 0x02u  /* rmsd threshold or a logistic vote decided within 1e-9       */
+#define EMM_HIT_PASS       0x04u  /* Match.predicted_correct (jess_run.py:298-346)               */
+#define EMM_HIT_NO_MODEL   0x08u  /* size has models but none for this distance -> host KeyError */
+#define EMM_HIT_ORIENTED   0x10u  /* orientation was computed (template has residue triplets)    */
+
+/*
+ * Compiled template library.  Replaces pyjess.Jess(templates) (jess_run.py:800) together with
+ * pyjess.Template / pyjess.TemplateAtom (template.py:535, 679) and the constants EnzyMM derives
+ * per template residue (Residue.calc_residue_orientation, template.py:213-304).
+ *
+ * Atoms are stored twice: in TEMPLATE order for superposition/output (xyz), and as a SEARCH PLAN
+ * (plan_*) -- a permutation chosen by the host so that selective atoms are placed first.  Any
+ * permutation yields the same match set; only speed changes.
+ *
+ * Typing is data driven: template atom i carries a row index `ttype` into the bit matrix
+ * compat[n_ttype][class_words]; a query atom of class c may bind it iff bit c of the row is set
+ * (SURVEY.md 8c rules 2-3 are evaluated on the host when the matrix is built).  Class 0 is the
+ * "binds nothing" class.
+ */
+typedef struct emm_library_desc {
+    int32_t n_templates;
+    int32_t n_atoms;               /* total template atoms                                      */
+    const int32_t *atom_off;       /* [n_templates+1] CSR into per-atom arrays                  */
+    const double *xyz;             /* [n_atoms][3] template coordinates, template order         */
+    const double *weight;          /* [n_atoms] distance_weight, template order                 */
+    const uint16_t *chain;         /* [n_atoms] chain id code, template order (ignore_chain=0)  */
+    /* search plan, plan position k of template t lives at atom_off[t]+k */
+    const uint8_t *plan_atom;      /* [n_atoms] template-order index of the atom placed at k    */
+    const uint16_t *plan_ttype;    /* [n_atoms] compat row of that atom                         */
+    const int16_t *plan_src;       /* [n_atoms] >=0: same residue as plan position src;         */
+                                   /*           <0 : leader, candidates = leader list (-1-src)  */
+    const int64_t *pair_off;       /* [n_templates+1] CSR into pair_dist (k*(k-1)/2 + j, j<k)   */
+    const double *pair_dist;       /* template distances between plan positions, FP64           */
+    /* typing */
+    int32_t n_ttype;
+    int32_t class_words;           /* 32-bit words per compat row                               */
+    const uint32_t *compat;        /* [n_ttype][class_words]                                    */
+    int32_t n_leader;              /* distinct leader types                                     */
+    const uint16_t *leader_ttype;  /* [n_leader] compat row each leader list is built from      */
+    /* per-template thresholds (jess_run.py:564-571, 724-736) */
+    const double *rmsd_threshold;  /* [n_templates]                                             */
+    const double *distance_cutoff; /* [n_templates]                                             */
+    const double *max_dynamic_distance; /* [n_templates]                                        */
+    /* orientation + logistic filter (jess_run.py:298-346, 425-478; template.py:213-304) */
+    const int32_t *n_residues;     /* [n_templates] atom triplets; 0 = no orientation           */
+    const uint8_t *orient_idx;     /* [n_templates][EMM_MAX_RESIDUES][2] (first, second|9)      */
+    const double *orient_vec;      /* [n_templates][EMM_MAX_RESIDUES][3] template vectors       */
+    const int32_t *lr_index;       /* [n_templates] row of lr_table; -1 pass always; -2 no model */
+    int32_t n_lr;
+    const double *lr_table;        /* [n_lr][EMM_LR_MODELS][4] = coef_rmsd, coef_orient, intercept, threshold */
+} emm_library_desc;
+
+typedef struct emm_library emm_library;
+
+int emm_abi_version(void);
+int emm_hit_size(void);             /* sizeof(emm_hit), for binding sanity checks */
+const char *emm_last_error(void);
+int emm_device_count(void);
+
+int emm_library_create(int device, const emm_library_desc *desc, emm_library **out);
+/* Replace the compat matrix (same n_ttype; class_words may grow up to the value at creation). */
+int emm_library_set_compat(emm_library *lib, int32_t class_words, const uint32_t *compat);
+/* Replace per-template thresholds (the rmsd/distance/max_dynamic triple of Jess.query). */
+int emm_library_set_thresholds(emm_library *lib, const double *rmsd_threshold,
+                               const double *distance_cutoff, const double *max_dynamic_distance);
+/* Replace the logistic-filter assignment (it is keyed by the distance cutoff, jess_run.py:309-311).
+ * n_lr may not exceed max(64, n_lr at creation). */
+int emm_library_set_filter(emm_library *lib, const int32_t *lr_index, int32_t n_lr, const double *lr_table);
+void emm_library_destroy(emm_library *lib);
+
+/*
+ * A batch of query structures as SoA columns.  Replaces pyjess.Molecule / pyjess.Atom on the
+ * matching path (jess_run.py:538-548): the host parses and classifies, the device gets numbers.
+ *
+ * Input contract (violations -> EMM_ERR_INPUT): within one structure `residue` is non-decreasing
+ * (atoms of a residue are contiguous; the host reorders odd files and reports original indices
+ * through atom_id).  A residue is a distinct (chain_id, residue_number) (SURVEY.md 8c rule 4).
+ */
+typedef struct emm_batch {
+    int32_t n_structures;
+    int64_t n_atoms;
+    const int64_t *atom_off;   /* [n_structures+1]                                              */
+    const double *xyz;         /* [n_atoms][3] exactly the doubles the PDB text parses to        */
+    const uint16_t *klass;     /* [n_atoms] typing class (column of compat); 0 binds nothing     */
+    const int32_t *residue;    /* [n_atoms] residue ordinal inside its structure                 */
+    const float *bfactor;      /* [n_atoms] temperature factor / pLDDT, or NULL                  */
+    const uint16_t *chain;     /* [n_atoms] chain id code, or NULL (needed for ignore_chain=0)   */
+    const int32_t *atom_id;    /* [n_atoms] index reported in hits, or NULL = position in structure */
+} emm_batch;
+
+typedef struct emm_query_params {
+    int64_t max_candidates;       /* Jess.query(max_candidates=...), jess_run.py:808; <=0 = unlimited */
+    int32_t ignore_chain;         /* Jess.query(ignore_chain=...),   jess_run.py:810              */
+    float conservation_cutoff;    /* keep atoms with bfactor >= cutoff (Molecule.conserved); 0 = all */
+    int32_t template_begin;       /* templates [begin, end) of the library                        */
+    int32_t template_end;
+    int32_t skip_mode;            /* 0 search all; 1 skip structures that already hold a PASSing  */
+                                  /* hit; 2 ... that hold any hit (--skip-smaller-hits, jess_run.py:951-958) */
+    int32_t reset_structure_state;/* 1: clear per-structure hit counters before this run          */
+} emm_query_params;
+
+typedef struct emm_hit {
+    int32_t structure;            /* index in the batch                                           */
+    int32_t template_index;
+    uint32_t n_complete;          /* complete assignments examined ("candidates")                 */
+    uint16_t n_atoms;
+    uint16_t flags;
+    double rmsd;                  /* Hit.rmsd                                                     */
+    double orientation;           /* Match.orientation (radians); NaN if not EMM_HIT_ORIENTED     */
+    double rot[9];                /* row-major R: q' = R (q - qbar) + tbar (query -> template)    */
+    double qbar[3];
+    double tbar[3];
+    int32_t atoms[EMM_MAX_TEMPLATE_ATOMS]; /* matched query atoms in TEMPLATE order (Hit.atoms)   */
+} emm_hit;
+
+typedef struct emm_stats {
+    uint64_t pairs;               /* (template, structure) pairs searched                         */
+    uint64_t sweeps;              /* 32-lane candidate sweeps                                     */
+    uint64_t dist_evals;          /* FP32 pairwise-distance constraint evaluations                */
+    uint64_t exact_rechecks;      /* candidates re-evaluated in FP64 (guard band)                 */
+    uint64_t complete;            /* complete assignments superposed                              */
+    uint64_t kept_atoms;          /* atoms surviving mask + class-0 removal                       */
+    uint64_t staged_bytes;        /* bytes of structure blobs staged into shared memory           */
+    uint64_t global_blobs;        /* work items whose blob did not fit shared memory              */
+} emm_stats;
+
+/*
+ * Session = device buffers for batches up to the given sizes, on the library's device.
+ * upload / run / download are asynchronous on `stream` except where noted, so a caller can time
+ * the resident path (run only) and the end-to-end path (all three) separately.
+ */
+typedef struct emm_session emm_session;
+
+int emm_session_create(emm_library *lib, int64_t max_atoms, int32_t max_structures,
+                       int64_t hit_capacity, emm_session **out);
+void emm_session_destroy(emm_session *s);
+
+/* Host -> device copy of a batch (async; host buffers must stay valid until the stream reaches
+ * this point -- use pinned memory for true overlap). */
+int emm_session_upload(emm_session *s, const emm_batch *batch, void *stream);
+
+/* Launch prepare + search kernels on the uploaded batch (async).  Replaces the loop
+ * `for mol in molecules: Jess(templates).query(mol, ...)` of Matcher.run (jess_run.py:930-986). */
+int emm_session_run(emm_session *s, const emm_query_params *params, void *stream);
+
+/* Device -> host copy of the hits produced since the last reset; synchronises `stream`.
+ * Hits come back sorted by (structure, template_index).  stats may be NULL. */
+int emm_session_download(emm_session *s, emm_hit *hits, int64_t capacity, int64_t *n_hits,
+                         emm_stats *stats, void *stream);
+
+/* Number of kernel launches issued by the last emm_session_run (for bench accounting). */
+int emm_session_last_launches(const emm_session *s);
+
+/* Convenience: upload + run + download on the default stream (the end-to-end call). */
+int emm_query_batch(emm_library *lib, const emm_batch *batch, const emm_query_params *params,
+                    emm_hit *hits, int64_t capacity, int64_t *n_hits, emm_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENZYMM_B200_H */
