@@ -86,6 +86,8 @@ struct emm_session {
     int prepared_version = -1;
     std::vector<int64_t> h_blob_off;
     int last_launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_prepare, ev_search;
+    size_t ev_prepare_used = 0, ev_search_used = 0;
 };
 
 template <typename T>
@@ -117,6 +119,21 @@ static void compute_class_leaders(emm_library *lib, int class_words, const uint3
         }
     }
     lib->compat_version++;
+}
+
+static bool next_events(std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &pool, size_t &used,
+                        cudaEvent_t *a, cudaEvent_t *b)
+{
+    if (used >= 4096) return false;             // bounded: timings are a diagnostic, not a log
+    if (used == pool.size()) {
+        cudaEvent_t x, y;
+        if (cudaEventCreate(&x) != cudaSuccess || cudaEventCreate(&y) != cudaSuccess) return false;
+        pool.emplace_back(x, y);
+    }
+    *a = pool[used].first;
+    *b = pool[used].second;
+    ++used;
+    return true;
 }
 
 extern "C" {
@@ -336,6 +353,8 @@ void emm_session_destroy(emm_session *s)
                     s->d_blob, s->d_blob_off, s->d_hits, s->d_hit_count, s->d_work, s->d_any, s->d_pass,
                     s->d_skip, s->d_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &e : s->ev_prepare) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : s->ev_search) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete s;
 }
 
@@ -433,8 +452,13 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     const float cutoff = q->conservation_cutoff > 0.f ? q->conservation_cutoff : 0.f;
     if (cutoff > 0.f && !s->has_bfactor) return fail(EMM_ERR_INVALID, "conservation_cutoff needs the bfactor column");
     unsigned long long *stats = s->d_stats;
-    if (!s->prepared || s->prepared_cutoff != cutoff || s->prepared_version != lib->compat_version) {
+    if (q->force_prepare || !s->prepared || s->prepared_cutoff != cutoff || s->prepared_version != lib->compat_version) {
+        cudaEvent_t e0, e1;
+        const bool timed = next_events(s->ev_prepare, s->ev_prepare_used, &e0, &e1);
+        if (timed) cudaEventRecord(e0, stream);
+        if (q->force_prepare) CUDA_TRY(cudaMemsetAsync(s->d_hit_count + 1, 0, 8, stream));
         launch_prepare(lib->d, B, cutoff, stats, s->d_hit_count + 1, lib->sm_count, stream);
+        if (timed) cudaEventRecord(e1, stream);
         CUDA_TRY(cudaGetLastError());
         s->prepared = true;
         s->prepared_cutoff = cutoff;
@@ -478,13 +502,38 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     O.struct_pass = s->d_pass;
     O.stats = s->d_stats;
     CUDA_TRY(cudaMemsetAsync(s->d_work, 0, 4, stream));
-    launch_search(lib->d, B, P, O, skip, lib->stats_enabled != 0, std::min(grid, P.n_items), smem, stream);
+    {
+        cudaEvent_t e0, e1;
+        const bool timed = next_events(s->ev_search, s->ev_search_used, &e0, &e1);
+        if (timed) cudaEventRecord(e0, stream);
+        launch_search(lib->d, B, P, O, skip, lib->stats_enabled != 0, std::min(grid, P.n_items), smem, stream);
+        if (timed) cudaEventRecord(e1, stream);
+    }
     CUDA_TRY(cudaGetLastError());
     s->last_launches++;
     return EMM_OK;
 }
 
 int emm_session_last_launches(const emm_session *s) { return s ? s->last_launches : 0; }
+
+int emm_session_kernel_ms(emm_session *s, int which, float *out_ms, int capacity, int *count)
+{
+    if (!s || !count || (which != 0 && which != 1)) return fail(EMM_ERR_INVALID, "bad argument");
+    auto &pool = which == 0 ? s->ev_prepare : s->ev_search;
+    const size_t used = which == 0 ? s->ev_prepare_used : s->ev_search_used;
+    *count = (int)used;
+    for (size_t i = 0; i < used && (int)i < capacity && out_ms; ++i)
+        CUDA_TRY(cudaEventElapsedTime(out_ms + i, pool[i].first, pool[i].second));
+    return EMM_OK;
+}
+
+int emm_session_clear_timings(emm_session *s)
+{
+    if (!s) return fail(EMM_ERR_INVALID, "null argument");
+    s->ev_prepare_used = 0;
+    s->ev_search_used = 0;
+    return EMM_OK;
+}
 
 int emm_session_download(emm_session *s, emm_hit *hits, int64_t capacity, int64_t *n_hits, emm_stats *stats,
                          void *stream_)

@@ -71,7 +71,7 @@ class _QueryParams(ctypes.Structure):
         ("max_candidates", ctypes.c_int64), ("ignore_chain", ctypes.c_int32),
         ("conservation_cutoff", ctypes.c_float), ("template_begin", ctypes.c_int32),
         ("template_end", ctypes.c_int32), ("skip_mode", ctypes.c_int32),
-        ("reset_structure_state", ctypes.c_int32),
+        ("reset_structure_state", ctypes.c_int32), ("force_prepare", ctypes.c_int32),
     ]
 
 
@@ -99,6 +99,7 @@ def load_cdll() -> ctypes.CDLL:
         for name in ("emm_abi_version", "emm_hit_size", "emm_device_count", "emm_library_create", "emm_library_set_compat",
                      "emm_library_set_thresholds", "emm_library_set_filter", "emm_session_create", "emm_session_upload",
                      "emm_session_run", "emm_session_download", "emm_session_last_launches",
+                     "emm_session_kernel_ms", "emm_session_clear_timings",
                      "emm_query_batch"):
             getattr(lib, name).restype = ctypes.c_int
         lib.emm_library_destroy.restype = None
@@ -236,9 +237,10 @@ class Session:
 
     def run(self, *, max_candidates: int = 10000, ignore_chain: bool = True, conservation_cutoff: float = 0.0,
             template_begin: int = 0, template_end: int = 0, skip_mode: int = 0, reset: bool = True,
-            stream: int = 0):
+            force_prepare: bool = False, stream: int = 0):
         q = _QueryParams(int(max_candidates or 0), 1 if ignore_chain else 0, float(conservation_cutoff or 0.0),
-                         int(template_begin), int(template_end), int(skip_mode), 1 if reset else 0)
+                         int(template_begin), int(template_end), int(skip_mode), 1 if reset else 0,
+                         1 if force_prepare else 0)
         _check(self._lib.emm_session_run(self.handle, ctypes.byref(q), ctypes.c_void_p(stream)))
 
     def download(self, stream: int = 0, with_stats: bool = False):
@@ -255,6 +257,19 @@ class Session:
     @property
     def last_launches(self) -> int:
         return int(self._lib.emm_session_last_launches(self.handle))
+
+    def kernel_ms(self, which: str):
+        """Device durations (ms) of the 'prepare' / 'search' launches since ``clear_timings`` (CUDA
+        events recorded on the launching stream; call after synchronising it)."""
+        idx = {"prepare": 0, "search": 1}[which]
+        count = ctypes.c_int(0)
+        buf = np.zeros(4096, dtype=np.float32)
+        _check(self._lib.emm_session_kernel_ms(self.handle, ctypes.c_int(idx), _p(buf), ctypes.c_int(len(buf)),
+                                               ctypes.byref(count)))
+        return buf[:count.value].astype(float).tolist()
+
+    def clear_timings(self):
+        _check(self._lib.emm_session_clear_timings(self.handle))
 
     def close(self):
         if getattr(self, "handle", None):

@@ -1,0 +1,55 @@
+"""Multi-GPU sharding: by query structure, no collective on the data path.
+
+Every (template, structure) pair is independent and the only cross-pair state (skip-smaller
+flags, completeness) is per structure, so each rank takes a contiguous block of structures, runs
+all templates on its own GPU against its own copy of the ~5 MB compiled library, and rank 0
+concatenates the per-rank hit lists in input order.  ``torch.distributed`` is used for that one
+gather (and for barriers / max-over-ranks timing in ``bench.py``), never inside the search.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+__all__ = ["shard_bounds", "merge_hits", "gather_hits"]
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int, align: int = 1) -> Tuple[int, int]:
+    """Contiguous block ``[lo, hi)`` of ``n_items`` for ``rank``; block edges are multiples of
+    ``align`` (the synthetic generator's chunk size) except the last."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    units = (n_items + align - 1) // align
+    base, extra = divmod(units, world_size)
+    lo_u = rank * base + min(rank, extra)
+    hi_u = lo_u + base + (1 if rank < extra else 0)
+    return min(lo_u * align, n_items), min(hi_u * align, n_items)
+
+
+def merge_hits(parts: Sequence[Tuple[int, np.ndarray]]) -> np.ndarray:
+    """Concatenate per-shard hit arrays; ``parts`` = (first structure index of the shard, hits with
+    shard-local structure indices).  Result is sorted by (structure, template_index)."""
+    rebased = []
+    for first, hits in parts:
+        h = hits.copy()
+        h["structure"] += first
+        rebased.append(h)
+    if not rebased:
+        raise ValueError("no shards")
+    out = np.concatenate(rebased)
+    return out[np.lexsort((out["template_index"], out["structure"]))]
+
+
+def gather_hits(first: int, hits: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
+    """Gather every rank's (first, hits) on ``dst`` and merge; other ranks get None.
+    Works without an initialised process group (single process)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return merge_hits([(first, hits)])
+    payload = (int(first), hits)
+    gathered: Optional[List] = [None] * dist.get_world_size() if dist.get_rank() == dst else None
+    dist.gather_object(payload, gathered, dst=dst)
+    if dist.get_rank() != dst:
+        return None
+    return merge_hits(gathered)

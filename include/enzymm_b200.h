@@ -142,6 +142,7 @@ typedef struct emm_query_params {
     int32_t skip_mode;            /* 0 search all; 1 skip structures that already hold a PASSing  */
                                   /* hit; 2 ... that hold any hit (--skip-smaller-hits, jess_run.py:951-958) */
     int32_t reset_structure_state;/* 1: clear per-structure hit counters before this run          */
+    int32_t force_prepare;        /* 1: run the prepare kernel even if this batch is already prepared */
 } emm_query_params;
 
 typedef struct emm_hit {
@@ -195,6 +196,13 @@ int emm_session_download(emm_session *s, emm_hit *hits, int64_t capacity, int64_
 
 /* Number of kernel launches issued by the last emm_session_run (for bench accounting). */
 int emm_session_last_launches(const emm_session *s);
+
+/* Device time of the kernels launched since emm_session_clear_timings, measured with CUDA events
+ * recorded on the launching stream around each kernel (call after the stream was synchronised).
+ * which = 0: prepare kernel, 1: search kernel.  Writes up to capacity durations (ms), returns the
+ * number of launches recorded through *count. */
+int emm_session_kernel_ms(emm_session *s, int which, float *out_ms, int capacity, int *count);
+int emm_session_clear_timings(emm_session *s);
 
 /* Convenience: upload + run + download on the default stream (the end-to-end call). */
 int emm_query_batch(emm_library *lib, const emm_batch *batch, const emm_query_params *params,

@@ -1,0 +1,48 @@
+"""The C-ABI shared library loads and exports every symbol include/enzymm_b200.h declares.
+No compute calls here: without a GPU every entry point must fail loudly, never fall back."""
+import ctypes
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from enzymm_b200.engine import Engine, EngineError, HIT_DTYPE, library_path, load_cdll
+from enzymm_b200.library import CompiledLibrary
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "enzymm_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(emm_[a-z_]+)\s*\(", text)))
+
+
+def test_exports_every_declared_symbol():
+    lib = ctypes.CDLL(str(library_path()))
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+
+
+def test_abi_constants():
+    lib = load_cdll()
+    assert lib.emm_abi_version() == 1
+    assert lib.emm_hit_size() == HIT_DTYPE.itemsize == 280
+
+
+def test_product_path_never_touches_the_oracle():
+    """No import, include, link or dlopen of anything under oracle/ from the product package."""
+    pkg = ROOT / "enzymm_b200"
+    for path in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        text = path.read_text() if path.suffix in (".py", ".cu", ".cuh") or path.name == "Makefile" else ""
+        assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), path
+        assert not re.search(r"#include\s*[\"<][^\">]*oracle", text), path
+        assert "libjess_oracle" not in text, path
+
+
+@pytest.mark.skipif(load_cdll().emm_device_count() > 0, reason="only meaningful without a GPU")
+def test_no_cpu_fallback(active_templates):
+    with pytest.raises(EngineError) as info:
+        Engine(CompiledLibrary(active_templates[:3], 2.0, 1.5, 1.5))
+    assert info.value.status == -3

@@ -1,0 +1,375 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's goldens.
+
+Bar (BASELINE.json north_star): the match set -- template, query atom indices -- is bit-exact; RMSD
+and orientation within 1e-4 (in fact RMSD is bit-identical: both sides evaluate the same FP64
+expressions); post-filter decisions identical.
+"""
+import io
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+from enzymm_b200 import jess_run, pyjess
+from enzymm_b200.engine import (Engine, EngineError, HIT_NO_MODEL, HIT_OVERFLOW, HIT_PASS, PackedBatch)
+from enzymm_b200.library import CompiledLibrary
+from enzymm_b200.packing import pack_molecules
+from enzymm_b200.structures import Molecule
+from enzymm_b200.synth import SynthConfig, generate_chunk
+from enzymm_b200.templates import load_templates
+from helpers import DEFAULT_PARAMS, default_distances, oracle_matcher_run
+from test_oracle_golden import SIX, SIX_PARAMS, T1_PATH, T2_PATH, bundle_templates
+
+pytestmark = pytest.mark.gpu
+
+RMSD_TOL = 1e-4      # stated tolerance of north_star (Angstrom / radians)
+
+
+def compare_with_oracle(engine, templates, molecules, dist, *, rmsd=2.0, max_candidates=10000,
+                        ignore_chain=True, cutoff=0.0, oracle_molecules=None, atom_maps=None):
+    """Run both sides on the same inputs and assert the north_star bar.  Returns the GPU hits."""
+    batch = pack_molecules(molecules, engine.compiled)
+    hits = engine.query(batch, max_candidates=max_candidates, ignore_chain=ignore_chain,
+                        conservation_cutoff=cutoff)
+    dist = np.broadcast_to(np.asarray(dist, dtype=np.float64), (len(templates),)).copy()
+    omols = oracle_molecules if oracle_molecules is not None else molecules
+    raw = oracle.query_raw(omols, oracle.OracleTemplates(templates), rmsd, dist, dist,
+                           max_candidates=max_candidates, ignore_chain=ignore_chain, threads=8)
+    gpu = {(int(h["structure"]), int(h["template_index"])): h for h in hits}
+    for mi in range(len(molecules)):
+        for ti in range(len(templates)):
+            r, h = raw[mi, ti], gpu.get((mi, ti))
+            if r["overflow"] or (h is not None and int(h["flags"]) & HIT_OVERFLOW):
+                # enumeration-order dependent by definition: both sides must agree that the cap was hit
+                assert h is None or bool(int(h["flags"]) & HIT_OVERFLOW) == bool(r["overflow"])
+                continue
+            assert bool(r["found"]) == (h is not None), (mi, ti, templates[ti].template_id_string)
+            if h is None:
+                continue
+            m = len(templates[ti])
+            want = [int(v) for v in r["atoms"][:m]]
+            if atom_maps is not None:        # oracle ran on a masked copy: map back to original indices
+                want = [int(atom_maps[mi][v]) for v in want]
+            assert [int(v) for v in h["atoms"][:m]] == want, (mi, ti)
+            assert float(h["rmsd"]) == float(r["rmsd"])                 # bit-identical, well inside RMSD_TOL
+            assert abs(float(h["rmsd"]) - float(r["rmsd"])) <= RMSD_TOL
+            assert int(h["n_complete"]) == int(r["n_complete"])
+            t = templates[ti]
+            if getattr(t, "residues", None):
+                xyz = (omols[mi].xyz[[int(v) for v in r["atoms"][:m]]] - r["qbar"]) @ r["rot"].reshape(3, 3).T + r["tbar"]
+                o_orient = oracle.orientation(t, xyz)
+                assert abs(float(h["orientation"]) - o_orient) <= RMSD_TOL
+                try:
+                    o_pass = oracle.predicted_correct(t.effective_size, dist[ti], float(r["rmsd"]), o_orient)
+                except KeyError:
+                    assert int(h["flags"]) & HIT_NO_MODEL
+                else:
+                    assert bool(int(h["flags"]) & HIT_PASS) == o_pass
+    return hits
+
+
+@pytest.fixture(scope="module")
+def full_engine(active_templates):
+    dist = default_distances(active_templates)
+    eng = Engine(CompiledLibrary(active_templates, 2.0, dist, dist))
+    yield eng
+    eng.close()
+
+
+# ---- config 1: fixture structures vs the full shipped library -------------------------------------
+
+def test_fixtures_full_library(full_engine, active_templates, mol_1amy, mol_af):
+    hits = compare_with_oracle(full_engine, active_templates, [mol_1amy, mol_af], default_distances(active_templates))
+    per_mol = np.bincount(hits["structure"], minlength=2).tolist()
+    assert per_mol == [13, 11]
+    passing = np.bincount(hits["structure"][(hits["flags"] & HIT_PASS) != 0], minlength=2).tolist()
+    assert passing == [11, 6]
+
+
+def test_reference_golden_through_jess_api(mol_1amy):
+    """tests/test_jess_run.py:32-145 of the reference, run against the drop-in API."""
+    t1, t2 = bundle_templates([T1_PATH, T2_PATH])
+    best = list(pyjess.Jess([t1]).query(mol_1amy, 2, 1.5, 1.5, max_candidates=10000, best_match=True))
+    match1 = jess_run.Match(hit=best[0], pairwise_distance=1.5, complete=True, index=0)
+    assert match1.hit.molecule().id == "1AMY"
+    assert match1.hit.template is t1
+    assert match1.query_atom_count == 3339 and match1.query_residue_count == 403
+    assert match1.hit.rmsd == pytest.approx(0.32093143, abs=5e-8)
+    assert match1.orientation == pytest.approx(0.15327054322, abs=5e-8)
+    assert match1.hit.orientation == pytest.approx(match1.orientation, abs=1e-9)      # fused filter value
+    expected = [(0.2290067979141952, -0.3853409610281773, 0.377114677867322),
+                (0.4249816660862038, -0.21966898402981627, -0.3540863184957992),
+                (0.45459385444007694, -0.34869961601989985, 0.10687378206512577),
+                (-0.8733960645698886, 0.2563504028143271, -0.9840695023070225),
+                (-0.510183600042339, -0.1958417994791759, 0.18963368325429997)]
+    for a, e in zip(match1.match_vector_list, expected):
+        assert math.isclose(a.x, e[0], rel_tol=1e-9, abs_tol=1e-9)
+        assert math.isclose(a.y, e[1], rel_tol=1e-9, abs_tol=1e-9)
+        assert math.isclose(a.z, e[2], rel_tol=1e-9, abs_tol=1e-9)
+    assert match1.template_vector_list == [r.orientation_vector for r in t1.residues]
+    assert match1.preserved_resid_order is True and match1.multimeric is False
+    assert match1.matched_residues == [("GLU", "A", "204"), ("ASP", "A", "87"), ("ASP", "A", "179"),
+                                       ("HIS", "A", "288"), ("ASP", "A", "289")]
+    assert match1.predicted_correct is True and match1.hit.device_pass
+
+    best2 = list(pyjess.Jess([t2]).query(mol_1amy, 2, 1, 1, max_candidates=10000, best_match=True))
+    match2 = jess_run.Match(hit=best2[0])
+    assert match2.hit.rmsd == pytest.approx(1.7353479120, abs=5e-8)
+    assert match2.orientation == pytest.approx(1.6503123465442575, abs=1e-9)
+    assert match2.preserved_resid_order is False
+    assert match2.matched_residues == [("TRP", "A", "38"), ("HIS", "A", "288"), ("ASP", "A", "289")]
+
+
+def test_reference_golden_files(mol_1amy):
+    """Byte parity of the writers against the reference's golden files (test_jess_run.py:147-179).
+    log_evalue and the M-CSA annotation columns are outside the hot path."""
+    (t1,) = bundle_templates([T1_PATH])
+    hit = next(pyjess.Jess([t1]).query(mol_1amy, 2, 1.5, 1.5, max_candidates=10000, best_match=True))
+    match = jess_run.Match(hit=hit, pairwise_distance=1.5, complete=True, index=0)
+    for name, kwargs in (("1AMY_matches_no_query.pdb", dict(transform=False, include_query=False)),
+                         ("1AMY_matches_query_included.pdb", dict(transform=False, include_query=True)),
+                         ("1AMY_matches_template.pdb", dict(transform=True, include_query=False))):
+        buffer = io.StringIO()
+        match.dump2pdb(buffer, **kwargs)
+        assert buffer.getvalue() == (GOLDEN / name).read_text(), name
+    got_header, got_row = [l.split("\t") for l in match.dumps(header=True).splitlines()]
+    want_header, want_row = [l.split("\t") for l in (GOLDEN / "results.tsv").read_text().splitlines()]
+    assert got_header == want_header
+    skip = {"log_evalue", "number_of_mutated_residues", "number_of_side_chain_residues_(template,reference)",
+            "number_of_metal_ligands_(template,reference)", "number_of_ptm_residues_(template, reference)",
+            "total_reference_residues"}
+    for col, got, want in zip(want_header, got_row, want_row):
+        if col not in skip:
+            assert got == want, col
+
+
+# ---- Matcher semantics (reference TestMatcher) -------------------------------------------------------
+
+def test_matcher_run_counts(mol_1amy, mol_af):
+    res5 = list(load_templates(subset="5_residues/results/csa3d_0285/"))
+    res4 = list(load_templates(subset="4_residues/results/csa3d_0285/"))
+    res3 = list(load_templates(subset="3_residues/results/csa3d_0344/"))
+    m1 = jess_run.Matcher(templates=res5 + res4, cpus=2)
+    assert m1.template_effective_sizes == [5, 4] and m1.cpus == 2
+    mol3 = mol_af.conserved(80)
+    out1 = m1.run(molecules=[mol_1amy, mol_af])
+    assert list(out1.keys()) == [mol_1amy, mol_af]
+    assert len(out1[mol_1amy]) == 2 and len(out1[mol_af]) == 2
+    assert [m.query_residue_count for m in out1[mol_af]] == [511, 511]
+    out2 = jess_run.Matcher(templates=res5 + res4, skip_smaller_hits=True).run(molecules=[mol_1amy, mol3])
+    assert len(out2[mol_1amy]) == 1 and len(out2[mol3]) == 1
+    assert [m.query_residue_count for m in out2[mol3]] == [494]
+    with pytest.warns(Warning):
+        m3 = jess_run.Matcher(templates=res5 + res4 + res3, match_small_templates=True, warn=True, cpus=-1)
+    assert len(m3.run(molecules=[mol_1amy])[mol_1amy]) == 3
+    with pytest.raises(ValueError):
+        jess_run.Matcher(templates=res5 + res5)
+
+
+def test_matcher_single_run_and_filter(mol_1amy):
+    templates = bundle_templates(SIX)
+    params = {k: {"rmsd": v[0], "distance": v[1], "max_dynamic_distance": v[2]} for k, v in SIX_PARAMS.items()}
+    unfiltered = jess_run.Matcher(templates=templates, jess_params=params, filter_matches=False).run_single(mol_1amy)
+    filtered = jess_run.Matcher(templates=templates, jess_params=params, filter_matches=True).run_single(mol_1amy)
+    assert sorted(m.hit.template.pdb_id for m in filtered) == ["1bf2", "1uh3", "1uh3", "1uh3", "2cxg"]
+    assert sorted(m.hit.template.pdb_id for m in unfiltered) == ["1bf2", "1uh3", "1uh3", "1uh3", "2cxg", "2qy1"]
+    want = oracle_matcher_run(templates, [mol_1amy], jess_params=SIX_PARAMS, filter_matches=False)[0]
+    assert [(m.hit.template.pdb_id, m.complete) for m in unfiltered] == [(m.template.pdb_id, m.complete) for m in want]
+    for m in unfiltered:       # the fused GPU verdict equals the reference formula evaluated in Python
+        assert m.hit.device_pass == m.predicted_correct
+    # a distance without logistic models is a KeyError, as in the reference (test_cli.py:131-132)
+    odd = {k: {"rmsd": 2, "distance": 0.5, "max_dynamic_distance": 0.5} for k in range(3, 9)}
+    (t2,) = bundle_templates([T2_PATH])
+    loose = {k: {"rmsd": 2, "distance": 1.05, "max_dynamic_distance": 1.05} for k in range(3, 9)}
+    with pytest.raises(KeyError):
+        jess_run.Matcher(templates=[t2], jess_params=loose).run_single(mol_1amy)
+    assert jess_run.Matcher(templates=[t2], jess_params=odd).run_single(mol_1amy) == []
+
+
+def test_matcher_full_library_vs_oracle(active_templates, mol_1amy, mol_af):
+    for kwargs in (dict(), dict(filter_matches=False), dict(skip_smaller_hits=True)):
+        got = jess_run.Matcher(templates=active_templates, **kwargs).run([mol_1amy, mol_af])
+        want = oracle_matcher_run(active_templates, [mol_1amy, mol_af], threads=8, **kwargs)
+        mols = [mol_1amy, mol_af]
+        assert [mols.index(k) for k in got.keys()] == list(want.keys())
+        for mi, wm in want.items():
+            gm = got[mols[mi]]
+            assert [m.hit.template.id or m.hit.template.template_id_string for m in gm] == \
+                   [m.template.id or m.template.template_id_string for m in wm]
+            assert [m.hit.atom_indices for m in gm] == [m.hit.atoms for m in wm]
+            assert [m.complete for m in gm] == [m.complete for m in wm]
+
+
+# ---- config 2 (reduced) and edge cases -----------------------------------------------------------------
+
+def test_synthetic_structures(full_engine, active_templates):
+    chunk = generate_chunk(0, SynthConfig(), active_templates, 24)
+    mols = [chunk.to_molecule(i) for i in range(chunk.n_structures)]
+    hits = compare_with_oracle(full_engine, active_templates, mols, default_distances(active_templates))
+    found = {(int(h["structure"]), int(h["template_index"])) for h in hits}
+    recovered = sum(1 for p in chunk.planted if p in found)
+    assert recovered >= len(chunk.planted) // 2
+    # the generator's packed columns are the same input as the Molecule route
+    again = full_engine.query(chunk.to_packed(full_engine.compiled))
+    assert np.array_equal(again["atoms"], hits["atoms"]) and np.array_equal(again["rmsd"], hits["rmsd"])
+
+
+def test_empty_and_degenerate_inputs(full_engine, active_templates, mol_1amy):
+    gly = Molecule.loads("".join(
+        f"ATOM  {i + 1:>5}  CA  GLY A{i + 1:>4}    {i * 3.8:8.3f}{0.0:8.3f}{0.0:8.3f}  1.00 50.00           C\n" for i in range(30)))
+    water = Molecule.loads("HETATM    1  O   HOH A 600      -3.288  67.042  32.622  1.00  2.00           O\n")
+    mols = [Molecule(), gly, water, mol_1amy, Molecule()]
+    hits = compare_with_oracle(full_engine, active_templates, mols, default_distances(active_templates))
+    assert set(hits["structure"].tolist()) == {3}
+    empty = full_engine.query(pack_molecules([], full_engine.compiled))
+    assert len(empty) == 0
+
+
+def test_conservation_mask_device_equals_host(full_engine, active_templates, mol_af):
+    """--conservation-cutoff as a real mask: device-side masking == querying Molecule.conserved()."""
+    cutoff = 70.0
+    masked = mol_af.conserved(cutoff)
+    keep = np.nonzero(mol_af.column("temperature_factor") >= cutoff)[0]
+    dist = default_distances(active_templates)
+    compare_with_oracle(full_engine, active_templates, [mol_af], dist, cutoff=cutoff,
+                        oracle_molecules=[masked], atom_maps=[keep])
+    host_side = full_engine.query(pack_molecules([masked], full_engine.compiled))
+    dev_side = full_engine.query(pack_molecules([mol_af], full_engine.compiled), conservation_cutoff=cutoff)
+    assert np.array_equal(dev_side["template_index"], host_side["template_index"])
+    assert np.array_equal(dev_side["rmsd"], host_side["rmsd"])
+    assert [keep[a] for a in host_side["atoms"][0][:host_side["n_atoms"][0]]] == \
+        dev_side["atoms"][0][:dev_side["n_atoms"][0]].tolist()
+
+
+def test_translation_invariance_guard_band(active_templates, mol_1amy):
+    """Far-from-origin coordinates stress the FP32 guard band: results must not move."""
+    subset = active_templates[::9]
+    dist = default_distances(subset)
+    eng = Engine(CompiledLibrary(subset, 2.0, dist, dist))
+    try:
+        base = compare_with_oracle(eng, subset, [mol_1amy], dist)
+        shifted = mol_1amy.with_xyz(np.round(mol_1amy.xyz + np.array([9000.0, -8000.0, 7000.5]), 3))
+        moved = compare_with_oracle(eng, subset, [shifted], dist)
+        assert np.array_equal(base["template_index"], moved["template_index"])
+        assert np.array_equal(base["atoms"], moved["atoms"])
+        np.testing.assert_allclose(base["rmsd"], moved["rmsd"], atol=1e-6)
+    finally:
+        eng.close()
+
+
+def test_loose_cutoffs_and_candidate_cap(active_templates, mol_1amy):
+    """Config 4 in miniature: loosened distance cutoff; and the max_candidates cap raises OVERFLOW."""
+    subset = [t for t in active_templates if t.effective_size == 3][::60]
+    eng = Engine(CompiledLibrary(subset, 2.0, 3.0, 3.0))
+    try:
+        hits = compare_with_oracle(eng, subset, [mol_1amy], 3.0, max_candidates=10 ** 7)
+        assert len(hits) > 0 and int(hits["n_complete"].max()) > 50
+        capped = compare_with_oracle(eng, subset, [mol_1amy], 3.0, max_candidates=5)
+        assert (capped["flags"] & HIT_OVERFLOW).any()
+    finally:
+        eng.close()
+
+
+def test_dynamic_distance_and_chain_rule(active_templates):
+    """max_dynamic_distance != distance_cutoff (per-pair deltas from distance weights) and
+    ignore_chain=False on a two-chain structure -- both unpinned upstream, but GPU == oracle."""
+    subset = [t for t in active_templates if t.multimeric][:40] + active_templates[:40]
+    chunk = generate_chunk(1, SynthConfig(n_residues=150, n_chains=2), subset, 6)
+    mols = [chunk.to_molecule(i) for i in range(chunk.n_structures)]
+    for cut, dyn, ignore in ((1.5, 1.5, False), (1.0, 2.5, True), (1.0, 2.5, False)):
+        eng = Engine(CompiledLibrary(subset, 2.0, cut, dyn))
+        try:
+            batch = pack_molecules(mols, eng.compiled)
+            hits = eng.query(batch, max_candidates=10000, ignore_chain=ignore)
+            dist = np.full(len(subset), cut)
+            raw = oracle.query_raw(mols, oracle.OracleTemplates(subset), 2.0, dist, np.full(len(subset), dyn),
+                                   max_candidates=10000, ignore_chain=ignore, threads=8)
+            got = {(int(h["structure"]), int(h["template_index"])): h for h in hits}
+            assert {k for k in got} == {(int(a), int(b)) for a, b in zip(*np.nonzero(raw["found"]))}
+            for (mi, ti), h in got.items():
+                assert h["atoms"][:len(subset[ti])].tolist() == raw[mi, ti]["atoms"][:len(subset[ti])].tolist()
+                assert float(h["rmsd"]) == float(raw[mi, ti]["rmsd"])
+        finally:
+            eng.close()
+
+
+def test_large_structure_global_memory_path(full_engine, active_templates):
+    """A 4 x 400-residue assembly (config 5 shape) does not fit the shared-memory staging area and
+    takes the global-memory path; with pLDDT masking + skip-smaller semantics checked at Matcher level."""
+    chunk = generate_chunk(0, SynthConfig(n_chains=4), active_templates, 2)
+    mols = [chunk.to_molecule(i) for i in range(2)]
+    subset = active_templates[::15]
+    dist = default_distances(subset)
+    eng = Engine(CompiledLibrary(subset, 2.0, dist, dist))
+    try:
+        hits, stats = None, None
+        batch = pack_molecules(mols, eng.compiled)
+        compare_with_oracle(eng, subset, mols, dist)
+        masked = [m.conserved(70) for m in mols]
+        keeps = [np.nonzero(m.column("temperature_factor") >= 70)[0] for m in mols]
+        compare_with_oracle(eng, subset, mols, dist, cutoff=70.0, oracle_molecules=masked, atom_maps=keeps)
+    finally:
+        eng.close()
+    got = jess_run.Matcher(templates=subset, skip_smaller_hits=True, conservation_cutoff=70,
+                           apply_conservation_mask=True).run(mols)
+    want = oracle_matcher_run(subset, masked, skip_smaller_hits=True, threads=8)
+    assert [mols.index(k) for k in got] == list(want)
+    for mi, wm in want.items():
+        assert [[int(keeps[mi][a]) for a in m.hit.atoms] for m in wm] == [m.hit.atom_indices for m in got[mols[mi]]]
+
+
+def test_split_residue_is_reordered(active_templates, mol_1amy):
+    """Atoms of one residue split over two runs of the file: the host reorders, hits report file indices."""
+    order = np.arange(len(mol_1amy))
+    asp87 = np.nonzero((mol_1amy.column("residue_number") == 87) & (mol_1amy.column("residue_name") == "ASP"))[0]
+    moved = np.concatenate([np.delete(order, asp87[-2:]), asp87[-2:]])      # OD1/OD2 of ASP 87 go to the end
+    shuffled = mol_1amy.select(moved)
+    (t1,) = bundle_templates([T1_PATH])
+    a = next(pyjess.Jess([t1]).query(mol_1amy, 2, 1.5, 1.5, max_candidates=10000, best_match=True))
+    b = next(pyjess.Jess([t1]).query(shuffled, 2, 1.5, 1.5, max_candidates=10000, best_match=True))
+    assert b.rmsd == pytest.approx(a.rmsd, abs=1e-12)
+    assert [int(moved[i]) for i in b.atom_indices] == a.atom_indices
+
+
+def test_hit_buffer_overflow_is_loud_then_recovers(full_engine, active_templates, mol_1amy):
+    from enzymm_b200.engine import Session
+    batch = pack_molecules([mol_1amy], full_engine.compiled)
+    sess = Session(full_engine.device_library, batch.n_atoms, 1, hit_capacity=4)
+    try:
+        sess.upload(batch)
+        sess.run()
+        with pytest.raises(EngineError) as info:
+            sess.download()
+        assert info.value.status == -4
+    finally:
+        sess.close()
+    assert len(full_engine.query(batch)) == 13
+
+
+def test_input_contract_violation_is_loud(full_engine):
+    xyz = np.zeros((4, 3))
+    bad = PackedBatch(np.array([0, 4]), xyz, np.ones(4, dtype=np.uint16), np.array([0, 1, 0, 1], dtype=np.int32))
+    with pytest.raises(EngineError) as info:
+        full_engine.query(bad)
+    assert info.value.status == -5
+
+
+def test_determinism_and_shard_union(full_engine, active_templates):
+    """Size-independent properties at a larger size: two runs agree exactly, and searching two
+    halves separately gives the same hits as searching the whole batch (what multi-GPU sharding does)."""
+    from enzymm_b200.sharding import merge_hits, shard_bounds
+    chunk = generate_chunk(2, SynthConfig(), active_templates, 96)
+    batch = chunk.to_packed(full_engine.compiled)
+    a = full_engine.query(batch)
+    b = full_engine.query(batch)
+    assert a.tobytes() == b.tobytes()
+    parts = []
+    for rank in range(2):
+        lo, hi = shard_bounds(batch.n_structures, 2, rank)
+        parts.append((lo, full_engine.query(batch.slice(lo, hi))))
+    merged = merge_hits(parts)
+    assert merged.tobytes() == a.tobytes()
+    found = {(int(h["structure"]), int(h["template_index"])) for h in a}
+    assert sum(1 for p in chunk.planted if p in found) >= 0.5 * len(chunk.planted)

@@ -1,0 +1,169 @@
+"""Host-side logic: PDB ingest, template parsing, typing, search plans, packing (no GPU)."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from enzymm_b200 import pyjess
+from enzymm_b200.library import CompiledLibrary, type_match
+from enzymm_b200.packing import chain_codes, pack_molecules, residue_ordinals
+from enzymm_b200.structures import Atom, Molecule
+from enzymm_b200.template_atoms import JessTemplate, TemplateAtom
+from enzymm_b200.templates import (Cluster, Residue, Template, Vec3, check_template, load_templates,
+                                   rank_order)
+
+
+def test_molecule_load(mol_1amy, mol_af):
+    assert len(mol_1amy) == 3339 and bool(mol_1amy)
+    assert (mol_1amy.column("name") == "CA").sum() > 400          # CA atoms + 3 calcium HETATM
+    a = mol_1amy.atom(0)
+    assert (a.name, a.residue_name, a.chain_id, a.residue_number) == ("N", "GLN", "A", 1)
+    assert mol_af.id is None and len(mol_af) == 4079
+    assert len(mol_af.conserved(80)) == 3933
+    assert mol_af.conserved(0) == mol_af and hash(mol_af.conserved(0)) == hash(mol_af)
+    assert not Molecule()
+    with pytest.raises(FileNotFoundError):
+        Molecule.load("/no/such/file.pdb")
+    with pytest.raises(IsADirectoryError):
+        Molecule.load(str(GOLDEN))
+
+
+def test_molecule_endmdl():
+    text = ("ATOM      1  N   GLY A   1       0.000   0.000   0.000  1.00 10.00           N\n"
+            "ENDMDL\n"
+            "ATOM      2  CA  GLY A   1       1.000   0.000   0.000  1.00 10.00           C\n")
+    assert len(Molecule.loads(text)) == 1
+
+
+def test_template_atom_loads():
+    a = TemplateAtom.loads("ATOM      3  CG ZASP A 262      49.175  39.646  17.664 DE    1.90 ")
+    assert a.match_mode == 3 and a.atom_names == ("CG",) and a.residue_names == ("ASP", "GLU")
+    assert (a.chain_id, a.residue_number, a.distance_weight) == ("A", 262, 1.9)
+    assert (a.x, a.y, a.z) == (49.175, 39.646, 17.664)
+    b = TemplateAtom.loads("ATOM      0  CG ZHISAA 180      17.497  30.652  21.394 H     0.55 ")
+    assert b.chain_id == "AA" and b.residue_names == ("HIS",) and b.residue_number == 180
+    c = TemplateAtom.loads("ATOM      0  CA ZANY A  70       9.165   4.861  36.502 AXSCG 0.40 ")
+    assert c.residue_names == ("ANY", "ALA", "XXX", "SER", "CYS", "GLY") and c.distance_weight == 0.4
+    assert a == a.copy() and hash(a) == hash(a.copy()) and a != b
+    with pytest.raises(ValueError):
+        TemplateAtom.loads("ATOM      1  N   GLN A   1      -8.553  67.654  28.389  1.00 31.38           N")
+    with pytest.raises(ValueError):
+        TemplateAtom.loads("HETATM    1  N   GLN A   1      -8.553  67.654  28.389")
+
+
+def test_library_loads(all_templates):
+    import collections
+    assert len(all_templates) == 7607                                   # test_template.py:35
+    sizes = collections.Counter(t.effective_size for t in all_templates)
+    assert [sizes[s] for s in (8, 7, 6, 5, 4, 3)] == [179, 359, 654, 1046, 1841, 2701]
+    assert sum(len(t) for t in all_templates if t.effective_size >= 3) == 90543
+
+
+def test_template_metadata(template_1uh3):
+    t = template_1uh3
+    assert (t.pdb_id, t.mcsa_id, t.uniprot_id) == ("1uh3", 285, "Q60053")
+    assert t.cluster == Cluster(1, 1, 1) and t.dimension == 5 and t.effective_size == 5
+    assert t.ec == ("3.2.1.10", "3.2.1.135") and t.cath == ("2.60.40.10", "2.60.40.1180", "3.20.20.80")
+    assert not t.multimeric and t.relative_order == rank_order([396, 262, 356, 471, 472])
+    assert [r.orientation_vector_indices for r in t.residues] == [(0, 9), (0, 9), (0, 9), (0, 1), (0, 9)]
+    assert t == t.copy() and hash(t) == hash(t.copy())
+    assert check_template(t, warn=False)
+
+
+def test_bad_templates():
+    bad = GOLDEN / "bad_templates"
+    for name in ("hetatm.pdb", "malformed_residues_1.pdb", "malformed_residues_2.pdb", "malformed_residues_3.pdb",
+                 "not_a_template.pdb", "bad_atom_names_1.pdb", "bad_atom_names_2.pdb", "bad_atom_names_3.pdb"):
+        with pytest.raises(ValueError):
+            Template.loads((bad / name).read_text(), warn=True)
+    with pytest.raises(KeyError):
+        Template.loads((bad / "unk_residue.pdb").read_text(), warn=True)
+    Template.loads((bad / "no_remark.pdb").read_text())
+    Template.loads((bad / "new_remark.pdb").read_text())
+    with pytest.raises(NotADirectoryError):
+        list(load_templates("/some/bogus/folder"))
+    with pytest.raises(ValueError):
+        list(load_templates(GOLDEN))           # a folder of non-template .pdb files
+
+
+def test_vec3():
+    v = Vec3(1.0, 2.0, 3.0)
+    assert v.norm == math.sqrt(14) and v.normalize().x == 1 / math.sqrt(14)
+    assert Vec3(0, 0, 0).normalize() == Vec3(0, 0, 0)
+    assert (v + 5) == Vec3(6, 7, 8) and (v - Vec3(1, 1, 1)) == Vec3(0, 1, 2) and (v / 2) == Vec3(0.5, 1, 1.5)
+    assert v @ Vec3(1, 0, 0) == 1.0
+    assert Vec3(1.00000000001, 0, 0).angle_to(Vec3(-1, 0, 0)) == pytest.approx(math.pi)
+    with pytest.raises(TypeError):
+        v + (0, 3, 5)
+    with pytest.raises(ValueError):
+        Vec3(float("nan"), 0, 0)
+
+
+def test_type_match_rules():
+    assert type_match(0, ("HIS",), ("CG",), "HIS", "CG") and not type_match(0, ("HIS",), ("CG",), "HIS", "CB")
+    assert not type_match(0, ("HIS",), ("CG",), "ASP", "CG")
+    assert type_match(3, ("ASP", "GLU"), ("OD1",), "GLU", "OE2") and not type_match(3, ("ASP",), ("OD1",), "ASP", "CG")
+    assert type_match(8, ("HIS",), ("ND1",), "HIS", "CD2") and not type_match(8, ("HIS",), ("ND1",), "HIS", "NE2")
+    assert type_match(1, ("ASN", "GLN"), ("OD1",), "GLN", "NE2") and not type_match(1, ("ASN",), ("OD1",), "ASN", "CG")
+    assert type_match(100, ("ANY",), ("CA",), "TRP", "CA") and not type_match(100, ("ANY",), ("CA",), "TRP", "CB")
+    with pytest.raises(ValueError):
+        type_match(7, ("ALA",), ("CA",), "ALA", "CA")
+
+
+def test_compiled_library_invariants(active_templates, mol_1amy):
+    subset = active_templates[::40]
+    lib = CompiledLibrary(subset, 2.0, 1.5, 1.5)
+    cm = lib.compat_matrix()
+    assert cm.shape == (lib.n_ttype, lib.class_words) and not cm[:, 0].astype(np.uint32)[0] & 1
+    for ti, t in enumerate(subset):
+        lo, hi = lib.atom_off[ti], lib.atom_off[ti + 1]
+        assert sorted(lib.plan_atom[lo:hi].tolist()) == list(range(hi - lo))
+        assert lib.plan_src[lo] < 0
+        atoms = list(t)
+        for k in range(hi - lo):
+            src = int(lib.plan_src[lo + k])
+            a = atoms[lib.plan_atom[lo + k]]
+            if src >= 0:      # follower: same template residue as its leader, which is itself a leader
+                lead = atoms[lib.plan_atom[lo + src]]
+                assert (lead.chain_id, lead.residue_number) == (a.chain_id, a.residue_number)
+                assert lib.plan_src[lo + src] < 0
+            assert lib.keys[lib.plan_ttype[lo + k]] == a.typing_key()
+    # typing matrix agrees with the predicate for every atom of a real structure
+    klass = lib.classify(mol_1amy.column("residue_name"), mol_1amy.column("name"))
+    cm = lib.compat_matrix()
+    for tt in range(0, lib.n_ttype, 7):
+        mode, resnames, names = lib.keys[tt]
+        want = np.array([type_match(mode, resnames, names, str(r), str(n))
+                         for r, n in zip(mol_1amy.column("residue_name"), mol_1amy.column("name"))])
+        got = ((cm[tt][klass >> 5] >> (klass & 31)) & 1).astype(bool)
+        assert np.array_equal(got, want)
+    assert (klass[mol_1amy.column("residue_name") == "HOH"] == 0).all() or lib.n_classes > 0
+
+
+def test_residue_ordinals_and_packing(mol_1amy, active_templates):
+    lib = CompiledLibrary(active_templates[:20], 2.0, 1.5, 1.5)
+    batch = pack_molecules([mol_1amy, Molecule(), mol_1amy.conserved(20)], lib)
+    assert batch.n_structures == 3 and batch.atom_off.tolist()[1:3] == [3339, 3339]
+    assert batch.atom_id is None
+    for s in range(3):
+        r = batch.residue[batch.atom_off[s]:batch.atom_off[s + 1]]
+        assert (np.diff(r) >= 0).all()
+    # a residue split over two runs gets reordered, and atom_id maps back
+    chain = chain_codes(np.array(["A", "A", "A", "A"]))
+    ordinal, order = residue_ordinals(chain, np.array([5, 6, 5, 7]))
+    assert order.tolist() == [0, 2, 1, 3] and ordinal.tolist() == [0, 0, 1, 2]
+    ordinal, order = residue_ordinals(chain, np.array([5, 5, 6, 7]))
+    assert order is None and ordinal.tolist() == [0, 0, 1, 2]
+
+
+def test_pyjess_surface():
+    assert isinstance(pyjess.__version__, str)
+    for name in ("Atom", "Molecule", "TemplateAtom", "Template", "Jess", "Query", "Hit"):
+        assert hasattr(pyjess, name)
+    atom = TemplateAtom(chain_id="A", residue_number=51, residue_names=["ANY"], atom_names=["C"],
+                        distance_weight=1.5, match_mode=1, x=1.0, y=0, z=-99.5)
+    t = JessTemplate([atom], id="x")
+    assert t.dimension == 1 and len(t) == 1 and list(t) == [atom] and t.copy() == t
+    with pytest.raises(NotImplementedError):
+        pyjess.Jess([t]).query(Molecule(), 2, 1, 1)          # best_match=False is not implemented

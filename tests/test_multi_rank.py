@@ -1,0 +1,80 @@
+"""World-size-2 run of the sharding path on CPU (gloo): shard by structure, no data-path
+collective, rank 0 merges hit lists in input order.  The per-shard search is done
+by the oracle here -- the GPU equivalent is tests/test_gpu_parity.py::test_determinism_and_shard_union."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from enzymm_b200.engine import HIT_DTYPE
+from enzymm_b200.sharding import gather_hits, merge_hits, shard_bounds
+from enzymm_b200.synth import SynthConfig, generate_chunk
+from enzymm_b200.templates import load_templates
+
+
+def test_shard_bounds_cover_everything():
+    for n, world, align in ((10, 3, 1), (1000, 8, 256), (5, 8, 1), (0, 2, 1), (1024, 4, 256)):
+        spans = [shard_bounds(n, world, r, align) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and a <= b
+        for lo, hi in spans[:-1]:
+            assert (lo % align == 0 or lo == n) and (hi % align == 0 or hi == n)
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _oracle_hits(templates, mols) -> np.ndarray:
+    raw = oracle.query_raw(mols, oracle.OracleTemplates(templates), 2.0, 1.5, 1.5, threads=1)
+    out = []
+    for mi, ti in zip(*np.nonzero(raw["found"])):
+        h = np.zeros((), dtype=HIT_DTYPE)
+        h["structure"], h["template_index"], h["rmsd"] = mi, ti, raw[mi, ti]["rmsd"]
+        h["atoms"] = raw[mi, ti]["atoms"]
+        out.append(h)
+    return np.array(out, dtype=HIT_DTYPE)
+
+
+def _inputs():
+    templates = list(load_templates(subset="3_residues/results/csa3d_000"))[:30]
+    chunk = generate_chunk(5, SynthConfig(n_residues=80, max_motifs=2), templates, 6)
+    return templates, [chunk.to_molecule(i) for i in range(6)]
+
+
+def _worker(rank: int, world: int, port: int, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        templates, mols = _inputs()
+        lo, hi = shard_bounds(len(mols), world, rank)
+        merged = gather_hits(lo, _oracle_hits(templates, mols[lo:hi]))
+        dist.barrier()
+        if rank == 0:
+            queue.put(merged.tobytes())
+        else:
+            assert merged is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single_process():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = queue.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    templates, mols = _inputs()
+    want = merge_hits([(0, _oracle_hits(templates, mols))])
+    assert len(want) > 0
+    assert got == want.tobytes()
