@@ -85,6 +85,7 @@ struct emm_session {
     float prepared_cutoff = -1.f;
     int prepared_version = -1;
     std::vector<int64_t> h_blob_off;
+    int64_t max_staged = 0;        // largest staged blob prefix in the uploaded batch (upper bound)
     int last_launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_prepare, ev_search;
     size_t ev_prepare_used = 0, ev_search_used = 0;
@@ -178,6 +179,8 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
             if (src >= k) return fail(EMM_ERR_INVALID, "plan_src must refer to an earlier position");
             if (src < 0 && -1 - src >= desc->n_leader) return fail(EMM_ERR_INVALID, "leader list index out of range");
             if (desc->plan_ttype[a0 + k] >= desc->n_ttype) return fail(EMM_ERR_INVALID, "plan_ttype out of range");
+            const int an = desc->plan_anchor[a0 + k];
+            if (k > 0 && (an >= k || (src >= 0 && an != src))) return fail(EMM_ERR_INVALID, "plan_anchor must be an earlier position (the leader for same-residue positions)");
             const int pa = desc->plan_atom[a0 + k];
             if (pa >= m || (seen >> pa) & 1u) return fail(EMM_ERR_INVALID, "plan_atom is not a permutation");
             seen |= 1u << pa;
@@ -219,6 +222,7 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
     COPY(p_u8, desc->plan_atom, A); d.plan_atom = p_u8;
     COPY(p_u16, desc->plan_ttype, A); d.plan_ttype = p_u16;
     COPY(p_i16, desc->plan_src, A); d.plan_src = p_i16;
+    COPY(p_u8, desc->plan_anchor, A); d.plan_anchor = p_u8;
     COPY(p_i64, desc->pair_off, T + 1); d.pair_off = p_i64;
     COPY(p_f64, desc->pair_dist, npairs); d.pair_dist = p_f64;
     {
@@ -333,12 +337,12 @@ int emm_session_create(emm_library *lib, int64_t max_atoms, int32_t max_structur
     ALLOC(s->d_any, 4 * (size_t)max_structures);
     ALLOC(s->d_pass, 4 * (size_t)max_structures);
     ALLOC(s->d_skip, (size_t)max_structures);
-    ALLOC(s->d_stats, 8 * 8);
+    ALLOC(s->d_stats, 8 * 136);
     s->blob_capacity = 64 * max_atoms + (1024 + 4 * (int64_t)lib->d.n_leader) * max_structures;   // grown on demand at upload
     ALLOC(s->d_blob, s->blob_capacity);
 #undef ALLOC
     cudaMemset(s->d_hit_count, 0, 16);
-    cudaMemset(s->d_stats, 0, 64);
+    cudaMemset(s->d_stats, 0, 8 * 136);
     cudaMemset(s->d_any, 0, 4 * (size_t)max_structures);
     cudaMemset(s->d_pass, 0, 4 * (size_t)max_structures);
     *out = s;
@@ -371,6 +375,7 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     CUDA_TRY(cudaSetDevice(lib->device));
     const int n = b->n_structures;
     s->h_blob_off.assign((size_t)n + 1, 0);
+    int64_t max_staged = 0;
     const uint16_t *cl = lib->class_leaders.data();
     const size_t n_class = lib->class_leaders.size();
     for (int i = 0; i < n; ++i) {
@@ -382,8 +387,11 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
             if (k >= n_class) return fail(EMM_ERR_INVALID, "typing class out of range");
             entries += cl[k];
         }
-        s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + blob_bytes(a1 - a0, lib->d.n_leader, entries);
+        const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries);
+        s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + bytes;
+        max_staged = std::max(max_staged, bytes - align16(4 * (a1 - a0)));
     }
+    s->max_staged = max_staged;
     if (s->h_blob_off[(size_t)n] > s->blob_capacity) {
         CUDA_TRY(cudaStreamSynchronize(stream));
         cudaFree(s->d_blob);
@@ -428,7 +436,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     if (tb < 0) tb = 0;
     if (q->reset_structure_state) {
         CUDA_TRY(cudaMemsetAsync(s->d_hit_count, 0, 8, stream));
-        CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, 64, stream));
+        CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, 8 * 136, stream));
         if (n > 0) {
             CUDA_TRY(cudaMemsetAsync(s->d_any, 0, 4 * (size_t)n, stream));
             CUDA_TRY(cudaMemsetAsync(s->d_pass, 0, 4 * (size_t)n, stream));
@@ -490,6 +498,9 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     int cap = lib->smem_optin - fixed - 1024;
     cap &= ~15;
     if (cap < 0) return fail(EMM_ERR_INVALID, "not enough shared memory for the search queues");
+    // stage no more than the batch needs: every KB not claimed here stays L1 for the template tables
+    const int64_t want = (s->max_staged + 1023) & ~int64_t(1023);
+    if (want < cap) cap = (int)want;
     P.blob_cap = cap;
     const size_t smem = search_smem_bytes(cap, P.levels);
     CUDA_TRY(configure_search((int)smem));
@@ -524,6 +535,14 @@ int emm_session_kernel_ms(emm_session *s, int which, float *out_ms, int capacity
     *count = (int)used;
     for (size_t i = 0; i < used && (int)i < capacity && out_ms; ++i)
         CUDA_TRY(cudaEventElapsedTime(out_ms + i, pool[i].first, pool[i].second));
+    return EMM_OK;
+}
+
+/* Debug: per-level sweep / survivor counters of the stats build (EMM_STATS=1); 128 values. */
+int emm_session_debug_counters(emm_session *s, unsigned long long *out128)
+{
+    if (!s || !out128) return fail(EMM_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaMemcpy(out128, s->d_stats + 8, 8 * 128, cudaMemcpyDeviceToHost));
     return EMM_OK;
 }
 

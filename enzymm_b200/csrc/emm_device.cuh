@@ -20,7 +20,7 @@ namespace emm {
 constexpr int kMaxAtoms = EMM_MAX_TEMPLATE_ATOMS;
 constexpr int kSearchThreads = 512;
 constexpr int kSearchWarps = kSearchThreads / 32;
-constexpr int kQueueCap = 64;          // entries per search level per warp
+constexpr int kQueueCap = 48;          // entries per search level per warp (parent index is 8 bits)
 constexpr int kPrepThreads = 256;
 constexpr float kCellSize = 6.0f;      // uniform grid cell edge (Angstrom)
 constexpr int kMaxCellsPerAxis = 64;
@@ -34,6 +34,7 @@ struct DevLibrary {
     const uint8_t *plan_atom;
     const uint16_t *plan_ttype;
     const int16_t *plan_src;
+    const uint8_t *plan_anchor;
     const int64_t *pair_off;
     const double *pair_dist;
     const float *pair_dist32;

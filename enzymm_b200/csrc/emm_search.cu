@@ -4,27 +4,31 @@
 // Replaces pyjess.Jess(templates).query(...) + Match.predicted_correct for a whole batch
 // (reference enzymm/jess_run.py:785-843, 298-346, 425-478).
 //
-// Mapping.  Persistent CTAs (one per SM, 16 warps).  A work item is (structure, template chunk):
-// the CTA stages the structure blob into shared memory once, then each WARP pulls templates off a
-// shared counter and runs a warp-synchronous search:
+// Mapping.  Persistent CTAs (one per SM, kSearchWarps warps).  A work item is (structure,
+// template chunk): the CTA stages the structure blob into shared memory once, then each WARP
+// pulls templates off a shared counter and runs a warp-synchronous depth-first search:
 //
-//   * level k of the search places plan position k of the template.  Partial assignments live in
-//     per-level shared-memory queues as (parent slot, atom) pairs -- a trie, so a partial costs
-//     4 bytes whatever its depth;
-//   * one SWEEP evaluates 32 (partial, candidate) items, one per lane: candidates come from the
-//     structure's leader list (first atom of a template residue) or from the query residue of an
-//     already placed atom (same-residue rule); the lane walks the partial's chain and tests the
-//     pairwise-distance constraint against every placed atom; survivors are compacted with
-//     ballot/popc into the next level's queue;
-//   * queues are drained depth-first in chunks, so memory is bounded however many candidates a
-//     loose cutoff produces (config 4);
+//   * level k places plan position k of the template.  Partial assignments live in per-level
+//     shared-memory queues as 4-byte (parent slot, atom) entries -- a trie, so a partial costs
+//     4 bytes whatever its depth; queues are drained depth-first in chunks of <= 32 entries, so
+//     memory is bounded however many candidates a loose cutoff produces (config 4);
+//   * EXPANDING a chunk is a cheap, dense filter: for leader positions every lane holds one
+//     candidate atom of the structure's leader list in registers and the warp loops over the
+//     chunk's partials, testing ONE distance constraint against a broadcast "anchor" atom of the
+//     partial; for same-residue positions the lanes cover (partial, residue slot) items and test
+//     the typing bit + the anchor distance.  Survivors are ballot/popc-compacted into the next
+//     level's queue WITHOUT further checks;
+//   * ENTERING a level validates its chunk densely, one entry per lane: the lane walks its chain
+//     once, tests the new atom against every placed atom (injectivity + all pairwise-distance
+//     constraints) and records the anchor the next expansion needs.  So every constraint is
+//     checked exactly once per surviving partial, with all 32 lanes busy;
 //   * every accept/reject is decided in FP32 on centred coordinates unless it falls inside the
-//     guard band eps, in which case the lane re-evaluates the constraint in FP64 with separately
-//     rounded operations (__d*_rn) -- the same expressions as the CPU oracle, so the set of
-//     complete assignments is identical bit for bit;
-//   * complete assignments are superposed 32 at a time, one per lane, in FP64 registers (Horn's
-//     quaternion form of Kabsch + cyclic Jacobi), the per-template minimum is kept, and the
-//     winning hit gets EnzyMM's orientation + logistic filter before it is written out.
+//     guard band eps, in which case the lane re-evaluates in FP64 with separately rounded
+//     operations (__d*_rn) -- the same expressions as the CPU oracle, so the set of complete
+//     assignments is identical bit for bit;
+//   * complete assignments are superposed one per lane in FP64 registers (Horn's quaternion form
+//     of Kabsch + cyclic Jacobi), the per-template minimum is kept, and the winning hit gets
+//     EnzyMM's orientation + logistic filter before it is written out.
 //
 // No tensor cores: this is gather/compare-bound FP32 + integer work with a rare FP64 tail.
 #include <math_constants.h>
@@ -40,13 +44,21 @@ namespace emm {
 #define DDIV(a, b) __ddiv_rn((a), (b))
 #define DSQRT(a) __dsqrt_rn((a))
 
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kEntryValid = 1u << 24;   // entry passed validation
+constexpr uint32_t kEntryDead = 1u << 25;    // entry failed validation
+
 struct WarpState {
-    int n[kMaxAtoms + 1];
-    int cur[kMaxAtoms + 1];
+    int n[kMaxAtoms + 1];        // entries queued per level
+    int chunk[kMaxAtoms + 1];    // size of the level's current chunk (its last `chunk` entries)
+    int cur[kMaxAtoms + 1];      // expansion cursor inside the chunk
+    unsigned todo[kMaxAtoms + 1];// lanes of iteration `cur` still to be pushed (0 = fresh iteration)
+    float4 anchor[32];           // per chunk slot: anchor atom xyz, w = payload bits
+    unsigned char vslot[32];     // compacted list of valid chunk slots
     double best_rmsd;
+    unsigned long long n_complete;
     int best_valid;
     int overflow;
-    unsigned long long n_complete;
     uint16_t best_asg[kMaxAtoms];
 };
 
@@ -62,6 +74,14 @@ struct Blob {
     int res_shift;
     int n_kept;
     float eps;
+};
+
+struct SearchArgs {
+    DevLibrary L;
+    DevBatch B;
+    SearchParams P;
+    SearchOut O;
+    const unsigned char *skip;
 };
 
 __device__ __forceinline__ float fast_sqrt(float v)
@@ -235,10 +255,14 @@ __device__ double angle_between(const double (&u)[3], const double (&v)[3])
     return CUDART_NAN;
 }
 
+
+// ---- rare paths: kept out of line so their register needs do not burden the search loop ---------
+
 // Write the winning hit of (structure s, template t): superposition, orientation, logistic vote.
-__device__ void emit_hit(const DevLibrary &L, const Blob &S, const SearchOut &O, int s, int t,
-                         const WarpState *ws)
+__device__ __noinline__ void emit_hit(const SearchArgs &A, const Blob &S, int s, int t, const WarpState *ws)
 {
+    const DevLibrary &L = A.L;
+    const SearchOut &O = A.O;
     const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
     const double *txyz = L.xyz + 3 * (int64_t)a0;
     double rot[9], qbar[3], tbar[3];
@@ -317,90 +341,163 @@ __device__ void emit_hit(const DevLibrary &L, const Blob &S, const SearchOut &O,
     }
 }
 
-// Superpose the complete assignments queued at level m (one per lane) and keep the best.
-__device__ void process_complete(const DevLibrary &L, const Blob &S, const SearchParams &P, int t,
-                                 const uint32_t *Q, WarpState *ws, int lane)
+// Superpose the validated complete assignments of one chunk of level m (one per lane), keep the best.
+__device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S, int t, const uint32_t *Q,
+                                              WarpState *ws, int base, unsigned valid, int lane)
 {
+    const DevLibrary &L = A.L;
     const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
     const double *txyz = L.xyz + 3 * (int64_t)a0;
     const double thr = L.rmsd_thr[t];
-    const int total = ws->n[m];
-    for (int base = 0; base < total; base += 32) {
-        const int idx = base + lane;
-        bool have = idx < total;
-        uint16_t asg[kMaxAtoms];
-        if (have) {
-            uint32_t w = Q[m * kQueueCap + idx];
-            for (int pos = m - 1; pos >= 0; --pos) {
-                asg[L.plan_atom[a0 + pos]] = (uint16_t)(w & 0xffffu);
-                if (pos > 0) w = Q[pos * kQueueCap + (w >> 16)];
-            }
-            if (!P.ignore_chain && S.chain) {
-                // template atoms on equal chains <=> query atoms on equal chains (oracle rule 11)
-                for (int i = 0; i < m && have; ++i)
-                    for (int j = i + 1; j < m; ++j) {
-                        const bool st = L.chain[a0 + i] == L.chain[a0 + j];
-                        const bool sq = S.chain[S.orig[asg[i]]] == S.chain[S.orig[asg[j]]];
-                        if (st != sq) { have = false; break; }
-                    }
-            }
+    bool have = (valid >> lane) & 1u;
+    uint16_t asg[kMaxAtoms];
+    if (have) {
+        uint32_t w = Q[m * kQueueCap + base + lane];
+        for (int pos = m - 1; pos >= 0; --pos) {
+            asg[L.plan_atom[a0 + pos]] = (uint16_t)(w & 0xffffu);
+            if (pos > 0) w = Q[pos * kQueueCap + ((w >> 16) & 0xffu)];
         }
-        const unsigned counted = __ballot_sync(0xffffffffu, have);
-        double rmsd = CUDART_INF;
-        bool accept = false;
-        if (have) {
-            double rot[9], qbar[3], tbar[3];
-            rmsd = superpose(m, txyz, S, asg, rot, qbar, tbar);
-            accept = rmsd <= thr;
-        }
-        double key = accept ? rmsd : CUDART_INF;
-        double mn = key;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if (mn < CUDART_INF) {
-            unsigned tied = __ballot_sync(0xffffffffu, accept && key == mn);
-            if (__popc(tied) > 1) {  // exact RMSD tie: lexicographically smallest assignment wins
-                for (int i = 0; i < m && __popc(tied) > 1; ++i) {
-                    const unsigned v = ((tied >> lane) & 1u) ? (unsigned)asg[i] : 0xffffffffu;
-                    unsigned mv = v;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) mv = min(mv, __shfl_xor_sync(0xffffffffu, mv, o));
-                    tied &= __ballot_sync(0xffffffffu, v == mv);
+        if (!A.P.ignore_chain && S.chain) {
+            // template atoms on equal chains <=> query atoms on equal chains (oracle rule 11)
+            for (int i = 0; i < m && have; ++i)
+                for (int j = i + 1; j < m; ++j) {
+                    const bool st = L.chain[a0 + i] == L.chain[a0 + j];
+                    const bool sq = S.chain[S.orig[asg[i]]] == S.chain[S.orig[asg[j]]];
+                    if (st != sq) { have = false; break; }
                 }
-            }
-            const int win = __ffs(tied) - 1;
-            if (lane == win) {
-                bool better = !ws->best_valid || mn < ws->best_rmsd;
-                if (!better && mn == ws->best_rmsd) {
-                    for (int i = 0; i < m; ++i) {
-                        if (asg[i] != ws->best_asg[i]) { better = asg[i] < ws->best_asg[i]; break; }
-                    }
-                }
-                if (better) {
-                    ws->best_valid = 1;
-                    ws->best_rmsd = mn;
-                    for (int i = 0; i < m; ++i) ws->best_asg[i] = asg[i];
-                }
-            }
         }
-        if (lane == 0) {
-            ws->n_complete += (unsigned long long)__popc(counted);
-            if (P.max_candidates > 0 && ws->n_complete >= (unsigned long long)P.max_candidates) ws->overflow = 1;
-        }
-        __syncwarp();
-        if (ws->overflow) break;
     }
+    const unsigned counted = __ballot_sync(kFull, have);
+    double rmsd = CUDART_INF;
+    bool accept = false;
+    if (have) {
+        double rot[9], qbar[3], tbar[3];
+        rmsd = superpose(m, txyz, S, asg, rot, qbar, tbar);
+        accept = rmsd <= thr;
+    }
+    const double key = accept ? rmsd : CUDART_INF;
+    double mn = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(kFull, mn, o));
+    if (mn < CUDART_INF) {
+        unsigned tied = __ballot_sync(kFull, accept && key == mn);
+        if (__popc(tied) > 1) {  // exact RMSD tie: lexicographically smallest assignment wins
+            for (int i = 0; i < m && __popc(tied) > 1; ++i) {
+                const unsigned v = ((tied >> lane) & 1u) ? (unsigned)asg[i] : 0xffffffffu;
+                unsigned mv = v;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mv = min(mv, __shfl_xor_sync(kFull, mv, o));
+                tied &= __ballot_sync(kFull, v == mv);
+            }
+        }
+        const int win = __ffs(tied) - 1;
+        if (lane == win) {
+            bool better = !ws->best_valid || mn < ws->best_rmsd;
+            if (!better && mn == ws->best_rmsd) {
+                for (int i = 0; i < m; ++i) {
+                    if (asg[i] != ws->best_asg[i]) { better = asg[i] < ws->best_asg[i]; break; }
+                }
+            }
+            if (better) {
+                ws->best_valid = 1;
+                ws->best_rmsd = mn;
+                for (int i = 0; i < m; ++i) ws->best_asg[i] = asg[i];
+            }
+        }
+    }
+    if (lane == 0) {
+        ws->n_complete += (unsigned long long)__popc(counted);
+        if (A.P.max_candidates > 0 && ws->n_complete >= (unsigned long long)A.P.max_candidates) ws->overflow = 1;
+    }
+    __syncwarp();
+}
+
+// Guard band: decide one entry of level k (new atom at plan position k-1) with the oracle's FP64
+// expressions against every placed atom.
+__device__ __noinline__ bool exact_validate(const DevLibrary &L, const Blob &S, const uint32_t *Q, int a0,
+                                            int64_t p0, int k, uint32_t e, double cut, double dyn)
+{
+    const int oa = S.orig[e & 0xffffu];
+    const double *row64 = L.pair_dist + p0 + ((k - 1) * (k - 2)) / 2;
+    uint32_t w = e;
+    for (int pos = k - 2; pos >= 0; --pos) {
+        w = Q[(pos + 1) * kQueueCap + ((w >> 16) & 0xffu)];
+        const double d = exact_dist(S.xyz64, oa, S.orig[w & 0xffffu]);
+        const double delta = pair_delta(L, a0, k - 1, pos, cut, dyn);
+        if (!(fabs(DSUB(d, row64[pos])) <= delta)) return false;
+    }
+    return true;
+}
+
+struct LaneStats {
+    unsigned long long sweeps, evals, exact;
+};
+
+// Enter level k (k atoms placed; the chunk = entries [base, base+size) of queue k, one per lane):
+// validate entries that were only filtered so far, and record for every valid entry the anchor
+// the expansion of this level needs.  Returns the mask of valid chunk slots.
+template <bool kStats>
+__device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob &S, uint32_t *Q, WarpState *ws,
+                                                int a0, int64_t p0, int m, int k, int base, int size,
+                                                float cut32, double cut64, double dyn64, int lane, LaneStats &st)
+{
+    const DevLibrary &L = A.L;
+    const bool have = lane < size;
+    uint32_t e = have ? Q[k * kQueueCap + base + lane] : kEntryDead;
+    bool alive = !(e & kEntryDead);
+    const bool check = alive && !(e & kEntryValid);
+    const int a = (int)(e & 0xffffu);
+    const int anchor_pos = k < m ? (int)L.plan_anchor[a0 + k] : -1;     // warp-uniform
+    const bool dynamic = dyn64 != cut64;
+    const float eps = S.eps;
+    const float xa = S.x[a], ya = S.y[a], za = S.z[a];
+    float ax = xa, ay = ya, az = za;
+    int aatom = a;
+    bool border = false;
+    const float *row = L.pair_dist32 + p0 + ((k - 1) * (k - 2)) / 2;
+    uint32_t w = e;
+    for (int pos = k - 2; pos >= 0; --pos) {
+        w = Q[(pos + 1) * kQueueCap + ((w >> 16) & 0xffu)];
+        const int b = (int)(w & 0xffffu);
+        const float xb = S.x[b], yb = S.y[b], zb = S.z[b];
+        if (pos == anchor_pos) { ax = xb; ay = yb; az = zb; aatom = b; }
+        if (check) {
+            const float dx = xa - xb, dy = ya - yb, dz = za - zb;
+            const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            const float delta = dynamic ? (float)pair_delta(L, a0, k - 1, pos, cut64, dyn64) : cut32;
+            const float err = fabsf(d - __ldg(row + pos));
+            if (err > delta + eps || b == a) alive = false;
+            else if (err >= delta - eps) border = true;
+            if (kStats) ++st.evals;
+        }
+    }
+    if (check && alive && border) {
+        if (kStats) ++st.exact;
+        alive = exact_validate(L, S, Q, a0, p0, k, e, cut64, dyn64);
+    }
+    if (check) Q[k * kQueueCap + base + lane] = e | (alive ? kEntryValid : kEntryDead);
+    const unsigned valid = __ballot_sync(kFull, alive);
+    if (alive && k < m) {
+        int payload = aatom;
+        if ((int)L.plan_src[a0 + k] >= 0) {        // same-residue level: the anchor's residue span
+            const int r = S.res_of[aatom];
+            const int rs = S.res_start[r];
+            payload = rs | (((int)S.res_start[r + 1] - rs) << 16);
+        }
+        ws->anchor[lane] = make_float4(ax, ay, az, __int_as_float(payload));
+        ws->vslot[__popc(valid & ((1u << lane) - 1u))] = (unsigned char)lane;
+    }
+    __syncwarp();
+    return valid;
 }
 
 template <bool kStats>
-__device__ void search_template(const DevLibrary &L, const Blob &S, const SearchParams &P,
-                                const SearchOut &O, int s, int t, uint32_t *Q, WarpState *ws,
-                                int lane, unsigned long long *st_sweeps, unsigned long long *st_evals,
-                                unsigned long long *st_exact)
+__device__ __forceinline__ void search_template(const SearchArgs &A, const Blob &S, int s, int t, uint32_t *Q,
+                                                WarpState *ws, int lane, LaneStats &st)
 {
+    const DevLibrary &L = A.L;
     const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
     const int64_t p0 = L.pair_off[t];
-    const float *pair32 = L.pair_dist32 + p0;
 
     // a template with an empty leader list cannot match this structure
     {
@@ -409,147 +506,197 @@ __device__ void search_template(const DevLibrary &L, const Blob &S, const Search
             const int src = L.plan_src[a0 + lane];
             if (src < 0) empty = S.lead_off[-src] == S.lead_off[-1 - src];
         }
-        if (__any_sync(0xffffffffu, empty)) return;
+        if (__any_sync(kFull, empty)) return;
     }
 
     const double cut64 = L.dist_cut[t], dyn64 = L.max_dyn[t];
     const bool dynamic = dyn64 != cut64;
     const float cut32 = (float)cut64;
     const float eps = S.eps;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
-    if (lane <= m) { ws->n[lane] = lane == 0 ? 1 : 0; ws->cur[lane] = 0; }
+    if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0u; }
     if (lane == 0) { ws->best_valid = 0; ws->overflow = 0; ws->n_complete = 0ull; ws->best_rmsd = CUDART_INF; }
     __syncwarp();
 
-    int k = 0;
+    int k = 0, base = 0;
+    unsigned valid = 1u;          // level 0: the empty partial
+    bool entered = true;
     for (;;) {
         if (ws->overflow) break;
-        const int src = L.plan_src[a0 + k];
-        int stride, lbase = 0;
-        if (src < 0) {
-            lbase = (int)S.lead_off[-1 - src];
-            stride = (int)S.lead_off[-src] - lbase;
-        } else {
-            stride = 1 << S.res_shift;
-        }
-        const int nk = ws->n[k];
-        const int total = nk * stride;
-        const int cur = ws->cur[k];
-        const int nnext = ws->n[k + 1];
-        if (cur < total && nnext + 32 <= kQueueCap) {
-            // ---------------- one sweep: 32 (partial, candidate) items ----------------
-            const int i = cur + lane;
-            bool alive = i < total;
-            int p = 0, c = 0;
-            if (src < 0) { p = i / stride; c = i - p * stride; }
-            else { p = i >> S.res_shift; c = i & (stride - 1); }
-            uint32_t e = 0;
-            if (k > 0 && alive) e = Q[k * kQueueCap + p];
-            int a = 0;
-            if (src < 0) {
-                if (alive) a = S.lead[lbase + c];
-            } else if (alive) {
-                uint32_t w = e;
-                for (int pos = k - 1; pos > src; --pos) w = Q[pos * kQueueCap + (w >> 16)];
-                const int r = S.res_of[w & 0xffffu];
-                const int rs = S.res_start[r], rl = (int)S.res_start[r + 1] - rs;
-                alive = c < rl;
-                a = rs + c;
-                if (alive) {
-                    const unsigned kl = S.klass[a];
-                    const uint32_t word = __ldg(L.compat + (size_t)L.plan_ttype[a0 + k] * L.class_words_cap + (kl >> 5));
-                    alive = (word >> (kl & 31)) & 1u;
-                }
+        if (!entered) {
+            const int size = ws->chunk[k];
+            base = ws->n[k] - size;
+            valid = k == 0 ? 1u : enter_level<kStats>(A, S, Q, ws, a0, p0, m, k, base, size, cut32, cut64, dyn64, lane, st);
+            entered = true;
+            if (kStats && lane == 0 && k > 0) {
+                atomicAdd(A.O.stats + 72 + k, (unsigned long long)__popc(valid));
+                atomicAdd(A.O.stats + 104 + k, 1ull);
             }
-            bool border = false;
+            if (k == m && valid) process_complete(A, S, t, Q, ws, base, valid, lane);
+        }
+        if (k < m && valid) {
+            // ---------------- expand the chunk of level k: a cheap dense filter ----------------
+            const int src = L.plan_src[a0 + k];
+            const int P = __popc(valid);
+            int n_next = ws->n[k + 1];
+            int cur = ws->cur[k];
+            unsigned todo = ws->todo[k];
+            uint32_t *Qn = Q + (k + 1) * kQueueCap;
+            const int apos = L.plan_anchor[a0 + k];
+            float dt_anchor = 0.f, rej = 0.f;
             if (k > 0) {
-                const float xa = alive ? S.x[a] : 0.f, ya = alive ? S.y[a] : 0.f, za = alive ? S.z[a] : 0.f;
-                const float *row = pair32 + (k * (k - 1)) / 2;
-                uint32_t w = e;
-                for (int pos = k - 1; pos >= 0; --pos) {
-                    if (!__any_sync(0xffffffffu, alive)) break;
-                    const int b = (int)(w & 0xffffu);
-                    if (pos > 0) w = Q[pos * kQueueCap + (w >> 16)];
-                    if (alive) {
-                        const float dx = xa - S.x[b], dy = ya - S.y[b], dz = za - S.z[b];
-                        const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-                        float delta = cut32;
-                        if (dynamic) delta = (float)pair_delta(L, a0, k, pos, cut64, dyn64);
-                        const float err = fabsf(d - __ldg(row + pos));
-                        if (err > delta + eps || b == a) alive = false;
-                        else if (err >= delta - eps) border = true;
-                        if (kStats) ++(*st_evals);
-                    }
-                }
-                if (alive && border) {
-                    // guard band: decide with the oracle's FP64 expression
-                    if (kStats) ++(*st_exact);
-                    const double *row64 = L.pair_dist + p0 + (k * (k - 1)) / 2;
-                    const int oa = S.orig[a];
-                    uint32_t w2 = e;
-                    for (int pos = k - 1; pos >= 0; --pos) {
-                        const int b = (int)(w2 & 0xffffu);
-                        if (pos > 0) w2 = Q[pos * kQueueCap + (w2 >> 16)];
-                        const double d = exact_dist(S.xyz64, oa, S.orig[b]);
-                        const double delta = pair_delta(L, a0, k, pos, cut64, dyn64);
-                        if (!(fabs(DSUB(d, row64[pos])) <= delta)) { alive = false; break; }
-                    }
-                }
+                dt_anchor = __ldg(L.pair_dist32 + p0 + (k * (k - 1)) / 2 + apos);
+                rej = (dynamic ? (float)pair_delta(L, a0, k, apos, cut64, dyn64) : cut32) + eps;
             }
-            const unsigned surv = __ballot_sync(0xffffffffu, alive);
-            if (alive) Q[(k + 1) * kQueueCap + nnext + __popc(surv & ((1u << lane) - 1u))] = ((uint32_t)p << 16) | (uint32_t)a;
-            if (lane == 0) { ws->cur[k] = cur + 32; ws->n[k + 1] = nnext + __popc(surv); }
-            if (kStats && lane == 0) ++(*st_sweeps);
-            __syncwarp();
-        } else if (nnext > 0) {
-            if (k + 1 == m) {
-                process_complete(L, S, P, t, Q, ws, lane);
-                if (lane == 0) ws->n[m] = 0;
-                __syncwarp();
+            bool full = false, done = false;
+            const int n_before = n_next;
+            if (src < 0) {
+                // leader position: lane <-> candidate of the leader list, loop over partials
+                const int lbase = (int)S.lead_off[-1 - src];
+                const int B = (int)S.lead_off[-src] - lbase;
+                const int nrows = (B + 31) >> 5;
+                int r = cur / P, pidx = cur - r * P;
+                while (r < nrows) {
+                    const int c = (r << 5) + lane;
+                    const bool have = c < B;
+                    const int a = have ? (int)S.lead[lbase + c] : 0;
+                    const float xa = S.x[a], ya = S.y[a], za = S.z[a];
+                    for (; pidx < P; ++pidx) {
+                        if (n_next >= kQueueCap) { full = true; break; }
+                        bool alive = have && (todo == 0u || ((todo >> lane) & 1u));
+                        int slot = 0;
+                        if (k > 0) {
+                            slot = ws->vslot[pidx];
+                            const float4 an = ws->anchor[slot];
+                            const float dx = xa - an.x, dy = ya - an.y, dz = za - an.z;
+                            const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                            alive = alive && fabsf(d - dt_anchor) <= rej && a != __float_as_int(an.w);
+                            if (kStats) st.evals += have;
+                        }
+                        if (kStats && lane == 0) ++st.sweeps;
+                        const unsigned sv = __ballot_sync(kFull, alive);
+                        if (sv) {
+                            const int room = kQueueCap - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
+                            if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)(base + slot) << 16) | (uint32_t)a;
+                            if (cnt > room) {
+                                n_next = kQueueCap;
+                                todo = __ballot_sync(kFull, alive && rank >= room);
+                                full = true;
+                                break;
+                            }
+                            n_next += cnt;
+                        }
+                        todo = 0u;
+                    }
+                    if (full) break;
+                    pidx = 0;
+                    ++r;
+                }
+                cur = r * P + pidx;
+                done = r >= nrows;
             } else {
-                ++k;
-                if (lane == 0) ws->cur[k] = 0;
-                __syncwarp();
+                // same-residue position: lanes cover (partial, residue slot) items
+                const int shift = S.res_shift;
+                const int n_it = ((P << shift) + 31) >> 5;
+                const uint32_t *crow = L.compat + (size_t)L.plan_ttype[a0 + k] * L.class_words_cap;
+                int it = cur;
+                for (; it < n_it; ++it) {
+                    if (n_next >= kQueueCap) { full = true; break; }
+                    const int item = (it << 5) + lane;
+                    const int pidx = item >> shift, sidx = item & ((1 << shift) - 1);
+                    bool alive = pidx < P && (todo == 0u || ((todo >> lane) & 1u));
+                    const int slot = alive ? (int)ws->vslot[pidx] : 0;
+                    const float4 an = ws->anchor[slot];
+                    const int payload = __float_as_int(an.w);
+                    const int a = (payload & 0xffff) + sidx;
+                    alive = alive && sidx < (payload >> 16);
+                    if (alive) {
+                        const unsigned kl = S.klass[a];
+                        alive = (__ldg(crow + (kl >> 5)) >> (kl & 31u)) & 1u;
+                    }
+                    if (alive) {
+                        const float dx = S.x[a] - an.x, dy = S.y[a] - an.y, dz = S.z[a] - an.z;
+                        const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                        alive = fabsf(d - dt_anchor) <= rej;
+                        if (kStats) ++st.evals;
+                    }
+                    if (kStats && lane == 0) ++st.sweeps;
+                    const unsigned sv = __ballot_sync(kFull, alive);
+                    if (sv) {
+                        const int room = kQueueCap - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
+                        if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)(base + slot) << 16) | (uint32_t)a;
+                        if (cnt > room) {
+                            n_next = kQueueCap;
+                            todo = __ballot_sync(kFull, alive && rank >= room);
+                            full = true;
+                            break;
+                        }
+                        n_next += cnt;
+                    }
+                    todo = 0u;
+                }
+                cur = it;
+                done = it >= n_it;
             }
-        } else {
-            if (k == 0) break;
-            if (lane == 0) ws->n[k] = 0;
+            if (lane == 0) { ws->n[k + 1] = n_next; ws->cur[k] = cur; ws->todo[k] = todo; }
+            if (kStats && lane == 0) atomicAdd(A.O.stats + 40 + k, (unsigned long long)(n_next - n_before));
+            if (full || (done && n_next > 0)) {
+                // descend: the last <= 32 entries of the next level form its chunk
+                ++k;
+                if (lane == 0) { ws->chunk[k] = min(32, n_next); ws->cur[k] = 0; ws->todo[k] = 0u; }
+                __syncwarp();
+                entered = false;
+                continue;
+            }
             __syncwarp();
-            --k;
         }
+        // the chunk of level k is exhausted (or dead, or its complete assignments are processed)
+        if (k == 0) break;
+        if (lane == 0) {
+            ws->n[k] = base;
+            ws->chunk[k] = min(32, base);
+            ws->cur[k] = 0;
+            ws->todo[k] = 0u;
+        }
+        __syncwarp();
+        if (base == 0) --k;           // back to the parent level: its chunk, cursor and todo are intact
+        entered = false;
     }
-    if (kStats && lane == 0 && ws->n_complete) atomicAdd(O.stats + 4, ws->n_complete);
-    if (ws->best_valid && lane == 0) emit_hit(L, S, O, s, t, ws);
+    if (kStats && lane == 0 && ws->n_complete) atomicAdd(A.O.stats + 4, ws->n_complete);
+    if (ws->best_valid && lane == 0) emit_hit(A, S, s, t, ws);
     __syncwarp();
 }
 
 template <bool kStats>
 __global__ void __launch_bounds__(kSearchThreads, 1)
-emm_search_kernel(DevLibrary L, DevBatch B, SearchParams P, SearchOut O, const unsigned char *skip)
+emm_search_kernel(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item, s_next_tpl;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const SearchParams &P = A.P;
     unsigned char *stage = smem;
     uint32_t *Q = reinterpret_cast<uint32_t *>(smem + P.blob_cap) + (size_t)wid * P.levels * kQueueCap;
     WarpState *ws = reinterpret_cast<WarpState *>(smem + P.blob_cap + (size_t)kSearchWarps * P.levels * kQueueCap * 4) + wid;
 
-    unsigned long long st_sweeps = 0, st_evals = 0, st_exact = 0, st_pairs = 0, st_staged = 0, st_global = 0;
+    LaneStats st = {0ull, 0ull, 0ull};
+    unsigned long long st_pairs = 0, st_staged = 0, st_global = 0;
 
     for (;;) {
-        if (tid == 0) s_item = (int)atomicAdd(O.work_counter, 1u);
+        if (tid == 0) s_item = (int)atomicAdd(A.O.work_counter, 1u);
         __syncthreads();
         const int item = s_item;
         if (item >= P.n_items) break;
         const int s = item / P.n_chunks, chunk = item - s * P.n_chunks;
-        const unsigned char *gblob = B.blob + B.blob_off[s];
+        const unsigned char *gblob = A.B.blob + A.B.blob_off[s];
         const BlobHeader hdr = *reinterpret_cast<const BlobHeader *>(gblob);
         const int span = P.template_end - P.template_begin;
         const int per = (span + P.n_chunks - 1) / P.n_chunks;
         const int tb = P.template_begin + chunk * per;
         const int te = min(P.template_end, tb + per);
-        const bool run = hdr.status == 0 && hdr.n_kept > 0 && tb < te && !(skip && skip[s]);
+        const bool run = hdr.status == 0 && hdr.n_kept > 0 && tb < te && !(A.skip && A.skip[s]);
         if (run) {
             const unsigned char *base = gblob;
             if (hdr.staged_bytes <= P.blob_cap) {
@@ -573,38 +720,37 @@ emm_search_kernel(DevLibrary L, DevBatch B, SearchParams P, SearchOut O, const u
             S.lead_off = reinterpret_cast<const uint32_t *>(base + hdr.off_leadoff);
             S.lead = reinterpret_cast<const uint16_t *>(base + hdr.off_lead);
             S.orig = reinterpret_cast<const int32_t *>(gblob + hdr.off_orig);
-            const int64_t abase = B.atom_off[s];
-            S.xyz64 = B.xyz + 3 * abase;
-            S.chain = B.chain ? B.chain + abase : nullptr;
-            S.atom_id = B.atom_id ? B.atom_id + abase : nullptr;
+            const int64_t abase = A.B.atom_off[s];
+            S.xyz64 = A.B.xyz + 3 * abase;
+            S.chain = A.B.chain ? A.B.chain + abase : nullptr;
+            S.atom_id = A.B.atom_id ? A.B.atom_id + abase : nullptr;
             S.res_shift = hdr.res_shift;
             S.n_kept = hdr.n_kept;
             S.eps = hdr.eps;
             for (;;) {
                 int t = 0;
                 if (lane == 0) t = atomicAdd(&s_next_tpl, 1);
-                t = __shfl_sync(0xffffffffu, t, 0);
+                t = __shfl_sync(kFull, t, 0);
                 if (t >= te) break;
-                search_template<kStats>(L, S, P, O, s, t, Q, ws, lane, &st_sweeps, &st_evals, &st_exact);
+                search_template<kStats>(A, S, s, t, Q, ws, lane, st);
                 if (kStats && lane == 0) ++st_pairs;
             }
         }
         __syncthreads();
     }
     if (kStats) {
-        // per-lane counters -> one atomic per warp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            st_evals += __shfl_xor_sync(0xffffffffu, st_evals, o);
-            st_exact += __shfl_xor_sync(0xffffffffu, st_exact, o);
+            st.evals += __shfl_xor_sync(kFull, st.evals, o);
+            st.exact += __shfl_xor_sync(kFull, st.exact, o);
         }
         if (lane == 0) {
-            atomicAdd(O.stats + 0, st_pairs);
-            atomicAdd(O.stats + 1, st_sweeps);
-            atomicAdd(O.stats + 2, st_evals);
-            atomicAdd(O.stats + 3, st_exact);
-            atomicAdd(O.stats + 6, st_staged);
-            atomicAdd(O.stats + 7, st_global);
+            atomicAdd(A.O.stats + 0, st_pairs);
+            atomicAdd(A.O.stats + 1, st.sweeps);
+            atomicAdd(A.O.stats + 2, st.evals);
+            atomicAdd(A.O.stats + 3, st.exact);
+            atomicAdd(A.O.stats + 6, st_staged);
+            atomicAdd(A.O.stats + 7, st_global);
         }
     }
 }
@@ -638,8 +784,10 @@ void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P
                    const unsigned char *skip, bool stats, int grid, size_t smem, cudaStream_t stream)
 {
     if (P.n_items <= 0) return;
-    if (stats) emm_search_kernel<true><<<grid, kSearchThreads, smem, stream>>>(L, B, P, O, skip);
-    else emm_search_kernel<false><<<grid, kSearchThreads, smem, stream>>>(L, B, P, O, skip);
+    SearchArgs A;
+    A.L = L; A.B = B; A.P = P; A.O = O; A.skip = skip;
+    if (stats) emm_search_kernel<true><<<grid, kSearchThreads, smem, stream>>>(A);
+    else emm_search_kernel<false><<<grid, kSearchThreads, smem, stream>>>(A);
 }
 
 }  // namespace emm

@@ -47,7 +47,8 @@ class _LibraryDesc(ctypes.Structure):
         ("n_templates", ctypes.c_int32), ("n_atoms", ctypes.c_int32),
         ("atom_off", ctypes.c_void_p), ("xyz", ctypes.c_void_p), ("weight", ctypes.c_void_p),
         ("chain", ctypes.c_void_p), ("plan_atom", ctypes.c_void_p), ("plan_ttype", ctypes.c_void_p),
-        ("plan_src", ctypes.c_void_p), ("pair_off", ctypes.c_void_p), ("pair_dist", ctypes.c_void_p),
+        ("plan_src", ctypes.c_void_p), ("plan_anchor", ctypes.c_void_p), ("pair_off", ctypes.c_void_p),
+        ("pair_dist", ctypes.c_void_p),
         ("n_ttype", ctypes.c_int32), ("class_words", ctypes.c_int32), ("compat", ctypes.c_void_p),
         ("n_leader", ctypes.c_int32), ("leader_ttype", ctypes.c_void_p),
         ("rmsd_threshold", ctypes.c_void_p), ("distance_cutoff", ctypes.c_void_p),
@@ -99,7 +100,7 @@ def load_cdll() -> ctypes.CDLL:
         for name in ("emm_abi_version", "emm_hit_size", "emm_device_count", "emm_library_create", "emm_library_set_compat",
                      "emm_library_set_thresholds", "emm_library_set_filter", "emm_session_create", "emm_session_upload",
                      "emm_session_run", "emm_session_download", "emm_session_last_launches",
-                     "emm_session_kernel_ms", "emm_session_clear_timings",
+                     "emm_session_kernel_ms", "emm_session_clear_timings", "emm_session_debug_counters",
                      "emm_query_batch"):
             getattr(lib, name).restype = ctypes.c_int
         lib.emm_library_destroy.restype = None
@@ -178,7 +179,7 @@ class DeviceLibrary:
         self._keep = [self._compat, c.leader_ttype_arr]
         desc = _LibraryDesc(
             len(c.templates), int(c.atom_off[-1]), _p(c.atom_off), _p(c.xyz), _p(c.weight), _p(c.chain),
-            _p(c.plan_atom), _p(c.plan_ttype), _p(c.plan_src), _p(c.pair_off), _p(c.pair_dist),
+            _p(c.plan_atom), _p(c.plan_ttype), _p(c.plan_src), _p(c.plan_anchor), _p(c.pair_off), _p(c.pair_dist),
             c.n_ttype, c.class_words, _p(self._compat), len(c.leader_ttype), _p(c.leader_ttype_arr),
             _p(c.rmsd_threshold), _p(c.distance_cutoff), _p(c.max_dynamic_distance),
             _p(c.n_residues), _p(c.orient_idx), _p(c.orient_vec), _p(c.lr_index), c.n_lr, _p(c.lr_table))
@@ -267,6 +268,11 @@ class Session:
         _check(self._lib.emm_session_kernel_ms(self.handle, ctypes.c_int(idx), _p(buf), ctypes.c_int(len(buf)),
                                                ctypes.byref(count)))
         return buf[:count.value].astype(float).tolist()
+
+    def debug_counters(self):
+        buf = np.zeros(128, dtype=np.uint64)
+        _check(self._lib.emm_session_debug_counters(self.handle, _p(buf)))
+        return buf
 
     def clear_timings(self):
         _check(self._lib.emm_session_clear_timings(self.handle))

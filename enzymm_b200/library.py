@@ -144,7 +144,7 @@ class CompiledLibrary:
         atom_off = [0]
         pair_off = [0]
         xyz, weight, chain = [], [], []
-        plan_atom, plan_ttype, plan_src = [], [], []
+        plan_atom, plan_ttype, plan_src, plan_anchor = [], [], [], []
         pair_dist: List[np.ndarray] = []
         leader_of_ttype: Dict[int, int] = {}
         self.leader_ttype: List[int] = []
@@ -169,6 +169,15 @@ class CompiledLibrary:
                     plan_src.append(pos_of_atom[lead_atom])
             pc = coords[np.asarray(order)]
             tri = [_canonical_dist(pc[k], pc[j]) for k in range(m) for j in range(k)]
+            for k in range(m):
+                src = plan_src[len(plan_src) - m + k]
+                if k == 0:
+                    plan_anchor.append(0)
+                elif src >= 0:
+                    plan_anchor.append(src)                      # same-residue position: its leader
+                else:                                            # leader: the nearest placed atom gives the thinnest shell
+                    row = tri[k * (k - 1) // 2: k * (k - 1) // 2 + k]
+                    plan_anchor.append(int(np.argmin(row)))
             pair_dist.append(np.asarray(tri, dtype=np.float64))
             pair_off.append(pair_off[-1] + m * (m - 1) // 2)
             xyz.append(coords)
@@ -185,6 +194,7 @@ class CompiledLibrary:
         self.plan_atom = np.asarray(plan_atom, dtype=np.uint8)
         self.plan_ttype = np.asarray(plan_ttype, dtype=np.uint16)
         self.plan_src = np.asarray(plan_src, dtype=np.int16)
+        self.plan_anchor = np.asarray(plan_anchor, dtype=np.uint8)
         self.pair_dist = np.ascontiguousarray(np.concatenate(pair_dist) if pair_dist else np.zeros(0), dtype=np.float64)
         if self.pair_dist.size == 0:
             self.pair_dist = np.zeros(1, dtype=np.float64)

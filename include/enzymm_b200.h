@@ -74,6 +74,9 @@ typedef struct emm_library_desc {
     const uint16_t *plan_ttype;    /* [n_atoms] compat row of that atom                         */
     const int16_t *plan_src;       /* [n_atoms] >=0: same residue as plan position src;         */
                                    /*           <0 : leader, candidates = leader list (-1-src)  */
+    const uint8_t *plan_anchor;    /* [n_atoms] earlier plan position (< k) whose distance constraint */
+                                   /*           filters candidates first; position 0: unused;   */
+                                   /*           same-residue positions: must equal plan_src      */
     const int64_t *pair_off;       /* [n_templates+1] CSR into pair_dist (k*(k-1)/2 + j, j<k)   */
     const double *pair_dist;       /* template distances between plan positions, FP64           */
     /* typing */
@@ -203,6 +206,10 @@ int emm_session_last_launches(const emm_session *s);
  * number of launches recorded through *count. */
 int emm_session_kernel_ms(emm_session *s, int which, float *out_ms, int capacity, int *count);
 int emm_session_clear_timings(emm_session *s);
+
+/* Diagnostics of the EMM_STATS=1 build path: sweeps[64] then survivors[64], indexed by search level
+ * (+32 for same-residue levels). */
+int emm_session_debug_counters(emm_session *s, unsigned long long *out128);
 
 /* Convenience: upload + run + download on the default stream (the end-to-end call). */
 int emm_query_batch(emm_library *lib, const emm_batch *batch, const emm_query_params *params,

@@ -1,0 +1,45 @@
+"""Small fixed workload for ncu / stats runs: N synthetic structures vs the full library.
+usage: python tools/profile_workload.py [n_structures] [steps]"""
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from bench import DEFAULT_DIST, active_templates, make_workload  # noqa: E402
+from enzymm_b200.engine import Engine  # noqa: E402
+from enzymm_b200.library import CompiledLibrary  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 592
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    templates = active_templates()
+    dists = [DEFAULT_DIST[min(t.effective_size, 8)] for t in templates]
+    workload = make_workload(0, n, 400, 1, 8)
+    engine = Engine(CompiledLibrary(templates, 2.0, dists, dists))
+    batch = workload.to_packed(engine.compiled)
+    sess = engine.session_for(batch.n_atoms, batch.n_structures)
+    sess.upload(batch)
+    for i in range(steps):
+        t0 = time.perf_counter()
+        sess.run(force_prepare=True)
+        hits, stats = sess.download(with_stats=True)
+        dt = time.perf_counter() - t0
+        print(f"step {i}: {n / dt:.1f} structures/s, {len(hits)} hits, kernels ms: prepare {sess.kernel_ms('prepare')[-1]:.2f} "
+              f"search {sess.kernel_ms('search')[-1]:.2f}")
+    if os.environ.get("EMM_STATS") == "1":
+        print("stats", stats)
+        c = sess.debug_counters()
+        pairs = max(stats["pairs"], 1)
+        print("per pair: sweeps %.1f evals %.1f" % (stats["sweeps"] / pairs, stats["dist_evals"] / pairs))
+        print("level: pushed-from-level | validated-alive entering | enter calls   (per pair)")
+        for k in range(26):
+            print(k, "%.2f | %.2f | %.2f" % (c[32 + k] / pairs, c[64 + k] / pairs, c[96 + k] / pairs))
+
+
+if __name__ == "__main__":
+    main()
