@@ -19,7 +19,7 @@ size_t search_fixed_smem(int levels);
 cudaError_t configure_search(int smem_bytes);
 void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream);
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, bool stats, int grid, size_t smem, cudaStream_t stream);
+                   const unsigned char *skip, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream);
 }  // namespace emm
 
 using namespace emm;
@@ -499,8 +499,10 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     cap &= ~15;
     if (cap < 0) return fail(EMM_ERR_INVALID, "not enough shared memory for the search queues");
     // stage no more than the batch needs: every KB not claimed here stays L1 for the template tables
+    // (a batch with a structure too large to stage is searched in place from global memory)
     const int64_t want = (s->max_staged + 1023) & ~int64_t(1023);
-    if (want < cap) cap = (int)want;
+    const bool staged = want <= cap;
+    cap = staged ? (int)want : 0;
     P.blob_cap = cap;
     const size_t smem = search_smem_bytes(cap, P.levels);
     CUDA_TRY(configure_search((int)smem));
@@ -517,7 +519,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
         cudaEvent_t e0, e1;
         const bool timed = next_events(s->ev_search, s->ev_search_used, &e0, &e1);
         if (timed) cudaEventRecord(e0, stream);
-        launch_search(lib->d, B, P, O, skip, lib->stats_enabled != 0, std::min(grid, P.n_items), smem, stream);
+        launch_search(lib->d, B, P, O, skip, lib->stats_enabled != 0, staged, std::min(grid, P.n_items), smem, stream);
         if (timed) cudaEventRecord(e1, stream);
     }
     CUDA_TRY(cudaGetLastError());

@@ -62,18 +62,41 @@ struct WarpState {
     uint16_t best_asg[kMaxAtoms];
 };
 
+// Dynamic shared memory: [staged blob][per-warp queues][per-warp state].
+extern __shared__ __align__(16) unsigned char g_smem[];
+
+// Global-memory side of a structure, used only by the rare FP64 paths; one copy per CTA in
+// shared memory so the out-of-line functions do not drag a struct through local memory.
 struct Blob {
-    const float *x, *y, *z;
-    const uint16_t *res_of, *res_start, *klass;
-    const uint32_t *lead_off;
-    const uint16_t *lead;
-    const int32_t *orig;      // global memory
-    const double *xyz64;      // global memory, structure base
-    const uint16_t *chain;    // global, structure base (may be null)
-    const int32_t *atom_id;   // global, structure base (may be null)
+    const int32_t *orig;      // local atom id -> position inside the structure
+    const double *xyz64;      // structure base, FP64 coordinates as uploaded
+    const uint16_t *chain;    // may be null
+    const int32_t *atom_id;   // may be null
+};
+
+// Hot-path view of the structure blob.  kStaged: the blob sits at the start of dynamic shared
+// memory and every access compiles to LDS with 32-bit addressing; otherwise it is read in place
+// from global memory (structures too large to stage).
+template <bool kStaged>
+struct View {
+    const unsigned char *gbase;
+    int off_x, off_y, off_z, off_res, off_resstart, off_klass, off_leadoff, off_lead;
     int res_shift;
-    int n_kept;
     float eps;
+    template <typename T>
+    __device__ __forceinline__ T ld(int byte_off) const
+    {
+        if (kStaged) return *reinterpret_cast<const T *>(g_smem + byte_off);
+        return __ldg(reinterpret_cast<const T *>(gbase + byte_off));
+    }
+    __device__ __forceinline__ float x(int i) const { return ld<float>(off_x + 4 * i); }
+    __device__ __forceinline__ float y(int i) const { return ld<float>(off_y + 4 * i); }
+    __device__ __forceinline__ float z(int i) const { return ld<float>(off_z + 4 * i); }
+    __device__ __forceinline__ int res_of(int i) const { return ld<uint16_t>(off_res + 2 * i); }
+    __device__ __forceinline__ int res_start(int r) const { return ld<uint16_t>(off_resstart + 2 * r); }
+    __device__ __forceinline__ unsigned klass(int i) const { return ld<uint16_t>(off_klass + 2 * i); }
+    __device__ __forceinline__ int lead_off(int l) const { return (int)ld<uint32_t>(off_leadoff + 4 * l); }
+    __device__ __forceinline__ int lead(int i) const { return ld<uint16_t>(off_lead + 2 * i); }
 };
 
 struct SearchArgs {
@@ -436,8 +459,9 @@ struct LaneStats {
 // Enter level k (k atoms placed; the chunk = entries [base, base+size) of queue k, one per lane):
 // validate entries that were only filtered so far, and record for every valid entry the anchor
 // the expansion of this level needs.  Returns the mask of valid chunk slots.
-template <bool kStats>
-__device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob &S, uint32_t *Q, WarpState *ws,
+template <bool kStats, bool kStaged>
+__device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob &S, const View<kStaged> &V,
+                                                uint32_t *Q, WarpState *ws,
                                                 int a0, int64_t p0, int m, int k, int base, int size,
                                                 float cut32, double cut64, double dyn64, int lane, LaneStats &st)
 {
@@ -449,8 +473,8 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     const int a = (int)(e & 0xffffu);
     const int anchor_pos = k < m ? (int)L.plan_anchor[a0 + k] : -1;     // warp-uniform
     const bool dynamic = dyn64 != cut64;
-    const float eps = S.eps;
-    const float xa = S.x[a], ya = S.y[a], za = S.z[a];
+    const float eps = V.eps;
+    const float xa = V.x(a), ya = V.y(a), za = V.z(a);
     float ax = xa, ay = ya, az = za;
     int aatom = a;
     bool border = false;
@@ -459,7 +483,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     for (int pos = k - 2; pos >= 0; --pos) {
         w = Q[(pos + 1) * kQueueCap + ((w >> 16) & 0xffu)];
         const int b = (int)(w & 0xffffu);
-        const float xb = S.x[b], yb = S.y[b], zb = S.z[b];
+        const float xb = V.x(b), yb = V.y(b), zb = V.z(b);
         if (pos == anchor_pos) { ax = xb; ay = yb; az = zb; aatom = b; }
         if (check) {
             const float dx = xa - xb, dy = ya - yb, dz = za - zb;
@@ -480,9 +504,9 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     if (alive && k < m) {
         int payload = aatom;
         if ((int)L.plan_src[a0 + k] >= 0) {        // same-residue level: the anchor's residue span
-            const int r = S.res_of[aatom];
-            const int rs = S.res_start[r];
-            payload = rs | (((int)S.res_start[r + 1] - rs) << 16);
+            const int r = V.res_of(aatom);
+            const int rs = V.res_start(r);
+            payload = rs | ((V.res_start(r + 1) - rs) << 16);
         }
         ws->anchor[lane] = make_float4(ax, ay, az, __int_as_float(payload));
         ws->vslot[__popc(valid & ((1u << lane) - 1u))] = (unsigned char)lane;
@@ -491,9 +515,9 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     return valid;
 }
 
-template <bool kStats>
-__device__ __forceinline__ void search_template(const SearchArgs &A, const Blob &S, int s, int t, uint32_t *Q,
-                                                WarpState *ws, int lane, LaneStats &st)
+template <bool kStats, bool kStaged>
+__device__ __forceinline__ void search_template(const SearchArgs &A, const Blob &S, const View<kStaged> &V, int s,
+                                                int t, uint32_t *Q, WarpState *ws, int lane, LaneStats &st)
 {
     const DevLibrary &L = A.L;
     const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
@@ -504,7 +528,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
         bool empty = false;
         if (lane < m) {
             const int src = L.plan_src[a0 + lane];
-            if (src < 0) empty = S.lead_off[-src] == S.lead_off[-1 - src];
+            if (src < 0) empty = V.lead_off(-src) == V.lead_off(-1 - src);
         }
         if (__any_sync(kFull, empty)) return;
     }
@@ -512,7 +536,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
     const double cut64 = L.dist_cut[t], dyn64 = L.max_dyn[t];
     const bool dynamic = dyn64 != cut64;
     const float cut32 = (float)cut64;
-    const float eps = S.eps;
+    const float eps = V.eps;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0u; }
@@ -527,7 +551,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
         if (!entered) {
             const int size = ws->chunk[k];
             base = ws->n[k] - size;
-            valid = k == 0 ? 1u : enter_level<kStats>(A, S, Q, ws, a0, p0, m, k, base, size, cut32, cut64, dyn64, lane, st);
+            valid = k == 0 ? 1u : enter_level<kStats, kStaged>(A, S, V, Q, ws, a0, p0, m, k, base, size, cut32, cut64, dyn64, lane, st);
             entered = true;
             if (kStats && lane == 0 && k > 0) {
                 atomicAdd(A.O.stats + 72 + k, (unsigned long long)__popc(valid));
@@ -553,15 +577,15 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             const int n_before = n_next;
             if (src < 0) {
                 // leader position: lane <-> candidate of the leader list, loop over partials
-                const int lbase = (int)S.lead_off[-1 - src];
-                const int B = (int)S.lead_off[-src] - lbase;
+                const int lbase = V.lead_off(-1 - src);
+                const int B = V.lead_off(-src) - lbase;
                 const int nrows = (B + 31) >> 5;
                 int r = cur / P, pidx = cur - r * P;
                 while (r < nrows) {
                     const int c = (r << 5) + lane;
                     const bool have = c < B;
-                    const int a = have ? (int)S.lead[lbase + c] : 0;
-                    const float xa = S.x[a], ya = S.y[a], za = S.z[a];
+                    const int a = have ? V.lead(lbase + c) : 0;
+                    const float xa = V.x(a), ya = V.y(a), za = V.z(a);
                     for (; pidx < P; ++pidx) {
                         if (n_next >= kQueueCap) { full = true; break; }
                         bool alive = have && (todo == 0u || ((todo >> lane) & 1u));
@@ -597,7 +621,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                 done = r >= nrows;
             } else {
                 // same-residue position: lanes cover (partial, residue slot) items
-                const int shift = S.res_shift;
+                const int shift = V.res_shift;
                 const int n_it = ((P << shift) + 31) >> 5;
                 const uint32_t *crow = L.compat + (size_t)L.plan_ttype[a0 + k] * L.class_words_cap;
                 int it = cur;
@@ -612,11 +636,11 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     const int a = (payload & 0xffff) + sidx;
                     alive = alive && sidx < (payload >> 16);
                     if (alive) {
-                        const unsigned kl = S.klass[a];
+                        const unsigned kl = V.klass(a);
                         alive = (__ldg(crow + (kl >> 5)) >> (kl & 31u)) & 1u;
                     }
                     if (alive) {
-                        const float dx = S.x[a] - an.x, dy = S.y[a] - an.y, dz = S.z[a] - an.z;
+                        const float dx = V.x(a) - an.x, dy = V.y(a) - an.y, dz = V.z(a) - an.z;
                         const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
                         alive = fabsf(d - dt_anchor) <= rej;
                         if (kStats) ++st.evals;
@@ -668,18 +692,17 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
     __syncwarp();
 }
 
-template <bool kStats>
+template <bool kStats, bool kStaged>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 emm_search_kernel(const __grid_constant__ SearchArgs A)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item, s_next_tpl;
+    __shared__ Blob s_blob;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const SearchParams &P = A.P;
-    unsigned char *stage = smem;
-    uint32_t *Q = reinterpret_cast<uint32_t *>(smem + P.blob_cap) + (size_t)wid * P.levels * kQueueCap;
-    WarpState *ws = reinterpret_cast<WarpState *>(smem + P.blob_cap + (size_t)kSearchWarps * P.levels * kQueueCap * 4) + wid;
+    uint32_t *Q = reinterpret_cast<uint32_t *>(g_smem + P.blob_cap) + (size_t)wid * P.levels * kQueueCap;
+    WarpState *ws = reinterpret_cast<WarpState *>(g_smem + P.blob_cap + (size_t)kSearchWarps * P.levels * kQueueCap * 4) + wid;
 
     LaneStats st = {0ull, 0ull, 0ull};
     unsigned long long st_pairs = 0, st_staged = 0, st_global = 0;
@@ -698,41 +721,35 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
         const int te = min(P.template_end, tb + per);
         const bool run = hdr.status == 0 && hdr.n_kept > 0 && tb < te && !(A.skip && A.skip[s]);
         if (run) {
-            const unsigned char *base = gblob;
-            if (hdr.staged_bytes <= P.blob_cap) {
+            if (kStaged) {
+                // host guarantees staged_bytes <= blob_cap for every structure of the batch
                 const int4 *src = reinterpret_cast<const int4 *>(gblob);
-                int4 *dst = reinterpret_cast<int4 *>(stage);
+                int4 *dst = reinterpret_cast<int4 *>(g_smem);
                 for (int i = tid; i < hdr.staged_bytes / 16; i += kSearchThreads) dst[i] = __ldg(src + i);
-                base = stage;
                 if (kStats && tid == 0) st_staged += hdr.staged_bytes;
             } else if (kStats && tid == 0) {
                 ++st_global;
             }
-            if (tid == 0) s_next_tpl = tb;
+            if (tid == 0) {
+                s_next_tpl = tb;
+                const int64_t abase = A.B.atom_off[s];
+                s_blob.orig = reinterpret_cast<const int32_t *>(gblob + hdr.off_orig);
+                s_blob.xyz64 = A.B.xyz + 3 * abase;
+                s_blob.chain = A.B.chain ? A.B.chain + abase : nullptr;
+                s_blob.atom_id = A.B.atom_id ? A.B.atom_id + abase : nullptr;
+            }
             __syncthreads();
-            Blob S;
-            S.x = reinterpret_cast<const float *>(base + hdr.off_x);
-            S.y = reinterpret_cast<const float *>(base + hdr.off_y);
-            S.z = reinterpret_cast<const float *>(base + hdr.off_z);
-            S.res_of = reinterpret_cast<const uint16_t *>(base + hdr.off_res);
-            S.res_start = reinterpret_cast<const uint16_t *>(base + hdr.off_resstart);
-            S.klass = reinterpret_cast<const uint16_t *>(base + hdr.off_klass);
-            S.lead_off = reinterpret_cast<const uint32_t *>(base + hdr.off_leadoff);
-            S.lead = reinterpret_cast<const uint16_t *>(base + hdr.off_lead);
-            S.orig = reinterpret_cast<const int32_t *>(gblob + hdr.off_orig);
-            const int64_t abase = A.B.atom_off[s];
-            S.xyz64 = A.B.xyz + 3 * abase;
-            S.chain = A.B.chain ? A.B.chain + abase : nullptr;
-            S.atom_id = A.B.atom_id ? A.B.atom_id + abase : nullptr;
-            S.res_shift = hdr.res_shift;
-            S.n_kept = hdr.n_kept;
-            S.eps = hdr.eps;
+            View<kStaged> V;
+            V.gbase = gblob;
+            V.off_x = hdr.off_x; V.off_y = hdr.off_y; V.off_z = hdr.off_z; V.off_res = hdr.off_res;
+            V.off_resstart = hdr.off_resstart; V.off_klass = hdr.off_klass; V.off_leadoff = hdr.off_leadoff;
+            V.off_lead = hdr.off_lead; V.res_shift = hdr.res_shift; V.eps = hdr.eps;
             for (;;) {
                 int t = 0;
                 if (lane == 0) t = atomicAdd(&s_next_tpl, 1);
                 t = __shfl_sync(kFull, t, 0);
                 if (t >= te) break;
-                search_template<kStats>(A, S, s, t, Q, ws, lane, st);
+                search_template<kStats, kStaged>(A, s_blob, V, s, t, Q, ws, lane, st);
                 if (kStats && lane == 0) ++st_pairs;
             }
         }
@@ -770,9 +787,11 @@ size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels); }
 
 cudaError_t configure_search(int smem_bytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(emm_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(emm_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(emm_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    return e;
 }
 
 void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream)
@@ -781,13 +800,15 @@ void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsi
 }
 
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, bool stats, int grid, size_t smem, cudaStream_t stream)
+                   const unsigned char *skip, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream)
 {
     if (P.n_items <= 0) return;
     SearchArgs A;
     A.L = L; A.B = B; A.P = P; A.O = O; A.skip = skip;
-    if (stats) emm_search_kernel<true><<<grid, kSearchThreads, smem, stream>>>(A);
-    else emm_search_kernel<false><<<grid, kSearchThreads, smem, stream>>>(A);
+    if (stats && staged) emm_search_kernel<true, true><<<grid, kSearchThreads, smem, stream>>>(A);
+    else if (stats) emm_search_kernel<true, false><<<grid, kSearchThreads, smem, stream>>>(A);
+    else if (staged) emm_search_kernel<false, true><<<grid, kSearchThreads, smem, stream>>>(A);
+    else emm_search_kernel<false, false><<<grid, kSearchThreads, smem, stream>>>(A);
 }
 
 }  // namespace emm
