@@ -480,7 +480,9 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     bool border = false;
     const float *row = L.pair_dist32 + p0 + ((k - 1) * (k - 2)) / 2;
     uint32_t w = e;
-    for (int pos = k - 2; pos >= 0; --pos) {
+    // a chunk that was validated on an earlier visit only needs its anchors again: stop the walk there
+    const int stop = __any_sync(kFull, check) ? 0 : (anchor_pos < 0 ? k - 1 : anchor_pos);
+    for (int pos = k - 2; pos >= stop; --pos) {
         w = Q[(pos + 1) * kQueueCap + ((w >> 16) & 0xffu)];
         const int b = (int)(w & 0xffffu);
         const float xb = V.x(b), yb = V.y(b), zb = V.z(b);

@@ -97,7 +97,10 @@ class CompiledLibrary:
     """
 
     def __init__(self, templates: Sequence[JessTemplate], rmsd_threshold, distance_cutoff,
-                 max_dynamic_distance, lr_models: Optional[dict] = None):
+                 max_dynamic_distance, lr_models: Optional[dict] = None, plan_order: str = "leaders_first"):
+        if plan_order not in ("leaders_first", "residue_major"):
+            raise ValueError("plan_order must be 'leaders_first' or 'residue_major'")
+        self.plan_order = plan_order
         self.templates = list(templates)
         if not self.templates:
             raise ValueError("cannot compile an empty template list")
@@ -291,6 +294,18 @@ class CompiledLibrary:
             remaining.remove(nxt)
         order: List[int] = []
         src_of: Dict[int, Optional[int]] = {}
+        if self.plan_order == "leaders_first":
+            # every residue's leader first (cheap one-distance filters prune whole residues), then
+            # the remaining atoms of each residue, which only have to be looked up inside it
+            for g in seq:
+                order.append(leaders[g])
+                src_of[leaders[g]] = None
+            for g in seq:
+                for i in glist[g]:
+                    if i != leaders[g]:
+                        order.append(i)
+                        src_of[i] = leaders[g]
+            return order, src_of
         for g in seq:
             lead = leaders[g]
             order.append(lead)

@@ -20,7 +20,7 @@ def main():
     templates = active_templates()
     dists = [DEFAULT_DIST[min(t.effective_size, 8)] for t in templates]
     workload = make_workload(0, n, 400, 1, 8)
-    engine = Engine(CompiledLibrary(templates, 2.0, dists, dists))
+    engine = Engine(CompiledLibrary(templates, 2.0, dists, dists, plan_order=os.environ.get("EMM_PLAN", "leaders_first")))
     batch = workload.to_packed(engine.compiled)
     sess = engine.session_for(batch.n_atoms, batch.n_structures)
     sess.upload(batch)
