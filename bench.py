@@ -142,12 +142,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def committed_traffic_bytes():
-    """dram bytes per search launch from the committed ncu capture, if one is recorded."""
+def committed_traffic_bytes(n_structures: int):
+    """dram__bytes_read+write of the search kernel per launch, from the committed ncu --set full
+    capture (taken at a smaller batch; scaled per structure to this launch's batch)."""
     path = ROOT / "profiles" / "roofline_traffic.json"
     if path.exists():
         try:
-            return json.loads(path.read_text()).get("search_kernel_dram_bytes_per_launch")
+            return int(json.loads(path.read_text())["search_kernel_dram_bytes_per_structure"] * n_structures)
         except Exception:
             return None
     return None
@@ -321,7 +322,7 @@ def run_b200(args, rank, local_rank, world):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": committed_traffic_bytes(),
+                     "frac": achieved / peak if peak else None, "traffic": committed_traffic_bytes(host.n_structures),
                      "peak_source": peak_src, "kernel": "emm_search_kernel",
                      "kernel_ms_avg": avg_search_ms, "prepare_kernel_ms_avg": sum(prepare_ms) / max(len(prepare_ms), 1),
                      "algorithmic_bytes_per_launch": int(alg_bytes),
