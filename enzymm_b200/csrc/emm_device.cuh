@@ -18,9 +18,15 @@
 namespace emm {
 
 constexpr int kMaxAtoms = EMM_MAX_TEMPLATE_ATOMS;
-constexpr int kSearchThreads = 512;
+constexpr int kSearchThreads = 768;
 constexpr int kSearchWarps = kSearchThreads / 32;
-constexpr int kQueueCap = 48;          // entries per search level per warp (parent index is 8 bits)
+// Per-warp trie queues: the first kWideLevels levels hold kQueueCap entries, deeper (rarely
+// populated) levels kDeepCap.  Parent indices are 8 bits.
+constexpr int kQueueCap = 48;
+constexpr int kDeepCap = 16;
+constexpr int kWideLevels = 9;
+__host__ __device__ constexpr int queue_off(int k) { return k <= kWideLevels ? k * kQueueCap : kWideLevels * kQueueCap + (k - kWideLevels) * kDeepCap; }
+__host__ __device__ constexpr int queue_cap(int k) { return k < kWideLevels ? kQueueCap : kDeepCap; }
 constexpr int kPrepThreads = 256;
 constexpr float kCellSize = 6.0f;      // uniform grid cell edge (Angstrom)
 constexpr int kMaxCellsPerAxis = 64;

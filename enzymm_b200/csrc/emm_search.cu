@@ -52,7 +52,7 @@ struct WarpState {
     int n[kMaxAtoms + 1];        // entries queued per level
     int chunk[kMaxAtoms + 1];    // size of the level's current chunk (its last `chunk` entries)
     int cur[kMaxAtoms + 1];      // expansion cursor inside the chunk
-    unsigned todo[kMaxAtoms + 1];// lanes of iteration `cur` still to be pushed (0 = fresh iteration)
+    unsigned long long todo[kMaxAtoms + 1];   // lanes (two candidate rows) of iteration `cur` still to be pushed
     float4 anchor[32];           // per chunk slot: anchor atom xyz, w = payload bits
     unsigned char vslot[32];     // compacted list of valid chunk slots
     double best_rmsd;
@@ -110,7 +110,7 @@ struct SearchArgs {
 __device__ __forceinline__ float fast_sqrt(float v)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
 
@@ -375,10 +375,10 @@ __device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S
     bool have = (valid >> lane) & 1u;
     uint16_t asg[kMaxAtoms];
     if (have) {
-        uint32_t w = Q[m * kQueueCap + base + lane];
+        uint32_t w = Q[queue_off(m) + base + lane];
         for (int pos = m - 1; pos >= 0; --pos) {
             asg[L.plan_atom[a0 + pos]] = (uint16_t)(w & 0xffffu);
-            if (pos > 0) w = Q[pos * kQueueCap + ((w >> 16) & 0xffu)];
+            if (pos > 0) w = Q[queue_off(pos) + ((w >> 16) & 0xffu)];
         }
         if (!A.P.ignore_chain && S.chain) {
             // template atoms on equal chains <=> query atoms on equal chains (oracle rule 11)
@@ -444,7 +444,7 @@ __device__ __noinline__ bool exact_validate(const DevLibrary &L, const Blob &S, 
     const double *row64 = L.pair_dist + p0 + ((k - 1) * (k - 2)) / 2;
     uint32_t w = e;
     for (int pos = k - 2; pos >= 0; --pos) {
-        w = Q[(pos + 1) * kQueueCap + ((w >> 16) & 0xffu)];
+        w = Q[queue_off(pos + 1) + ((w >> 16) & 0xffu)];
         const double d = exact_dist(S.xyz64, oa, S.orig[w & 0xffffu]);
         const double delta = pair_delta(L, a0, k - 1, pos, cut, dyn);
         if (!(fabs(DSUB(d, row64[pos])) <= delta)) return false;
@@ -467,7 +467,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
 {
     const DevLibrary &L = A.L;
     const bool have = lane < size;
-    uint32_t e = have ? Q[k * kQueueCap + base + lane] : kEntryDead;
+    uint32_t e = have ? Q[queue_off(k) + base + lane] : kEntryDead;
     bool alive = !(e & kEntryDead);
     const bool check = alive && !(e & kEntryValid);
     const int a = (int)(e & 0xffffu);
@@ -483,7 +483,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     // a chunk that was validated on an earlier visit only needs its anchors again: stop the walk there
     const int stop = __any_sync(kFull, check) ? 0 : (anchor_pos < 0 ? k - 1 : anchor_pos);
     for (int pos = k - 2; pos >= stop; --pos) {
-        w = Q[(pos + 1) * kQueueCap + ((w >> 16) & 0xffu)];
+        w = Q[queue_off(pos + 1) + ((w >> 16) & 0xffu)];
         const int b = (int)(w & 0xffffu);
         const float xb = V.x(b), yb = V.y(b), zb = V.z(b);
         if (pos == anchor_pos) { ax = xb; ay = yb; az = zb; aatom = b; }
@@ -501,7 +501,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
         if (kStats) ++st.exact;
         alive = exact_validate(L, S, Q, a0, p0, k, e, cut64, dyn64);
     }
-    if (check) Q[k * kQueueCap + base + lane] = e | (alive ? kEntryValid : kEntryDead);
+    if (check) Q[queue_off(k) + base + lane] = e | (alive ? kEntryValid : kEntryDead);
     const unsigned valid = __ballot_sync(kFull, alive);
     if (alive && k < m) {
         int payload = aatom;
@@ -510,8 +510,9 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
             const int rs = V.res_start(r);
             payload = rs | ((V.res_start(r + 1) - rs) << 16);
         }
-        ws->anchor[lane] = make_float4(ax, ay, az, __int_as_float(payload));
-        ws->vslot[__popc(valid & ((1u << lane) - 1u))] = (unsigned char)lane;
+        const int rank = __popc(valid & ((1u << lane) - 1u));      // anchors are stored compacted
+        ws->anchor[rank] = make_float4(ax, ay, az, __int_as_float(payload));
+        ws->vslot[rank] = (unsigned char)lane;
     }
     __syncwarp();
     return valid;
@@ -541,7 +542,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
     const float eps = V.eps;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0u; }
+    if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0ull; }
     if (lane == 0) { ws->best_valid = 0; ws->overflow = 0; ws->n_complete = 0ull; ws->best_rmsd = CUDART_INF; }
     __syncwarp();
 
@@ -567,57 +568,82 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             const int P = __popc(valid);
             int n_next = ws->n[k + 1];
             int cur = ws->cur[k];
-            unsigned todo = ws->todo[k];
-            uint32_t *Qn = Q + (k + 1) * kQueueCap;
-            const int apos = L.plan_anchor[a0 + k];
-            float dt_anchor = 0.f, rej = 0.f;
+            unsigned long long todo = ws->todo[k];
+            uint32_t *Qn = Q + queue_off(k + 1);
+            const int cap_next = queue_cap(k + 1);
+            // squared acceptance band of the anchor constraint (widened by eps and FP32 rounding)
+            float lo2 = 0.f, hi2 = 3.0e38f;
             if (k > 0) {
-                dt_anchor = __ldg(L.pair_dist32 + p0 + (k * (k - 1)) / 2 + apos);
-                rej = (dynamic ? (float)pair_delta(L, a0, k, apos, cut64, dyn64) : cut32) + eps;
+                const int apos = L.plan_anchor[a0 + k];
+                const float dt = __ldg(L.pair_dist32 + p0 + (k * (k - 1)) / 2 + apos);
+                const float rej = (dynamic ? (float)pair_delta(L, a0, k, apos, cut64, dyn64) : cut32) + eps;
+                const float lo = fmaxf(dt - rej, 0.f), hi = dt + rej;
+                lo2 = lo * lo * 0.999999f;
+                hi2 = hi * hi * 1.000001f;
             }
             bool full = false, done = false;
             const int n_before = n_next;
+            // push the lanes of `sv` (ballot of `alive`) into the next queue; returns the lanes that
+            // did not fit (0 = all pushed)
+            auto push = [&](unsigned sv, bool alive, int a, int parent) -> unsigned {
+                const int room = cap_next - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
+                if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)parent << 16) | (uint32_t)a;
+                if (cnt > room) {
+                    n_next = cap_next;
+                    return __ballot_sync(kFull, alive && rank >= room);
+                }
+                n_next += cnt;
+                return 0u;
+            };
             if (src < 0) {
-                // leader position: lane <-> candidate of the leader list, loop over partials
+                // leader position: every lane holds up to two candidates of the leader list in
+                // registers (rows r, r+1) and the warp loops over the chunk's partials
                 const int lbase = V.lead_off(-1 - src);
                 const int B = V.lead_off(-src) - lbase;
                 const int nrows = (B + 31) >> 5;
-                int r = cur / P, pidx = cur - r * P;
+                int r = cur / P, pidx = cur - r * P;       // r is always even or the last row
                 while (r < nrows) {
-                    const int c = (r << 5) + lane;
-                    const bool have = c < B;
-                    const int a = have ? V.lead(lbase + c) : 0;
-                    const float xa = V.x(a), ya = V.y(a), za = V.z(a);
+                    const int c0 = (r << 5) + lane, c1 = c0 + 32;
+                    const bool have0 = c0 < B, have1 = c1 < B;
+                    const bool two = ((r + 1) << 5) < B;       // warp-uniform: a second row exists
+                    const int a_0 = have0 ? V.lead(lbase + c0) : 0, a_1 = have1 ? V.lead(lbase + c1) : 0;
+                    const float x0 = V.x(a_0), y0 = V.y(a_0), z0 = V.z(a_0);
+                    const float x1 = V.x(a_1), y1 = V.y(a_1), z1 = V.z(a_1);
                     for (; pidx < P; ++pidx) {
-                        if (n_next >= kQueueCap) { full = true; break; }
-                        bool alive = have && (todo == 0u || ((todo >> lane) & 1u));
-                        int slot = 0;
+                        if (n_next >= cap_next) { full = true; break; }
+                        bool alive0 = have0, alive1 = have1;
+                        if (todo) { alive0 = alive0 && ((todo >> lane) & 1ull); alive1 = alive1 && ((todo >> (32 + lane)) & 1ull); }
                         if (k > 0) {
-                            slot = ws->vslot[pidx];
-                            const float4 an = ws->anchor[slot];
-                            const float dx = xa - an.x, dy = ya - an.y, dz = za - an.z;
-                            const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-                            alive = alive && fabsf(d - dt_anchor) <= rej && a != __float_as_int(an.w);
-                            if (kStats) st.evals += have;
+                            const float4 an = ws->anchor[pidx];
+                            float dx = x0 - an.x, dy = y0 - an.y, dz = z0 - an.z;
+                            const float d0 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                            alive0 = alive0 && d0 >= lo2 && d0 <= hi2;
+                            if (two) {
+                                dx = x1 - an.x; dy = y1 - an.y; dz = z1 - an.z;
+                                const float d1 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                                alive1 = alive1 && d1 >= lo2 && d1 <= hi2;
+                            }
+                            if (kStats) st.evals += (int)have0 + (int)have1;
                         }
                         if (kStats && lane == 0) ++st.sweeps;
-                        const unsigned sv = __ballot_sync(kFull, alive);
-                        if (sv) {
-                            const int room = kQueueCap - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
-                            if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)(base + slot) << 16) | (uint32_t)a;
-                            if (cnt > room) {
-                                n_next = kQueueCap;
-                                todo = __ballot_sync(kFull, alive && rank >= room);
+                        const unsigned sv0 = __ballot_sync(kFull, alive0);
+                        const unsigned sv1 = two ? __ballot_sync(kFull, alive1) : 0u;
+                        todo = 0ull;
+                        if (sv0 | sv1) {
+                            const int parent = k > 0 ? base + (int)ws->vslot[pidx] : 0;
+                            unsigned left0 = 0u, left1 = 0u;
+                            if (sv0) left0 = push(sv0, alive0, a_0, parent);
+                            if (sv1) left1 = left0 ? sv1 : push(sv1, alive1, a_1, parent);
+                            if (left0 | left1) {
+                                todo = (unsigned long long)left0 | ((unsigned long long)left1 << 32);
                                 full = true;
                                 break;
                             }
-                            n_next += cnt;
                         }
-                        todo = 0u;
                     }
                     if (full) break;
                     pidx = 0;
-                    ++r;
+                    r += 2;
                 }
                 cur = r * P + pidx;
                 done = r >= nrows;
@@ -628,12 +654,11 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                 const uint32_t *crow = L.compat + (size_t)L.plan_ttype[a0 + k] * L.class_words_cap;
                 int it = cur;
                 for (; it < n_it; ++it) {
-                    if (n_next >= kQueueCap) { full = true; break; }
+                    if (n_next >= cap_next) { full = true; break; }
                     const int item = (it << 5) + lane;
                     const int pidx = item >> shift, sidx = item & ((1 << shift) - 1);
-                    bool alive = pidx < P && (todo == 0u || ((todo >> lane) & 1u));
-                    const int slot = alive ? (int)ws->vslot[pidx] : 0;
-                    const float4 an = ws->anchor[slot];
+                    bool alive = pidx < P && (todo == 0ull || ((todo >> lane) & 1ull));
+                    const float4 an = ws->anchor[alive ? pidx : 0];
                     const int payload = __float_as_int(an.w);
                     const int a = (payload & 0xffff) + sidx;
                     alive = alive && sidx < (payload >> 16);
@@ -643,24 +668,18 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     }
                     if (alive) {
                         const float dx = V.x(a) - an.x, dy = V.y(a) - an.y, dz = V.z(a) - an.z;
-                        const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-                        alive = fabsf(d - dt_anchor) <= rej;
+                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        alive = d2 >= lo2 && d2 <= hi2;
                         if (kStats) ++st.evals;
                     }
                     if (kStats && lane == 0) ++st.sweeps;
                     const unsigned sv = __ballot_sync(kFull, alive);
+                    todo = 0ull;
                     if (sv) {
-                        const int room = kQueueCap - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
-                        if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)(base + slot) << 16) | (uint32_t)a;
-                        if (cnt > room) {
-                            n_next = kQueueCap;
-                            todo = __ballot_sync(kFull, alive && rank >= room);
-                            full = true;
-                            break;
-                        }
-                        n_next += cnt;
+                        const int parent = alive ? base + (int)ws->vslot[pidx] : 0;
+                        const unsigned left = push(sv, alive, a, parent);
+                        if (left) { todo = left; full = true; break; }
                     }
-                    todo = 0u;
                 }
                 cur = it;
                 done = it >= n_it;
@@ -670,7 +689,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             if (full || (done && n_next > 0)) {
                 // descend: the last <= 32 entries of the next level form its chunk
                 ++k;
-                if (lane == 0) { ws->chunk[k] = min(32, n_next); ws->cur[k] = 0; ws->todo[k] = 0u; }
+                if (lane == 0) { ws->chunk[k] = min(32, n_next); ws->cur[k] = 0; ws->todo[k] = 0ull; }
                 __syncwarp();
                 entered = false;
                 continue;
@@ -683,7 +702,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             ws->n[k] = base;
             ws->chunk[k] = min(32, base);
             ws->cur[k] = 0;
-            ws->todo[k] = 0u;
+            ws->todo[k] = 0ull;
         }
         __syncwarp();
         if (base == 0) --k;           // back to the parent level: its chunk, cursor and todo are intact
@@ -703,8 +722,9 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const SearchParams &P = A.P;
-    uint32_t *Q = reinterpret_cast<uint32_t *>(g_smem + P.blob_cap) + (size_t)wid * P.levels * kQueueCap;
-    WarpState *ws = reinterpret_cast<WarpState *>(g_smem + P.blob_cap + (size_t)kSearchWarps * P.levels * kQueueCap * 4) + wid;
+    const int qwords = queue_off(P.levels);      // queue words per warp
+    uint32_t *Q = reinterpret_cast<uint32_t *>(g_smem + P.blob_cap) + (size_t)wid * qwords;
+    WarpState *ws = reinterpret_cast<WarpState *>(g_smem + P.blob_cap + (size_t)kSearchWarps * qwords * 4) + wid;
 
     LaneStats st = {0ull, 0ull, 0ull};
     unsigned long long st_pairs = 0, st_staged = 0, st_global = 0;
@@ -782,7 +802,7 @@ __global__ void emm_skip_snapshot_kernel(int n, int mode, const int *any, const 
 
 size_t search_smem_bytes(int blob_cap, int levels)
 {
-    return (size_t)blob_cap + (size_t)kSearchWarps * levels * kQueueCap * 4 + (size_t)kSearchWarps * sizeof(WarpState);
+    return (size_t)blob_cap + (size_t)kSearchWarps * queue_off(levels) * 4 + (size_t)kSearchWarps * sizeof(WarpState);
 }
 
 size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels); }
