@@ -249,12 +249,17 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms: float) -> float:
+    per_rank = {}
+
+    def max_over_ranks(ms: float, label: str = "") -> float:
         if world == 1:
+            per_rank[label] = [ms]
             return ms
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank[label] = [float(x.item()) for x in every]
+        return max(per_rank[label])
 
     hits = None
     for _ in range(args.warmup):
@@ -277,7 +282,7 @@ def run_b200(args, rank, local_rank, world):
     e1.record()
     barrier()
     windows.append((w0, time.time()))
-    resident_ms = max_over_ranks(e0.elapsed_time(e1))
+    resident_ms = max_over_ranks(e0.elapsed_time(e1), "resident")
     search_ms = session.kernel_ms("search")
     prepare_ms = session.kernel_ms("prepare")
     launches = session.last_launches * args.steps
@@ -297,7 +302,7 @@ def run_b200(args, rank, local_rank, world):
     f1.record()
     barrier()
     windows.append((w0, time.time()))
-    e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+    e2e_ms = max_over_ranks(f0.elapsed_time(f1), "e2e")
     clocks = sampler.stop(windows) if sampler else None
 
     # ---- sanity outside the timed regions: planted motifs are being found ---------------------------
@@ -332,6 +337,7 @@ def run_b200(args, rank, local_rank, world):
         "planted_recovered": f"{recovered}/{len(workload.planted)}",
         "atoms_per_structure": host.n_atoms / max(host.n_structures, 1),
         "clocks": clocks, "generation_s": t_gen,
+        "per_rank_ms": {k: [round(v / args.steps, 2) for v in vals] for k, vals in per_rank.items()},
     })
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()

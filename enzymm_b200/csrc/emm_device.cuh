@@ -18,7 +18,10 @@
 namespace emm {
 
 constexpr int kMaxAtoms = EMM_MAX_TEMPLATE_ATOMS;
-constexpr int kSearchThreads = 768;
+#ifndef EMM_SEARCH_THREADS
+#define EMM_SEARCH_THREADS 768
+#endif
+constexpr int kSearchThreads = EMM_SEARCH_THREADS;
 constexpr int kSearchWarps = kSearchThreads / 32;
 // Per-warp trie queues: the first kWideLevels levels hold kQueueCap entries, deeper (rarely
 // populated) levels kDeepCap.  Parent indices are 8 bits.

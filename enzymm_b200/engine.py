@@ -81,7 +81,8 @@ class _Stats(ctypes.Structure):
 
 
 def library_path() -> Path:
-    return Path(__file__).resolve().parent / "libenzymm_b200.so"
+    override = os.environ.get("EMM_LIBRARY")          # development: try another build of the same ABI
+    return Path(override) if override else Path(__file__).resolve().parent / "libenzymm_b200.so"
 
 
 _cdll = None
