@@ -1,0 +1,300 @@
+// emm_pdb.cpp -- native PDB ingest for the matching path (replaces what
+// pyjess.Molecule.load does in C inside Jess, call site enzymm/jess_run.py:538).
+//
+// Fixed-column reader: ATOM and HETATM records, in file order, up to the first ENDMDL (SURVEY 8c
+// rule 1); coordinates go through strtod, i.e. they are exactly the doubles Python's float()
+// yields for the same text.  emm_pdb_load_files reads and parses many files on a thread pool into
+// one SoA batch, which is what the batched upload wants.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/enzymm_b200.h"
+
+namespace {
+
+thread_local std::string t_error;
+
+inline bool is_coord_record(const char *p, int64_t n)
+{
+    return n >= 6 && (memcmp(p, "ATOM  ", 6) == 0 || memcmp(p, "HETATM", 6) == 0);
+}
+
+// copy columns [a, b) of a line (clipped to its length) stripped of blanks, NUL padded to width
+inline void field(const char *line, int64_t len, int a, int b, char *dst, int width)
+{
+    memset(dst, 0, (size_t)width);
+    int lo = a, hi = std::min<int64_t>(b, len);
+    while (lo < hi && (line[lo] == ' ' || line[lo] == '\t')) ++lo;
+    while (hi > lo && (line[hi - 1] == ' ' || line[hi - 1] == '\t' || line[hi - 1] == '\r')) --hi;
+    for (int i = 0; lo + i < hi && i < width; ++i) dst[i] = line[lo + i];
+}
+
+inline bool parse_int(const char *line, int64_t len, int a, int b, int32_t *out)
+{
+    char buf[16];
+    field(line, len, a, b, buf, 15);
+    buf[15] = 0;
+    if (!buf[0]) return false;
+    char *end = nullptr;
+    const long v = strtol(buf, &end, 10);
+    if (*end) return false;
+    *out = (int32_t)v;
+    return true;
+}
+
+// Plain fixed-point decimals ("-12.345") are converted as mantissa / 10^k with one correctly
+// rounded division: mantissa < 2^53 and 10^k (k <= 18) are exact doubles, so the quotient is the
+// double nearest to the decimal -- bit-identical to strtod.  Anything else falls back to strtod.
+inline bool fast_real(const char *p, const char *end, double *out)
+{
+    static const double pow10[19] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12,
+                                     1e13, 1e14, 1e15, 1e16, 1e17, 1e18};
+    bool neg = false;
+    if (p < end && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    uint64_t mant = 0;
+    int digits = 0, frac = 0;
+    bool dot = false;
+    for (; p < end; ++p) {
+        if (*p >= '0' && *p <= '9') {
+            mant = mant * 10 + (uint64_t)(*p - '0');
+            ++digits;
+            if (dot) ++frac;
+        } else if (*p == '.' && !dot) {
+            dot = true;
+        } else {
+            return false;
+        }
+    }
+    if (digits == 0 || digits > 15 || frac > 18) return false;
+    const double v = (double)mant / pow10[frac];
+    *out = neg ? -v : v;
+    return true;
+}
+
+inline bool parse_real(const char *line, int64_t len, int a, int b, double *out, bool optional)
+{
+    {
+        int lo = a, hi = (int)std::min<int64_t>(b, len);
+        while (lo < hi && line[lo] == ' ') ++lo;
+        while (hi > lo && (line[hi - 1] == ' ' || line[hi - 1] == '\r')) --hi;
+        if (lo == hi) { *out = 0.0; return optional; }
+        if (fast_real(line + lo, line + hi, out)) return true;
+    }
+    char buf[24];
+    field(line, len, a, b, buf, 23);
+    buf[23] = 0;
+    if (!buf[0]) { *out = 0.0; return optional; }
+    char *end = nullptr;
+    *out = strtod(buf, &end);
+    return *end == 0;
+}
+
+struct Columns {
+    int32_t *serial; char *name; char *altloc; char *resname; char *chain; int32_t *resnum; char *icode;
+    double *xyz; double *occupancy; double *bfactor; char *segment; char *element; int8_t *charge;
+};
+
+int64_t count_atoms(const char *text, int64_t len)
+{
+    int64_t n = 0, pos = 0;
+    while (pos < len) {
+        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
+        const int64_t end = nl ? nl - text : len;
+        const char *line = text + pos;
+        const int64_t ll = end - pos;
+        if (is_coord_record(line, ll)) ++n;
+        else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) break;
+        pos = end + 1;
+    }
+    return n;
+}
+
+// returns atoms parsed, or -1 (t_error set)
+int64_t parse_into(const char *text, int64_t len, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
+{
+    int64_t n = 0, pos = 0;
+    bool have_header = false;
+    memset(header_id, 0, 5);
+    while (pos < len) {
+        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
+        const int64_t end = nl ? nl - text : len;
+        const char *line = text + pos;
+        int64_t ll = end - pos;
+        while (ll > 0 && line[ll - 1] == '\r') --ll;
+        if (is_coord_record(line, ll)) {
+            if (n >= capacity) { t_error = "atom capacity exceeded"; return -1; }
+            const int64_t i = base + n;
+            double x, y, z;
+            if (ll < 54 || !parse_int(line, ll, 6, 11, c.serial + i) || !parse_int(line, ll, 22, 26, c.resnum + i) ||
+                !parse_real(line, ll, 30, 38, &x, false) || !parse_real(line, ll, 38, 46, &y, false) ||
+                !parse_real(line, ll, 46, 54, &z, false) || !parse_real(line, ll, 54, 60, c.occupancy + i, true) ||
+                !parse_real(line, ll, 60, 66, c.bfactor + i, true)) {
+                t_error = "malformed PDB coordinate record: " + std::string(line, (size_t)std::min<int64_t>(ll, 80));
+                return -1;
+            }
+            c.xyz[3 * i] = x; c.xyz[3 * i + 1] = y; c.xyz[3 * i + 2] = z;
+            field(line, ll, 12, 16, c.name + 4 * i, 4);
+            c.altloc[i] = ll > 16 ? line[16] : ' ';
+            field(line, ll, 17, 20, c.resname + 4 * i, 4);
+            field(line, ll, 20, 22, c.chain + 2 * i, 2);
+            c.icode[i] = ll > 26 ? line[26] : ' ';
+            field(line, ll, 72, 76, c.segment + 4 * i, 4);
+            field(line, ll, 76, 78, c.element + 2 * i, 2);
+            char chg[3];
+            field(line, ll, 78, 80, chg, 2);
+            chg[2] = 0;
+            int8_t q = 0;
+            if (chg[0] >= '0' && chg[0] <= '9') q = (int8_t)((chg[0] - '0') * ((chg[1] == '-') ? -1 : 1));
+            c.charge[i] = q;
+            ++n;
+        } else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) {
+            break;
+        } else if (!have_header && ll >= 6 && memcmp(line, "HEADER", 6) == 0) {
+            have_header = true;
+            char id[5];
+            field(line, ll, 62, 66, id, 4);
+            id[4] = 0;
+            memcpy(header_id, id, 5);
+        }
+        pos = end + 1;
+    }
+    return n;
+}
+
+bool read_file(const char *path, std::string &out, int *err)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { *err = 1; return false; }
+    if (fseek(f, 0, SEEK_END) != 0) { fclose(f); *err = 2; return false; }   // directories fail here or at read
+    const long size = ftell(f);
+    if (size < 0) { fclose(f); *err = 2; return false; }
+    rewind(f);
+    out.resize((size_t)size);
+    const size_t got = size ? fread(&out[0], 1, (size_t)size, f) : 0;
+    fclose(f);
+    if (got != (size_t)size) { *err = 2; return false; }
+    return true;
+}
+
+}  // namespace
+
+struct emm_pdb_batch {
+    int32_t n_files = 0;
+    int64_t n_atoms = 0;
+    std::vector<int64_t> atom_off;
+    std::vector<int32_t> serial, resnum;
+    std::vector<char> name, altloc, resname, chain, icode, segment, element, header_id;
+    std::vector<double> xyz, occupancy, bfactor;
+    std::vector<int8_t> charge;
+};
+
+extern "C" {
+
+const char *emm_pdb_last_error(void) { return t_error.c_str(); }
+
+int emm_pdb_count_atoms(const char *text, int64_t len, int64_t *n_atoms)
+{
+    if (!text || !n_atoms || len < 0) return EMM_ERR_INVALID;
+    *n_atoms = count_atoms(text, len);
+    return EMM_OK;
+}
+
+int emm_pdb_parse(const char *text, int64_t len, int64_t capacity, int32_t *serial, char *name, char *altloc,
+                  char *resname, char *chain, int32_t *resnum, char *icode, double *xyz, double *occupancy,
+                  double *bfactor, char *segment, char *element, int8_t *charge, char *header_id, int64_t *n_atoms)
+{
+    if (!text || !n_atoms || len < 0 || !header_id) return EMM_ERR_INVALID;
+    Columns c{serial, name, altloc, resname, chain, resnum, icode, xyz, occupancy, bfactor, segment, element, charge};
+    const int64_t n = parse_into(text, len, c, 0, capacity, header_id);
+    if (n < 0) return EMM_ERR_INPUT;
+    *n_atoms = n;
+    return EMM_OK;
+}
+
+int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out)
+{
+    if (!paths || !out || n_files < 0) return EMM_ERR_INVALID;
+    *out = nullptr;
+    emm_pdb_batch *b = new emm_pdb_batch();
+    b->n_files = n_files;
+    std::vector<std::string> texts((size_t)n_files);
+    std::vector<int64_t> counts((size_t)n_files, 0);
+    std::vector<int> errs((size_t)n_files, 0);
+    if (n_threads < 1) n_threads = 1;
+    n_threads = std::min<int32_t>(n_threads, std::max(n_files, 1));
+    {
+        std::atomic<int> next(0);
+        auto work = [&]() {
+            for (int i; (i = next.fetch_add(1)) < n_files;) {
+                if (read_file(paths[i], texts[(size_t)i], &errs[(size_t)i]))
+                    counts[(size_t)i] = count_atoms(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size());
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    }
+    for (int i = 0; i < n_files; ++i)
+        if (errs[(size_t)i]) {
+            t_error = std::string(errs[(size_t)i] == 1 ? "cannot open " : "cannot read ") + paths[i];
+            const int rc = errs[(size_t)i] == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
+            delete b;
+            return rc;
+        }
+    b->atom_off.assign((size_t)n_files + 1, 0);
+    for (int i = 0; i < n_files; ++i) b->atom_off[(size_t)i + 1] = b->atom_off[(size_t)i] + counts[(size_t)i];
+    const size_t n = (size_t)b->atom_off[(size_t)n_files];
+    b->n_atoms = (int64_t)n;
+    b->serial.resize(n); b->resnum.resize(n); b->name.resize(4 * n); b->altloc.resize(n); b->resname.resize(4 * n);
+    b->chain.resize(2 * n); b->icode.resize(n); b->segment.resize(4 * n); b->element.resize(2 * n);
+    b->xyz.resize(3 * n); b->occupancy.resize(n); b->bfactor.resize(n); b->charge.resize(n);
+    b->header_id.assign(5 * (size_t)n_files, 0);
+    Columns c{b->serial.data(), b->name.data(), b->altloc.data(), b->resname.data(), b->chain.data(), b->resnum.data(),
+              b->icode.data(), b->xyz.data(), b->occupancy.data(), b->bfactor.data(), b->segment.data(),
+              b->element.data(), b->charge.data()};
+    std::atomic<int> next(0), failed(-1);
+    std::vector<std::string> messages((size_t)n_files);
+    auto work = [&]() {
+        for (int i; (i = next.fetch_add(1)) < n_files;) {
+            const int64_t got = parse_into(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size(), c,
+                                           b->atom_off[(size_t)i], counts[(size_t)i], &b->header_id[5 * (size_t)i]);
+            if (got != counts[(size_t)i]) { messages[(size_t)i] = t_error; failed.store(i); }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (failed.load() >= 0) {
+        t_error = std::string(paths[failed.load()]) + ": " + messages[(size_t)failed.load()];
+        delete b;
+        return EMM_ERR_INPUT;
+    }
+    *out = b;
+    return EMM_OK;
+}
+
+int emm_pdb_batch_columns(const emm_pdb_batch *b, emm_pdb_columns *out)
+{
+    if (!b || !out) return EMM_ERR_INVALID;
+    out->n_files = b->n_files;
+    out->n_atoms = b->n_atoms;
+    out->atom_off = b->atom_off.data();
+    out->serial = b->serial.data(); out->name = b->name.data(); out->altloc = b->altloc.data();
+    out->resname = b->resname.data(); out->chain = b->chain.data(); out->resnum = b->resnum.data();
+    out->icode = b->icode.data(); out->xyz = b->xyz.data(); out->occupancy = b->occupancy.data();
+    out->bfactor = b->bfactor.data(); out->segment = b->segment.data(); out->element = b->element.data();
+    out->charge = b->charge.data(); out->header_id = b->header_id.data();
+    return EMM_OK;
+}
+
+void emm_pdb_batch_free(emm_pdb_batch *b) { delete b; }
+
+}  // extern "C"

@@ -16,14 +16,16 @@ Behaviour pinned by the reference's goldens (SURVEY.md §8c rule 1):
 """
 from __future__ import annotations
 
+import ctypes
 import hashlib
 import io
 import os
+from pathlib import Path
 from typing import IO, Iterable, Iterator, List, Optional, Sequence, Union
 
 import numpy as np
 
-__all__ = ["Atom", "Molecule"]
+__all__ = ["Atom", "Molecule", "load_many"]
 
 _STR4 = "U4"
 
@@ -155,6 +157,75 @@ def _parse_pdb_text(lines: Iterable[str]):
     return arrays, xyz, header_id
 
 
+# ---- native ingest (enzymm_b200/csrc/emm_pdb.cpp through the C ABI) -----------------------------
+_native = None
+
+
+def _native_lib():
+    """libenzymm_b200.so for its host-only PDB entry points (they need no GPU)."""
+    global _native
+    if _native is None:
+        path = Path(__file__).resolve().parent / "libenzymm_b200.so"
+        if not path.exists():
+            raise ImportError(f"{path} is missing: build it with `make -C enzymm_b200/csrc`")
+        lib = ctypes.CDLL(str(path))
+        lib.emm_pdb_last_error.restype = ctypes.c_char_p
+        _native = lib
+    return _native
+
+
+class _PdbColumns(ctypes.Structure):
+    _fields_ = [("n_files", ctypes.c_int32), ("n_atoms", ctypes.c_int64), ("atom_off", ctypes.c_void_p)] + \
+               [(k, ctypes.c_void_p) for k in ("serial", "name", "altloc", "resname", "chain", "resnum", "icode",
+                                               "xyz", "occupancy", "bfactor", "segment", "element", "charge",
+                                               "header_id")]
+
+
+def _fixed_to_str(raw: np.ndarray, width: int) -> np.ndarray:
+    """[n*width] NUL padded bytes -> NumPy unicode column."""
+    return raw.view(f"S{width}").astype(f"U{width}") if raw.size else np.zeros(0, dtype=f"U{max(width, 1)}")
+
+
+def _columns_from_native(n, serial, name, altloc, resname, chain, resnum, icode, occ, bfac, segment, element, charge):
+    alt = altloc.view("S1")
+    ic = icode.view("S1")
+    return {
+        "serial": serial, "name": _fixed_to_str(name, 4).astype(_STR4),
+        "altloc": alt.astype("U1") if n else np.zeros(0, dtype="U1"),
+        "residue_name": _fixed_to_str(resname, 4).astype(_STR4), "chain_id": _fixed_to_str(chain, 2).astype("U2"),
+        "residue_number": resnum,
+        "insertion_code": ic.astype("U1") if n else np.zeros(0, dtype="U1"),
+        "occupancy": occ, "temperature_factor": bfac, "segment": _fixed_to_str(segment, 4).astype(_STR4),
+        "element": _fixed_to_str(element, 2).astype("U2"), "charge": charge,
+    }
+
+
+def _parse_pdb_native(data: bytes):
+    """One PDB text through emm_pdb_parse; same columns as ``_parse_pdb_text``."""
+    lib = _native_lib()
+    n = ctypes.c_int64(0)
+    lib.emm_pdb_count_atoms(data, ctypes.c_int64(len(data)), ctypes.byref(n))
+    cap = max(n.value, 1)
+    serial = np.zeros(cap, np.int32); resnum = np.zeros(cap, np.int32)
+    name = np.zeros(4 * cap, np.uint8); resname = np.zeros(4 * cap, np.uint8); chain = np.zeros(2 * cap, np.uint8)
+    segment = np.zeros(4 * cap, np.uint8); element = np.zeros(2 * cap, np.uint8)
+    altloc = np.zeros(cap, np.uint8); icode = np.zeros(cap, np.uint8)
+    xyz = np.zeros((cap, 3), np.float64); occ = np.zeros(cap, np.float64); bfac = np.zeros(cap, np.float64)
+    charge = np.zeros(cap, np.int8)
+    header = ctypes.create_string_buffer(5)
+    got = ctypes.c_int64(0)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.emm_pdb_parse(data, ctypes.c_int64(len(data)), ctypes.c_int64(cap), p(serial), p(name), p(altloc),
+                           p(resname), p(chain), p(resnum), p(icode), p(xyz), p(occ), p(bfac), p(segment),
+                           p(element), p(charge), header, ctypes.byref(got))
+    if rc != 0:
+        raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
+    k = got.value
+    cols = _columns_from_native(k, serial[:k], name[:4 * k], altloc[:k], resname[:4 * k], chain[:2 * k], resnum[:k],
+                                icode[:k], occ[:k], bfac[:k], segment[:4 * k], element[:2 * k], charge[:k])
+    return cols, xyz[:k], (header.value.decode() or None)
+
+
 class Molecule:
     """An ordered atom list (mirror of ``pyjess.Molecule``).
 
@@ -192,10 +263,13 @@ class Molecule:
         """Read a PDB file (path or text file object).  OS errors propagate unchanged
         (``FileNotFoundError`` / ``IsADirectoryError`` -> CLI errno, ``enzymm/_cli.py:318-328``)."""
         if isinstance(file, (str, os.PathLike)):
-            with open(os.fspath(file), "r") as handle:
-                cols, xyz, header_id = _parse_pdb_text(handle)
+            with open(os.fspath(file), "rb") as handle:
+                data = handle.read()
         else:
-            cols, xyz, header_id = _parse_pdb_text(file)
+            data = file.read()
+            if isinstance(data, str):
+                data = data.encode("ascii", "replace")
+        cols, xyz, header_id = _parse_pdb_native(data)
         return cls._from_columns(cols, xyz, id if id is not None else header_id)
 
     @classmethod
@@ -282,3 +356,52 @@ class Molecule:
 
     def __repr__(self):
         return f"Molecule(id={self.id!r}, atoms={len(self)})"
+
+
+def load_many(paths: Sequence[Union[str, os.PathLike]], ids: Optional[Sequence[Optional[str]]] = None,
+              threads: int = 0) -> List[Molecule]:
+    """Read and parse many PDB files on a native thread pool (``emm_pdb_load_files``); the returned
+    molecules are views into one SoA batch.  ``ids`` default to each file's HEADER idCode."""
+    lib = _native_lib()
+    paths = [os.fspath(p) for p in paths]
+    if not paths:
+        return []
+    for p in paths:                      # keep Python's exception types for the CLI's errno mapping
+        if os.path.isdir(p):
+            raise IsADirectoryError(21, "Is a directory", p)
+        if not os.path.exists(p):
+            raise FileNotFoundError(2, "No such file or directory", p)
+    arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
+    handle = ctypes.c_void_p()
+    n_threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1)
+    rc = lib.emm_pdb_load_files(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.byref(handle))
+    if rc != 0:
+        raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
+    try:
+        c = _PdbColumns()
+        lib.emm_pdb_batch_columns(handle, ctypes.byref(c))
+        n, nf = c.n_atoms, c.n_files
+
+        def grab(ptr, dtype, count):
+            if count == 0:
+                return np.zeros(0, dtype=dtype)
+            buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+        off = grab(c.atom_off, np.int64, nf + 1)
+        cols = _columns_from_native(
+            n, grab(c.serial, np.int32, n), grab(c.name, np.uint8, 4 * n), grab(c.altloc, np.uint8, n),
+            grab(c.resname, np.uint8, 4 * n), grab(c.chain, np.uint8, 2 * n), grab(c.resnum, np.int32, n),
+            grab(c.icode, np.uint8, n), grab(c.occupancy, np.float64, n), grab(c.bfactor, np.float64, n),
+            grab(c.segment, np.uint8, 4 * n), grab(c.element, np.uint8, 2 * n), grab(c.charge, np.int8, n))
+        xyz = grab(c.xyz, np.float64, 3 * n).reshape(n, 3)
+        headers = grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5)
+    finally:
+        lib.emm_pdb_batch_free(handle)
+    out = []
+    for i in range(nf):
+        lo, hi = int(off[i]), int(off[i + 1])
+        hid = bytes(headers[i]).split(b"\0")[0].decode() or None
+        mol_id = ids[i] if ids is not None and ids[i] is not None else hid
+        out.append(Molecule._from_columns({k: v[lo:hi] for k, v in cols.items()}, xyz[lo:hi], mol_id))
+    return out

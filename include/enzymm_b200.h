@@ -215,6 +215,34 @@ int emm_session_debug_counters(emm_session *s, unsigned long long *out128);
 int emm_query_batch(emm_library *lib, const emm_batch *batch, const emm_query_params *params,
                     emm_hit *hits, int64_t capacity, int64_t *n_hits, emm_stats *stats);
 
+/*
+ * Native PDB ingest (host only; needs no GPU).  Replaces pyjess.Molecule.load on the matching path
+ * (jess_run.py:538): ATOM and HETATM records in file order up to the first ENDMDL; coordinates are
+ * the doubles strtod / Python float() produce.  Strings are blank-stripped, NUL padded fixed-width
+ * fields: name[4], resname[4], chain[2], segment[4], element[2]; altloc / icode are single chars.
+ */
+int emm_pdb_count_atoms(const char *text, int64_t len, int64_t *n_atoms);
+int emm_pdb_parse(const char *text, int64_t len, int64_t capacity, int32_t *serial, char *name, char *altloc,
+                  char *resname, char *chain, int32_t *resnum, char *icode, double *xyz, double *occupancy,
+                  double *bfactor, char *segment, char *element, int8_t *charge, char *header_id /* [5] */,
+                  int64_t *n_atoms);
+const char *emm_pdb_last_error(void);
+
+/* Many files at once on n_threads threads into one SoA batch owned by the library. */
+typedef struct emm_pdb_batch emm_pdb_batch;
+typedef struct emm_pdb_columns {
+    int32_t n_files;
+    int64_t n_atoms;
+    const int64_t *atom_off;      /* [n_files+1] */
+    const int32_t *serial; const char *name; const char *altloc; const char *resname; const char *chain;
+    const int32_t *resnum; const char *icode; const double *xyz; const double *occupancy; const double *bfactor;
+    const char *segment; const char *element; const int8_t *charge;
+    const char *header_id;        /* [n_files][5] HEADER idCode or empty */
+} emm_pdb_columns;
+int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
+int emm_pdb_batch_columns(const emm_pdb_batch *batch, emm_pdb_columns *out);
+void emm_pdb_batch_free(emm_pdb_batch *batch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,3 +167,27 @@ def test_pyjess_surface():
     assert t.dimension == 1 and len(t) == 1 and list(t) == [atom] and t.copy() == t
     with pytest.raises(NotImplementedError):
         pyjess.Jess([t]).query(Molecule(), 2, 1, 1)          # best_match=False is not implemented
+
+
+def test_native_pdb_ingest_matches_python_parser(mol_1amy):
+    """emm_pdb.cpp (C ABI, host only) yields the same columns and bit-identical doubles as the
+    pure-Python fixed-column reader; the threaded batch loader returns the same molecules."""
+    from enzymm_b200.structures import _COLUMNS, _parse_pdb_text, load_many
+    for name in ("1AMY.pdb", "AF-P0DUB6-F1-model_v4.pdb", "1AMY_matches_query_included.pdb"):
+        native = Molecule.load(GOLDEN / name)
+        cols, xyz, header = _parse_pdb_text(open(GOLDEN / name))
+        assert np.array_equal(native.xyz, xyz) and native.id == header
+        for key, _ in _COLUMNS:
+            assert np.array_equal(native.column(key), cols[key]), key
+    rng = np.random.default_rng(5)
+    values = [float(f"{v:8.3f}") for v in rng.uniform(-999, 9999, 5000)]
+    text = "".join(f"ATOM  {i % 99999:>5}  CA  GLY A{i % 9999:>4}    {v:8.3f}{v:8.3f}{v:8.3f}  1.00 50.00           C\n"
+                   for i, v in enumerate(values))
+    assert np.array_equal(Molecule.loads(text).xyz[:, 2], np.array(values))
+    many = load_many([GOLDEN / "1AMY.pdb", GOLDEN / "AF-P0DUB6-F1-model_v4.pdb"] * 3, threads=3)
+    assert len(many) == 6 and many[0] == mol_1amy and many[2] == mol_1amy and many[1].id is None
+    assert load_many([GOLDEN / "1AMY.pdb"], ids=["x"])[0].id == "x"
+    with pytest.raises(FileNotFoundError):
+        load_many(["/no/such.pdb"])
+    with pytest.raises(ValueError):
+        Molecule.loads("ATOM      1  CA  GLY A   1      xx.xxx   0.000   0.000\n")
