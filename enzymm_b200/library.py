@@ -16,7 +16,9 @@ Three things are decided here and nowhere else:
 """
 from __future__ import annotations
 
+import hashlib
 import json
+import pickle
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -369,3 +371,42 @@ class CompiledLibrary:
 
     def __len__(self):
         return len(self.templates)
+
+    # ---- compiled-library cache: compile the 7607-file library once ---------------
+    _CACHE_VERSION = 3
+
+    @staticmethod
+    def _digest(templates, rmsd_threshold, distance_cutoff, max_dynamic_distance, plan_order) -> str:
+        h = hashlib.blake2b(digest_size=16)
+        h.update(repr((CompiledLibrary._CACHE_VERSION, plan_order, np.asarray(rmsd_threshold, dtype=np.float64).tolist(),
+                       [str(d) for d in np.atleast_1d(np.asarray(distance_cutoff, dtype=object))],
+                       np.asarray(max_dynamic_distance, dtype=np.float64).tolist())).encode())
+        for t in templates:
+            h.update(repr((getattr(t, "effective_size", None), [a._key() for a in t])).encode())
+        return h.hexdigest()
+
+    @classmethod
+    def cached(cls, templates: Sequence[JessTemplate], rmsd_threshold, distance_cutoff, max_dynamic_distance,
+               cache_dir, plan_order: str = "leaders_first") -> "CompiledLibrary":
+        """Compile, or reload the tables compiled earlier for exactly these templates and thresholds
+        from ``cache_dir`` (keyed by a digest of the template atoms and parameters)."""
+        templates = list(templates)
+        cache_dir = Path(cache_dir)
+        key = cls._digest(templates, rmsd_threshold, distance_cutoff, max_dynamic_distance, plan_order)
+        path = cache_dir / f"emm_library_{key}.pkl"
+        if path.exists():
+            with open(path, "rb") as handle:
+                state = pickle.load(handle)
+            self = cls.__new__(cls)
+            self.__dict__.update(state)
+            self.templates = templates
+            self.compat_dirty = True
+            return self
+        self = cls(templates, rmsd_threshold, distance_cutoff, max_dynamic_distance, plan_order=plan_order)
+        cache_dir.mkdir(parents=True, exist_ok=True)
+        state = {k: v for k, v in self.__dict__.items() if k != "templates"}
+        tmp = path.with_suffix(".tmp")
+        with open(tmp, "wb") as handle:
+            pickle.dump(state, handle, protocol=pickle.HIGHEST_PROTOCOL)
+        tmp.replace(path)
+        return self

@@ -41,7 +41,7 @@ from .engine import Engine
 from .library import CompiledLibrary, load_lr_models
 from .packing import pack_molecules
 from .pyjess_api import Hit
-from .structures import Molecule
+from .structures import Molecule, load_many
 from .templates import AnnotatedTemplate, Template, Vec3, check_template, rank_order
 
 __all__ = ["LogisticRegressionModel", "Match", "Matcher", "load_molecules"]
@@ -277,10 +277,13 @@ def load_molecules(molecule_paths: Sequence[Path], conservation_cutoff: float = 
     """
     molecules: List[Molecule] = []
     seen: Dict[str, int] = collections.defaultdict(int)
+    ids = []
     for path in molecule_paths:
         stem = Path(path).stem
         seen[stem] += 1
-        mol = Molecule.load(str(path), id=stem if seen[stem] == 1 else f"{stem}_{seen[stem]}")
+        ids.append(stem if seen[stem] == 1 else f"{stem}_{seen[stem]}")
+    # native, multi-threaded ingest (emm_pdb_load_files); OS errors keep their Python types
+    for path, mol in zip(molecule_paths, load_many([str(p) for p in molecule_paths], ids=ids)):
         if conservation_cutoff:
             mol.conserved(conservation_cutoff)
         if mol:

@@ -191,3 +191,35 @@ def test_native_pdb_ingest_matches_python_parser(mol_1amy):
         load_many(["/no/such.pdb"])
     with pytest.raises(ValueError):
         Molecule.loads("ATOM      1  CA  GLY A   1      xx.xxx   0.000   0.000\n")
+
+
+def test_compiled_library_cache(tmp_path, active_templates):
+    subset = active_templates[::50]
+    dist = [0.9 if t.effective_size == 3 else 2.0 for t in subset]
+    first = CompiledLibrary.cached(subset, 2.0, dist, dist, tmp_path)
+    again = CompiledLibrary.cached(subset, 2.0, dist, dist, tmp_path)
+    assert len(list(tmp_path.glob("emm_library_*.pkl"))) == 1
+    for name in ("atom_off", "plan_atom", "plan_ttype", "plan_src", "plan_anchor", "pair_dist", "lr_index", "lr_table"):
+        assert np.array_equal(getattr(first, name), getattr(again, name)), name
+    assert np.array_equal(first.compat_matrix(), again.compat_matrix())
+    assert again.templates[0] is subset[0]
+    CompiledLibrary.cached(subset, 2.0, 1.5, 1.5, tmp_path)             # other thresholds: a second entry
+    assert len(list(tmp_path.glob("emm_library_*.pkl"))) == 2
+
+
+def test_load_molecules_ids_and_errors(tmp_path):
+    from enzymm_b200.matcher import load_molecules
+    a = tmp_path / "a" / "1AMY.pdb"
+    b = tmp_path / "b" / "1AMY.pdb"
+    for p in (a, b):
+        p.parent.mkdir()
+        p.write_text((GOLDEN / "1AMY.pdb").read_text())
+    empty = tmp_path / "empty.pdb"
+    empty.write_text("REMARK nothing\n")
+    with pytest.warns(UserWarning):
+        mols = load_molecules([a, b, empty], conservation_cutoff=80, warn=True)
+    assert [m.id for m in mols] == ["1AMY", "1AMY_2"] and len(mols[0]) == 3339     # cutoff result is discarded upstream
+    with pytest.raises(FileNotFoundError):
+        load_molecules([tmp_path / "missing.pdb"])
+    with pytest.raises(IsADirectoryError):
+        load_molecules([tmp_path])
