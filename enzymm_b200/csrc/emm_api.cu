@@ -492,6 +492,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     if (n < 2 * grid) chunks = (2 * grid + n - 1) / n;
     chunks = std::min(chunks, std::max(1, (te - tb) / 8));
     chunks = std::max(1, std::min(chunks, 256));
+    if (const char *env = getenv("EMM_CHUNKS")) chunks = std::max(1, std::min(atoi(env), 256));   // tuning knob
     P.n_chunks = chunks;
     P.n_items = n * chunks;
     const int fixed = (int)search_fixed_smem(P.levels);
