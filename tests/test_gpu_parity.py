@@ -373,3 +373,43 @@ def test_determinism_and_shard_union(full_engine, active_templates):
     assert merged.tobytes() == a.tobytes()
     found = {(int(h["structure"]), int(h["template_index"])) for h in a}
     assert sum(1 for p in chunk.planted if p in found) >= 0.5 * len(chunk.planted)
+
+
+def test_full_size_properties(full_engine, active_templates):
+    """Size-independent properties on a batch too large for the oracle (2 560 structures x 6 780
+    templates = 17 M pairs): determinism, shard-union, planted-motif recovery, and an independent
+    numpy re-derivation of every reported hit (SVD Kabsch RMSD, same-residue rule, thresholds)."""
+    from enzymm_b200.synth import generate_batch
+    from enzymm_b200.sharding import merge_hits, shard_bounds
+    from helpers import svd_kabsch
+    work = generate_batch(1024, 2560, SynthConfig(), active_templates)
+    batch = work.to_packed(full_engine.compiled)
+    hits = full_engine.query(batch)
+    assert full_engine.query(batch).tobytes() == hits.tobytes()
+    parts = [(lo, full_engine.query(batch.slice(lo, hi)))
+             for lo, hi in (shard_bounds(batch.n_structures, 4, r, 256) for r in range(4))]
+    assert merge_hits(parts).tobytes() == hits.tobytes()
+    found = set(zip(hits["structure"].tolist(), hits["template_index"].tolist()))
+    assert len(found) == len(hits)                                   # at most one hit per (structure, template)
+    assert sum(1 for p in work.planted if p in found) >= 0.7 * len(work.planted)
+    dist = default_distances(active_templates)
+    rng = np.random.default_rng(0)
+    for h in hits[rng.choice(len(hits), size=400, replace=False)]:
+        t = active_templates[int(h["template_index"])]
+        m = int(h["n_atoms"])
+        lo = int(work.atom_off[int(h["structure"])])
+        atoms = h["atoms"][:m] + lo
+        assert len(set(atoms.tolist())) == m                         # injective
+        q = work.xyz[atoms]
+        txyz = np.array([(a.x, a.y, a.z) for a in t])
+        rmsd, _ = svd_kabsch(txyz, q)
+        assert abs(rmsd - float(h["rmsd"])) < 1e-6 and float(h["rmsd"]) <= 2.0
+        res = work.residue[atoms]
+        tres = [(a.chain_id, a.residue_number) for a in t]
+        for i in range(m):                                           # same template residue -> same query residue
+            for j in range(i):
+                if tres[i] == tres[j]:
+                    assert res[i] == res[j]
+        dq = np.linalg.norm(q[:, None] - q[None], axis=-1)
+        dt = np.linalg.norm(txyz[:, None] - txyz[None], axis=-1)
+        assert np.abs(dq - dt).max() <= dist[int(h["template_index"])] + 1e-9
