@@ -33,6 +33,8 @@
 // No tensor cores: this is gather/compare-bound FP32 + integer work with a rare FP64 tail.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "emm_device.cuh"
 
 namespace emm {
@@ -609,16 +611,22 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     const int a_0 = have0 ? V.lead(lbase + c0) : 0, a_1 = have1 ? V.lead(lbase + c1) : 0;
                     const float x0 = V.x(a_0), y0 = V.y(a_0), z0 = V.z(a_0);
                     const float x1 = V.x(a_1), y1 = V.y(a_1), z1 = V.z(a_1);
-                    for (; pidx < P; ++pidx) {
-                        if (n_next >= cap_next) { full = true; break; }
-                        bool alive0 = have0, alive1 = have1;
-                        if (todo) { alive0 = alive0 && ((todo >> lane) & 1ull); alive1 = alive1 && ((todo >> (32 + lane)) & 1ull); }
-                        if (k > 0) {
+                    // one (row pair, partial) iteration, specialised at compile time on: a second
+                    // candidate row exists / level 0 (no anchor) / resuming a partly pushed iteration.
+                    // Returns true when the next queue could not take every survivor.
+                    auto one = [&](auto TWO, auto ROOT, auto TODO) -> bool {
+                        bool alive0 = have0, alive1 = TWO() && have1;
+                        if (TODO()) {
+                            alive0 = alive0 && ((todo >> lane) & 1ull);
+                            alive1 = alive1 && ((todo >> (32 + lane)) & 1ull);
+                            todo = 0ull;
+                        }
+                        if (!ROOT()) {
                             const float4 an = ws->anchor[pidx];
                             float dx = x0 - an.x, dy = y0 - an.y, dz = z0 - an.z;
                             const float d0 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                             alive0 = alive0 && d0 >= lo2 && d0 <= hi2;
-                            if (two) {
+                            if (TWO()) {
                                 dx = x1 - an.x; dy = y1 - an.y; dz = z1 - an.z;
                                 const float d1 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                                 alive1 = alive1 && d1 >= lo2 && d1 <= hi2;
@@ -627,20 +635,30 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                         }
                         if (kStats && lane == 0) ++st.sweeps;
                         const unsigned sv0 = __ballot_sync(kFull, alive0);
-                        const unsigned sv1 = two ? __ballot_sync(kFull, alive1) : 0u;
-                        todo = 0ull;
+                        const unsigned sv1 = TWO() ? __ballot_sync(kFull, alive1) : 0u;
                         if (sv0 | sv1) {
-                            const int parent = k > 0 ? base + (int)ws->vslot[pidx] : 0;
+                            const int parent = ROOT() ? 0 : base + (int)ws->vslot[pidx];
                             unsigned left0 = 0u, left1 = 0u;
                             if (sv0) left0 = push(sv0, alive0, a_0, parent);
-                            if (sv1) left1 = left0 ? sv1 : push(sv1, alive1, a_1, parent);
+                            if (TWO() && sv1) left1 = left0 ? sv1 : push(sv1, alive1, a_1, parent);
                             if (left0 | left1) {
                                 todo = (unsigned long long)left0 | ((unsigned long long)left1 << 32);
-                                full = true;
-                                break;
+                                return true;
                             }
                         }
-                    }
+                        return false;
+                    };
+                    auto sweep = [&](auto TWO, auto ROOT) -> bool {
+                        if (todo) {                       // finish the iteration a full queue interrupted
+                            if (n_next >= cap_next || one(TWO, ROOT, std::true_type{})) return true;
+                            ++pidx;
+                        }
+                        for (; pidx < P; ++pidx)
+                            if (n_next >= cap_next || one(TWO, ROOT, std::false_type{})) return true;
+                        return false;
+                    };
+                    if (k == 0) full = two ? sweep(std::true_type{}, std::true_type{}) : sweep(std::false_type{}, std::true_type{});
+                    else full = two ? sweep(std::true_type{}, std::false_type{}) : sweep(std::false_type{}, std::false_type{});
                     if (full) break;
                     pidx = 0;
                     r += 2;
