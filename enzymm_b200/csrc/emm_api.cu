@@ -389,7 +389,7 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
         }
         const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries);
         s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + bytes;
-        max_staged = std::max(max_staged, bytes - align16(4 * (a1 - a0)));
+        max_staged = std::max(max_staged, bytes - align16(4 * (a1 - a0)) - align16(2 * (int64_t)(kMaxCells + 1)) - align16(2 * (a1 - a0)));
     }
     s->max_staged = max_staged;
     if (s->h_blob_off[(size_t)n] > s->blob_capacity) {
@@ -487,6 +487,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     P.template_end = te;
     P.skip_mode = q->skip_mode;
     P.levels = lib->d.max_tpl_atoms + 1;
+    P.cell_threshold = q->cell_threshold > 0 ? q->cell_threshold : 0;   // opt-in: typed lists measured faster at every tested size
     const int grid = lib->sm_count;
     int chunks = 1;
     if (n < 2 * grid) chunks = (2 * grid + n - 1) / n;

@@ -31,8 +31,6 @@ constexpr int kWideLevels = 9;
 __host__ __device__ constexpr int queue_off(int k) { return k <= kWideLevels ? k * kQueueCap : kWideLevels * kQueueCap + (k - kWideLevels) * kDeepCap; }
 __host__ __device__ constexpr int queue_cap(int k) { return k < kWideLevels ? kQueueCap : kDeepCap; }
 constexpr int kPrepThreads = 256;
-constexpr float kCellSize = 6.0f;      // uniform grid cell edge (Angstrom)
-constexpr int kMaxCellsPerAxis = 64;
 
 struct DevLibrary {
     int n_templates, n_atoms, n_ttype, class_words, class_words_cap, n_leader, max_tpl_atoms, n_lr;
@@ -72,7 +70,10 @@ struct DevBatch {
     const int64_t *blob_off; // [n_structures+1]
 };
 
-// Blob header (64 bytes).  All off_* are byte offsets from the blob base, 16-byte aligned.
+constexpr int kMaxCells = 4096;        // uniform-grid cells per structure (cell edge grows to fit)
+constexpr float kMinCell = 6.0f;       // cell edge in Angstrom for ordinary structures
+
+// Blob header (128 bytes).  All off_* are byte offsets from the blob base, 16-byte aligned.
 struct BlobHeader {
     int32_t n_kept;        // atoms kept (mask + class != 0), local ids 0..n_kept-1 in input order
     int32_t n_res;         // residues holding at least one kept atom
@@ -87,9 +88,16 @@ struct BlobHeader {
     int32_t off_leadoff;   // uint32 lead_off[n_leader+1]
     int32_t off_lead;      // uint16 lead[...]
     int32_t off_orig;      // int32 orig[n_kept]: position of the atom inside its structure (NOT staged)
-    int32_t pad;
+    // uniform grid over the kept atoms (cell list): cell c = (iz*ny + iy)*nx + ix holds
+    // cell_atoms[cell_start[c] .. cell_start[c+1]) in ascending atom order
+    int32_t off_cellstart; // uint16 cell_start[nx*ny*nz + 1]
+    int32_t off_cellatoms; // uint16 cell_atoms[n_kept]
+    int32_t nx, ny, nz;
+    float cell;            // cell edge
+    float ox, oy, oz;      // grid origin in centred coordinates
+    int32_t pad[8];
 };
-static_assert(sizeof(BlobHeader) == 64, "blob header is 64 bytes");
+static_assert(sizeof(BlobHeader) == 128, "blob header is 128 bytes");
 
 struct SearchParams {
     long long max_candidates;
@@ -100,6 +108,7 @@ struct SearchParams {
     int n_items;
     int blob_cap;          // shared-memory bytes available for a staged blob
     int levels;            // queue levels per warp (max template atoms + 1)
+    int cell_threshold;    // leader lists at least this long are searched through the cell list
 };
 
 struct SearchOut {
@@ -125,6 +134,7 @@ inline __host__ __device__ int64_t blob_bytes(int64_t n, int n_leader, int64_t l
     b += align16(2 * n);                     // klass
     b += align16(4 * (int64_t)(n_leader + 1));
     b += align16(2 * lead_entries);
+    b += align16(2 * (int64_t)(kMaxCells + 1)) + align16(2 * n);   // cell_start, cell_atoms
     b += align16(4 * n);                     // orig
     return b;
 }

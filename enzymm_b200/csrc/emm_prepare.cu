@@ -64,6 +64,7 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
     __shared__ double s_scratch[kPrepThreads / 32];
     __shared__ int s_bad, s_maxres;
     __shared__ unsigned s_lead_cnt[1024];   // counts, then offsets (n_leader <= 1023 checked on host)
+    __shared__ int s_cell[kMaxCells + 1];   // uniform grid: counts, then start offsets / fill cursors
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool use_mask = (B.bfactor != nullptr) && (cutoff > 0.0f);
@@ -107,13 +108,14 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
 #pragma unroll
             for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], p[c]); hi[c] = fmax(hi[c], p[c]); }
         }
-        double ctr[3], half = 0.0;
+        double ctr[3], ext[3], half = 0.0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double mn = block_reduce_minmax(lo[c], false, s_scratch);
             const double mx = block_reduce_minmax(hi[c], true, s_scratch);
             ctr[c] = n_kept ? 0.5 * (mn + mx) : 0.0;
-            half = fmax(half, n_kept ? 0.5 * (mx - mn) : 0.0);
+            ext[c] = n_kept ? mx - mn : 0.0;
+            half = fmax(half, 0.5 * ext[c]);
         }
         // |d_fp32 - d_exact| <= ~36 * 2^-24 * half (DESIGN.md "guard band"); 64 gives ~1.8x margin
         const float eps = (float)(64.0 * 5.9604644775390625e-08 * fmax(half, 16.0) + 1e-5);
@@ -214,13 +216,63 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
         }
         __syncthreads();
 
+        // ---- pass E: uniform grid (cell list) over the kept atoms -------------------------------------
+        // Counting sort by cell; atoms inside a cell end up in ascending order, so the layout is
+        // deterministic.  The cell edge grows until the grid has at most kMaxCells cells.
+        const int off_cellstart = (int)align16(off_lead + 2 * (int64_t)s_lead_cnt[L.n_leader]);
+        float cell = kMinCell;
+        int nx = 1, ny = 1, nz = 1;
+        for (;;) {
+            nx = (int)(ext[0] / cell) + 1; ny = (int)(ext[1] / cell) + 1; nz = (int)(ext[2] / cell) + 1;
+            if ((long long)nx * ny * nz <= kMaxCells) break;
+            cell *= 1.25f;
+        }
+        const int n_cells = nx * ny * nz;
+        const float ox = (float)(-0.5 * ext[0]) - 1e-3f, oy = (float)(-0.5 * ext[1]) - 1e-3f, oz = (float)(-0.5 * ext[2]) - 1e-3f;
+        const int off_cellatoms = off_cellstart + (int)align16(2 * (int64_t)(n_cells + 1));
+        uint16_t *cell_start = reinterpret_cast<uint16_t *>(blob + off_cellstart);
+        uint16_t *cell_atoms = reinterpret_cast<uint16_t *>(blob + off_cellatoms);
+        auto cell_of = [&](int i) {
+            const int ix = min(nx - 1, max(0, (int)((bx[i] - ox) / cell)));
+            const int iy = min(ny - 1, max(0, (int)((by[i] - oy) / cell)));
+            const int iz = min(nz - 1, max(0, (int)((bz[i] - oz) / cell)));
+            return (iz * ny + iy) * nx + ix;
+        };
+        for (int c = tid; c <= n_cells; c += kPrepThreads) s_cell[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < n_kept; i += kPrepThreads) atomicAdd(&s_cell[cell_of(i)], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int c = 0; c < n_cells; ++c) { const int cnt = s_cell[c]; s_cell[c] = run; cell_start[c] = (uint16_t)run; run += cnt; }
+            s_cell[n_cells] = run;
+            cell_start[n_cells] = (uint16_t)run;
+        }
+        __syncthreads();
+        for (int i = tid; i < n_kept; i += kPrepThreads) cell_atoms[atomicAdd(&s_cell[cell_of(i)], 1)] = (uint16_t)i;
+        __syncthreads();
+        for (int c = tid; c < n_cells; c += kPrepThreads) {      // insertion sort inside each (small) cell
+            const int b0 = cell_start[c], b1 = cell_start[c + 1];
+            for (int i = b0 + 1; i < b1; ++i) {
+                const uint16_t v = cell_atoms[i];
+                int j = i - 1;
+                while (j >= b0 && cell_atoms[j] > v) { cell_atoms[j + 1] = cell_atoms[j]; --j; }
+                cell_atoms[j + 1] = v;
+            }
+        }
+        __syncthreads();
+
         if (tid == 0) {
             BlobHeader h;
             h.n_kept = n_kept; h.n_res = n_res; h.res_shift = res_shift; h.status = status; h.eps = eps;
-            h.staged_bytes = (int)align16(off_lead + 2 * (int64_t)s_lead_cnt[L.n_leader]);
+            // the cell list stays in global memory: it is consulted only for very long leader lists
+            h.staged_bytes = off_cellstart;
+            h.off_cellstart = off_cellstart; h.off_cellatoms = off_cellatoms; h.nx = nx; h.ny = ny; h.nz = nz;
+            h.cell = cell; h.ox = ox; h.oy = oy; h.oz = oz;
+            for (int i = 0; i < 8; ++i) h.pad[i] = 0;
             h.off_x = off_x; h.off_y = off_y; h.off_z = off_z; h.off_res = off_res;
             h.off_resstart = off_resstart; h.off_klass = off_klass; h.off_leadoff = off_leadoff;
-            h.off_lead = off_lead; h.off_orig = off_orig; h.pad = 0;
+            h.off_lead = off_lead; h.off_orig = off_orig;
             *reinterpret_cast<BlobHeader *>(blob) = h;
             if (stats) atomicAdd(stats + 5, (unsigned long long)n_kept);
             if (status != 0 && bad) atomicAdd(bad, 1ull);

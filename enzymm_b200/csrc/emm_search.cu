@@ -55,7 +55,9 @@ struct WarpState {
     int chunk[kMaxAtoms + 1];    // size of the level's current chunk (its last `chunk` entries)
     int cur[kMaxAtoms + 1];      // expansion cursor inside the chunk
     unsigned long long todo[kMaxAtoms + 1];   // lanes (two candidate rows) of iteration `cur` still to be pushed
-    float4 anchor[32];           // per chunk slot: anchor atom xyz, w = payload bits
+    int cellrow[kMaxAtoms + 1];  // cell-list expansion: row of the anchor's cell box being scanned ...
+    int celli[kMaxAtoms + 1];    // ... and next position inside that row (-1 = row not started)
+    float4 anchor[32];           // per valid partial (compacted): anchor atom xyz, w = payload bits
     unsigned char vslot[32];     // compacted list of valid chunk slots
     double best_rmsd;
     unsigned long long n_complete;
@@ -74,6 +76,10 @@ struct Blob {
     const double *xyz64;      // structure base, FP64 coordinates as uploaded
     const uint16_t *chain;    // may be null
     const int32_t *atom_id;   // may be null
+    // uniform grid (cell list) of the structure, see BlobHeader; read in place from global memory
+    const uint16_t *cell_start, *cell_atoms;
+    int nx, ny, nz;
+    float cell, ox, oy, oz;
 };
 
 // Hot-path view of the structure blob.  kStaged: the blob sits at the start of dynamic shared
@@ -454,6 +460,76 @@ __device__ __noinline__ bool exact_validate(const DevLibrary &L, const Blob &S, 
     return true;
 }
 
+// Leader expansion through the uniform-grid cell list, used when the leader list is long (mode-100
+// "any residue" atoms, very large assemblies): instead of testing every atom the type can bind,
+// scan the cells that intersect the anchor's distance shell and test typing + distance there.
+// Per partial the box of cells around its anchor is walked row by row (cells along x are
+// contiguous in the cell-sorted atom array), 32 atoms per step.  Returns true when the next queue
+// filled up; the resume point (partial, row, position, pending lanes) is kept in the warp state.
+template <bool kStaged>
+__device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, WarpState *ws, uint32_t *Qn, int cap_next,
+                                          int *n_next_io, int base, int P, const uint32_t *crow, float lo2, float hi2,
+                                          int k, int lane, bool *done)
+{
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float hi = sqrtf(hi2) + 1e-3f;
+    int n_next = *n_next_io;
+    int pidx = ws->cur[k], row = ws->cellrow[k], ipos = ws->celli[k];
+    unsigned todo = (unsigned)ws->todo[k];
+    bool full = false;
+    for (; pidx < P && !full; ++pidx, row = 0, ipos = -1) {
+        const float4 an = ws->anchor[pidx];
+        const int parent = base + (int)ws->vslot[pidx];
+        const int ix0 = max(0, (int)floorf((an.x - hi - S.ox) / S.cell)), ix1 = min(S.nx - 1, (int)floorf((an.x + hi - S.ox) / S.cell));
+        const int iy0 = max(0, (int)floorf((an.y - hi - S.oy) / S.cell)), iy1 = min(S.ny - 1, (int)floorf((an.y + hi - S.oy) / S.cell));
+        const int iz0 = max(0, (int)floorf((an.z - hi - S.oz) / S.cell)), iz1 = min(S.nz - 1, (int)floorf((an.z + hi - S.oz) / S.cell));
+        if (ix1 < ix0 || iy1 < iy0 || iz1 < iz0) continue;
+        const int nry = iy1 - iy0 + 1, nrows = nry * (iz1 - iz0 + 1);
+        for (; row < nrows && !full; ++row, ipos = -1) {
+            const int iz = iz0 + row / nry, iy = iy0 + row % nry;
+            const int c0 = (iz * S.ny + iy) * S.nx + ix0;
+            const int beg = __ldg(S.cell_start + c0);
+            const int end = __ldg(S.cell_start + c0 + ix1 - ix0 + 1);
+            if (ipos < 0) ipos = beg;
+            for (; ipos < end; ipos += 32) {
+                if (n_next >= cap_next) { full = true; break; }
+                const int i = ipos + lane;
+                bool alive = i < end && (todo == 0u || ((todo >> lane) & 1u));
+                todo = 0u;
+                int a = 0;
+                if (alive) {
+                    a = __ldg(S.cell_atoms + i);
+                    const unsigned kl = V.klass(a);
+                    alive = (__ldg(crow + (kl >> 5)) >> (kl & 31u)) & 1u;
+                }
+                if (alive) {
+                    const float dx = V.x(a) - an.x, dy = V.y(a) - an.y, dz = V.z(a) - an.z;
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    alive = d2 >= lo2 && d2 <= hi2;
+                }
+                const unsigned sv = __ballot_sync(kFull, alive);
+                if (sv) {
+                    const int room = cap_next - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
+                    if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)parent << 16) | (uint32_t)a;
+                    if (cnt > room) {
+                        n_next = cap_next;
+                        todo = __ballot_sync(kFull, alive && rank >= room);
+                        full = true;
+                        break;
+                    }
+                    n_next += cnt;
+                }
+            }
+            if (full) break;
+        }
+        if (full) break;
+    }
+    if (lane == 0) { ws->cur[k] = pidx; ws->cellrow[k] = row; ws->celli[k] = ipos; ws->todo[k] = todo; }
+    *n_next_io = n_next;
+    *done = !full && pidx >= P;
+    return full;
+}
+
 struct LaneStats {
     unsigned long long sweeps, evals, exact;
 };
@@ -520,7 +596,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     return valid;
 }
 
-template <bool kStats, bool kStaged>
+template <bool kStats, bool kStaged, bool kCells>
 __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob &S, const View<kStaged> &V, int s,
                                                 int t, uint32_t *Q, WarpState *ws, int lane, LaneStats &st)
 {
@@ -544,7 +620,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
     const float eps = V.eps;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0ull; }
+    if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0ull; if (kCells) { ws->cellrow[lane] = 0; ws->celli[lane] = -1; } }
     if (lane == 0) { ws->best_valid = 0; ws->overflow = 0; ws->n_complete = 0ull; ws->best_rmsd = CUDART_INF; }
     __syncwarp();
 
@@ -604,6 +680,16 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                 const int B = V.lead_off(-src) - lbase;
                 const int nrows = (B + 31) >> 5;
                 int r = cur / P, pidx = cur - r * P;       // r is always even or the last row
+                const bool by_cells = kCells && k > 0 && B >= A.P.cell_threshold;
+                if (by_cells) {
+                    const uint32_t *crow = L.compat + (size_t)L.plan_ttype[a0 + k] * L.class_words_cap;
+                    __syncwarp();
+                    full = expand_cells<kStaged>(V, S, ws, Qn, cap_next, &n_next, base, P, crow, lo2, hi2, k, lane, &done);
+                    __syncwarp();
+                    cur = ws->cur[k];
+                    todo = ws->todo[k];
+                    r = nrows;                              // skip the list loop below
+                }
                 while (r < nrows) {
                     const int c0 = (r << 5) + lane, c1 = c0 + 32;
                     const bool have0 = c0 < B, have1 = c1 < B;
@@ -663,8 +749,10 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     pidx = 0;
                     r += 2;
                 }
-                cur = r * P + pidx;
-                done = r >= nrows;
+                if (!by_cells) {
+                    cur = r * P + pidx;
+                    done = r >= nrows;
+                }
             } else {
                 // same-residue position: lanes cover (partial, residue slot) items
                 const int shift = V.res_shift;
@@ -707,7 +795,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             if (full || (done && n_next > 0)) {
                 // descend: the last <= 32 entries of the next level form its chunk
                 ++k;
-                if (lane == 0) { ws->chunk[k] = min(32, n_next); ws->cur[k] = 0; ws->todo[k] = 0ull; }
+                if (lane == 0) { ws->chunk[k] = min(32, n_next); ws->cur[k] = 0; ws->todo[k] = 0ull; if (kCells) { ws->cellrow[k] = 0; ws->celli[k] = -1; } }
                 __syncwarp();
                 entered = false;
                 continue;
@@ -721,6 +809,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             ws->chunk[k] = min(32, base);
             ws->cur[k] = 0;
             ws->todo[k] = 0ull;
+            if (kCells) { ws->cellrow[k] = 0; ws->celli[k] = -1; }
         }
         __syncwarp();
         if (base == 0) --k;           // back to the parent level: its chunk, cursor and todo are intact
@@ -731,7 +820,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
     __syncwarp();
 }
 
-template <bool kStats, bool kStaged>
+template <bool kStats, bool kStaged, bool kCells>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 emm_search_kernel(const __grid_constant__ SearchArgs A)
 {
@@ -777,6 +866,10 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                 s_blob.xyz64 = A.B.xyz + 3 * abase;
                 s_blob.chain = A.B.chain ? A.B.chain + abase : nullptr;
                 s_blob.atom_id = A.B.atom_id ? A.B.atom_id + abase : nullptr;
+                s_blob.cell_start = reinterpret_cast<const uint16_t *>(gblob + hdr.off_cellstart);
+                s_blob.cell_atoms = reinterpret_cast<const uint16_t *>(gblob + hdr.off_cellatoms);
+                s_blob.nx = hdr.nx; s_blob.ny = hdr.ny; s_blob.nz = hdr.nz;
+                s_blob.cell = hdr.cell; s_blob.ox = hdr.ox; s_blob.oy = hdr.oy; s_blob.oz = hdr.oz;
             }
             __syncthreads();
             View<kStaged> V;
@@ -789,7 +882,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                 if (lane == 0) t = atomicAdd(&s_next_tpl, 1);
                 t = __shfl_sync(kFull, t, 0);
                 if (t >= te) break;
-                search_template<kStats, kStaged>(A, s_blob, V, s, t, Q, ws, lane, st);
+                search_template<kStats, kStaged, kCells>(A, s_blob, V, s, t, Q, ws, lane, st);
                 if (kStats && lane == 0) ++st_pairs;
             }
         }
@@ -827,10 +920,13 @@ size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels); }
 
 cudaError_t configure_search(int smem_bytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(emm_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(emm_search_kernel<false, true, false>, attr, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<false, false, false>, attr, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<true, true, false>, attr, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<true, false, false>, attr, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<false, true, true>, attr, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emm_search_kernel<false, false, true>, attr, smem_bytes);
     return e;
 }
 
@@ -845,10 +941,13 @@ void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P
     if (P.n_items <= 0) return;
     SearchArgs A;
     A.L = L; A.B = B; A.P = P; A.O = O; A.skip = skip;
-    if (stats && staged) emm_search_kernel<true, true><<<grid, kSearchThreads, smem, stream>>>(A);
-    else if (stats) emm_search_kernel<true, false><<<grid, kSearchThreads, smem, stream>>>(A);
-    else if (staged) emm_search_kernel<false, true><<<grid, kSearchThreads, smem, stream>>>(A);
-    else emm_search_kernel<false, false><<<grid, kSearchThreads, smem, stream>>>(A);
+    const bool cells = P.cell_threshold > 0;       // the cell-list path is a separate instantiation
+    if (cells && staged) emm_search_kernel<false, true, true><<<grid, kSearchThreads, smem, stream>>>(A);
+    else if (cells) emm_search_kernel<false, false, true><<<grid, kSearchThreads, smem, stream>>>(A);
+    else if (stats && staged) emm_search_kernel<true, true, false><<<grid, kSearchThreads, smem, stream>>>(A);
+    else if (stats) emm_search_kernel<true, false, false><<<grid, kSearchThreads, smem, stream>>>(A);
+    else if (staged) emm_search_kernel<false, true, false><<<grid, kSearchThreads, smem, stream>>>(A);
+    else emm_search_kernel<false, false, false><<<grid, kSearchThreads, smem, stream>>>(A);
 }
 
 }  // namespace emm

@@ -73,6 +73,7 @@ class _QueryParams(ctypes.Structure):
         ("conservation_cutoff", ctypes.c_float), ("template_begin", ctypes.c_int32),
         ("template_end", ctypes.c_int32), ("skip_mode", ctypes.c_int32),
         ("reset_structure_state", ctypes.c_int32), ("force_prepare", ctypes.c_int32),
+        ("cell_threshold", ctypes.c_int32),
     ]
 
 
@@ -239,10 +240,10 @@ class Session:
 
     def run(self, *, max_candidates: int = 10000, ignore_chain: bool = True, conservation_cutoff: float = 0.0,
             template_begin: int = 0, template_end: int = 0, skip_mode: int = 0, reset: bool = True,
-            force_prepare: bool = False, stream: int = 0):
+            force_prepare: bool = False, cell_threshold: int = 0, stream: int = 0):
         q = _QueryParams(int(max_candidates or 0), 1 if ignore_chain else 0, float(conservation_cutoff or 0.0),
                          int(template_begin), int(template_end), int(skip_mode), 1 if reset else 0,
-                         1 if force_prepare else 0)
+                         1 if force_prepare else 0, int(cell_threshold))
         _check(self._lib.emm_session_run(self.handle, ctypes.byref(q), ctypes.c_void_p(stream)))
 
     def download(self, stream: int = 0, with_stats: bool = False):

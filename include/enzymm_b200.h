@@ -146,6 +146,8 @@ typedef struct emm_query_params {
                                   /* hit; 2 ... that hold any hit (--skip-smaller-hits, jess_run.py:951-958) */
     int32_t reset_structure_state;/* 1: clear per-structure hit counters before this run          */
     int32_t force_prepare;        /* 1: run the prepare kernel even if this batch is already prepared */
+    int32_t cell_threshold;       /* > 0: leader candidate lists at least this long are searched through  */
+                                  /* the uniform-grid cell list instead of scanned; <= 0: never (default) */
 } emm_query_params;
 
 typedef struct emm_hit {

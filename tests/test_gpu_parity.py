@@ -413,3 +413,33 @@ def test_full_size_properties(full_engine, active_templates):
         dq = np.linalg.norm(q[:, None] - q[None], axis=-1)
         dt = np.linalg.norm(txyz[:, None] - txyz[None], axis=-1)
         assert np.abs(dq - dt).max() <= dist[int(h["template_index"])] + 1e-9
+
+
+def test_cell_list_path_equals_list_path(full_engine, active_templates, mol_1amy, mol_af):
+    """Leader candidates through the uniform-grid cell list (forced for every leader level with
+    cell_threshold=1) give exactly the hits of the typed-list scan and of the oracle -- including
+    queue-overflow resumes inside a cell row (loose cutoffs)."""
+    chunk = generate_chunk(7, SynthConfig(), active_templates, 6)
+    mols = [mol_1amy, mol_af] + [chunk.to_molecule(i) for i in range(chunk.n_structures)]
+    batch = pack_molecules(mols, full_engine.compiled)
+    by_list = full_engine.query(batch, cell_threshold=-1)
+    by_cell = full_engine.query(batch, cell_threshold=1)
+    assert by_cell.tobytes() == by_list.tobytes()
+    raw = oracle.query_raw(mols, oracle.OracleTemplates(active_templates), 2.0,
+                           np.asarray(default_distances(active_templates)), np.asarray(default_distances(active_templates)),
+                           threads=8)
+    assert {(int(h["structure"]), int(h["template_index"])) for h in by_cell} == \
+        {(int(a), int(b)) for a, b in zip(*np.nonzero(raw["found"]))}
+    subset = [t for t in active_templates if t.effective_size == 3][::60]
+    eng = Engine(CompiledLibrary(subset, 2.0, 3.0, 3.0))
+    try:
+        loose = pack_molecules([mol_1amy], eng.compiled)
+        a = eng.query(loose, max_candidates=10 ** 7, cell_threshold=-1)
+        b = eng.query(loose, max_candidates=10 ** 7, cell_threshold=1)
+        assert a.tobytes() == b.tobytes() and int(a["n_complete"].max()) > 50
+    finally:
+        eng.close()
+    # a 4-chain assembly searched in place from global memory, cells forced
+    big = generate_chunk(0, SynthConfig(n_chains=4), active_templates, 1)
+    bb = big.to_packed(full_engine.compiled)
+    assert full_engine.query(bb, cell_threshold=1).tobytes() == full_engine.query(bb, cell_threshold=-1).tobytes()

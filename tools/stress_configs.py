@@ -4,6 +4,7 @@ config 4: --unfiltered, -j 2 3.0 3.0, max_candidates 10^7 (combinatorial blow-up
 config 5: 4 x 400-residue assemblies, conservation cutoff 70 as a real mask, --skip-smaller-hits
 usage: python tools/stress_configs.py [n4] [n5]
 """
+import os
 import sys
 import time
 from pathlib import Path
@@ -15,6 +16,9 @@ sys.path.insert(0, str(ROOT))
 from bench import DEFAULT_DIST, active_templates, make_workload  # noqa: E402
 from enzymm_b200.engine import Engine, HIT_OVERFLOW, HIT_PASS  # noqa: E402
 from enzymm_b200.library import CompiledLibrary  # noqa: E402
+
+
+CELL = int(os.environ.get("EMM_CELL", "0"))     # > 0: leader lists this long go through the cell list
 
 
 def config4(n):
@@ -55,13 +59,13 @@ def config5(n):
             for size in sorted(set(sizes.tolist()), reverse=True):
                 idx = np.nonzero(sizes == size)[0]
                 sess.run(conservation_cutoff=cutoff, template_begin=int(idx[0]), template_end=int(idx[-1]) + 1,
-                         skip_mode=1, reset=first, force_prepare=first)
+                         skip_mode=1, reset=first, force_prepare=first, cell_threshold=CELL)
                 first = False
         else:
-            sess.run(conservation_cutoff=cutoff, force_prepare=True)
+            sess.run(conservation_cutoff=cutoff, force_prepare=True, cell_threshold=CELL)
         hits, stats = sess.download(with_stats=True)
         dt = time.perf_counter() - t0
-        print(f"config5 {label}: {n} assemblies ({batch.n_atoms / n:.0f} atoms each) in {dt:.2f}s = {n / dt:.1f} structures/s; "
+        print(f"config5 [cell_threshold={CELL}] {label}: {n} assemblies ({batch.n_atoms / n:.0f} atoms each) in {dt:.2f}s = {n / dt:.1f} structures/s; "
               f"hits {len(hits)}, passing {int(((hits['flags'] & HIT_PASS) != 0).sum())}, kept atoms/structure "
               f"{stats['kept_atoms'] / n:.0f}", flush=True)
     engine.close()
