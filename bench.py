@@ -226,7 +226,7 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from enzymm_b200.engine import Engine, HIT_PASS, PackedBatch
+    from enzymm_b200.engine import Engine, HIT_PASS, PackedBatch, Session
     from enzymm_b200.library import CompiledLibrary
 
     templates = active_templates()
@@ -289,16 +289,35 @@ def run_b200(args, rank, local_rank, world):
     hits = session.download(stream=stream)
 
     # ---- end to end: pinned host buffers -> hits on the host, every step ----------------------------
+    # Two sessions on two streams: while step i is being searched, step i+1's batch is already
+    # crossing PCIe (every step still pays its own H2D copy, prepare, search and D2H of its hits).
+    second = Session(engine.device_library, host.n_atoms, host.n_structures, session.hit_capacity)
+    side = torch.cuda.Stream()
+    lanes = [(session, stream), (second, side.cuda_stream)]
+    e2e_kwargs = dict(run_kwargs)
+
+    def submit(i):
+        sess, st = lanes[i % 2]
+        e2e_kwargs["stream"] = st
+        sess.upload(host, stream=st)
+        sess.run(**e2e_kwargs)
+
+    for i in range(2):                         # warm the second lane
+        submit(i)
+        lanes[i % 2][0].download(stream=lanes[i % 2][1])
     barrier()
     w0 = time.time()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     d2h = 0
-    for _ in range(args.steps):
-        session.upload(host, stream=stream)
-        session.run(**run_kwargs)
-        hits = session.download(stream=stream)
+    submit(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            submit(i + 1)
+        sess, st = lanes[i % 2]
+        hits = sess.download(stream=st)
         d2h = 16 + hits.nbytes
+    torch.cuda.current_stream().wait_stream(side)
     f1.record()
     barrier()
     windows.append((w0, time.time()))

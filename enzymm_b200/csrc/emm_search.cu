@@ -790,6 +790,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                 cur = it;
                 done = it >= n_it;
             }
+            __syncwarp();          // every lane has read the level state before lane 0 updates it
             if (lane == 0) { ws->n[k + 1] = n_next; ws->cur[k] = cur; ws->todo[k] = todo; }
             if (kStats && lane == 0) atomicAdd(A.O.stats + 40 + k, (unsigned long long)(n_next - n_before));
             if (full || (done && n_next > 0)) {
