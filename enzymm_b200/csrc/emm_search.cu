@@ -4,16 +4,17 @@
 // Replaces pyjess.Jess(templates).query(...) + Match.predicted_correct for a whole batch
 // (reference enzymm/jess_run.py:785-843, 298-346, 425-478).
 //
-// Mapping.  Persistent CTAs (one per SM, kSearchWarps warps).  A work item is (structure,
-// template chunk): the CTA stages the structure blob into shared memory once, then each WARP
+// Mapping.  Persistent CTAs (one per SM, kSearchWarps = 24 warps).  A work item is (structure,
+// template chunk): the CTA stages the structure blob into shared memory with one TMA bulk copy
+// (cp.async.bulk + mbarrier), then each WARP
 // pulls templates off a shared counter and runs a warp-synchronous depth-first search:
 //
 //   * level k places plan position k of the template.  Partial assignments live in per-level
 //     shared-memory queues as 4-byte (parent slot, atom) entries -- a trie, so a partial costs
 //     4 bytes whatever its depth; queues are drained depth-first in chunks of <= 32 entries, so
 //     memory is bounded however many candidates a loose cutoff produces (config 4);
-//   * EXPANDING a chunk is a cheap, dense filter: for leader positions every lane holds one
-//     candidate atom of the structure's leader list in registers and the warp loops over the
+//   * EXPANDING a chunk is a cheap, dense filter: for leader positions every lane holds up to two
+//     candidate atoms of the structure's leader list in registers and the warp loops over the
 //     chunk's partials, testing ONE distance constraint against a broadcast "anchor" atom of the
 //     partial; for same-residue positions the lanes cover (partial, residue slot) items and test
 //     the typing bit + the anchor distance.  Survivors are ballot/popc-compacted into the next
@@ -114,6 +115,37 @@ struct SearchArgs {
     SearchOut O;
     const unsigned char *skip;
 };
+
+// ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier: global -> shared staging ----------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// One thread: order the CTA's earlier generic-proxy accesses to the staging area before the async
+// proxy overwrites it, announce the byte count, and start the copy (size: multiple of 16 bytes).
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ float fast_sqrt(float v)
 {
@@ -827,8 +859,14 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
 {
     __shared__ int s_item, s_next_tpl;
     __shared__ Blob s_blob;
+    __shared__ __align__(8) uint64_t s_bar;      // mbarrier the TMA bulk copy of a blob completes on
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned stage_parity = 0;
+    if (kStaged) {
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+    }
     const SearchParams &P = A.P;
     const int qwords = queue_off(P.levels);      // queue words per warp
     uint32_t *Q = reinterpret_cast<uint32_t *>(g_smem + P.blob_cap) + (size_t)wid * qwords;
@@ -852,10 +890,9 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
         const bool run = hdr.status == 0 && hdr.n_kept > 0 && tb < te && !(A.skip && A.skip[s]);
         if (run) {
             if (kStaged) {
-                // host guarantees staged_bytes <= blob_cap for every structure of the batch
-                const int4 *src = reinterpret_cast<const int4 *>(gblob);
-                int4 *dst = reinterpret_cast<int4 *>(g_smem);
-                for (int i = tid; i < hdr.staged_bytes / 16; i += kSearchThreads) dst[i] = __ldg(src + i);
+                // host guarantees staged_bytes <= blob_cap for every structure of the batch; one
+                // thread hands the copy to the TMA engine, everyone waits on the mbarrier below
+                if (tid == 0) bulk_load(g_smem, gblob, (unsigned)hdr.staged_bytes, &s_bar);
                 if (kStats && tid == 0) st_staged += hdr.staged_bytes;
             } else if (kStats && tid == 0) {
                 ++st_global;
@@ -871,6 +908,10 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                 s_blob.cell_atoms = reinterpret_cast<const uint16_t *>(gblob + hdr.off_cellatoms);
                 s_blob.nx = hdr.nx; s_blob.ny = hdr.ny; s_blob.nz = hdr.nz;
                 s_blob.cell = hdr.cell; s_blob.ox = hdr.ox; s_blob.oy = hdr.oy; s_blob.oz = hdr.oz;
+            }
+            if (kStaged) {
+                mbar_wait(&s_bar, stage_parity);
+                stage_parity ^= 1u;
             }
             __syncthreads();
             View<kStaged> V;
