@@ -443,3 +443,39 @@ def test_cell_list_path_equals_list_path(full_engine, active_templates, mol_1amy
     big = generate_chunk(0, SynthConfig(n_chains=4), active_templates, 1)
     bb = big.to_packed(full_engine.compiled)
     assert full_engine.query(bb, cell_threshold=1).tobytes() == full_engine.query(bb, cell_threshold=-1).tobytes()
+
+
+def test_query_batch_entry_point(active_templates, mol_1amy):
+    """emm_query_batch -- the one-call C-ABI entry point (upload + run + download with host buffers)
+    -- called through ctypes exactly as INTEGRATION.md shows, equals the session path."""
+    import ctypes
+    from enzymm_b200.engine import DeviceLibrary, HIT_DTYPE, _QueryParams, _Stats, load_cdll
+    subset = active_templates[::7]
+    dist = default_distances(subset)
+    compiled = CompiledLibrary(subset, 2.0, dist, dist)
+    dev = DeviceLibrary(compiled)
+    try:
+        batch = pack_molecules([mol_1amy, mol_1amy.conserved(15)], compiled)
+        dev.sync_compat()
+        lib = load_cdll()
+        hits = np.zeros(256, dtype=HIT_DTYPE)
+        n = ctypes.c_int64(0)
+        stats = _Stats()
+        params = _QueryParams(10000, 1, 0.0, 0, 0, 0, 1, 0, 0)
+        st = batch.as_struct()
+        rc = lib.emm_query_batch(dev.handle, ctypes.byref(st), ctypes.byref(params),
+                                 hits.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(hits)), ctypes.byref(n),
+                                 ctypes.byref(stats))
+        assert rc == 0, lib.emm_last_error()
+        eng = Engine(compiled)
+        try:
+            want = eng.query(batch)
+        finally:
+            eng.close()
+        assert n.value == len(want) > 0 and hits[:n.value].tobytes() == want.tobytes()
+        tiny = np.zeros(1, dtype=HIT_DTYPE)
+        rc = lib.emm_query_batch(dev.handle, ctypes.byref(st), ctypes.byref(params),
+                                 tiny.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(1), ctypes.byref(n), None)
+        assert rc == -4 and n.value == len(want)          # EMM_ERR_CAPACITY reports the required count
+    finally:
+        dev.close()
