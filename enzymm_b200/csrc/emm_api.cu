@@ -26,6 +26,10 @@ using namespace emm;
 
 static thread_local std::string g_error;
 
+// Largest dynamic shared-memory size the search kernels have been opted into, per device (the
+// attribute is per function and device, shared by every library handle of the process).
+static size_t g_configured_smem[64] = {0};
+
 static int fail(emm_status st, const std::string &msg)
 {
     g_error = msg;
@@ -507,7 +511,10 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     cap = staged ? (int)want : 0;
     P.blob_cap = cap;
     const size_t smem = search_smem_bytes(cap, P.levels);
-    CUDA_TRY(configure_search((int)smem));
+    if (lib->device >= 64 || smem > g_configured_smem[lib->device]) {   // raise only; never per launch
+        CUDA_TRY(configure_search((int)smem));
+        if (lib->device < 64) g_configured_smem[lib->device] = smem;
+    }
     SearchOut O{};
     O.hits = s->d_hits;
     O.hit_capacity = s->hit_capacity;

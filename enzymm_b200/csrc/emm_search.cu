@@ -711,7 +711,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                 const int lbase = V.lead_off(-1 - src);
                 const int B = V.lead_off(-src) - lbase;
                 const int nrows = (B + 31) >> 5;
-                int r = cur / P, pidx = cur - r * P;       // r is always even or the last row
+                int r = cur >> 5, pidx = cur & 31;         // cursor = candidate row * 32 + partial (P <= 32)
                 const bool by_cells = kCells && k > 0 && B >= A.P.cell_threshold;
                 if (by_cells) {
                     const uint32_t *crow = L.compat + (size_t)L.plan_ttype[a0 + k] * L.class_words_cap;
@@ -782,7 +782,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     r += 2;
                 }
                 if (!by_cells) {
-                    cur = r * P + pidx;
+                    cur = (r << 5) + pidx;
                     done = r >= nrows;
                 }
             } else {
