@@ -664,9 +664,15 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
         if (!entered) {
             const int size = ws->chunk[k];
             base = ws->n[k] - size;
-            valid = k == 0 ? 1u : enter_level<kStats, kStaged>(A, S, V, Q, ws, a0, p0, m, k, base, size, cut32, cut64, dyn64, lane, st);
             entered = true;
-            if (kStats && lane == 0 && k > 0) {
+            if (ws->cur[k] < 0) {
+                // back from the children of a chunk whose expansion had finished: nothing left to
+                // do with it, so do not re-derive its anchors -- fall through and pop it
+                valid = 0u;
+            } else {
+                valid = k == 0 ? 1u : enter_level<kStats, kStaged>(A, S, V, Q, ws, a0, p0, m, k, base, size, cut32, cut64, dyn64, lane, st);
+            }
+            if (kStats && lane == 0 && k > 0 && ws->cur[k] >= 0) {
                 atomicAdd(A.O.stats + 72 + k, (unsigned long long)__popc(valid));
                 atomicAdd(A.O.stats + 104 + k, 1ull);
             }
@@ -823,7 +829,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                 done = it >= n_it;
             }
             __syncwarp();          // every lane has read the level state before lane 0 updates it
-            if (lane == 0) { ws->n[k + 1] = n_next; ws->cur[k] = cur; ws->todo[k] = todo; }
+            if (lane == 0) { ws->n[k + 1] = n_next; ws->cur[k] = done ? -1 : cur; ws->todo[k] = todo; }   // -1: finished
             if (kStats && lane == 0) atomicAdd(A.O.stats + 40 + k, (unsigned long long)(n_next - n_before));
             if (full || (done && n_next > 0)) {
                 // descend: the last <= 32 entries of the next level form its chunk
