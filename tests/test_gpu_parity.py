@@ -479,3 +479,96 @@ def test_query_batch_entry_point(active_templates, mol_1amy):
         assert rc == -4 and n.value == len(want)          # EMM_ERR_CAPACITY reports the required count
     finally:
         dev.close()
+
+
+def _perturbed_molecule(rng, mol):
+    """A structure with the irregularities real files have: deleted atoms, waters / ions / a ligand
+    as HETATM, duplicated coordinates, renumbered residues, a second chain, insertion codes."""
+    keep = rng.random(len(mol)) > 0.03
+    m = mol.select(keep)
+    cols = {k: m.column(k).copy() for k in ("serial", "name", "altloc", "residue_name", "chain_id", "residue_number",
+                                           "insertion_code", "occupancy", "temperature_factor", "segment",
+                                           "element", "charge")}
+    xyz = m.xyz.copy()
+    n = len(m)
+    half = cols["residue_number"] > np.median(cols["residue_number"])
+    if rng.random() < 0.5:
+        cols["chain_id"][half] = "B"
+    if rng.random() < 0.5:
+        cols["residue_number"][half] -= int(np.median(cols["residue_number"]))      # numbers repeat across chains
+    for _ in range(3):                                                             # duplicated atoms
+        i = int(rng.integers(n))
+        xyz[int(rng.integers(n))] = xyz[i]
+    extra = int(rng.integers(5, 40))                                               # hetero atoms with odd names
+    het_names = ["O", "ZN", "MG", "C1'", "O5'", "N1", "CA", "OXT", "FE", "O1A"]
+    het_res = ["HOH", "ZN", "MG", "NAD", "HEM", "SO4", "CA", "MSE"]
+    ex = {k: [] for k in cols}
+    exyz = []
+    for j in range(extra):
+        nm = het_names[int(rng.integers(len(het_names)))]
+        ex["serial"].append(90000 + j); ex["name"].append(nm); ex["altloc"].append(" ")
+        ex["residue_name"].append(het_res[int(rng.integers(len(het_res)))]); ex["chain_id"].append("A")
+        ex["residue_number"].append(900 + j // 3); ex["insertion_code"].append(" "); ex["occupancy"].append(1.0)
+        ex["temperature_factor"].append(20.0); ex["segment"].append(""); ex["element"].append(nm[:1]); ex["charge"].append(0)
+        exyz.append(xyz[int(rng.integers(n))] + rng.normal(size=3) * 3.0)
+    cols = {k: np.concatenate([cols[k], np.asarray(ex[k], dtype=cols[k].dtype)]) for k in cols}
+    xyz = np.round(np.concatenate([xyz, np.asarray(exyz)]), 3)
+    return Molecule._from_columns(cols, xyz, mol.id)
+
+
+def test_randomized_inputs_and_parameters(active_templates):
+    """Fuzz: irregular structures x random template subsets x random thresholds, candidate caps and
+    chain rule -- the GPU must agree with the oracle everywhere."""
+    rng = np.random.default_rng(20230210)
+    chunk = generate_chunk(9, SynthConfig(n_residues=220, max_motifs=3), active_templates, 10)
+    for trial in range(5):
+        mols = [_perturbed_molecule(rng, chunk.to_molecule(int(i))) for i in rng.choice(10, size=3, replace=False)]
+        pick = rng.choice(len(active_templates), size=260, replace=False)
+        subset = [active_templates[int(i)] for i in sorted(pick)]
+        cut = float(rng.choice([0.7, 0.9, 1.3, 1.7, 2.0, 2.6]))
+        thr = float(rng.choice([0.6, 1.0, 2.0, 4.0]))
+        cap = int(rng.choice([40, 1000, 10000]))
+        ignore = bool(rng.integers(2))
+        eng = Engine(CompiledLibrary(subset, thr, cut, cut))
+        try:
+            compare_with_oracle(eng, subset, mols, cut, rmsd=thr, max_candidates=cap, ignore_chain=ignore)
+        finally:
+            eng.close()
+
+
+def test_plain_templates_with_odd_residue_groups(mol_1amy):
+    """pyjess-level templates (no EnzyMM residues): groups of 1, 2 and 4 atoms, a single-atom
+    template, mixed match modes -- exercised through Jess.query against the oracle."""
+    from enzymm_b200.template_atoms import JessTemplate, TemplateAtom
+
+    def atom(i, mode=0, names=None, resnames=None, chain=None, resnum=None):
+        return TemplateAtom(chain_id=chain if chain is not None else str(mol_1amy.column("chain_id")[i]),
+                            residue_number=int(mol_1amy.column("residue_number")[i]) if resnum is None else resnum,
+                            residue_names=resnames or [str(mol_1amy.column("residue_name")[i])],
+                            atom_names=names or [str(mol_1amy.column("name")[i])], match_mode=mode,
+                            x=float(mol_1amy.xyz[i, 0]) + 0.05 * (i % 3), y=float(mol_1amy.xyz[i, 1]),
+                            z=float(mol_1amy.xyz[i, 2]) - 0.04 * (i % 2))
+
+    resnum = mol_1amy.column("residue_number")
+    idx = lambda r: np.nonzero((resnum == r) & (mol_1amy.column("chain_id") == "A"))[0]
+    r87, r179, r204, r288 = idx(87), idx(179), idx(204), idx(288)
+    templates = [
+        JessTemplate([atom(r87[1])], id="one-atom"),
+        JessTemplate([atom(r87[1]), atom(r87[5], 3), atom(r179[1]), atom(r179[2]), atom(r179[5], 3), atom(r179[6], 3),
+                      atom(r204[1]), atom(r204[2])], id="groups-2-4-2"),
+        JessTemplate([atom(r288[1]), atom(r288[5]), atom(r288[6], 8), atom(r204[6], 3), atom(r87[0], 1)], id="mixed-modes"),
+        JessTemplate([atom(r87[1], 100), atom(r87[2], 100), atom(r179[1], 103), atom(r204[1], 100)], id="any-residue"),
+    ]
+    ot = oracle.OracleTemplates(templates)
+    for cut, ignore in ((0.8, True), (1.5, False)):
+        hits = list(pyjess.Jess(templates).query(mol_1amy, 2.0, cut, cut, max_candidates=10000, best_match=True,
+                                                 ignore_chain=ignore))
+        want = oracle.query([mol_1amy], ot, 2.0, cut, cut, max_candidates=10000, ignore_chain=ignore)[0]
+        assert [h.template.id for h in hits] == [templates[w.template_index].id for w in want]
+        assert len(hits) >= 3
+        for h, w in zip(hits, want):
+            if w.overflow or h.overflow:
+                assert h.overflow == w.overflow
+                continue
+            assert h.atom_indices == w.atoms and h.rmsd == w.rmsd and h.n_complete == w.n_complete
+            assert math.isnan(h.orientation) and h.device_pass
