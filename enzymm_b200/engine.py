@@ -164,6 +164,20 @@ class PackedBatch:
         return PackedBatch(self.atom_off[lo:hi + 1] - a0, self.xyz[a0:a1], self.klass[a0:a1],
                            self.residue[a0:a1], cut(self.bfactor), cut(self.chain), cut(self.atom_id))
 
+    # packed binary cache: parse and classify once, reload at memory speed
+    def save(self, path) -> None:
+        """Write the batch as an uncompressed ``.npz``.  Typing classes are only meaningful for
+        the compiled library that produced them, so store the library digest next to the file."""
+        cols = {k: getattr(self, k) for k in ("atom_off", "xyz", "klass", "residue", "bfactor", "chain", "atom_id")
+                if getattr(self, k) is not None}
+        np.savez(path, **cols)
+
+    @classmethod
+    def load(cls, path) -> "PackedBatch":
+        with np.load(path) as z:
+            get = lambda k: z[k] if k in z.files else None
+            return cls(z["atom_off"], z["xyz"], z["klass"], z["residue"], get("bfactor"), get("chain"), get("atom_id"))
+
     def as_struct(self) -> _Batch:
         return _Batch(self.n_structures, self.n_atoms, _p(self.atom_off), _p(self.xyz), _p(self.klass),
                       _p(self.residue), _p(self.bfactor), _p(self.chain), _p(self.atom_id))

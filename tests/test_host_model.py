@@ -223,3 +223,14 @@ def test_load_molecules_ids_and_errors(tmp_path):
         load_molecules([tmp_path / "missing.pdb"])
     with pytest.raises(IsADirectoryError):
         load_molecules([tmp_path])
+
+
+def test_packed_batch_binary_cache(tmp_path, active_templates, mol_1amy):
+    from enzymm_b200.engine import PackedBatch
+    lib = CompiledLibrary(active_templates[:30], 2.0, 1.5, 1.5)
+    batch = pack_molecules([mol_1amy, mol_1amy.conserved(30)], lib)
+    batch.save(tmp_path / "batch.npz")
+    again = PackedBatch.load(tmp_path / "batch.npz")
+    for name in ("atom_off", "xyz", "klass", "residue", "bfactor", "chain"):
+        assert np.array_equal(getattr(batch, name), getattr(again, name)), name
+    assert again.atom_id is None and again.n_structures == 2
