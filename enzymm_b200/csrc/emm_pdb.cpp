@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/enzymm_b200.h"
@@ -167,6 +168,175 @@ int64_t parse_into(const char *text, int64_t len, const Columns &c, int64_t base
     return n;
 }
 
+// ---- files -> emm_batch columns -------------------------------------------------------------------
+
+// blank-stripped field of width w (<= 4) as little-endian bytes, NUL padded: the same bytes field() yields
+inline uint32_t strip_field(const char *p, int w)
+{
+    int lo = 0, hi = w;
+    while (lo < hi && (p[lo] == ' ' || p[lo] == '\t')) ++lo;
+    while (hi > lo && (p[hi - 1] == ' ' || p[hi - 1] == '\t' || p[hi - 1] == '\r')) --hi;
+    uint32_t v = 0;
+    for (int i = 0; lo + i < hi; ++i) v |= (uint32_t)(unsigned char)p[lo + i] << (8 * i);
+    return v;
+}
+
+inline bool fast_int(const char *p, const char *e, int32_t *out)
+{
+    while (p < e && *p == ' ') ++p;
+    while (e > p && e[-1] == ' ') --e;
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    if (p == e || e - p > 9) return false;
+    int32_t v = 0;
+    for (; p < e; ++p) {
+        const unsigned d = (unsigned)(*p - '0');
+        if (d > 9u) return false;
+        v = v * 10 + (int32_t)d;
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+
+inline bool int_field(const char *line, int64_t ll, int a, int b, int32_t *out)
+{
+    return fast_int(line + a, line + std::min<int64_t>(b, ll), out) || parse_int(line, ll, a, b, out);
+}
+
+struct PackedCols {
+    double *xyz; uint32_t *kind; int32_t *residue; float *bfactor; uint16_t *chain;
+};
+
+// open-addressing table of the distinct (resname, name) kinds of one file, first-appearance order
+struct KindTable {
+    std::vector<uint64_t> keys;          // in order of first appearance
+    std::vector<uint32_t> slot;          // hash slots: index + 1, 0 = empty
+    KindTable() : slot(1024, 0) {}
+    void clear() { keys.clear(); std::fill(slot.begin(), slot.end(), 0u); }
+    uint32_t lookup(uint64_t key)
+    {
+        const size_t mask = slot.size() - 1;
+        size_t h = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+        for (;; h = (h + 1) & mask) {
+            const uint32_t v = slot[h];
+            if (!v) break;
+            if (keys[v - 1] == key) return v - 1;
+        }
+        keys.push_back(key);
+        slot[h] = (uint32_t)keys.size();
+        if (keys.size() * 2 > slot.size()) {                  // grow and rehash
+            std::vector<uint32_t> bigger(slot.size() * 4, 0u);
+            const size_t m2 = bigger.size() - 1;
+            for (size_t i = 0; i < keys.size(); ++i) {
+                size_t g = (size_t)((keys[i] * 0x9E3779B97F4A7C15ull) >> 40) & m2;
+                while (bigger[g]) g = (g + 1) & m2;
+                bigger[g] = (uint32_t)i + 1;
+            }
+            slot.swap(bigger);
+        }
+        return (uint32_t)keys.size() - 1;
+    }
+};
+
+// One file into the packed columns at [base, base+capacity).  kind[] receives file-local kind
+// indices; *split is set when a residue key reappears after another residue (the caller then
+// regroups the file).  Returns atoms parsed or -1 (t_error set).
+int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t base, int64_t capacity,
+                  KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5])
+{
+    int64_t n = 0, pos = 0;
+    bool have_header = false;
+    memset(header_id, 0, 5);
+    uint64_t prev_kind = ~0ull, prev_res = ~0ull;
+    uint32_t prev_kind_idx = 0;
+    int32_t run = -1;
+    run_keys.clear();
+    *split = false;
+    while (pos < len) {
+        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
+        const int64_t end = nl ? nl - text : len;
+        const char *line = text + pos;
+        int64_t ll = end - pos;
+        while (ll > 0 && line[ll - 1] == '\r') --ll;
+        if (is_coord_record(line, ll)) {
+            if (n >= capacity) { t_error = "atom capacity exceeded"; return -1; }
+            const int64_t i = base + n;
+            double x, y, z, occ, bf;
+            int32_t serial, resnum;
+            if (ll < 54 || !int_field(line, ll, 6, 11, &serial) || !int_field(line, ll, 22, 26, &resnum) ||
+                !parse_real(line, ll, 30, 38, &x, false) || !parse_real(line, ll, 38, 46, &y, false) ||
+                !parse_real(line, ll, 46, 54, &z, false) || !parse_real(line, ll, 54, 60, &occ, true) ||
+                !parse_real(line, ll, 60, 66, &bf, true)) {
+                t_error = "malformed PDB coordinate record: " + std::string(line, (size_t)std::min<int64_t>(ll, 80));
+                return -1;
+            }
+            c.xyz[3 * i] = x; c.xyz[3 * i + 1] = y; c.xyz[3 * i + 2] = z;
+            c.bfactor[i] = (float)bf;
+            const uint32_t name = strip_field(line + 12, 4), resname = strip_field(line + 17, 3);
+            const uint16_t chain = (uint16_t)strip_field(line + 20, 2);
+            const uint64_t kkey = (uint64_t)resname | ((uint64_t)name << 32);
+            if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
+            c.kind[i] = prev_kind_idx;
+            c.chain[i] = chain;
+            const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum;
+            if (rkey != prev_res || run < 0) {
+                prev_res = rkey;
+                ++run;
+                run_keys.push_back(rkey);
+            }
+            c.residue[i] = run;
+            ++n;
+        } else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) {
+            break;
+        } else if (!have_header && ll >= 6 && memcmp(line, "HEADER", 6) == 0) {
+            have_header = true;
+            char id[5];
+            field(line, ll, 62, 66, id, 4);
+            id[4] = 0;
+            memcpy(header_id, id, 5);
+        }
+        pos = end + 1;
+    }
+    {
+        std::vector<uint64_t> sorted(run_keys);
+        std::sort(sorted.begin(), sorted.end());
+        *split = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+    }
+    return n;
+}
+
+// A file with a split residue: number residues by first appearance of their key and make every
+// residue's atoms contiguous with a stable sort (packing.py residue_ordinals does the same).
+void regroup_file(const PackedCols &c, int64_t base, int64_t n, const std::vector<uint64_t> &run_keys, int32_t *atom_id)
+{
+    std::unordered_map<uint64_t, int32_t> rank_of;
+    std::vector<int32_t> rank_of_run(run_keys.size());
+    for (size_t r = 0; r < run_keys.size(); ++r)
+        rank_of_run[r] = rank_of.emplace(run_keys[r], (int32_t)rank_of.size()).first->second;
+    std::vector<int32_t> ordinal((size_t)n), order((size_t)n);
+    for (int64_t j = 0; j < n; ++j) {
+        ordinal[(size_t)j] = rank_of_run[(size_t)c.residue[base + j]];
+        order[(size_t)j] = (int32_t)j;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ordinal[(size_t)a] < ordinal[(size_t)b]; });
+    std::vector<double> xyz((size_t)(3 * n));
+    std::vector<uint32_t> kind((size_t)n);
+    std::vector<float> bf((size_t)n);
+    std::vector<uint16_t> chain((size_t)n);
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t src = base + order[(size_t)j];
+        xyz[(size_t)(3 * j)] = c.xyz[3 * src]; xyz[(size_t)(3 * j + 1)] = c.xyz[3 * src + 1]; xyz[(size_t)(3 * j + 2)] = c.xyz[3 * src + 2];
+        kind[(size_t)j] = c.kind[src]; bf[(size_t)j] = c.bfactor[src]; chain[(size_t)j] = c.chain[src];
+    }
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t dst = base + j;
+        c.xyz[3 * dst] = xyz[(size_t)(3 * j)]; c.xyz[3 * dst + 1] = xyz[(size_t)(3 * j + 1)]; c.xyz[3 * dst + 2] = xyz[(size_t)(3 * j + 2)];
+        c.kind[dst] = kind[(size_t)j]; c.bfactor[dst] = bf[(size_t)j]; c.chain[dst] = chain[(size_t)j];
+        c.residue[dst] = ordinal[(size_t)order[(size_t)j]];
+        atom_id[dst] = order[(size_t)j];
+    }
+}
+
 bool read_file(const char *path, std::string &out, int *err)
 {
     FILE *f = fopen(path, "rb");
@@ -192,6 +362,13 @@ struct emm_pdb_batch {
     std::vector<char> name, altloc, resname, chain, icode, segment, element, header_id;
     std::vector<double> xyz, occupancy, bfactor;
     std::vector<int8_t> charge;
+    // packed form (emm_pdb_pack_files)
+    bool packed = false, has_atom_id = false;
+    std::vector<uint32_t> kind;
+    std::vector<int32_t> residue, atom_id;
+    std::vector<float> bfactor32;
+    std::vector<uint16_t> chain16;
+    std::vector<char> kind_names;
 };
 
 extern "C" {
@@ -283,7 +460,7 @@ int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_thre
 
 int emm_pdb_batch_columns(const emm_pdb_batch *b, emm_pdb_columns *out)
 {
-    if (!b || !out) return EMM_ERR_INVALID;
+    if (!b || !out || b->packed) return EMM_ERR_INVALID;
     out->n_files = b->n_files;
     out->n_atoms = b->n_atoms;
     out->atom_off = b->atom_off.data();
@@ -292,6 +469,118 @@ int emm_pdb_batch_columns(const emm_pdb_batch *b, emm_pdb_columns *out)
     out->icode = b->icode.data(); out->xyz = b->xyz.data(); out->occupancy = b->occupancy.data();
     out->bfactor = b->bfactor.data(); out->segment = b->segment.data(); out->element = b->element.data();
     out->charge = b->charge.data(); out->header_id = b->header_id.data();
+    return EMM_OK;
+}
+
+int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out)
+{
+    if (!paths || !out || n_files < 0) return EMM_ERR_INVALID;
+    *out = nullptr;
+    emm_pdb_batch *b = new emm_pdb_batch();
+    b->n_files = n_files;
+    b->packed = true;
+    const size_t nf = (size_t)n_files;
+    std::vector<std::string> texts(nf);
+    std::vector<int64_t> counts(nf, 0);
+    std::vector<int> errs(nf, 0);
+    if (n_threads < 1) n_threads = 1;
+    n_threads = std::min<int32_t>(n_threads, std::max(n_files, 1));
+    auto run_pool = [&](auto &&work) {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    };
+    {
+        std::atomic<int> next(0);
+        run_pool([&]() {
+            for (int i; (i = next.fetch_add(1)) < n_files;)
+                if (read_file(paths[i], texts[(size_t)i], &errs[(size_t)i]))
+                    counts[(size_t)i] = count_atoms(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size());
+        });
+    }
+    for (int i = 0; i < n_files; ++i)
+        if (errs[(size_t)i]) {
+            t_error = std::string(errs[(size_t)i] == 1 ? "cannot open " : "cannot read ") + paths[i];
+            const int rc = errs[(size_t)i] == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
+            delete b;
+            return rc;
+        }
+    b->atom_off.assign(nf + 1, 0);
+    for (size_t i = 0; i < nf; ++i) b->atom_off[i + 1] = b->atom_off[i] + counts[i];
+    const size_t n = (size_t)b->atom_off[nf];
+    b->n_atoms = (int64_t)n;
+    b->xyz.resize(3 * n); b->kind.resize(n); b->residue.resize(n); b->bfactor32.resize(n); b->chain16.resize(n);
+    b->header_id.assign(5 * nf, 0);
+    const PackedCols c{b->xyz.data(), b->kind.data(), b->residue.data(), b->bfactor32.data(), b->chain16.data()};
+    std::vector<std::vector<uint64_t>> file_kinds(nf), split_keys(nf);
+    std::vector<char> split(nf, 0);
+    std::vector<std::string> messages(nf);
+    std::atomic<int> failed(-1);
+    {
+        std::atomic<int> next(0);
+        run_pool([&]() {
+            KindTable kinds;
+            std::vector<uint64_t> run_keys;
+            for (int i; (i = next.fetch_add(1)) < n_files;) {
+                const size_t f = (size_t)i;
+                kinds.clear();
+                bool sp = false;
+                const int64_t got = pack_into(texts[f].data(), (int64_t)texts[f].size(), c, b->atom_off[f], counts[f],
+                                              kinds, run_keys, &sp, &b->header_id[5 * f]);
+                if (got != counts[f]) { messages[f] = t_error; failed.store(i); continue; }
+                file_kinds[f] = kinds.keys;
+                if (sp) { split[f] = 1; split_keys[f] = run_keys; }
+                std::string().swap(texts[f]);
+            }
+        });
+    }
+    if (failed.load() >= 0) {
+        t_error = std::string(paths[failed.load()]) + ": " + messages[(size_t)failed.load()];
+        delete b;
+        return EMM_ERR_INPUT;
+    }
+    // merge the per-file kind lists in file order (deterministic whatever the thread count)
+    KindTable global;
+    std::vector<std::vector<uint32_t>> remap(nf);
+    for (size_t f = 0; f < nf; ++f) {
+        remap[f].resize(file_kinds[f].size());
+        for (size_t j = 0; j < file_kinds[f].size(); ++j) remap[f][j] = global.lookup(file_kinds[f][j]);
+    }
+    b->kind_names.assign(8 * global.keys.size(), 0);
+    for (size_t j = 0; j < global.keys.size(); ++j) memcpy(&b->kind_names[8 * j], &global.keys[j], 8);
+    b->has_atom_id = std::find(split.begin(), split.end(), (char)1) != split.end();
+    if (b->has_atom_id) b->atom_id.resize(n);
+    {
+        std::atomic<int> next(0);
+        run_pool([&]() {
+            for (int i; (i = next.fetch_add(1)) < n_files;) {
+                const size_t f = (size_t)i;
+                const int64_t lo = b->atom_off[f], hi = b->atom_off[f + 1];
+                const std::vector<uint32_t> &m = remap[f];
+                for (int64_t a = lo; a < hi; ++a) b->kind[(size_t)a] = m[b->kind[(size_t)a]];
+                if (split[f]) regroup_file(c, lo, hi - lo, split_keys[f], b->atom_id.data());
+                else if (b->has_atom_id)
+                    for (int64_t a = lo; a < hi; ++a) b->atom_id[(size_t)a] = (int32_t)(a - lo);
+            }
+        });
+    }
+    *out = b;
+    return EMM_OK;
+}
+
+int emm_pdb_batch_packed(const emm_pdb_batch *b, emm_pdb_packed *out)
+{
+    if (!b || !out || !b->packed) return EMM_ERR_INVALID;
+    out->n_files = b->n_files;
+    out->n_atoms = b->n_atoms;
+    out->atom_off = b->atom_off.data();
+    out->xyz = b->xyz.data(); out->kind = b->kind.data(); out->residue = b->residue.data();
+    out->bfactor = b->bfactor32.data(); out->chain = b->chain16.data();
+    out->atom_id = b->has_atom_id ? b->atom_id.data() : nullptr;
+    out->n_kinds = (int32_t)(b->kind_names.size() / 8);
+    out->kind_names = b->kind_names.data();
+    out->header_id = b->header_id.data();
     return EMM_OK;
 }
 

@@ -417,13 +417,10 @@ class Matcher:
             self._engine = Engine(CompiledLibrary(ordered, rmsd, dist, dyn), self.device)
         return self._engine
 
-    def run(self, molecules: List[Molecule]) -> Dict[Molecule, List[Match]]:
-        """Search every molecule against every size group; ``{molecule: [Match, ...]}``."""
-        processed: Dict[Molecule, List[Match]] = collections.defaultdict(list)
-        if not self._active_sizes() or not molecules:
-            return processed
+    def _search(self, batch) -> np.ndarray:
+        """One packed batch through the device: every size group, hit records sorted by
+        (structure, template index)."""
         engine = self._ensure_engine()
-        batch = pack_molecules(molecules, engine.compiled)
         cutoff = float(self.conservation_cutoff) if (self.apply_conservation_mask and self.conservation_cutoff) else 0.0
         session = engine.session_for(batch.n_atoms, batch.n_structures)
         session.upload(batch)
@@ -435,8 +432,49 @@ class Matcher:
                 session.run(template_begin=lo, template_end=hi, skip_mode=mode, reset=(gi == 0), **common)
         else:
             session.run(template_begin=0, template_end=len(self._ordered), skip_mode=0, reset=True, **common)
-        records = session.download()
+        return session.download()
 
+    def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0):
+        """Screen PDB files without building ``Molecule`` objects: a generator of
+        ``(chunk_paths, header_ids, records)`` per chunk of ``chunk_size`` files, ``records`` being the
+        hit records of the chunk (``structure`` indexes ``chunk_paths``; ``flags & 4`` = passes the
+        filter).  Files are read, parsed and packed natively (``packing.pack_files``) on a
+        background thread while the GPU searches the previous chunk.  ``matches_for`` turns the
+        records of one file into the ``Match`` objects ``run`` would have returned for it."""
+        import concurrent.futures
+        from .packing import pack_files
+        if not self._active_sizes():
+            return
+        engine = self._ensure_engine()
+        paths = [os.fspath(p) for p in paths]
+        chunks = [paths[i:i + chunk_size] for i in range(0, len(paths), chunk_size)]
+        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(pack_files, chunks[0], engine.compiled, True, threads) if chunks else None
+            for ci, chunk in enumerate(chunks):
+                batch, ids = pending.result()
+                pending = (pool.submit(pack_files, chunks[ci + 1], engine.compiled, True, threads)
+                           if ci + 1 < len(chunks) else None)
+                yield chunk, ids, self._search(batch)
+
+    def matches_for(self, molecule: Molecule, records: np.ndarray) -> List[Match]:
+        """``Match`` objects for the hit records of one structure (``records`` = the rows of a
+        ``scan_files`` chunk whose ``structure`` is this molecule), as ``run`` builds them."""
+        relabel = records.copy()
+        relabel["structure"] = 0
+        return self._assemble(relabel, [molecule]).get(molecule, [])
+
+    def run(self, molecules: List[Molecule]) -> Dict[Molecule, List[Match]]:
+        """Search every molecule against every size group; ``{molecule: [Match, ...]}``."""
+        processed: Dict[Molecule, List[Match]] = collections.defaultdict(list)
+        if not self._active_sizes() or not molecules:
+            return processed
+        engine = self._ensure_engine()
+        return self._assemble(self._search(pack_molecules(molecules, engine.compiled)), molecules)
+
+    def _assemble(self, records: np.ndarray, molecules: Sequence[Molecule]) -> Dict[Molecule, List[Match]]:
+        """Hit records -> ``{molecule: [Match]}`` with the reference's per-size-group completeness
+        check and filtering (``jess_run.py:845-894``)."""
+        processed: Dict[Molecule, List[Match]] = collections.defaultdict(list)
         by_cell: Dict[Tuple[int, int], List[np.void]] = collections.defaultdict(list)
         bounds = np.asarray([hi for _, _, hi in self._groups])
         for rec in records:

@@ -6,15 +6,17 @@ atom (a residue = one (chain_id, residue_number), SURVEY.md 8c rule 4), B-factor
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
 from .engine import PackedBatch
 from .library import CompiledLibrary
-from .structures import Molecule
+from .structures import Molecule, _native_lib
 
-__all__ = ["residue_ordinals", "pack_molecules", "chain_codes"]
+__all__ = ["residue_ordinals", "pack_molecules", "pack_files", "chain_codes"]
 
 
 def chain_codes(col: np.ndarray) -> np.ndarray:
@@ -90,3 +92,72 @@ def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
         bfactor[lo:hi] = bf
         chain[lo:hi] = codes
     return PackedBatch(atom_off, xyz, klass, residue, bfactor, chain if with_chain else None, atom_id)
+
+
+class _PdbPacked(ctypes.Structure):       # struct emm_pdb_packed
+    _fields_ = [("n_files", ctypes.c_int32), ("n_atoms", ctypes.c_int64)] + \
+               [(k, ctypes.c_void_p) for k in ("atom_off", "xyz", "kind", "residue", "bfactor", "chain", "atom_id")] + \
+               [("n_kinds", ctypes.c_int32), ("kind_names", ctypes.c_void_p), ("header_id", ctypes.c_void_p)]
+
+
+class _NativeBatch:
+    """Owns one ``emm_pdb_batch`` handle; freed when the last array viewing it goes away."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._handle = lib, handle
+
+    def __del__(self):
+        if self._handle:
+            self._lib.emm_pdb_batch_free(self._handle)
+            self._handle = None
+
+
+def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrary, with_chain: bool = True,
+               threads: int = 0) -> Tuple[PackedBatch, List[Optional[str]]]:
+    """PDB files -> ``PackedBatch`` on the native thread pool (``emm_pdb_pack_files``), without
+    building ``Molecule`` objects: the same columns ``pack_molecules(load_many(paths), library)``
+    gives, at parser speed.  Returns ``(batch, header_ids)``; what replaces the per-file
+    ``Molecule.load`` of ``jess_run.py:538-548`` when only the hits are wanted."""
+    lib = _native_lib()
+    paths = [os.fspath(p) for p in paths]
+    for p in paths:
+        if os.path.isdir(p):
+            raise IsADirectoryError(21, "Is a directory", p)
+        if not os.path.exists(p):
+            raise FileNotFoundError(2, "No such file or directory", p)
+    arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
+    handle = ctypes.c_void_p()
+    n_threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1)
+    rc = lib.emm_pdb_pack_files(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.byref(handle))
+    if rc != 0:
+        raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
+    owner = _NativeBatch(lib, handle)       # the big columns stay views of the native buffers
+    c = _PdbPacked()
+    if lib.emm_pdb_batch_packed(handle, ctypes.byref(c)) != 0:
+        raise RuntimeError("emm_pdb_batch_packed failed")
+    n, nf = c.n_atoms, c.n_files
+
+    def grab(ptr, dtype, count):
+        if count == 0 or not ptr:
+            return np.zeros(0, dtype=dtype)
+        buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+        buf._owner = owner                   # array -> memoryview -> buf -> owner keeps the batch alive
+        return np.frombuffer(buf, dtype=dtype, count=count)
+
+    atom_off = grab(c.atom_off, np.int64, nf + 1)
+    xyz = grab(c.xyz, np.float64, 3 * n).reshape(n, 3)
+    kind = grab(c.kind, np.uint32, n)
+    residue = grab(c.residue, np.int32, n)
+    bfactor = grab(c.bfactor, np.float32, n)
+    chain = grab(c.chain, np.uint16, n) if with_chain else None
+    atom_id = grab(c.atom_id, np.int32, n) if c.atom_id else None
+    names = grab(c.kind_names, np.uint8, 8 * c.n_kinds).reshape(-1, 8)
+    headers = grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5)
+    class_of_kind = np.zeros(max(len(names), 1), dtype=np.uint16)
+    for i, row in enumerate(names):
+        res = bytes(row[:4]).split(b"\0")[0].decode("ascii", "replace")
+        name = bytes(row[4:]).split(b"\0")[0].decode("ascii", "replace")
+        class_of_kind[i] = library.class_of(res, name)
+    klass = class_of_kind[kind] if n else np.zeros(0, dtype=np.uint16)
+    ids = [bytes(h).split(b"\0")[0].decode() or None for h in headers]
+    return PackedBatch(atom_off, xyz, klass, residue, bfactor, chain, atom_id), ids

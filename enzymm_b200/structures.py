@@ -170,6 +170,8 @@ def _native_lib():
             raise ImportError(f"{path} is missing: build it with `make -C enzymm_b200/csrc`")
         lib = ctypes.CDLL(str(path))
         lib.emm_pdb_last_error.restype = ctypes.c_char_p
+        lib.emm_pdb_batch_free.argtypes = [ctypes.c_void_p]
+        lib.emm_pdb_batch_free.restype = None
         _native = lib
     return _native
 

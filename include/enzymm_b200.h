@@ -245,6 +245,33 @@ int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_thre
 int emm_pdb_batch_columns(const emm_pdb_batch *batch, emm_pdb_columns *out);
 void emm_pdb_batch_free(emm_pdb_batch *batch);
 
+/*
+ * Files -> the columns of emm_batch in one native pass, without per-atom host objects: what
+ * jess_run.py:538-548 (Molecule.load per file) plus the packing of the batched upload do together.
+ * Typing needs the (residue name, atom name) of every atom; the reader returns a per-atom index
+ * into a table of the distinct kinds it saw (first-appearance order, files in argument order), and
+ * the caller maps kinds to typing classes of its compiled library (klass = class_of_kind[kind]).
+ * residue / atom_id follow emm_batch: residues numbered by first appearance of (chain, resSeq);
+ * atom_id is NULL unless some file had a residue split over several runs (then it holds, for every
+ * file, the original index of each packed atom).
+ */
+typedef struct emm_pdb_packed {
+    int32_t n_files;
+    int64_t n_atoms;
+    const int64_t *atom_off;      /* [n_files+1] */
+    const double *xyz;            /* [n_atoms][3] */
+    const uint32_t *kind;         /* [n_atoms] index into kind_names */
+    const int32_t *residue;       /* [n_atoms] */
+    const float *bfactor;         /* [n_atoms] */
+    const uint16_t *chain;        /* [n_atoms] chain id bytes: b0 | b1 << 8 */
+    const int32_t *atom_id;       /* [n_atoms] or NULL */
+    int32_t n_kinds;
+    const char *kind_names;       /* [n_kinds][8]: resname[4] name[4], blank-stripped, NUL padded */
+    const char *header_id;        /* [n_files][5] */
+} emm_pdb_packed;
+int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
+int emm_pdb_batch_packed(const emm_pdb_batch *batch, emm_pdb_packed *out);
+
 #ifdef __cplusplus
 }
 #endif

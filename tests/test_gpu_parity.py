@@ -572,3 +572,35 @@ def test_plain_templates_with_odd_residue_groups(mol_1amy):
                 continue
             assert h.atom_indices == w.atoms and h.rmsd == w.rmsd and h.n_complete == w.n_complete
             assert math.isnan(h.orientation) and h.device_pass
+
+
+# ---- file screening path: native ingest -> device, no Molecule objects ---------------------------------
+
+def test_scan_files_equals_matcher_run(tmp_path, active_templates):
+    """``Matcher.scan_files`` (files -> packed columns natively -> GPU, chunked and prefetched) gives,
+    file by file, the matches ``Matcher.run(load_molecules(files))`` gives."""
+    chunk = generate_chunk(11, SynthConfig(n_residues=160), templates=active_templates, count=5)
+    paths = []
+    for i in range(5):
+        p = tmp_path / f"synth{i}.pdb"
+        p.write_text(chunk.to_pdb(i))
+        paths.append(p)
+    paths[2:2] = [GOLDEN / "1AMY.pdb", GOLDEN / "AF-P0DUB6-F1-model_v4.pdb"]
+    for kwargs in (dict(), dict(filter_matches=False, skip_smaller_hits=True)):
+        matcher = jess_run.Matcher(templates=active_templates, **kwargs)
+        molecules = jess_run.load_molecules(paths)
+        want = matcher.run(molecules)
+        seen = 0
+        for chunk_paths, ids, records in matcher.scan_files(paths, chunk_size=3, threads=2):
+            assert chunk_paths == [str(p) for p in paths[seen:seen + 3]]
+            for j, path in enumerate(chunk_paths):
+                mol = molecules[seen + j]
+                assert ids[j] == Molecule.load(path).id
+                got = matcher.matches_for(mol, records[records["structure"] == j])
+                expect = want.get(mol, [])
+                assert [m.hit.template.id for m in got] == [m.hit.template.id for m in expect]
+                assert [m.hit.atom_indices for m in got] == [m.hit.atom_indices for m in expect]
+                assert [m.hit.rmsd for m in got] == [m.hit.rmsd for m in expect]
+                assert [m.complete for m in got] == [m.complete for m in expect]
+            seen += len(chunk_paths)
+        assert seen == len(paths)

@@ -234,3 +234,56 @@ def test_packed_batch_binary_cache(tmp_path, active_templates, mol_1amy):
     for name in ("atom_off", "xyz", "klass", "residue", "bfactor", "chain"):
         assert np.array_equal(getattr(batch, name), getattr(again, name)), name
     assert again.atom_id is None and again.n_structures == 2
+
+
+def _assert_batches_equal(a, b):
+    for name in ("atom_off", "xyz", "klass", "residue", "bfactor", "chain", "atom_id"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert (x is None) == (y is None), name
+        if x is not None:
+            assert x.dtype == y.dtype and np.array_equal(x, y), name
+
+
+def test_pack_files_matches_molecule_path(tmp_path, active_templates):
+    """files -> PackedBatch natively == pack_molecules(load_many(files)), incl. a split residue,
+    an empty file, CRLF line ends and a multi-model file (first model only)."""
+    from enzymm_b200.packing import pack_files
+    from enzymm_b200.structures import load_many
+    lib = CompiledLibrary(active_templates[:40], 2.0, 1.5, 1.5)
+    text = (GOLDEN / "1AMY.pdb").read_text()
+    lines = [l for l in text.splitlines() if l.startswith(("ATOM", "HETATM"))]
+    split = tmp_path / "split.pdb"          # residue 1's last atoms reappear after residue 3
+    first = [l for l in lines if int(l[22:26]) == 1]
+    rest = [l for l in lines if 1 < int(l[22:26]) <= 3]
+    split.write_text("\n".join(first[:3] + rest + first[3:] + lines[40:200]) + "\n")
+    empty = tmp_path / "empty.pdb"
+    empty.write_text("REMARK nothing here\nEND\n")
+    crlf = tmp_path / "crlf.pdb"
+    crlf.write_bytes(("\r\n".join(["HEADER    HYDROLASE" + " " * 43 + "9XYZ"] + lines[:300]) + "\r\n").encode())
+    models = tmp_path / "models.pdb"
+    models.write_text("MODEL        1\n" + "\n".join(lines[:50]) + "\nENDMDL\nMODEL        2\n" + "\n".join(lines[50:90]) + "\nENDMDL\n")
+    paths = [GOLDEN / "1AMY.pdb", split, empty, GOLDEN / "AF-P0DUB6-F1-model_v4.pdb", crlf, models]
+    for subset in (paths, [paths[0], paths[3]], [empty], []):
+        expect = pack_molecules(load_many(subset), lib)
+        for threads in (1, 3):
+            got, ids = pack_files(subset, lib, threads=threads)
+            _assert_batches_equal(expect, got)
+            assert ids == [m.id for m in load_many(subset)]
+    got, _ = pack_files(paths, lib)
+    assert got.atom_id is not None and got.n_structures == 6
+    assert np.diff(got.atom_off).tolist()[2] == 0 and np.diff(got.atom_off).tolist()[5] == 50
+    no_chain, _ = pack_files(paths[:1], lib, with_chain=False)
+    assert no_chain.chain is None
+
+
+def test_pack_files_errors(tmp_path, active_templates):
+    from enzymm_b200.packing import pack_files
+    lib = CompiledLibrary(active_templates[:5], 2.0, 1.5, 1.5)
+    with pytest.raises(FileNotFoundError):
+        pack_files([tmp_path / "missing.pdb"], lib)
+    with pytest.raises(IsADirectoryError):
+        pack_files([tmp_path], lib)
+    bad = tmp_path / "bad.pdb"
+    bad.write_text("ATOM      1  N   ALA A   1      xx.xxx  22.000  33.000  1.00  0.00           N\n")
+    with pytest.raises(ValueError, match="malformed PDB coordinate record"):
+        pack_files([bad], lib)
