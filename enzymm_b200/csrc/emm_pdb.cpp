@@ -5,11 +5,16 @@
 // rule 1); coordinates go through strtod, i.e. they are exactly the doubles Python's float()
 // yields for the same text.  emm_pdb_load_files reads and parses many files on a thread pool into
 // one SoA batch, which is what the batched upload wants.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -203,6 +208,41 @@ inline bool int_field(const char *line, int64_t ll, int a, int b, int32_t *out)
     return fast_int(line + a, line + std::min<int64_t>(b, ll), out) || parse_int(line, ll, a, b, out);
 }
 
+// The canonical "%W.Ff" layout (blanks, optional '-', digits, '.', F digits) without the generic
+// scanner: same mantissa and the same single division as fast_real, so the same double.
+template <int W, int F>
+inline bool real_layout(const char *p, double *out)
+{
+    static_assert(F >= 1 && F <= 3 && W - F - 2 >= 0, "layout");
+    if (p[W - F - 1] != '.') return false;
+    int i = W - F - 2;
+    unsigned d = (unsigned)(unsigned char)p[i] - '0';
+    if (d > 9u) return false;
+    uint64_t ip = d, scale = 10;
+    bool neg = false;
+    for (--i; i >= 0; --i) {
+        const unsigned c = (unsigned char)p[i];
+        d = c - '0';
+        if (d <= 9u) { ip += d * scale; scale *= 10; }
+        else if (c == '-') { neg = true; --i; break; }
+        else if (c == ' ') break;
+        else return false;
+    }
+    for (; i >= 0; --i)
+        if (p[i] != ' ') return false;
+    uint64_t frac = 0;
+    for (int j = W - F; j < W; ++j) {
+        d = (unsigned)(unsigned char)p[j] - '0';
+        if (d > 9u) return false;
+        frac = frac * 10 + d;
+    }
+    constexpr double div = F == 1 ? 1e1 : F == 2 ? 1e2 : 1e3;
+    constexpr uint64_t mul = F == 1 ? 10 : F == 2 ? 100 : 1000;
+    const double v = (double)(ip * mul + frac) / div;
+    *out = neg ? -v : v;
+    return true;
+}
+
 struct PackedCols {
     double *xyz; uint32_t *kind; int32_t *residue; float *bfactor; uint16_t *chain;
 };
@@ -263,10 +303,13 @@ int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t ba
             const int64_t i = base + n;
             double x, y, z, occ, bf;
             int32_t serial, resnum;
+            const bool wide = ll >= 66;
             if (ll < 54 || !int_field(line, ll, 6, 11, &serial) || !int_field(line, ll, 22, 26, &resnum) ||
-                !parse_real(line, ll, 30, 38, &x, false) || !parse_real(line, ll, 38, 46, &y, false) ||
-                !parse_real(line, ll, 46, 54, &z, false) || !parse_real(line, ll, 54, 60, &occ, true) ||
-                !parse_real(line, ll, 60, 66, &bf, true)) {
+                !(real_layout<8, 3>(line + 30, &x) || parse_real(line, ll, 30, 38, &x, false)) ||
+                !(real_layout<8, 3>(line + 38, &y) || parse_real(line, ll, 38, 46, &y, false)) ||
+                !(real_layout<8, 3>(line + 46, &z) || parse_real(line, ll, 46, 54, &z, false)) ||
+                !((wide && real_layout<6, 2>(line + 54, &occ)) || parse_real(line, ll, 54, 60, &occ, true)) ||
+                !((wide && real_layout<6, 2>(line + 60, &bf)) || parse_real(line, ll, 60, 66, &bf, true))) {
                 t_error = "malformed PDB coordinate record: " + std::string(line, (size_t)std::min<int64_t>(ll, 80));
                 return -1;
             }
@@ -352,7 +395,65 @@ bool read_file(const char *path, std::string &out, int *err)
     return true;
 }
 
+// whole file into a reusable buffer (grown, never shrunk: no mmap churn between files)
+bool read_file_into(const char *path, std::vector<char> &buf, int64_t *len, int *err)
+{
+    const int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) { *err = 1; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) { close(fd); *err = 2; return false; }
+    size_t size = (size_t)st.st_size, got = 0;
+    if (buf.size() < size + 1) buf.resize(size + size / 4 + 4096);
+    for (;;) {
+        if (got == buf.size()) buf.resize(buf.size() * 2);        // the file grew, or st_size lied (procfs)
+        const ssize_t r = read(fd, buf.data() + got, buf.size() - got);
+        if (r < 0) { close(fd); *err = 2; return false; }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    *len = (int64_t)got;
+    return true;
+}
+
+// the packed columns of one file, in one allocation
+struct FileBlock {
+    int64_t n = 0;
+    std::unique_ptr<char[]> mem;
+    std::unique_ptr<int32_t[]> atom_id;
+    double *xyz = nullptr; uint32_t *kind = nullptr; int32_t *residue = nullptr; float *bfactor = nullptr;
+    uint16_t *chain = nullptr;
+    std::vector<uint64_t> kinds;
+    bool split = false;
+    void allocate(int64_t count)
+    {
+        n = count;
+        const size_t c = (size_t)std::max<int64_t>(count, 1);
+        mem.reset(new char[c * (24 + 4 + 4 + 4 + 2) + 64]);
+        char *p = mem.get();
+        p += (8 - (reinterpret_cast<uintptr_t>(p) & 7)) & 7;
+        xyz = reinterpret_cast<double *>(p); p += c * 24;
+        kind = reinterpret_cast<uint32_t *>(p); p += c * 4;
+        residue = reinterpret_cast<int32_t *>(p); p += c * 4;
+        bfactor = reinterpret_cast<float *>(p); p += c * 4;
+        chain = reinterpret_cast<uint16_t *>(p);
+    }
+    void release() { mem.reset(); atom_id.reset(); std::vector<uint64_t>().swap(kinds); }
+};
+
 }  // namespace
+
+// array that is NOT value-initialised: its pages are first touched by the worker that fills them
+template <typename T>
+struct RawArray {
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void resize(size_t count) { p.reset(count ? new T[count] : nullptr); n = count; }
+    T *data() { return p.get(); }
+    const T *data() const { return p.get(); }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
 
 struct emm_pdb_batch {
     int32_t n_files = 0;
@@ -363,11 +464,14 @@ struct emm_pdb_batch {
     std::vector<double> xyz, occupancy, bfactor;
     std::vector<int8_t> charge;
     // packed form (emm_pdb_pack_files)
-    bool packed = false, has_atom_id = false;
-    std::vector<uint32_t> kind;
-    std::vector<int32_t> residue, atom_id;
-    std::vector<float> bfactor32;
-    std::vector<uint16_t> chain16;
+    bool packed = false, has_atom_id = false, has_klass = false;
+    int n_threads = 1;
+    RawArray<uint16_t> klass;
+    RawArray<double> pxyz;
+    RawArray<uint32_t> kind;
+    RawArray<int32_t> residue, atom_id;
+    RawArray<float> bfactor32;
+    RawArray<uint16_t> chain16;
     std::vector<char> kind_names;
 };
 
@@ -476,96 +580,126 @@ int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_thre
 {
     if (!paths || !out || n_files < 0) return EMM_ERR_INVALID;
     *out = nullptr;
-    emm_pdb_batch *b = new emm_pdb_batch();
+    std::unique_ptr<emm_pdb_batch> b(new emm_pdb_batch());
     b->n_files = n_files;
     b->packed = true;
     const size_t nf = (size_t)n_files;
-    std::vector<std::string> texts(nf);
-    std::vector<int64_t> counts(nf, 0);
-    std::vector<int> errs(nf, 0);
     if (n_threads < 1) n_threads = 1;
     n_threads = std::min<int32_t>(n_threads, std::max(n_files, 1));
+    b->n_threads = n_threads;
     auto run_pool = [&](auto &&work) {
         std::vector<std::thread> pool;
         for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
         work();
         for (auto &t : pool) t.join();
     };
-    {
-        std::atomic<int> next(0);
-        run_pool([&]() {
-            for (int i; (i = next.fetch_add(1)) < n_files;)
-                if (read_file(paths[i], texts[(size_t)i], &errs[(size_t)i]))
-                    counts[(size_t)i] = count_atoms(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size());
-        });
-    }
-    for (int i = 0; i < n_files; ++i)
-        if (errs[(size_t)i]) {
-            t_error = std::string(errs[(size_t)i] == 1 ? "cannot open " : "cannot read ") + paths[i];
-            const int rc = errs[(size_t)i] == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
-            delete b;
-            return rc;
-        }
-    b->atom_off.assign(nf + 1, 0);
-    for (size_t i = 0; i < nf; ++i) b->atom_off[i + 1] = b->atom_off[i] + counts[i];
-    const size_t n = (size_t)b->atom_off[nf];
-    b->n_atoms = (int64_t)n;
-    b->xyz.resize(3 * n); b->kind.resize(n); b->residue.resize(n); b->bfactor32.resize(n); b->chain16.resize(n);
-    b->header_id.assign(5 * nf, 0);
-    const PackedCols c{b->xyz.data(), b->kind.data(), b->residue.data(), b->bfactor32.data(), b->chain16.data()};
-    std::vector<std::vector<uint64_t>> file_kinds(nf), split_keys(nf);
-    std::vector<char> split(nf, 0);
+    // pass 1, one file at a time per worker: read into the worker's reusable text buffer, count,
+    // parse into a block sized for this file while the text is still cache-hot
+    std::vector<FileBlock> blocks(nf);
+    std::vector<int> errs(nf, 0);
     std::vector<std::string> messages(nf);
-    std::atomic<int> failed(-1);
+    b->header_id.assign(5 * nf, 0);
     {
         std::atomic<int> next(0);
         run_pool([&]() {
             KindTable kinds;
             std::vector<uint64_t> run_keys;
+            std::vector<char> text;
             for (int i; (i = next.fetch_add(1)) < n_files;) {
                 const size_t f = (size_t)i;
+                int64_t len = 0;
+                if (!read_file_into(paths[i], text, &len, &errs[f])) continue;
+                FileBlock &blk = blocks[f];
+                const int64_t count = count_atoms(text.data(), len);
+                blk.allocate(count);
                 kinds.clear();
-                bool sp = false;
-                const int64_t got = pack_into(texts[f].data(), (int64_t)texts[f].size(), c, b->atom_off[f], counts[f],
-                                              kinds, run_keys, &sp, &b->header_id[5 * f]);
-                if (got != counts[f]) { messages[f] = t_error; failed.store(i); continue; }
-                file_kinds[f] = kinds.keys;
-                if (sp) { split[f] = 1; split_keys[f] = run_keys; }
-                std::string().swap(texts[f]);
+                const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
+                const int64_t got = pack_into(text.data(), len, c, 0, count, kinds, run_keys, &blk.split, &b->header_id[5 * f]);
+                if (got != count) { messages[f] = t_error; errs[f] = 3; continue; }
+                blk.kinds = kinds.keys;
+                if (blk.split) {
+                    blk.atom_id.reset(new int32_t[(size_t)std::max<int64_t>(count, 1)]);
+                    regroup_file(c, 0, count, run_keys, blk.atom_id.get());
+                }
             }
         });
     }
-    if (failed.load() >= 0) {
-        t_error = std::string(paths[failed.load()]) + ": " + messages[(size_t)failed.load()];
-        delete b;
-        return EMM_ERR_INPUT;
+    for (int i = 0; i < n_files; ++i)
+        if (errs[(size_t)i]) {
+            const int e = errs[(size_t)i];
+            if (e == 3) t_error = std::string(paths[i]) + ": " + messages[(size_t)i];
+            else t_error = std::string(e == 1 ? "cannot open " : "cannot read ") + paths[i];
+            return e == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
+        }
+    b->atom_off.assign(nf + 1, 0);
+    bool any_split = false;
+    for (size_t i = 0; i < nf; ++i) {
+        b->atom_off[i + 1] = b->atom_off[i] + blocks[i].n;
+        any_split = any_split || blocks[i].split;
     }
+    const size_t n = (size_t)b->atom_off[nf];
+    b->n_atoms = (int64_t)n;
+    b->pxyz.resize(3 * n); b->kind.resize(n); b->residue.resize(n); b->bfactor32.resize(n); b->chain16.resize(n);
+    b->has_atom_id = any_split;
+    if (any_split) b->atom_id.resize(n);
     // merge the per-file kind lists in file order (deterministic whatever the thread count)
     KindTable global;
     std::vector<std::vector<uint32_t>> remap(nf);
     for (size_t f = 0; f < nf; ++f) {
-        remap[f].resize(file_kinds[f].size());
-        for (size_t j = 0; j < file_kinds[f].size(); ++j) remap[f][j] = global.lookup(file_kinds[f][j]);
+        remap[f].resize(blocks[f].kinds.size());
+        for (size_t j = 0; j < blocks[f].kinds.size(); ++j) remap[f][j] = global.lookup(blocks[f].kinds[j]);
     }
     b->kind_names.assign(8 * global.keys.size(), 0);
     for (size_t j = 0; j < global.keys.size(); ++j) memcpy(&b->kind_names[8 * j], &global.keys[j], 8);
-    b->has_atom_id = std::find(split.begin(), split.end(), (char)1) != split.end();
-    if (b->has_atom_id) b->atom_id.resize(n);
+    // pass 2: blocks -> their place in the batch columns (first touch of those pages, in parallel)
     {
         std::atomic<int> next(0);
+        emm_pdb_batch *bp = b.get();
         run_pool([&]() {
             for (int i; (i = next.fetch_add(1)) < n_files;) {
                 const size_t f = (size_t)i;
-                const int64_t lo = b->atom_off[f], hi = b->atom_off[f + 1];
-                const std::vector<uint32_t> &m = remap[f];
-                for (int64_t a = lo; a < hi; ++a) b->kind[(size_t)a] = m[b->kind[(size_t)a]];
-                if (split[f]) regroup_file(c, lo, hi - lo, split_keys[f], b->atom_id.data());
-                else if (b->has_atom_id)
-                    for (int64_t a = lo; a < hi; ++a) b->atom_id[(size_t)a] = (int32_t)(a - lo);
+                FileBlock &blk = blocks[f];
+                const size_t lo = (size_t)bp->atom_off[f], cnt = (size_t)blk.n;
+                if (cnt) {
+                    memcpy(bp->pxyz.data() + 3 * lo, blk.xyz, cnt * 3 * sizeof(double));
+                    memcpy(bp->residue.data() + lo, blk.residue, cnt * sizeof(int32_t));
+                    memcpy(bp->bfactor32.data() + lo, blk.bfactor, cnt * sizeof(float));
+                    memcpy(bp->chain16.data() + lo, blk.chain, cnt * sizeof(uint16_t));
+                    const std::vector<uint32_t> &m = remap[f];
+                    uint32_t *kd = bp->kind.data() + lo;
+                    for (size_t a = 0; a < cnt; ++a) kd[a] = m[blk.kind[a]];
+                    if (bp->has_atom_id) {
+                        int32_t *ad = bp->atom_id.data() + lo;
+                        if (blk.split) memcpy(ad, blk.atom_id.get(), cnt * sizeof(int32_t));
+                        else for (size_t a = 0; a < cnt; ++a) ad[a] = (int32_t)a;
+                    }
+                }
+                blk.release();
             }
         });
     }
-    *out = b;
+    *out = b.release();
+    return EMM_OK;
+}
+
+int emm_pdb_batch_classify(emm_pdb_batch *b, const uint16_t *class_of_kind, int32_t n_kinds)
+{
+    if (!b || !b->packed || !class_of_kind || n_kinds < (int32_t)(b->kind_names.size() / 8)) return EMM_ERR_INVALID;
+    const size_t n = (size_t)b->n_atoms;
+    b->klass.resize(n);
+    const int n_threads = std::max(1, std::min<int>(b->n_threads, (int)(n / 65536) + 1));
+    const size_t per = (n + (size_t)n_threads - 1) / (size_t)n_threads;
+    auto work = [&](int t) {
+        const size_t lo = std::min(n, per * (size_t)t), hi = std::min(n, lo + per);
+        const uint32_t *kd = b->kind.data();
+        uint16_t *out = b->klass.data();
+        for (size_t a = lo; a < hi; ++a) out[a] = class_of_kind[kd[a]];
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &t : pool) t.join();
+    b->has_klass = true;
     return EMM_OK;
 }
 
@@ -575,9 +709,10 @@ int emm_pdb_batch_packed(const emm_pdb_batch *b, emm_pdb_packed *out)
     out->n_files = b->n_files;
     out->n_atoms = b->n_atoms;
     out->atom_off = b->atom_off.data();
-    out->xyz = b->xyz.data(); out->kind = b->kind.data(); out->residue = b->residue.data();
+    out->xyz = b->pxyz.data(); out->kind = b->kind.data(); out->residue = b->residue.data();
     out->bfactor = b->bfactor32.data(); out->chain = b->chain16.data();
     out->atom_id = b->has_atom_id ? b->atom_id.data() : nullptr;
+    out->klass = b->has_klass ? b->klass.data() : nullptr;
     out->n_kinds = (int32_t)(b->kind_names.size() / 8);
     out->kind_names = b->kind_names.data();
     out->header_id = b->header_id.data();

@@ -96,7 +96,7 @@ def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
 
 class _PdbPacked(ctypes.Structure):       # struct emm_pdb_packed
     _fields_ = [("n_files", ctypes.c_int32), ("n_atoms", ctypes.c_int64)] + \
-               [(k, ctypes.c_void_p) for k in ("atom_off", "xyz", "kind", "residue", "bfactor", "chain", "atom_id")] + \
+               [(k, ctypes.c_void_p) for k in ("atom_off", "xyz", "kind", "residue", "bfactor", "chain", "atom_id", "klass")] + \
                [("n_kinds", ctypes.c_int32), ("kind_names", ctypes.c_void_p), ("header_id", ctypes.c_void_p)]
 
 
@@ -144,20 +144,22 @@ def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrar
         buf._owner = owner                   # array -> memoryview -> buf -> owner keeps the batch alive
         return np.frombuffer(buf, dtype=dtype, count=count)
 
-    atom_off = grab(c.atom_off, np.int64, nf + 1)
-    xyz = grab(c.xyz, np.float64, 3 * n).reshape(n, 3)
-    kind = grab(c.kind, np.uint32, n)
-    residue = grab(c.residue, np.int32, n)
-    bfactor = grab(c.bfactor, np.float32, n)
-    chain = grab(c.chain, np.uint16, n) if with_chain else None
-    atom_id = grab(c.atom_id, np.int32, n) if c.atom_id else None
     names = grab(c.kind_names, np.uint8, 8 * c.n_kinds).reshape(-1, 8)
-    headers = grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5)
     class_of_kind = np.zeros(max(len(names), 1), dtype=np.uint16)
     for i, row in enumerate(names):
         res = bytes(row[:4]).split(b"\0")[0].decode("ascii", "replace")
         name = bytes(row[4:]).split(b"\0")[0].decode("ascii", "replace")
         class_of_kind[i] = library.class_of(res, name)
-    klass = class_of_kind[kind] if n else np.zeros(0, dtype=np.uint16)
+    if lib.emm_pdb_batch_classify(handle, class_of_kind.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(len(class_of_kind))) != 0:
+        raise RuntimeError("emm_pdb_batch_classify failed")
+    lib.emm_pdb_batch_packed(handle, ctypes.byref(c))
+    atom_off = grab(c.atom_off, np.int64, nf + 1)
+    xyz = grab(c.xyz, np.float64, 3 * n).reshape(n, 3)
+    klass = grab(c.klass, np.uint16, n)
+    residue = grab(c.residue, np.int32, n)
+    bfactor = grab(c.bfactor, np.float32, n)
+    chain = grab(c.chain, np.uint16, n) if with_chain else None
+    atom_id = grab(c.atom_id, np.int32, n) if c.atom_id else None
+    headers = grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5)
     ids = [bytes(h).split(b"\0")[0].decode() or None for h in headers]
     return PackedBatch(atom_off, xyz, klass, residue, bfactor, chain, atom_id), ids

@@ -265,12 +265,15 @@ typedef struct emm_pdb_packed {
     const float *bfactor;         /* [n_atoms] */
     const uint16_t *chain;        /* [n_atoms] chain id bytes: b0 | b1 << 8 */
     const int32_t *atom_id;       /* [n_atoms] or NULL */
+    const uint16_t *klass;        /* [n_atoms] typing classes, NULL until emm_pdb_batch_classify */
     int32_t n_kinds;
     const char *kind_names;       /* [n_kinds][8]: resname[4] name[4], blank-stripped, NUL padded */
     const char *header_id;        /* [n_files][5] */
 } emm_pdb_packed;
 int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
 int emm_pdb_batch_packed(const emm_pdb_batch *batch, emm_pdb_packed *out);
+/* klass[a] = class_of_kind[kind[a]] for every atom, on the batch's thread pool */
+int emm_pdb_batch_classify(emm_pdb_batch *batch, const uint16_t *class_of_kind, int32_t n_kinds);
 
 #ifdef __cplusplus
 }

@@ -287,3 +287,26 @@ def test_pack_files_errors(tmp_path, active_templates):
     bad.write_text("ATOM      1  N   ALA A   1      xx.xxx  22.000  33.000  1.00  0.00           N\n")
     with pytest.raises(ValueError, match="malformed PDB coordinate record"):
         pack_files([bad], lib)
+
+
+def test_pack_files_coordinates_are_python_floats(tmp_path, active_templates):
+    """The fixed-layout number path of the native packer yields exactly float(text)."""
+    from enzymm_b200.packing import pack_files
+    lib = CompiledLibrary(active_templates[:5], 2.0, 1.5, 1.5)
+    rng = np.random.default_rng(5)
+    texts = ["%8.3f" % v for v in rng.uniform(-999.0, 9999.0, 3000)]
+    texts += ["  -0.000", "   0.000", "9999.999", "-999.999", "   -.500", "    .250", "  1e+002", " +12.500", "12.5    ", "     7.0"]
+    while len(texts) % 3:
+        texts.append("   1.000")
+    lines = []
+    for i in range(0, len(texts), 3):
+        x, y, z = texts[i:i + 3]
+        occ, bf = ("%6.2f" % rng.uniform(0, 1), "%6.2f" % rng.uniform(-9, 99)) if i % 2 else ("  1.0 ", "")
+        lines.append(f"ATOM  {i % 99999:5d}  CA  ALA A{i % 9999:4d}    {x}{y}{z}{occ}{bf}".ljust(80 if i % 4 else 60))
+    path = tmp_path / "numbers.pdb"
+    path.write_text("\n".join(lines) + "\n")
+    batch, _ = pack_files([path], lib)
+    want = np.asarray([float(t) for t in texts]).reshape(-1, 3)
+    assert batch.xyz.tobytes() == want.tobytes()
+    want_bf = np.asarray([float(l[60:66]) if l[60:66].strip() else 0.0 for l in lines]).astype(np.float32)
+    assert batch.bfactor.tobytes() == want_bf.tobytes()

@@ -20,14 +20,16 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
     templates = active_templates()
-    workload = make_workload(0, n, 400, 1, 8)
+    distinct = min(n, int(os.environ.get("EMM_DISTINCT", "1024")))     # file contents repeat beyond this
+    workload = make_workload(0, distinct, 400, 1, 8)
     d = tempfile.mkdtemp(prefix="emm_ingest_")
     paths = []
     t0 = time.perf_counter()
+    texts = [workload.to_pdb(i).encode() for i in range(distinct)]
     for i in range(n):
         p = os.path.join(d, f"s{i:06d}.pdb")
-        with open(p, "w") as f:
-            f.write(workload.to_pdb(i))
+        with open(p, "wb") as f:
+            f.write(texts[i % distinct])
         paths.append(p)
     size = sum(os.path.getsize(p) for p in paths)
     print(f"wrote {n} files, {size / 1e6:.0f} MB in {time.perf_counter() - t0:.1f} s; host threads {len(os.sched_getaffinity(0))}")
@@ -42,7 +44,17 @@ def main():
     t0 = time.perf_counter()
     pack_molecules(load_many(sample), engine.compiled)
     print(f"Molecule path (load_many + pack_molecules): {len(sample) / (time.perf_counter() - t0):.0f} files/s")
-    for rep in range(2):
+    # phase times of one chunk, not overlapped
+    t0 = time.perf_counter()
+    batch, _ = pack_files(paths[:chunk], engine.compiled)
+    t1 = time.perf_counter()
+    records = matcher._search(batch)
+    t2 = time.perf_counter()
+    records = matcher._search(batch)
+    t3 = time.perf_counter()
+    print(f"one chunk of {chunk}: pack {1e3 * (t1 - t0):.0f} ms, search (upload+run+download) {1e3 * (t2 - t1):.0f} ms, "
+          f"again {1e3 * (t3 - t2):.0f} ms; {len(records)} hits")
+    for rep in range(3):
         t0 = time.perf_counter()
         hits = passing = 0
         for _, _, records in matcher.scan_files(paths, chunk_size=chunk):
