@@ -156,6 +156,28 @@ int emm_device_count(void)
     return n;
 }
 
+int emm_stream_create(int device, void **stream)
+{
+    if (!stream) return fail(EMM_ERR_INVALID, "stream is null");
+    *stream = nullptr;
+    const int ndev = emm_device_count();
+    if (ndev <= 0) return fail(EMM_ERR_NO_DEVICE, "no CUDA device visible: enzymm_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EMM_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream = (void *)st;
+    return EMM_OK;
+}
+
+int emm_stream_destroy(int device, void *stream)
+{
+    if (!stream) return EMM_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamDestroy((cudaStream_t)stream));
+    return EMM_OK;
+}
+
 int emm_library_create(int device, const emm_library_desc *desc, emm_library **out)
 {
     if (!out) return fail(EMM_ERR_INVALID, "out is null");

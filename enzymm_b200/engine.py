@@ -103,6 +103,7 @@ def load_cdll() -> ctypes.CDLL:
                      "emm_library_set_thresholds", "emm_library_set_filter", "emm_session_create", "emm_session_upload",
                      "emm_session_run", "emm_session_download", "emm_session_last_launches",
                      "emm_session_kernel_ms", "emm_session_clear_timings", "emm_session_debug_counters",
+                     "emm_stream_create", "emm_stream_destroy",
                      "emm_query_batch"):
             getattr(lib, name).restype = ctypes.c_int
         lib.emm_library_destroy.restype = None
@@ -208,9 +209,8 @@ class DeviceLibrary:
         """Push the typing matrix again if classification created new classes."""
         c = self.compiled
         if c.compat_dirty:
-            self._compat = c.compat_matrix()
-            _check(self._lib.emm_library_set_compat(self.handle, ctypes.c_int32(c.class_words), _p(self._compat)))
-            c.compat_dirty = False
+            words, self._compat = c.take_compat()
+            _check(self._lib.emm_library_set_compat(self.handle, ctypes.c_int32(words), _p(self._compat)))
 
     def push_thresholds(self):
         c = self.compiled
@@ -237,6 +237,7 @@ class Session:
     def __init__(self, library: DeviceLibrary, max_atoms: int, max_structures: int, hit_capacity: int = 0):
         self.library = library
         self._lib = load_cdll()
+        self.max_atoms, self.max_structures = max(1, int(max_atoms)), max(1, int(max_structures))
         self.hit_capacity = int(hit_capacity or max(1024, 64 * max_structures))
         handle = ctypes.c_void_p()
         _check(self._lib.emm_session_create(library.handle, ctypes.c_int64(max(1, int(max_atoms))),
@@ -314,8 +315,19 @@ class Engine:
             raise EngineError(-3, "no CUDA device visible: enzymm_b200 has no CPU fallback")
         self.device_library = DeviceLibrary(compiled, device)
         self.compiled = compiled
+        self.device = device
         self._session: Optional[Session] = None
         self._cap = (0, 0, 0)
+
+    def new_stream(self) -> int:
+        """A non-blocking CUDA stream on this engine's device (handle for the ``stream=`` arguments)."""
+        st = ctypes.c_void_p()
+        _check(load_cdll().emm_stream_create(ctypes.c_int(self.device), ctypes.byref(st)))
+        return int(st.value or 0)
+
+    def free_stream(self, stream: int) -> None:
+        if stream:
+            _check(load_cdll().emm_stream_destroy(ctypes.c_int(self.device), ctypes.c_void_p(stream)))
 
     def session_for(self, n_atoms: int, n_structures: int, hit_capacity: int = 0) -> Session:
         need_hits = hit_capacity or max(1024, 64 * n_structures)

@@ -19,6 +19,7 @@ from __future__ import annotations
 import hashlib
 import json
 import pickle
+import threading
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -26,6 +27,8 @@ import numpy as np
 
 from .chem import BACKGROUND_PERCENT, RESIDUE_ATOMS
 from .template_atoms import JessTemplate
+
+_CLASS_LOCK = threading.RLock()      # guards the typing-class tables of every CompiledLibrary
 
 __all__ = ["type_match", "CompiledLibrary", "load_lr_models", "MAX_TEMPLATE_ATOMS",
            "MAX_RESIDUES", "LR_MODELS"]
@@ -324,6 +327,14 @@ class CompiledLibrary:
         kind = (residue_name, atom_name)
         c = self._class_of_kind.get(kind)
         if c is None:
+            with _CLASS_LOCK:
+                return self._new_kind(kind)
+        return c
+
+    def _new_kind(self, kind) -> int:
+        residue_name, atom_name = kind
+        c = self._class_of_kind.get(kind)
+        if c is None:
             column = np.fromiter((type_match(k[0], k[1], k[2], residue_name, atom_name) for k in self.keys),
                                  dtype=bool, count=self.n_ttype)
             sig = column.tobytes()
@@ -359,10 +370,20 @@ class CompiledLibrary:
     def class_words(self) -> int:
         return (self.n_classes + 31) // 32
 
+    def take_compat(self):
+        """``(class_words, matrix)`` of the current classes, clearing ``compat_dirty`` -- atomically
+        with respect to ``class_of`` running on another thread (the ingest thread of
+        ``Matcher.scan_files`` may meet new atom kinds while a batch is being uploaded)."""
+        with _CLASS_LOCK:
+            matrix = self.compat_matrix()
+            self.compat_dirty = False
+            return matrix.shape[1], matrix
+
     def compat_matrix(self) -> np.ndarray:
         """``uint32 [n_ttype, class_words]`` bit matrix: bit c of row r = class c binds ttype r."""
-        cw = self.class_words
-        cols = np.stack(self._columns, axis=1)                      # [n_ttype, n_classes]
+        columns = list(self._columns)
+        cw = (len(columns) + 31) // 32
+        cols = np.stack(columns, axis=1)                            # [n_ttype, n_classes]
         padded = np.zeros((self.n_ttype, cw * 32), dtype=bool)
         padded[:, :cols.shape[1]] = cols
         bits = padded.reshape(self.n_ttype, cw, 32)

@@ -417,14 +417,11 @@ class Matcher:
             self._engine = Engine(CompiledLibrary(ordered, rmsd, dist, dyn), self.device)
         return self._engine
 
-    def _search(self, batch) -> np.ndarray:
-        """One packed batch through the device: every size group, hit records sorted by
-        (structure, template index)."""
-        engine = self._ensure_engine()
+    def _submit(self, session, batch, stream: int = 0) -> None:
+        """Upload one packed batch and enqueue every size group's search on ``stream``."""
         cutoff = float(self.conservation_cutoff) if (self.apply_conservation_mask and self.conservation_cutoff) else 0.0
-        session = engine.session_for(batch.n_atoms, batch.n_structures)
-        session.upload(batch)
-        common = dict(max_candidates=self.max_candidates, ignore_chain=True, conservation_cutoff=cutoff)
+        session.upload(batch, stream=stream)
+        common = dict(max_candidates=self.max_candidates, ignore_chain=True, conservation_cutoff=cutoff, stream=stream)
         if self.skip_smaller_hits:
             # one launch per size group; the device skips structures that already hold a surviving hit
             mode = 1 if self.filter_matches else 2
@@ -432,29 +429,67 @@ class Matcher:
                 session.run(template_begin=lo, template_end=hi, skip_mode=mode, reset=(gi == 0), **common)
         else:
             session.run(template_begin=0, template_end=len(self._ordered), skip_mode=0, reset=True, **common)
+
+    def _search(self, batch) -> np.ndarray:
+        """One packed batch through the device: every size group, hit records sorted by
+        (structure, template index)."""
+        engine = self._ensure_engine()
+        session = engine.session_for(batch.n_atoms, batch.n_structures)
+        self._submit(session, batch)
         return session.download()
 
     def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0):
         """Screen PDB files without building ``Molecule`` objects: a generator of
         ``(chunk_paths, header_ids, records)`` per chunk of ``chunk_size`` files, ``records`` being the
         hit records of the chunk (``structure`` indexes ``chunk_paths``; ``flags & 4`` = passes the
-        filter).  Files are read, parsed and packed natively (``packing.pack_files``) on a
-        background thread while the GPU searches the previous chunk.  ``matches_for`` turns the
-        records of one file into the ``Match`` objects ``run`` would have returned for it."""
+        filter).  Three stages overlap: files are read, parsed and packed natively
+        (``packing.pack_files``) on a background thread; the packed chunk crosses PCIe on one CUDA
+        stream while the previous chunk is searched on another (two device sessions).
+        ``matches_for`` turns the records of one file into the ``Match`` objects ``run`` would have
+        returned for it."""
         import concurrent.futures
+        from .engine import Session
         from .packing import pack_files
         if not self._active_sizes():
             return
         engine = self._ensure_engine()
         paths = [os.fspath(p) for p in paths]
         chunks = [paths[i:i + chunk_size] for i in range(0, len(paths), chunk_size)]
-        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-            pending = pool.submit(pack_files, chunks[0], engine.compiled, True, threads) if chunks else None
-            for ci, chunk in enumerate(chunks):
-                batch, ids = pending.result()
-                pending = (pool.submit(pack_files, chunks[ci + 1], engine.compiled, True, threads)
-                           if ci + 1 < len(chunks) else None)
-                yield chunk, ids, self._search(batch)
+        if not chunks:
+            return
+        lanes: List[list] = [[None, engine.new_stream()], [None, engine.new_stream()]]   # [session, stream]
+        in_flight: collections.deque = collections.deque()      # (lane, chunk paths, ids, batch)
+        try:
+            with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
+                pending = pool.submit(pack_files, chunks[0], engine.compiled, True, threads)
+                for ci, chunk in enumerate(chunks):
+                    batch, ids = pending.result()
+                    pending = (pool.submit(pack_files, chunks[ci + 1], engine.compiled, True, threads)
+                               if ci + 1 < len(chunks) else None)
+                    lane = lanes[ci % 2]
+                    sess = lane[0]
+                    need_hits = max(1024, 64 * batch.n_structures)
+                    if sess is None or batch.n_atoms > sess.max_atoms or batch.n_structures > sess.max_structures \
+                            or need_hits > sess.hit_capacity:
+                        if sess is not None:
+                            sess.close()
+                        grow = lambda v, old: max(int(v * 1.1) + 1, old)
+                        sess = lane[0] = Session(engine.device_library,
+                                                 grow(batch.n_atoms, sess.max_atoms if sess else 0),
+                                                 grow(batch.n_structures, sess.max_structures if sess else 0), need_hits)
+                    self._submit(sess, batch, stream=lane[1])
+                    in_flight.append((lane, chunk, ids, batch))
+                    if len(in_flight) == 2:
+                        done_lane, done_chunk, done_ids, _ = in_flight.popleft()
+                        yield done_chunk, done_ids, done_lane[0].download(stream=done_lane[1])
+                while in_flight:
+                    done_lane, done_chunk, done_ids, _ = in_flight.popleft()
+                    yield done_chunk, done_ids, done_lane[0].download(stream=done_lane[1])
+        finally:
+            for sess, stream in lanes:          # destroying a session waits for its device work
+                if sess is not None:
+                    sess.close()
+                engine.free_stream(stream)
 
     def matches_for(self, molecule: Molecule, records: np.ndarray) -> List[Match]:
         """``Match`` objects for the hit records of one structure (``records`` = the rows of a

@@ -104,6 +104,10 @@ int emm_abi_version(void);
 int emm_hit_size(void);             /* sizeof(emm_hit), for binding sanity checks */
 const char *emm_last_error(void);
 int emm_device_count(void);
+/* A non-blocking CUDA stream on `device` for the `stream` arguments below (NULL = the default
+ * stream).  Two sessions on two streams overlap one batch's upload with another's search. */
+int emm_stream_create(int device, void **stream);
+int emm_stream_destroy(int device, void *stream);
 
 int emm_library_create(int device, const emm_library_desc *desc, emm_library **out);
 /* Replace the compat matrix (same n_ttype; class_words may grow up to the value at creation). */
