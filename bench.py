@@ -240,6 +240,9 @@ def run_b200(args, rank, local_rank, world):
     host = PackedBatch(pinned(packed.atom_off), pinned(packed.xyz), pinned(packed.klass), pinned(packed.residue),
                        pinned(packed.bfactor), None, None)
     session = engine.session_for(host.n_atoms, host.n_structures, hit_capacity=64 * host.n_structures)
+    # everything below runs on explicit streams: the legacy default stream would serialise the two
+    # lanes of the end-to-end pipeline (blocking streams synchronise with it)
+    torch.cuda.set_stream(torch.cuda.Stream())
     stream = torch.cuda.current_stream().cuda_stream
     run_kwargs = dict(max_candidates=10000, ignore_chain=True, reset=True, force_prepare=True, stream=stream)
 

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -19,7 +21,8 @@ size_t search_fixed_smem(int levels);
 cudaError_t configure_search(int smem_bytes);
 void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream);
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream);
+                   const unsigned char *skip, const int *sched, bool stats, bool staged, int grid, size_t smem,
+                   cudaStream_t stream);
 }  // namespace emm
 
 using namespace emm;
@@ -43,6 +46,8 @@ static int fail(emm_status st, const std::string &msg)
             return fail(EMM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
     } while (0)
 
+constexpr int kHeavyAtoms = 15;       // templates with at least this many atoms (5+ residues) form the first phase
+
 struct emm_library {
     int device = 0;
     int sm_count = 0;
@@ -57,6 +62,12 @@ struct emm_library {
     double *d_rmsd = nullptr, *d_cut = nullptr, *d_dyn = nullptr, *d_lr_table = nullptr;
     int32_t *d_lr_index = nullptr;
     int lr_capacity = 0;
+    // visiting order of the templates of a range [tb, te): most expensive first
+    struct Sched { int *d_ids = nullptr; int n = 0, n_heavy = 0; };
+    std::vector<int> h_tpl_atoms;
+    std::vector<double> h_cut;
+    std::map<std::pair<int, int>, Sched> sched;
+    std::mutex sched_mutex;
 };
 
 struct emm_session {
@@ -226,6 +237,9 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
     lib->sm_count = prop.multiProcessorCount;
     lib->smem_optin = (int)prop.sharedMemPerBlockOptin;
     lib->h_leader_ttype.assign(desc->leader_ttype, desc->leader_ttype + desc->n_leader);
+    lib->h_tpl_atoms.resize((size_t)desc->n_templates);
+    for (int t = 0; t < desc->n_templates; ++t) lib->h_tpl_atoms[(size_t)t] = desc->atom_off[t + 1] - desc->atom_off[t];
+    lib->h_cut.assign(desc->distance_cutoff, desc->distance_cutoff + desc->n_templates);
 
     DevLibrary &d = lib->d;
     d.n_templates = desc->n_templates;
@@ -310,6 +324,38 @@ int emm_library_set_thresholds(emm_library *lib, const double *rmsd_threshold, c
     CUDA_TRY(cudaMemcpy(lib->d_rmsd, rmsd_threshold, bytes, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(lib->d_cut, distance_cutoff, bytes, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(lib->d_dyn, max_dynamic_distance, bytes, cudaMemcpyHostToDevice));
+    {
+        std::lock_guard<std::mutex> guard(lib->sched_mutex);
+        lib->h_cut.assign(distance_cutoff, distance_cutoff + lib->d.n_templates);
+        for (auto &kv : lib->sched) cudaFree(kv.second.d_ids);
+        lib->sched.clear();
+    }
+    return EMM_OK;
+}
+
+// Visiting order for the templates of [tb, te): more atoms first, then the wider cutoff (the two
+// things the cost of a pair grows with), cached per range on the device.
+static int get_sched(emm_library *lib, int tb, int te, emm_library::Sched *out)
+{
+    std::lock_guard<std::mutex> guard(lib->sched_mutex);
+    auto it = lib->sched.find({tb, te});
+    if (it == lib->sched.end()) {
+        std::vector<int> ids((size_t)(te - tb));
+        for (int t = tb; t < te; ++t) ids[(size_t)(t - tb)] = t;
+        std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
+            if (lib->h_tpl_atoms[(size_t)a] != lib->h_tpl_atoms[(size_t)b]) return lib->h_tpl_atoms[(size_t)a] > lib->h_tpl_atoms[(size_t)b];
+            return lib->h_cut[(size_t)a] > lib->h_cut[(size_t)b];
+        });
+        emm_library::Sched sc;
+        sc.n = te - tb;
+        int heavy_atoms = kHeavyAtoms;
+        if (const char *env = getenv("EMM_HEAVY_ATOMS")) heavy_atoms = atoi(env);                  // tuning knob
+        for (int id : ids) sc.n_heavy += lib->h_tpl_atoms[(size_t)id] >= heavy_atoms;
+        CUDA_TRY(cudaMalloc(&sc.d_ids, sizeof(int) * (size_t)std::max(sc.n, 1)));
+        if (sc.n) CUDA_TRY(cudaMemcpy(sc.d_ids, ids.data(), sizeof(int) * (size_t)sc.n, cudaMemcpyHostToDevice));
+        it = lib->sched.emplace(std::make_pair(tb, te), sc).first;
+    }
+    *out = it->second;
     return EMM_OK;
 }
 
@@ -333,6 +379,7 @@ void emm_library_destroy(emm_library *lib)
     if (!lib) return;
     cudaSetDevice(lib->device);
     for (void *p : lib->allocs) cudaFree(p);
+    for (auto &kv : lib->sched) cudaFree(kv.second.d_ids);
     delete lib;
 }
 
@@ -520,6 +567,15 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     chunks = std::min(chunks, std::max(1, (te - tb) / 8));
     chunks = std::max(1, std::min(chunks, 256));
     if (const char *env = getenv("EMM_CHUNKS")) chunks = std::max(1, std::min(atoi(env), 256));   // tuning knob
+    emm_library::Sched sc;
+    if (int rc = get_sched(lib, tb, te, &sc)) return rc;
+    P.n_sched = sc.n;
+    P.n_heavy = sc.n_heavy;
+    P.n_structures = n;
+    // large batch with a mixed library: heavy templates of every structure first (see SearchParams)
+    P.two_phase = chunks == 1 && n >= 2 * grid && sc.n_heavy >= 48 && sc.n_heavy <= sc.n - 48;
+    if (const char *env = getenv("EMM_TWO_PHASE")) P.two_phase = P.two_phase && env[0] != '0';   // tuning knob
+    if (P.two_phase) chunks = 2;
     P.n_chunks = chunks;
     P.n_items = n * chunks;
     const int fixed = (int)search_fixed_smem(P.levels);
@@ -550,7 +606,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
         cudaEvent_t e0, e1;
         const bool timed = next_events(s->ev_search, s->ev_search_used, &e0, &e1);
         if (timed) cudaEventRecord(e0, stream);
-        launch_search(lib->d, B, P, O, skip, lib->stats_enabled != 0, staged, std::min(grid, P.n_items), smem, stream);
+        launch_search(lib->d, B, P, O, skip, sc.d_ids, lib->stats_enabled != 0, staged, std::min(grid, P.n_items), smem, stream);
         if (timed) cudaEventRecord(e1, stream);
     }
     CUDA_TRY(cudaGetLastError());

@@ -106,6 +106,14 @@ struct SearchParams {
     int skip_mode;
     int n_chunks;          // template chunks per structure (work item = structure x chunk)
     int n_items;
+    // Templates are visited in the order of `sched` (most expensive first).  Two-phase mode (large
+    // batches): items [0, n_structures) run the first n_heavy entries for every structure, items
+    // [n_structures, 2 n_structures) the rest -- a pair that takes 100x the average starts early and
+    // cannot become the tail of the launch.  Otherwise chunk c of a structure takes entries
+    // c, c + n_chunks, ... of the order.
+    int two_phase;
+    int n_structures;
+    int n_sched, n_heavy;
     int blob_cap;          // shared-memory bytes available for a staged blob
     int levels;            // queue levels per warp (max template atoms + 1)
     int cell_threshold;    // leader lists at least this long are searched through the cell list

@@ -114,6 +114,7 @@ struct SearchArgs {
     SearchParams P;
     SearchOut O;
     const unsigned char *skip;
+    const int *sched;          // [P.n_sched] template ids in visiting order
 };
 
 // ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier: global -> shared staging ----------
@@ -562,6 +563,19 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
     return full;
 }
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ int log2_bucket_us(unsigned long long ns, int buckets)
+{
+    const unsigned long long us = ns >> 10;
+    return min(buckets - 1, us ? 64 - __clzll(us) : 0);
+}
+
 struct LaneStats {
     unsigned long long sweeps, evals, exact;
 };
@@ -863,7 +877,7 @@ template <bool kStats, bool kStaged, bool kCells>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 emm_search_kernel(const __grid_constant__ SearchArgs A)
 {
-    __shared__ int s_item, s_next_tpl;
+    __shared__ int s_item, s_next_pos;
     __shared__ Blob s_blob;
     __shared__ __align__(8) uint64_t s_bar;      // mbarrier the TMA bulk copy of a blob completes on
 
@@ -886,14 +900,24 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
         __syncthreads();
         const int item = s_item;
         if (item >= P.n_items) break;
-        const int s = item / P.n_chunks, chunk = item - s * P.n_chunks;
+        int s, pos0, pos1, stride;
+        if (P.two_phase) {
+            const bool heavy = item < P.n_structures;
+            s = heavy ? item : item - P.n_structures;
+            pos0 = heavy ? 0 : P.n_heavy;
+            pos1 = heavy ? P.n_heavy : P.n_sched;
+            stride = 1;
+        } else {
+            s = item / P.n_chunks;
+            pos0 = item - s * P.n_chunks;
+            pos1 = P.n_sched;
+            stride = P.n_chunks;
+        }
         const unsigned char *gblob = A.B.blob + A.B.blob_off[s];
         const BlobHeader hdr = *reinterpret_cast<const BlobHeader *>(gblob);
-        const int span = P.template_end - P.template_begin;
-        const int per = (span + P.n_chunks - 1) / P.n_chunks;
-        const int tb = P.template_begin + chunk * per;
-        const int te = min(P.template_end, tb + per);
-        const bool run = hdr.status == 0 && hdr.n_kept > 0 && tb < te && !(A.skip && A.skip[s]);
+        const bool run = hdr.status == 0 && hdr.n_kept > 0 && pos0 < pos1 && !(A.skip && A.skip[s]);
+        unsigned long long item_t0 = 0;
+        if (kStats && tid == 0) item_t0 = global_ns();
         if (run) {
             if (kStaged) {
                 // host guarantees staged_bytes <= blob_cap for every structure of the batch; one
@@ -904,7 +928,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                 ++st_global;
             }
             if (tid == 0) {
-                s_next_tpl = tb;
+                s_next_pos = pos0;
                 const int64_t abase = A.B.atom_off[s];
                 s_blob.orig = reinterpret_cast<const int32_t *>(gblob + hdr.off_orig);
                 s_blob.xyz64 = A.B.xyz + 3 * abase;
@@ -926,15 +950,39 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             V.off_resstart = hdr.off_resstart; V.off_klass = hdr.off_klass; V.off_leadoff = hdr.off_leadoff;
             V.off_lead = hdr.off_lead; V.res_shift = hdr.res_shift; V.eps = hdr.eps;
             for (;;) {
-                int t = 0;
-                if (lane == 0) t = atomicAdd(&s_next_tpl, 1);
+                int t = -1;
+                if (lane == 0) {
+                    const int pos = atomicAdd(&s_next_pos, stride);
+                    if (pos < pos1) t = __ldg(A.sched + pos);
+                }
                 t = __shfl_sync(kFull, t, 0);
-                if (t >= te) break;
+                if (t < 0) break;
+                unsigned long long pair_t0 = 0;
+                if (kStats) pair_t0 = global_ns();
                 search_template<kStats, kStaged, kCells>(A, s_blob, V, s, t, Q, ws, lane, st);
-                if (kStats && lane == 0) ++st_pairs;
+                if (kStats && lane == 0) {
+                    ++st_pairs;
+                    const unsigned long long dt = global_ns() - pair_t0;
+                    atomicMax(A.O.stats + 13, ((dt >> 10) << 24) | (unsigned long long)t);     // slowest pair: us, template
+                    atomicAdd(A.O.stats + 28 + log2_bucket_us(dt, 12), 1ull);
+                }
             }
         }
+        unsigned long long warp_done = 0;
+        if (kStats) warp_done = global_ns();
         __syncthreads();
+        if (kStats && lane == 0 && run) atomicAdd(A.O.stats + 14, global_ns() - warp_done);    // warp-ns spent waiting
+        if (kStats && tid == 0 && run) {
+            const unsigned long long dt = global_ns() - item_t0;
+            atomicMax(A.O.stats + 8, ((dt >> 10) << 24) | (unsigned long long)s);              // slowest structure: us, index
+            atomicAdd(A.O.stats + 15, dt * kSearchWarps);                                      // warp-ns available
+            atomicAdd(A.O.stats + 16 + min(11, (int)(dt >> 21)), 1ull);                        // ~2 ms buckets
+        }
+    }
+    if (kStats && tid == 0) {
+        const unsigned long long now = global_ns();
+        atomicMax(A.O.stats + 11, now);                                   // last CTA out
+        atomicMax(A.O.stats + 10, ~now);                                  // first CTA out, as max of the complement
     }
     if (kStats) {
 #pragma unroll
@@ -984,11 +1032,11 @@ void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsi
 }
 
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream)
+                   const unsigned char *skip, const int *sched, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream)
 {
     if (P.n_items <= 0) return;
     SearchArgs A;
-    A.L = L; A.B = B; A.P = P; A.O = O; A.skip = skip;
+    A.L = L; A.B = B; A.P = P; A.O = O; A.skip = skip; A.sched = sched;
     const bool cells = P.cell_threshold > 0;       // the cell-list path is a separate instantiation
     if (cells && staged) emm_search_kernel<false, true, true><<<grid, kSearchThreads, smem, stream>>>(A);
     else if (cells) emm_search_kernel<false, false, true><<<grid, kSearchThreads, smem, stream>>>(A);

@@ -1,5 +1,5 @@
 """Small fixed workload for ncu / stats runs: N synthetic structures vs the full library.
-usage: python tools/profile_workload.py [n_structures] [steps]"""
+usage: python tools/profile_workload.py [n_structures] [steps] [rank whose structures to use]"""
 import os
 import sys
 import time
@@ -19,7 +19,8 @@ def main():
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     templates = active_templates()
     dists = [DEFAULT_DIST[min(t.effective_size, 8)] for t in templates]
-    workload = make_workload(0, n, 400, 1, 8)
+    first = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    workload = make_workload(first, n, 400, 1, 8)
     engine = Engine(CompiledLibrary(templates, 2.0, dists, dists, plan_order=os.environ.get("EMM_PLAN", "leaders_first")))
     batch = workload.to_packed(engine.compiled)
     sess = engine.session_for(batch.n_atoms, batch.n_structures)
@@ -36,6 +37,14 @@ def main():
         c = sess.debug_counters()
         pairs = max(stats["pairs"], 1)
         print("per pair: sweeps %.1f evals %.1f" % (stats["sweeps"] / pairs, stats["dist_evals"] / pairs))
+        mask = 2 ** 64 - 1
+        us, idx = int(c[0]) >> 24, int(c[0]) & 0xFFFFFF
+        first_out, last_out = (~int(c[2])) & mask, int(c[3])
+        print(f"slowest structure: {us / 1e3:.2f} ms (index {idx}); slowest pair: {(int(c[5]) >> 24) / 1e3:.2f} ms "
+              f"(template {int(c[5]) & 0xFFFFFF}); first CTA out {(last_out - first_out) / 1e6:.2f} ms before the last")
+        print(f"warps waiting at the end of a structure: {100.0 * int(c[6]) / max(int(c[7]), 1):.1f} % of warp time")
+        print("structure time histogram (2.1 ms buckets, last = more):", [int(v) for v in c[8:20]])
+        print("pair time histogram (<1 us, 1, 2-3, 4-7, ... >= 1 ms):", [int(v) for v in c[20:32]])
         print("level: pushed-from-level | validated-alive entering | enter calls   (per pair)")
         for k in range(26):
             print(k, "%.2f | %.2f | %.2f" % (c[32 + k] / pairs, c[64 + k] / pairs, c[96 + k] / pairs))
