@@ -749,28 +749,23 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     const int a_0 = have0 ? V.lead(lbase + c0) : 0, a_1 = have1 ? V.lead(lbase + c1) : 0;
                     const float x0 = V.x(a_0), y0 = V.y(a_0), z0 = V.z(a_0);
                     const float x1 = V.x(a_1), y1 = V.y(a_1), z1 = V.z(a_1);
-                    // one (row pair, partial) iteration, specialised at compile time on: a second
-                    // candidate row exists / level 0 (no anchor) / resuming a partly pushed iteration.
-                    // Returns true when the next queue could not take every survivor.
-                    auto one = [&](auto TWO, auto ROOT, auto TODO) -> bool {
-                        bool alive0 = have0, alive1 = TWO() && have1;
-                        if (TODO()) {
-                            alive0 = alive0 && ((todo >> lane) & 1ull);
-                            alive1 = alive1 && ((todo >> (32 + lane)) & 1ull);
-                            todo = 0ull;
+                    // (row pair, partial) iterations, specialised at compile time on: a second candidate
+                    // row exists / level 0 (no anchor) / resuming a partly pushed iteration.
+                    // test: the squared-distance band of both rows against one partial's anchor
+                    auto test = [&](auto TWO, const float4 an, bool &alive0, bool &alive1) {
+                        float dx = x0 - an.x, dy = y0 - an.y, dz = z0 - an.z;
+                        const float d0 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        alive0 = alive0 && d0 >= lo2 && d0 <= hi2;
+                        if (TWO()) {
+                            dx = x1 - an.x; dy = y1 - an.y; dz = z1 - an.z;
+                            const float d1 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                            alive1 = alive1 && d1 >= lo2 && d1 <= hi2;
                         }
-                        if (!ROOT()) {
-                            const float4 an = ws->anchor[pidx];
-                            float dx = x0 - an.x, dy = y0 - an.y, dz = z0 - an.z;
-                            const float d0 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                            alive0 = alive0 && d0 >= lo2 && d0 <= hi2;
-                            if (TWO()) {
-                                dx = x1 - an.x; dy = y1 - an.y; dz = z1 - an.z;
-                                const float d1 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                                alive1 = alive1 && d1 >= lo2 && d1 <= hi2;
-                            }
-                            if (kStats) st.evals += (int)have0 + (int)have1;
-                        }
+                        if (kStats) st.evals += (int)have0 + (int)have1;
+                    };
+                    // commit: push the survivors of partial `pidx`; true when the next queue could not
+                    // take all of them (the rest is remembered in `todo`)
+                    auto commit = [&](auto TWO, auto ROOT, bool alive0, bool alive1) -> bool {
                         if (kStats && lane == 0) ++st.sweeps;
                         const unsigned sv0 = __ballot_sync(kFull, alive0);
                         const unsigned sv1 = TWO() ? __ballot_sync(kFull, alive1) : 0u;
@@ -786,10 +781,41 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                         }
                         return false;
                     };
+                    auto one = [&](auto TWO, auto ROOT, auto TODO) -> bool {
+                        bool alive0 = have0, alive1 = TWO() && have1;
+                        if (TODO()) {
+                            alive0 = alive0 && ((todo >> lane) & 1ull);
+                            alive1 = alive1 && ((todo >> (32 + lane)) & 1ull);
+                            todo = 0ull;
+                        }
+                        if (!ROOT()) test(TWO, ws->anchor[pidx], alive0, alive1);
+                        return commit(TWO, ROOT, alive0, alive1);
+                    };
                     auto sweep = [&](auto TWO, auto ROOT) -> bool {
                         if (todo) {                       // finish the iteration a full queue interrupted
                             if (n_next >= cap_next || one(TWO, ROOT, std::true_type{})) return true;
                             ++pidx;
+                        }
+                        if (!ROOT()) {
+                            // two partials per iteration: independent dependency chains, and one vote
+                            // rejects both when (as usual) nothing survives
+                            while (pidx + 1 < P) {
+                                if (n_next >= cap_next) return true;
+                                const float4 an_a = ws->anchor[pidx], an_b = ws->anchor[pidx + 1];
+                                bool a0 = have0, a1 = TWO() && have1, b0 = have0, b1 = TWO() && have1;
+                                test(TWO, an_a, a0, a1);
+                                test(TWO, an_b, b0, b1);
+                                if (__any_sync(kFull, a0 | a1 | b0 | b1)) {
+                                    if (commit(TWO, ROOT, a0, a1)) return true;
+                                    ++pidx;
+                                    if (n_next >= cap_next) return true;      // resumes by re-testing this partial
+                                    if (commit(TWO, ROOT, b0, b1)) return true;
+                                    ++pidx;
+                                } else {
+                                    if (kStats && lane == 0) st.sweeps += 2;
+                                    pidx += 2;
+                                }
+                            }
                         }
                         for (; pidx < P; ++pidx)
                             if (n_next >= cap_next || one(TWO, ROOT, std::false_type{})) return true;
