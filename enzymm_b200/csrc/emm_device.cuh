@@ -25,10 +25,21 @@ constexpr int kSearchThreads = EMM_SEARCH_THREADS;
 constexpr int kSearchWarps = kSearchThreads / 32;
 // Per-warp trie queues: the first kWideLevels levels hold kQueueCap entries, deeper (rarely
 // populated) levels kDeepCap.  Parent indices are 8 bits.
-constexpr int kQueueCap = 48;
-constexpr int kDeepCap = 16;
-constexpr int kWideLevels = 9;
-__host__ __device__ constexpr int queue_off(int k) { return k <= kWideLevels ? k * kQueueCap : kWideLevels * kQueueCap + (k - kWideLevels) * kDeepCap; }
+#ifndef EMM_QUEUE_CAP
+#define EMM_QUEUE_CAP 48
+#endif
+#ifndef EMM_DEEP_CAP
+#define EMM_DEEP_CAP 16
+#endif
+#ifndef EMM_WIDE_LEVELS
+#define EMM_WIDE_LEVELS 9
+#endif
+constexpr int kQueueCap = EMM_QUEUE_CAP;
+constexpr int kDeepCap = EMM_DEEP_CAP;
+constexpr int kWideLevels = EMM_WIDE_LEVELS;
+// = k <= kWideLevels ? k * kQueueCap : kWideLevels * kQueueCap + (k - kWideLevels) * kDeepCap, branch-free
+__host__ __device__ constexpr int queue_off(int k) { return k * kDeepCap + (k < kWideLevels ? k : kWideLevels) * (kQueueCap - kDeepCap); }
+static_assert(queue_off(kWideLevels + 3) == kWideLevels * kQueueCap + 3 * kDeepCap && queue_off(4) == 4 * kQueueCap, "queue layout");
 __host__ __device__ constexpr int queue_cap(int k) { return k < kWideLevels ? kQueueCap : kDeepCap; }
 constexpr int kPrepThreads = 256;
 

@@ -907,7 +907,12 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
     __shared__ Blob s_blob;
     __shared__ __align__(8) uint64_t s_bar;      // mbarrier the TMA bulk copy of a blob completes on
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
+    int lane = tid & 31, wid = tid >> 5;
+    // through a shuffle, so that ptxas keeps both in registers instead of re-reading SR_TID (S2R is
+    // slow) wherever register pressure tempts it to rematerialise them
+    lane = __shfl_sync(0xffffffffu, lane, lane);
+    wid = __shfl_sync(0xffffffffu, wid, lane);
     unsigned stage_parity = 0;
     if (kStaged) {
         if (tid == 0) mbar_init(&s_bar, 1);
