@@ -154,6 +154,25 @@ def committed_traffic_bytes(n_structures: int):
     return None
 
 
+def committed_issue_figure(pairs_per_launch: float, kernel_ms: float, sm_mhz):
+    """Issue-slot view of the search kernel (it is instruction-bound, not HBM-bound): warp
+    instructions per (template, structure) pair from the committed ncu capture x the pairs of this
+    launch / the kernel time measured here, against one warp instruction per SM sub-partition per
+    clock (SMs x 4 x SM clock).  Extra information next to the HBM roofline the contract asks for."""
+    path = ROOT / "profiles" / "roofline_traffic.json"
+    try:
+        per_pair = float(json.loads(path.read_text())["search_kernel_warp_instructions_per_pair"])
+        import torch
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        mhz = float(sm_mhz or 1965.0)
+        achieved = per_pair * pairs_per_launch / (kernel_ms / 1000.0) / 1e9
+        peak = sms * 4 * mhz * 1e6 / 1e9
+        return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
+                "warp_inst_per_pair": per_pair, "source": "profiles/roofline_traffic.json (ncu smsp__inst_executed.sum)"}
+    except Exception:
+        return None
+
+
 def cpu_oracle_rate(workload, n_structures: int, threads: int):
     """Oracle (CPU port) over the first ``n_structures`` structures with ``threads`` threads."""
     import oracle
@@ -354,6 +373,8 @@ def run_b200(args, rank, local_rank, world):
                      "kernel_ms_avg": avg_search_ms, "prepare_kernel_ms_avg": sum(prepare_ms) / max(len(prepare_ms), 1),
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "note": "gather/compare-bound search: issue and latency bind long before HBM does"},
+        "roofline_issue": committed_issue_figure(host.n_structures * len(templates), avg_search_ms,
+                                                  (clocks or {}).get("sm_mhz")) if avg_search_ms else None,
         "pairs_per_s": value * len(templates),
         "hits_per_step": int(len(hits)), "hits_passing_filter": n_pass,
         "planted_recovered": f"{recovered}/{len(workload.planted)}",
