@@ -252,6 +252,7 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
     d.n_lr = desc->n_lr;
     const int T = desc->n_templates, A = desc->n_atoms;
     const int64_t npairs = desc->pair_off[T];
+    if (npairs >= (int64_t)1 << 31) { delete lib; return fail(EMM_ERR_INVALID, "template pair table exceeds 2^31 entries"); }
     int rc;
 #define COPY(field, src, count) if ((rc = dev_copy(lib, src, (size_t)(count), &field)) != EMM_OK) { emm_library_destroy(lib); return rc; }
     int32_t *p_i32; double *p_f64; uint16_t *p_u16; uint8_t *p_u8; int16_t *p_i16; int64_t *p_i64; float *p_f32; uint32_t *p_u32;
@@ -462,7 +463,7 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
         }
         const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries);
         s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + bytes;
-        max_staged = std::max(max_staged, bytes - align16(4 * (a1 - a0)) - align16(2 * (int64_t)(kMaxCells + 1)) - align16(2 * (a1 - a0)));
+        max_staged = std::max(max_staged, bytes - align16(4 * (a1 - a0)) - align16(2 * (int64_t)(kMaxCells + 1)) - 2 * align16(2 * (a1 - a0)));
     }
     s->max_staged = max_staged;
     if (s->h_blob_off[(size_t)n] > s->blob_capacity) {

@@ -92,10 +92,9 @@ struct BlobHeader {
     int32_t status;        // 0 ok, 1 residue order violated, 2 too many atoms for 16-bit ids
     float eps;             // FP32 guard band (Angstrom) for this structure
     int32_t staged_bytes;  // prefix of the blob the search kernel stages into shared memory
-    int32_t off_x, off_y, off_z;   // float[n_kept] centred coordinates
-    int32_t off_res;       // uint16 res_of[n_kept]
+    int32_t off_atom;      // float4[n_kept] atom records: centred x, y, z; w = bits (res_of << 16 | klass)
+    int32_t reserved[4];
     int32_t off_resstart;  // uint16 res_start[n_res+1]
-    int32_t off_klass;     // uint16 klass[n_kept]
     int32_t off_leadoff;   // uint32 lead_off[n_leader+1]
     int32_t off_lead;      // uint16 lead[...]
     int32_t off_orig;      // int32 orig[n_kept]: position of the atom inside its structure (NOT staged)
@@ -147,13 +146,12 @@ inline __host__ __device__ int64_t align16(int64_t v) { return (v + 15) & ~int64
 inline __host__ __device__ int64_t blob_bytes(int64_t n, int n_leader, int64_t lead_entries)
 {
     int64_t b = sizeof(BlobHeader);
-    b += 3 * align16(4 * n);                 // x y z
-    b += align16(2 * n);                     // res_of
+    b += 16 * n;                             // atom records (x, y, z, res_of | klass)
     b += align16(2 * (n + 1));               // res_start
-    b += align16(2 * n);                     // klass
     b += align16(4 * (int64_t)(n_leader + 1));
     b += align16(2 * lead_entries);
     b += align16(2 * (int64_t)(kMaxCells + 1)) + align16(2 * n);   // cell_start, cell_atoms
+    b += align16(2 * n);                     // compact klass copy (prepare-kernel scratch, not staged)
     b += align16(4 * n);                     // orig
     return b;
 }

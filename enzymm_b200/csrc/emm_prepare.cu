@@ -76,6 +76,8 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
         const int64_t bound = B.blob_off[s + 1] - B.blob_off[s];
         const int off_orig = (int)(bound - align16(4 * (int64_t)N));
         int32_t *orig = reinterpret_cast<int32_t *>(blob + off_orig);
+        // compact copy of the kept atoms' classes: pass D scans it once per leader type
+        uint16_t *bklass = reinterpret_cast<uint16_t *>(blob + off_orig - align16(2 * (int64_t)N));
         const uint16_t *klass_in = B.klass + base;
         const int32_t *res_in = B.residue + base;
         const double *xyz = B.xyz + 3 * base;
@@ -121,17 +123,11 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
         const float eps = (float)(64.0 * 5.9604644775390625e-08 * fmax(half, 16.0) + 1e-5);
 
         // ---- layout of the staged part ------------------------------------------------------------
-        const int off_x = (int)sizeof(BlobHeader);
-        const int sz_f = (int)align16(4 * (int64_t)n_kept);
-        const int off_y = off_x + sz_f, off_z = off_y + sz_f;
-        const int off_res = off_z + sz_f;
-        const int off_klass = off_res + (int)align16(2 * (int64_t)n_kept);
-        const int off_resstart = off_klass + (int)align16(2 * (int64_t)n_kept);
-        float *bx = reinterpret_cast<float *>(blob + off_x);
-        float *by = reinterpret_cast<float *>(blob + off_y);
-        float *bz = reinterpret_cast<float *>(blob + off_z);
-        uint16_t *res_of = reinterpret_cast<uint16_t *>(blob + off_res);
-        uint16_t *bklass = reinterpret_cast<uint16_t *>(blob + off_klass);
+        // one 16-byte record per atom -- x, y, z and (res_of << 16 | klass) in w -- so that the search
+        // kernel gets everything it needs about an atom with one 128-bit shared-memory load
+        const int off_atom = (int)sizeof(BlobHeader);
+        const int off_resstart = off_atom + 16 * n_kept;
+        float4 *atoms = reinterpret_cast<float4 *>(blob + off_atom);
         uint16_t *res_start = reinterpret_cast<uint16_t *>(blob + off_resstart);
 
         // ---- pass C: coordinates, classes, residue CSR ---------------------------------------------
@@ -142,11 +138,6 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
             int a = 0;
             if (i < n_kept) {
                 a = orig[i];
-                const double *p = xyz + 3 * (int64_t)a;
-                bx[i] = (float)(p[0] - ctr[0]);
-                by[i] = (float)(p[1] - ctr[1]);
-                bz[i] = (float)(p[2] - ctr[2]);
-                bklass[i] = klass_in[a];
                 if (i == 0) {
                     starts = true;
                 } else {
@@ -160,7 +151,10 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
             // residue id of atom i = (#starts at or before i) - 1
             if (i < n_kept) {
                 const int rid = n_res + pre + (starts ? 1 : 0) - 1;
-                res_of[i] = (uint16_t)rid;
+                const double *p = xyz + 3 * (int64_t)a;
+                atoms[i] = make_float4((float)(p[0] - ctr[0]), (float)(p[1] - ctr[1]), (float)(p[2] - ctr[2]),
+                                       __uint_as_float(((uint32_t)rid << 16) | (uint32_t)klass_in[a]));
+                bklass[i] = klass_in[a];
                 if (starts) res_start[rid] = (uint16_t)i;
             }
             n_res += tot;
@@ -233,9 +227,10 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
         uint16_t *cell_start = reinterpret_cast<uint16_t *>(blob + off_cellstart);
         uint16_t *cell_atoms = reinterpret_cast<uint16_t *>(blob + off_cellatoms);
         auto cell_of = [&](int i) {
-            const int ix = min(nx - 1, max(0, (int)((bx[i] - ox) / cell)));
-            const int iy = min(ny - 1, max(0, (int)((by[i] - oy) / cell)));
-            const int iz = min(nz - 1, max(0, (int)((bz[i] - oz) / cell)));
+            const float4 p = atoms[i];
+            const int ix = min(nx - 1, max(0, (int)((p.x - ox) / cell)));
+            const int iy = min(ny - 1, max(0, (int)((p.y - oy) / cell)));
+            const int iz = min(nz - 1, max(0, (int)((p.z - oz) / cell)));
             return (iz * ny + iy) * nx + ix;
         };
         for (int c = tid; c <= n_cells; c += kPrepThreads) s_cell[c] = 0;
@@ -270,8 +265,9 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
             h.off_cellstart = off_cellstart; h.off_cellatoms = off_cellatoms; h.nx = nx; h.ny = ny; h.nz = nz;
             h.cell = cell; h.ox = ox; h.oy = oy; h.oz = oz;
             for (int i = 0; i < 8; ++i) h.pad[i] = 0;
-            h.off_x = off_x; h.off_y = off_y; h.off_z = off_z; h.off_res = off_res;
-            h.off_resstart = off_resstart; h.off_klass = off_klass; h.off_leadoff = off_leadoff;
+            h.off_atom = off_atom;
+            for (int i = 0; i < 4; ++i) h.reserved[i] = 0;
+            h.off_resstart = off_resstart; h.off_leadoff = off_leadoff;
             h.off_lead = off_lead; h.off_orig = off_orig;
             *reinterpret_cast<BlobHeader *>(blob) = h;
             if (stats) atomicAdd(stats + 5, (unsigned long long)n_kept);

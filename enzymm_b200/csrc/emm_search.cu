@@ -89,7 +89,7 @@ struct Blob {
 template <bool kStaged>
 struct View {
     const unsigned char *gbase;
-    int off_x, off_y, off_z, off_res, off_resstart, off_klass, off_leadoff, off_lead;
+    int off_atom, off_resstart, off_leadoff, off_lead;
     int res_shift;
     float eps;
     template <typename T>
@@ -98,12 +98,11 @@ struct View {
         if (kStaged) return *reinterpret_cast<const T *>(g_smem + byte_off);
         return __ldg(reinterpret_cast<const T *>(gbase + byte_off));
     }
-    __device__ __forceinline__ float x(int i) const { return ld<float>(off_x + 4 * i); }
-    __device__ __forceinline__ float y(int i) const { return ld<float>(off_y + 4 * i); }
-    __device__ __forceinline__ float z(int i) const { return ld<float>(off_z + 4 * i); }
-    __device__ __forceinline__ int res_of(int i) const { return ld<uint16_t>(off_res + 2 * i); }
+    // atom record: centred x, y, z and (res_of << 16 | klass) as the bits of w -- one 128-bit load
+    __device__ __forceinline__ float4 atom(int i) const { return ld<float4>(off_atom + 16 * i); }
+    static __device__ __forceinline__ unsigned klass_of(const float4 &p) { return __float_as_uint(p.w) & 0xffffu; }
+    static __device__ __forceinline__ int res_of(const float4 &p) { return (int)(__float_as_uint(p.w) >> 16); }
     __device__ __forceinline__ int res_start(int r) const { return ld<uint16_t>(off_resstart + 2 * r); }
-    __device__ __forceinline__ unsigned klass(int i) const { return ld<uint16_t>(off_klass + 2 * i); }
     __device__ __forceinline__ int lead_off(int l) const { return (int)ld<uint32_t>(off_leadoff + 4 * l); }
     __device__ __forceinline__ int lead(int i) const { return ld<uint16_t>(off_lead + 2 * i); }
 };
@@ -530,13 +529,15 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
                 bool alive = i < end && (todo == 0u || ((todo >> lane) & 1u));
                 todo = 0u;
                 int a = 0;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (alive) {
                     a = __ldg(S.cell_atoms + i);
-                    const unsigned kl = V.klass(a);
+                    p = V.atom(a);
+                    const unsigned kl = V.klass_of(p);
                     alive = (__ldg(crow + (kl >> 5)) >> (kl & 31u)) & 1u;
                 }
                 if (alive) {
-                    const float dx = V.x(a) - an.x, dy = V.y(a) - an.y, dz = V.z(a) - an.z;
+                    const float dx = p.x - an.x, dy = p.y - an.y, dz = p.z - an.z;
                     const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                     alive = d2 >= lo2 && d2 <= hi2;
                 }
@@ -598,9 +599,10 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     const int anchor_pos = k < m ? (int)L.plan_anchor[a0 + k] : -1;     // warp-uniform
     const bool dynamic = dyn64 != cut64;
     const float eps = V.eps;
-    const float xa = V.x(a), ya = V.y(a), za = V.z(a);
+    const float4 pa = V.atom(a);
+    const float xa = pa.x, ya = pa.y, za = pa.z;
     float ax = xa, ay = ya, az = za;
-    int aatom = a;
+    int aatom = a, ares = V.res_of(pa);
     bool border = false;
     const float *row = L.pair_dist32 + p0 + ((k - 1) * (k - 2)) / 2;
     uint32_t w = e;
@@ -609,8 +611,9 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     for (int pos = k - 2; pos >= stop; --pos) {
         w = Q[queue_off(pos + 1) + ((w >> 16) & 0xffu)];
         const int b = (int)(w & 0xffffu);
-        const float xb = V.x(b), yb = V.y(b), zb = V.z(b);
-        if (pos == anchor_pos) { ax = xb; ay = yb; az = zb; aatom = b; }
+        const float4 pb = V.atom(b);
+        const float xb = pb.x, yb = pb.y, zb = pb.z;
+        if (pos == anchor_pos) { ax = xb; ay = yb; az = zb; aatom = b; ares = V.res_of(pb); }
         if (check) {
             const float dx = xa - xb, dy = ya - yb, dz = za - zb;
             const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
@@ -630,9 +633,8 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     if (alive && k < m) {
         int payload = aatom;
         if ((int)L.plan_src[a0 + k] >= 0) {        // same-residue level: the anchor's residue span
-            const int r = V.res_of(aatom);
-            const int rs = V.res_start(r);
-            payload = rs | ((V.res_start(r + 1) - rs) << 16);
+            const int rs = V.res_start(ares);
+            payload = rs | ((V.res_start(ares + 1) - rs) << 16);
         }
         const int rank = __popc(valid & ((1u << lane) - 1u));      // anchors are stored compacted
         ws->anchor[rank] = make_float4(ax, ay, az, __int_as_float(payload));
@@ -747,8 +749,9 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     const bool have0 = c0 < B, have1 = c1 < B;
                     const bool two = ((r + 1) << 5) < B;       // warp-uniform: a second row exists
                     const int a_0 = have0 ? V.lead(lbase + c0) : 0, a_1 = have1 ? V.lead(lbase + c1) : 0;
-                    const float x0 = V.x(a_0), y0 = V.y(a_0), z0 = V.z(a_0);
-                    const float x1 = V.x(a_1), y1 = V.y(a_1), z1 = V.z(a_1);
+                    const float4 p_0 = V.atom(a_0), p_1 = V.atom(a_1);
+                    const float x0 = p_0.x, y0 = p_0.y, z0 = p_0.z;
+                    const float x1 = p_1.x, y1 = p_1.y, z1 = p_1.z;
                     // (row pair, partial) iterations, specialised at compile time on: a second candidate
                     // row exists / level 0 (no anchor) / resuming a partly pushed iteration.
                     // test: the squared-distance band of both rows against one partial's anchor
@@ -846,12 +849,14 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     const int payload = __float_as_int(an.w);
                     const int a = (payload & 0xffff) + sidx;
                     alive = alive && sidx < (payload >> 16);
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (alive) {
-                        const unsigned kl = V.klass(a);
+                        p = V.atom(a);
+                        const unsigned kl = V.klass_of(p);
                         alive = (__ldg(crow + (kl >> 5)) >> (kl & 31u)) & 1u;
                     }
                     if (alive) {
-                        const float dx = V.x(a) - an.x, dy = V.y(a) - an.y, dz = V.z(a) - an.z;
+                        const float dx = p.x - an.x, dy = p.y - an.y, dz = p.z - an.z;
                         const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                         alive = d2 >= lo2 && d2 <= hi2;
                         if (kStats) ++st.evals;
@@ -977,8 +982,8 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             __syncthreads();
             View<kStaged> V;
             V.gbase = gblob;
-            V.off_x = hdr.off_x; V.off_y = hdr.off_y; V.off_z = hdr.off_z; V.off_res = hdr.off_res;
-            V.off_resstart = hdr.off_resstart; V.off_klass = hdr.off_klass; V.off_leadoff = hdr.off_leadoff;
+            V.off_atom = hdr.off_atom;
+            V.off_resstart = hdr.off_resstart; V.off_leadoff = hdr.off_leadoff;
             V.off_lead = hdr.off_lead; V.res_shift = hdr.res_shift; V.eps = hdr.eps;
             for (;;) {
                 int t = -1;
