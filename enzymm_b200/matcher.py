@@ -37,7 +37,7 @@ from typing import ClassVar, Dict, IO, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import pyjess_api as pyjess
-from .engine import Engine
+from .engine import Engine, EngineError
 from .library import CompiledLibrary, load_lr_models
 from .packing import pack_molecules
 from .pyjess_api import Hit
@@ -364,6 +364,8 @@ class Matcher:
                 self.verbose_print([t.id for t in small])
         self._engine: Optional[Engine] = None
         self._groups: List[Tuple[int, int, int]] = []
+        self.hits_per_structure = 64          # initial hit-buffer sizing; grown on demand
+        self._hit_floor = 1024
 
     def verbose_print(self, *args):
         if self.verbose:
@@ -430,13 +432,26 @@ class Matcher:
         else:
             session.run(template_begin=0, template_end=len(self._ordered), skip_mode=0, reset=True, **common)
 
+    def _hit_capacity(self, n_structures: int) -> int:
+        return max(self._hit_floor, self.hits_per_structure * n_structures)
+
     def _search(self, batch) -> np.ndarray:
         """One packed batch through the device: every size group, hit records sorted by
-        (structure, template index)."""
+        (structure, template index).  A hit buffer that turns out too small (many hits per
+        structure, e.g. unfiltered runs with loose cutoffs) is enlarged and the batch run again."""
         engine = self._ensure_engine()
-        session = engine.session_for(batch.n_atoms, batch.n_structures)
-        self._submit(session, batch)
-        return session.download()
+        capacity = self._hit_capacity(batch.n_structures)
+        for _ in range(6):
+            session = engine.session_for(batch.n_atoms, batch.n_structures, capacity)
+            self._submit(session, batch)
+            try:
+                return session.download()
+            except EngineError as exc:
+                if exc.status != -4:
+                    raise
+                capacity = 4 * session.hit_capacity
+                self.hits_per_structure = max(self.hits_per_structure, capacity // max(batch.n_structures, 1))
+        raise EngineError(-4, "hit buffer kept overflowing")
 
     def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0):
         """Screen PDB files without building ``Molecule`` objects: a generator of
@@ -458,6 +473,15 @@ class Matcher:
         if not chunks:
             return
         lanes: List[list] = [[None, engine.new_stream()], [None, engine.new_stream()]]   # [session, stream]
+
+        def collect(lane, chunk, ids, batch):
+            try:
+                return chunk, ids, lane[0].download(stream=lane[1])
+            except EngineError as exc:
+                if exc.status != -4:
+                    raise
+            return chunk, ids, self._search(batch)       # rare: rerun this chunk alone with a larger hit buffer
+
         in_flight: collections.deque = collections.deque()      # (lane, chunk paths, ids, batch)
         try:
             with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
@@ -468,7 +492,7 @@ class Matcher:
                                if ci + 1 < len(chunks) else None)
                     lane = lanes[ci % 2]
                     sess = lane[0]
-                    need_hits = max(1024, 64 * batch.n_structures)
+                    need_hits = self._hit_capacity(batch.n_structures)
                     if sess is None or batch.n_atoms > sess.max_atoms or batch.n_structures > sess.max_structures \
                             or need_hits > sess.hit_capacity:
                         if sess is not None:
@@ -480,11 +504,9 @@ class Matcher:
                     self._submit(sess, batch, stream=lane[1])
                     in_flight.append((lane, chunk, ids, batch))
                     if len(in_flight) == 2:
-                        done_lane, done_chunk, done_ids, _ = in_flight.popleft()
-                        yield done_chunk, done_ids, done_lane[0].download(stream=done_lane[1])
+                        yield collect(*in_flight.popleft())
                 while in_flight:
-                    done_lane, done_chunk, done_ids, _ = in_flight.popleft()
-                    yield done_chunk, done_ids, done_lane[0].download(stream=done_lane[1])
+                    yield collect(*in_flight.popleft())
         finally:
             for sess, stream in lanes:          # destroying a session waits for its device work
                 if sess is not None:

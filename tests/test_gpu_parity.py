@@ -604,3 +604,18 @@ def test_scan_files_equals_matcher_run(tmp_path, active_templates):
                 assert [m.complete for m in got] == [m.complete for m in expect]
             seen += len(chunk_paths)
         assert seen == len(paths)
+
+
+def test_matcher_grows_its_hit_buffer(tmp_path, active_templates, mol_1amy, mol_af):
+    """More hits than the initial buffer holds: ``run`` and ``scan_files`` enlarge it and rerun."""
+    reference = jess_run.Matcher(templates=active_templates, filter_matches=False).run([mol_1amy, mol_af])
+    small = jess_run.Matcher(templates=active_templates, filter_matches=False)
+    small.hits_per_structure, small._hit_floor = 1, 4
+    got = small.run([mol_1amy, mol_af])
+    assert small.hits_per_structure > 1
+    for mol in (mol_1amy, mol_af):
+        assert [m.hit.template.id for m in got[mol]] == [m.hit.template.id for m in reference[mol]]
+    small.hits_per_structure, small._hit_floor = 1, 4
+    paths = [GOLDEN / "1AMY.pdb", GOLDEN / "AF-P0DUB6-F1-model_v4.pdb"]
+    counts = [len(records) for _, _, records in small.scan_files(paths, chunk_size=1)]
+    assert counts == [len(reference[mol_1amy]), len(reference[mol_af])]
