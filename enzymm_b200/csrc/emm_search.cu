@@ -675,6 +675,36 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
     int k = 0, base = 0;
     unsigned valid = 1u;          // level 0: the empty partial
     bool entered = true;
+    // Fast start.  Level 0 has nothing to test: its expansion copies the first leader list into
+    // queue 1 and entering level 1 only derives anchors.  When the list fits one chunk (the usual
+    // case: plans start with the rarest type) do both here, without the level machinery.
+    if (m > 1) {
+        const int src0 = L.plan_src[a0];
+        const int lbase = V.lead_off(-1 - src0), B0 = V.lead_off(-src0) - lbase;
+        if (B0 <= 32) {
+            if (lane < B0) {
+                const int a = V.lead(lbase + lane);
+                const float4 p = V.atom(a);
+                Q[queue_off(1) + lane] = (uint32_t)a | kEntryValid;          // parent: slot 0 of level 0
+                int payload = a;
+                if ((int)L.plan_src[a0 + 1] >= 0) {                           // position 1 shares this atom's residue
+                    const int r = V.res_of(p), rs = V.res_start(r);
+                    payload = rs | ((V.res_start(r + 1) - rs) << 16);
+                }
+                ws->anchor[lane] = make_float4(p.x, p.y, p.z, __int_as_float(payload));
+                ws->vslot[lane] = (unsigned char)lane;
+            }
+            if (lane == 0) { ws->n[1] = B0; ws->chunk[1] = B0; ws->cur[0] = -1; }
+            if (kStats && lane == 0) {
+                atomicAdd(A.O.stats + 40, (unsigned long long)B0);
+                atomicAdd(A.O.stats + 72 + 1, (unsigned long long)B0);
+                atomicAdd(A.O.stats + 104 + 1, 1ull);
+            }
+            __syncwarp();
+            k = 1;
+            valid = B0 >= 32 ? 0xffffffffu : (1u << B0) - 1u;
+        }
+    }
     for (;;) {
         if (ws->overflow) break;
         if (!entered) {
