@@ -916,17 +916,26 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             }
             __syncwarp();
         }
-        // the chunk of level k is exhausted (or dead, or its complete assignments are processed)
-        if (k == 0) break;
-        if (lane == 0) {
-            ws->n[k] = base;
-            ws->chunk[k] = min(32, base);
-            ws->cur[k] = 0;
-            ws->todo[k] = 0ull;
-            if (kCells) { ws->cellrow[k] = 0; ws->celli[k] = -1; }
+        // the chunk of level k is exhausted (or dead, or its complete assignments are processed):
+        // pop it, and with it every ancestor chunk whose own expansion had already finished
+        bool finished = false;
+        for (;;) {
+            if (k == 0) { finished = true; break; }
+            if (lane == 0) {
+                ws->n[k] = base;
+                ws->chunk[k] = min(32, base);
+                ws->cur[k] = 0;
+                ws->todo[k] = 0ull;
+                if (kCells) { ws->cellrow[k] = 0; ws->celli[k] = -1; }
+            }
+            __syncwarp();
+            if (base != 0) break;                 // more entries at this level: enter its next chunk
+            --k;                                  // back to the parent: its chunk, cursor and todo are intact
+            if (ws->cur[k] >= 0) break;           // the parent still has candidates to try: re-enter it
+            if (k == 0) { finished = true; break; }       // the root was expanded completely
+            base = ws->n[k] - ws->chunk[k];
         }
-        __syncwarp();
-        if (base == 0) --k;           // back to the parent level: its chunk, cursor and todo are intact
+        if (finished) break;
         entered = false;
     }
     if (kStats && lane == 0 && ws->n_complete) atomicAdd(A.O.stats + 4, ws->n_complete);
