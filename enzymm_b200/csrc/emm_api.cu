@@ -270,6 +270,14 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
         std::vector<float> p32((size_t)std::max<int64_t>(npairs, 1));
         for (int64_t i = 0; i < npairs; ++i) p32[(size_t)i] = (float)desc->pair_dist[i];
         COPY(p_f32, p32.data(), npairs); d.pair_dist32 = p_f32;
+        // band centre of every plan position's cheap filter, so an expansion reads it with one load
+        std::vector<float> ad((size_t)A, 0.f);
+        for (int t = 0; t < T; ++t) {
+            const int a0 = desc->atom_off[t], m = desc->atom_off[t + 1] - a0;
+            for (int k = 1; k < m; ++k)
+                ad[(size_t)(a0 + k)] = p32[(size_t)(desc->pair_off[t] + (int64_t)k * (k - 1) / 2 + desc->plan_anchor[a0 + k])];
+        }
+        COPY(p_f32, ad.data(), A); d.anchor_dist32 = p_f32;
     }
     {
         std::vector<uint32_t> wide((size_t)d.n_ttype * d.class_words_cap, 0u);

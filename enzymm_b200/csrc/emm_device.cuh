@@ -56,6 +56,7 @@ struct DevLibrary {
     const int64_t *pair_off;
     const double *pair_dist;
     const float *pair_dist32;
+    const float *anchor_dist32;   // [n_atoms] template distance between plan position k and its anchor position
     const uint32_t *compat;
     const uint16_t *leader_ttype;
     const double *rmsd_thr;

@@ -736,9 +736,8 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             // squared acceptance band of the anchor constraint (widened by eps and FP32 rounding)
             float lo2 = 0.f, hi2 = 3.0e38f;
             if (k > 0) {
-                const int apos = L.plan_anchor[a0 + k];
-                const float dt = __ldg(L.pair_dist32 + p0 + (k * (k - 1)) / 2 + apos);
-                const float rej = (dynamic ? (float)pair_delta(L, a0, k, apos, cut64, dyn64) : cut32) + eps;
+                const float dt = __ldg(L.anchor_dist32 + a0 + k);
+                const float rej = (dynamic ? (float)pair_delta(L, a0, k, (int)L.plan_anchor[a0 + k], cut64, dyn64) : cut32) + eps;
                 const float lo = fmaxf(dt - rej, 0.f), hi = dt + rej;
                 lo2 = lo * lo * 0.999999f;
                 hi2 = hi * hi * 1.000001f;
