@@ -21,8 +21,8 @@ size_t search_fixed_smem(int levels);
 cudaError_t configure_search(int smem_bytes);
 void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream);
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, const int *sched, bool stats, bool staged, int grid, size_t smem,
-                   cudaStream_t stream);
+                   const unsigned char *skip, const int *sched, const int *ids, bool stats, bool staged, int grid,
+                   size_t smem, cudaStream_t stream);
 }  // namespace emm
 
 using namespace emm;
@@ -91,6 +91,7 @@ struct emm_session {
     unsigned int *d_work = nullptr;
     int *d_any = nullptr, *d_pass = nullptr;
     unsigned char *d_skip = nullptr;
+    int *d_ids = nullptr;          // structures that can be staged first, then the ones too large for shared memory
     unsigned long long *d_stats = nullptr;
     // current batch
     int32_t n_structures = 0;
@@ -100,7 +101,9 @@ struct emm_session {
     float prepared_cutoff = -1.f;
     int prepared_version = -1;
     std::vector<int64_t> h_blob_off;
-    int64_t max_staged = 0;        // largest staged blob prefix in the uploaded batch (upper bound)
+    int64_t max_staged = 0;        // largest staged blob prefix among the stageable structures (upper bound)
+    int32_t n_small = 0;           // structures searched from shared memory; the rest are read in place
+    std::vector<int> h_ids;
     int last_launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_prepare, ev_search;
     size_t ev_prepare_used = 0, ev_search_used = 0;
@@ -419,6 +422,7 @@ int emm_session_create(emm_library *lib, int64_t max_atoms, int32_t max_structur
     ALLOC(s->d_any, 4 * (size_t)max_structures);
     ALLOC(s->d_pass, 4 * (size_t)max_structures);
     ALLOC(s->d_skip, (size_t)max_structures);
+    ALLOC(s->d_ids, 4 * (size_t)max_structures);
     ALLOC(s->d_stats, 8 * 136);
     s->blob_capacity = 64 * max_atoms + (1024 + 4 * (int64_t)lib->d.n_leader) * max_structures;   // grown on demand at upload
     ALLOC(s->d_blob, s->blob_capacity);
@@ -437,7 +441,7 @@ void emm_session_destroy(emm_session *s)
     cudaSetDevice(s->lib->device);
     void *ptrs[] = {s->d_atom_off, s->d_xyz, s->d_klass, s->d_residue, s->d_bfactor, s->d_chain, s->d_atom_id,
                     s->d_blob, s->d_blob_off, s->d_hits, s->d_hit_count, s->d_work, s->d_any, s->d_pass,
-                    s->d_skip, s->d_stats};
+                    s->d_skip, s->d_stats, s->d_ids};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : s->ev_prepare) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : s->ev_search) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -458,6 +462,10 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     const int n = b->n_structures;
     s->h_blob_off.assign((size_t)n + 1, 0);
     int64_t max_staged = 0;
+    // shared memory left for a staged blob next to the queues of this library's deepest template
+    const int64_t stage_cap = (int64_t)((lib->smem_optin - (int)search_fixed_smem(lib->d.max_tpl_atoms + 1) - 1024) & ~15);
+    std::vector<int> large;
+    s->h_ids.clear();
     const uint16_t *cl = lib->class_leaders.data();
     const size_t n_class = lib->class_leaders.size();
     for (int i = 0; i < n; ++i) {
@@ -471,9 +479,17 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
         }
         const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries);
         s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + bytes;
-        max_staged = std::max(max_staged, bytes - align16(4 * (a1 - a0)) - align16(2 * (int64_t)(kMaxCells + 1)) - 2 * align16(2 * (a1 - a0)));
+        const int64_t staged = bytes - align16(4 * (a1 - a0)) - align16(2 * (int64_t)(kMaxCells + 1)) - 2 * align16(2 * (a1 - a0));
+        if (((staged + 1023) & ~int64_t(1023)) <= stage_cap) {
+            max_staged = std::max(max_staged, staged);
+            s->h_ids.push_back(i);
+        } else {
+            large.push_back(i);      // searched in place from global memory, in a launch of their own
+        }
     }
     s->max_staged = max_staged;
+    s->n_small = (int32_t)s->h_ids.size();
+    s->h_ids.insert(s->h_ids.end(), large.begin(), large.end());
     if (s->h_blob_off[(size_t)n] > s->blob_capacity) {
         CUDA_TRY(cudaStreamSynchronize(stream));
         cudaFree(s->d_blob);
@@ -486,6 +502,7 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     if (n > 0) {
         CUDA_TRY(cudaMemcpyAsync(s->d_atom_off, b->atom_off, 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(s->d_blob_off, s->h_blob_off.data(), 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
+        if (s->n_small != n) CUDA_TRY(cudaMemcpyAsync(s->d_ids, s->h_ids.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, stream));
     }
     if (na > 0) {
         CUDA_TRY(cudaMemcpyAsync(s->d_xyz, b->xyz, 24 * na, cudaMemcpyHostToDevice, stream));
@@ -571,37 +588,13 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     P.levels = lib->d.max_tpl_atoms + 1;
     P.cell_threshold = q->cell_threshold > 0 ? q->cell_threshold : 0;   // opt-in: typed lists measured faster at every tested size
     const int grid = lib->sm_count;
-    int chunks = 1;
-    if (n < 2 * grid) chunks = (2 * grid + n - 1) / n;
-    chunks = std::min(chunks, std::max(1, (te - tb) / 8));
-    chunks = std::max(1, std::min(chunks, 256));
-    if (const char *env = getenv("EMM_CHUNKS")) chunks = std::max(1, std::min(atoi(env), 256));   // tuning knob
     emm_library::Sched sc;
     if (int rc = get_sched(lib, tb, te, &sc)) return rc;
     P.n_sched = sc.n;
     P.n_heavy = sc.n_heavy;
-    P.n_structures = n;
-    // large batch with a mixed library: heavy templates of every structure first (see SearchParams)
-    P.two_phase = chunks == 1 && n >= 2 * grid && sc.n_heavy >= 48 && sc.n_heavy <= sc.n - 48;
-    if (const char *env = getenv("EMM_TWO_PHASE")) P.two_phase = P.two_phase && env[0] != '0';   // tuning knob
-    if (P.two_phase) chunks = 2;
-    P.n_chunks = chunks;
-    P.n_items = n * chunks;
     const int fixed = (int)search_fixed_smem(P.levels);
-    int cap = lib->smem_optin - fixed - 1024;
-    cap &= ~15;
-    if (cap < 0) return fail(EMM_ERR_INVALID, "not enough shared memory for the search queues");
-    // stage no more than the batch needs: every KB not claimed here stays L1 for the template tables
-    // (a batch with a structure too large to stage is searched in place from global memory)
-    const int64_t want = (s->max_staged + 1023) & ~int64_t(1023);
-    const bool staged = want <= cap;
-    cap = staged ? (int)want : 0;
-    P.blob_cap = cap;
-    const size_t smem = search_smem_bytes(cap, P.levels);
-    if (lib->device >= 64 || smem > g_configured_smem[lib->device]) {   // raise only; never per launch
-        CUDA_TRY(configure_search((int)smem));
-        if (lib->device < 64) g_configured_smem[lib->device] = smem;
-    }
+    const int stage_cap = (lib->smem_optin - fixed - 1024) & ~15;
+    if (stage_cap < 0) return fail(EMM_ERR_INVALID, "not enough shared memory for the search queues");
     SearchOut O{};
     O.hits = s->d_hits;
     O.hit_capacity = s->hit_capacity;
@@ -610,16 +603,43 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     O.struct_any = s->d_any;
     O.struct_pass = s->d_pass;
     O.stats = s->d_stats;
-    CUDA_TRY(cudaMemsetAsync(s->d_work, 0, 4, stream));
-    {
+    // One launch over the structures whose blob fits in shared memory and, if the batch holds
+    // larger ones, a second launch that reads those in place from global memory.
+    auto launch_subset = [&](const int *ids, int count, bool staged) -> int {
+        if (count <= 0) return EMM_OK;
+        int chunks = 1;
+        if (count < 2 * grid) chunks = (2 * grid + count - 1) / count;
+        chunks = std::min(chunks, std::max(1, (te - tb) / 8));
+        chunks = std::max(1, std::min(chunks, 256));
+        if (const char *env = getenv("EMM_CHUNKS")) chunks = std::max(1, std::min(atoi(env), 256));   // tuning knob
+        P.n_structures = count;
+        // large batch with a mixed library: heavy templates of every structure first (see SearchParams)
+        P.two_phase = chunks == 1 && count >= 2 * grid && sc.n_heavy >= 48 && sc.n_heavy <= sc.n - 48;
+        if (const char *env = getenv("EMM_TWO_PHASE")) P.two_phase = P.two_phase && env[0] != '0';   // tuning knob
+        if (P.two_phase) chunks = 2;
+        P.n_chunks = chunks;
+        P.n_items = count * chunks;
+        // stage no more than the batch needs: every KB not claimed here stays L1 for the template tables
+        const int cap = staged ? (int)((s->max_staged + 1023) & ~int64_t(1023)) : 0;
+        P.blob_cap = cap;
+        const size_t smem = search_smem_bytes(cap, P.levels);
+        if (lib->device >= 64 || smem > g_configured_smem[lib->device]) {   // raise only; never per launch
+            CUDA_TRY(configure_search((int)smem));
+            if (lib->device < 64) g_configured_smem[lib->device] = smem;
+        }
+        CUDA_TRY(cudaMemsetAsync(s->d_work, 0, 4, stream));
         cudaEvent_t e0, e1;
         const bool timed = next_events(s->ev_search, s->ev_search_used, &e0, &e1);
         if (timed) cudaEventRecord(e0, stream);
-        launch_search(lib->d, B, P, O, skip, sc.d_ids, lib->stats_enabled != 0, staged, std::min(grid, P.n_items), smem, stream);
+        launch_search(lib->d, B, P, O, skip, sc.d_ids, ids, lib->stats_enabled != 0, staged, std::min(grid, P.n_items), smem, stream);
         if (timed) cudaEventRecord(e1, stream);
-    }
-    CUDA_TRY(cudaGetLastError());
-    s->last_launches++;
+        CUDA_TRY(cudaGetLastError());
+        s->last_launches++;
+        return EMM_OK;
+    };
+    const bool mixed = s->n_small != n;
+    if (int rc = launch_subset(mixed ? s->d_ids : nullptr, s->n_small, true)) return rc;
+    if (int rc = launch_subset(s->d_ids + s->n_small, n - s->n_small, false)) return rc;
     return EMM_OK;
 }
 

@@ -114,6 +114,7 @@ struct SearchArgs {
     SearchOut O;
     const unsigned char *skip;
     const int *sched;          // [P.n_sched] template ids in visiting order
+    const int *ids;            // [P.n_structures] structures of this launch, or null for 0..n-1
 };
 
 // ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier: global -> shared staging ----------
@@ -987,6 +988,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             pos1 = P.n_sched;
             stride = P.n_chunks;
         }
+        if (A.ids) s = __ldg(A.ids + s);
         const unsigned char *gblob = A.B.blob + A.B.blob_off[s];
         const BlobHeader hdr = *reinterpret_cast<const BlobHeader *>(gblob);
         const bool run = hdr.status == 0 && hdr.n_kept > 0 && pos0 < pos1 && !(A.skip && A.skip[s]);
@@ -1106,11 +1108,11 @@ void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsi
 }
 
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, const int *sched, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream)
+                   const unsigned char *skip, const int *sched, const int *ids, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream)
 {
     if (P.n_items <= 0) return;
     SearchArgs A;
-    A.L = L; A.B = B; A.P = P; A.O = O; A.skip = skip; A.sched = sched;
+    A.L = L; A.B = B; A.P = P; A.O = O; A.skip = skip; A.sched = sched; A.ids = ids;
     const bool cells = P.cell_threshold > 0;       // the cell-list path is a separate instantiation
     if (cells && staged) emm_search_kernel<false, true, true><<<grid, kSearchThreads, smem, stream>>>(A);
     else if (cells) emm_search_kernel<false, false, true><<<grid, kSearchThreads, smem, stream>>>(A);

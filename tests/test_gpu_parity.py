@@ -619,3 +619,28 @@ def test_matcher_grows_its_hit_buffer(tmp_path, active_templates, mol_1amy, mol_
     paths = [GOLDEN / "1AMY.pdb", GOLDEN / "AF-P0DUB6-F1-model_v4.pdb"]
     counts = [len(records) for _, _, records in small.scan_files(paths, chunk_size=1)]
     assert counts == [len(reference[mol_1amy]), len(reference[mol_af])]
+
+
+def test_mixed_batch_stages_what_fits(active_templates, mol_1amy, monkeypatch):
+    """One assembly too large for shared memory in a batch of ordinary structures: the ordinary ones
+    are still searched from shared memory (their own launch), the large one in place -- same hits."""
+    monkeypatch.setenv("EMM_STATS", "1")              # stats build: exposes staged / in-place counters
+    big = generate_chunk(0, SynthConfig(n_chains=4), active_templates, 1).to_molecule(0)
+    small = generate_chunk(3, SynthConfig(n_residues=200), active_templates, 3)
+    mols = [small.to_molecule(0), big, mol_1amy, small.to_molecule(1), small.to_molecule(2)]
+    subset = active_templates[::12]
+    dist = default_distances(subset)
+    eng = Engine(CompiledLibrary(subset, 2.0, dist, dist))
+    try:
+        compare_with_oracle(eng, subset, mols, dist)
+        batch = pack_molecules(mols, eng.compiled)
+        hits, stats = eng.query(batch, with_stats=True)
+        assert stats["global_blobs"] >= 1 and stats["staged_bytes"] > 0
+        assert stats["pairs"] == len(mols) * len(subset)
+        alone = [eng.query(pack_molecules([m], eng.compiled)) for m in mols]
+        for i, part in enumerate(alone):
+            mine = hits[hits["structure"] == i]
+            assert mine["template_index"].tolist() == part["template_index"].tolist()
+            assert mine["rmsd"].tolist() == part["rmsd"].tolist()
+    finally:
+        eng.close()
