@@ -59,6 +59,7 @@ struct emm_library {
     std::vector<void *> allocs;
     std::vector<uint16_t> h_leader_ttype;
     uint32_t *d_compat = nullptr;
+    uint32_t *d_class_mask = nullptr;
     double *d_rmsd = nullptr, *d_cut = nullptr, *d_dyn = nullptr, *d_lr_table = nullptr;
     int32_t *d_lr_index = nullptr;
     int lr_capacity = 0;
@@ -123,21 +124,29 @@ static int dev_copy(emm_library *lib, const T *host, size_t count, T **out)
     return EMM_OK;
 }
 
-static void compute_class_leaders(emm_library *lib, int class_words, const uint32_t *compat)
+// Per typing class: how many leader lists it appears in (blob sizing) and which (class_mask, for
+// the prepare kernel).  Call with the device idle: it rewrites a table the kernels read.
+static int compute_class_leaders(emm_library *lib, int class_words, const uint32_t *compat)
 {
-    lib->class_leaders.assign((size_t)lib->d.class_words_cap * 32, 0);
-    for (uint16_t tt : lib->h_leader_ttype) {
-        const uint32_t *row = compat + (size_t)tt * class_words;
+    const size_t n_class = (size_t)lib->d.class_words_cap * 32, mw = (size_t)lib->d.mask_words;
+    lib->class_leaders.assign(n_class, 0);
+    std::vector<uint32_t> mask(n_class * mw, 0u);
+    for (size_t l = 0; l < lib->h_leader_ttype.size(); ++l) {
+        const uint32_t *row = compat + (size_t)lib->h_leader_ttype[l] * class_words;
         for (int w = 0; w < class_words; ++w) {
             uint32_t bits = row[w];
             while (bits) {
                 const int b = __builtin_ctz(bits);
-                lib->class_leaders[(size_t)w * 32 + b]++;
+                const size_t c = (size_t)w * 32 + b;
+                lib->class_leaders[c]++;
+                mask[c * mw + (l >> 5)] |= 1u << (l & 31);
                 bits &= bits - 1;
             }
         }
     }
+    CUDA_TRY(cudaMemcpy(lib->d_class_mask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice));
     lib->compat_version++;
+    return EMM_OK;
 }
 
 static bool next_events(std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &pool, size_t &used,
@@ -303,7 +312,18 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
         COPY(p_f64, tab.data(), tab.size()); d.lr_table = p_f64; lib->d_lr_table = p_f64;
     }
 #undef COPY
-    compute_class_leaders(lib, desc->class_words, desc->compat);
+    d.mask_words = ((desc->n_leader + 255) / 256) * 8;
+    {
+        void *p = nullptr;
+        if (cudaMalloc(&p, (size_t)d.class_words_cap * 32 * d.mask_words * 4) != cudaSuccess) {
+            emm_library_destroy(lib);
+            return fail(EMM_ERR_NOMEM, "cudaMalloc(class mask)");
+        }
+        lib->allocs.push_back(p);
+        lib->d_class_mask = (uint32_t *)p;
+        d.class_mask = lib->d_class_mask;
+    }
+    if (int rc2 = compute_class_leaders(lib, desc->class_words, desc->compat)) { emm_library_destroy(lib); return rc2; }
     const char *env = getenv("EMM_STATS");
     lib->stats_enabled = env && env[0] == '1';
     *out = lib;
@@ -322,8 +342,7 @@ int emm_library_set_compat(emm_library *lib, int32_t class_words, const uint32_t
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(lib->d_compat, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice));
     lib->d.class_words = class_words;
-    compute_class_leaders(lib, class_words, compat);
-    return EMM_OK;
+    return compute_class_leaders(lib, class_words, compat);
 }
 
 int emm_library_set_thresholds(emm_library *lib, const double *rmsd_threshold, const double *distance_cutoff,

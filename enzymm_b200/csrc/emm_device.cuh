@@ -59,6 +59,10 @@ struct DevLibrary {
     const float *anchor_dist32;   // [n_atoms] template distance between plan position k and its anchor position
     const uint32_t *compat;
     const uint16_t *leader_ttype;
+    // per typing class: bit l set = the class belongs to leader list l ([classes][mask_words] words,
+    // mask_words a multiple of 8); lets the prepare kernel build all leader lists in one pass
+    const uint32_t *class_mask;
+    int mask_words;
     const double *rmsd_thr;
     const double *dist_cut;
     const double *max_dyn;

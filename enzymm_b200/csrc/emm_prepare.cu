@@ -64,6 +64,7 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
     __shared__ double s_scratch[kPrepThreads / 32];
     __shared__ int s_bad, s_maxres;
     __shared__ unsigned s_lead_cnt[1024];   // counts, then offsets (n_leader <= 1023 checked on host)
+    __shared__ int s_hist[1024];            // kept atoms per typing class (at most 1024 classes)
     __shared__ int s_cell[kMaxCells + 1];   // uniform grid: counts, then start offsets / fill cursors
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -176,16 +177,20 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
         const int off_lead = off_leadoff + (int)align16(4 * (int64_t)(L.n_leader + 1));
         uint32_t *lead_off = reinterpret_cast<uint32_t *>(blob + off_leadoff);
         uint16_t *lead = reinterpret_cast<uint16_t *>(blob + off_lead);
-        const int cw = L.class_words_cap;
+        // Counts: a class histogram of the kept atoms, then per list the sum over its classes.
+        const int n_class = L.class_words * 32, mw = L.mask_words;
+        for (int c = tid; c < n_class; c += kPrepThreads) s_hist[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < n_kept; i += kPrepThreads) atomicAdd(&s_hist[bklass[i]], 1);
+        __syncthreads();
         for (int l = wid; l < L.n_leader; l += kPrepThreads / 32) {
-            const uint32_t *row = L.compat + (size_t)L.leader_ttype[l] * cw;
             unsigned cnt = 0;
-            for (int i0 = 0; i0 < n_kept; i0 += 32) {
-                const int i = i0 + lane;
-                bool ok = false;
-                if (i < n_kept) { const unsigned k = bklass[i]; ok = (__ldg(row + (k >> 5)) >> (k & 31)) & 1u; }
-                cnt += __popc(__ballot_sync(0xffffffffu, ok));
+            for (int c = lane; c < n_class; c += 32) {
+                const unsigned h = (unsigned)s_hist[c];
+                if (h) cnt += h * ((__ldg(L.class_mask + (size_t)c * mw + (l >> 5)) >> (l & 31)) & 1u);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             if (lane == 0) s_lead_cnt[l] = cnt;
         }
         __syncthreads();
@@ -196,16 +201,40 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
             lead_off[L.n_leader] = run;
         }
         __syncthreads();
-        for (int l = wid; l < L.n_leader; l += kPrepThreads / 32) {
-            const uint32_t *row = L.compat + (size_t)L.leader_ttype[l] * cw;
-            unsigned pos = s_lead_cnt[l];
+        // Fill: one pass over the atoms per group of 256 lists.  A lane holds its atom's 256-bit
+        // membership mask in registers; warp w owns the lists whose bit position within a mask word is
+        // w, w + 8, w + 16, w + 24 (32 lists per group), so every test is a shift of a register and
+        // every list receives its atoms in ascending order through ballot + popc.
+        for (int g = 0; g < mw / 8; ++g) {
+            unsigned pos[8][4];
+#pragma unroll
+            for (int wd = 0; wd < 8; ++wd)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int l = 256 * g + 32 * wd + wid + 8 * j;
+                    pos[wd][j] = l < L.n_leader ? s_lead_cnt[l] : 0u;
+                }
             for (int i0 = 0; i0 < n_kept; i0 += 32) {
                 const int i = i0 + lane;
-                bool ok = false;
-                if (i < n_kept) { const unsigned k = bklass[i]; ok = (__ldg(row + (k >> 5)) >> (k & 31)) & 1u; }
-                const unsigned b = __ballot_sync(0xffffffffu, ok);
-                if (ok) lead[pos + warp_excl_prefix(b, lane)] = (uint16_t)i;
-                pos += __popc(b);
+                uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0;
+                if (i < n_kept) {
+                    const uint4 *row = reinterpret_cast<const uint4 *>(L.class_mask + (size_t)bklass[i] * mw + 8 * g);
+                    m0 = __ldg(row);
+                    m1 = __ldg(row + 1);
+                }
+                const unsigned words[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int wd = 0; wd < 8; ++wd) {
+                    const unsigned mine = words[wd] >> wid;
+                    if (__any_sync(0xffffffffu, mine & 0x01010101u) == 0) continue;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = (mine >> (8 * j)) & 1u;
+                        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                        if (ok) lead[pos[wd][j] + warp_excl_prefix(bal, lane)] = (uint16_t)i;
+                        pos[wd][j] += __popc(bal);
+                    }
+                }
             }
         }
         __syncthreads();
