@@ -14,7 +14,7 @@
 #include "emm_device.cuh"
 
 namespace emm {
-void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff,
+void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff, bool build_cells,
                     unsigned long long *stats, unsigned long long *bad, int sm_count, cudaStream_t stream);
 size_t search_smem_bytes(int blob_cap, int levels);
 size_t search_fixed_smem(int levels);
@@ -100,6 +100,7 @@ struct emm_session {
     bool has_bfactor = false, has_chain = false, has_atom_id = false;
     bool prepared = false;
     float prepared_cutoff = -1.f;
+    bool prepared_cells = false;    // the uniform grid was built (only runs with cell_threshold > 0 need it)
     int prepared_version = -1;
     std::vector<int64_t> h_blob_off;
     int64_t max_staged = 0;        // largest staged blob prefix among the stageable structures (upper bound)
@@ -578,16 +579,19 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     const float cutoff = q->conservation_cutoff > 0.f ? q->conservation_cutoff : 0.f;
     if (cutoff > 0.f && !s->has_bfactor) return fail(EMM_ERR_INVALID, "conservation_cutoff needs the bfactor column");
     unsigned long long *stats = s->d_stats;
-    if (q->force_prepare || !s->prepared || s->prepared_cutoff != cutoff || s->prepared_version != lib->compat_version) {
+    const bool want_cells = q->cell_threshold > 0;
+    if (q->force_prepare || !s->prepared || s->prepared_cutoff != cutoff || s->prepared_version != lib->compat_version ||
+        (want_cells && !s->prepared_cells)) {
         cudaEvent_t e0, e1;
         const bool timed = next_events(s->ev_prepare, s->ev_prepare_used, &e0, &e1);
         if (timed) cudaEventRecord(e0, stream);
         if (q->force_prepare) CUDA_TRY(cudaMemsetAsync(s->d_hit_count + 1, 0, 8, stream));
-        launch_prepare(lib->d, B, cutoff, stats, s->d_hit_count + 1, lib->sm_count, stream);
+        launch_prepare(lib->d, B, cutoff, want_cells, stats, s->d_hit_count + 1, lib->sm_count, stream);
         if (timed) cudaEventRecord(e1, stream);
         CUDA_TRY(cudaGetLastError());
         s->prepared = true;
         s->prepared_cutoff = cutoff;
+        s->prepared_cells = want_cells;
         s->prepared_version = lib->compat_version;
         s->last_launches++;
     }

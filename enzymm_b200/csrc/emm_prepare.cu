@@ -57,7 +57,7 @@ __device__ __forceinline__ double block_reduce_minmax(double v, bool is_max, dou
 }
 
 __global__ void __launch_bounds__(kPrepThreads)
-emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
+emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
                    unsigned long long *stats, unsigned long long *bad)
 {
     __shared__ int s_warp_tot[kPrepThreads / 32];
@@ -244,15 +244,20 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
         // deterministic.  The cell edge grows until the grid has at most kMaxCells cells.
         const int off_cellstart = (int)align16(off_lead + 2 * (int64_t)s_lead_cnt[L.n_leader]);
         float cell = kMinCell;
-        int nx = 1, ny = 1, nz = 1;
+        int nx = 0, ny = 0, nz = 0;
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        int off_cellatoms = off_cellstart;
+        if (build_cells) {       // opt-in (cell_threshold > 0): the default search never reads the grid
         for (;;) {
             nx = (int)(ext[0] / cell) + 1; ny = (int)(ext[1] / cell) + 1; nz = (int)(ext[2] / cell) + 1;
             if ((long long)nx * ny * nz <= kMaxCells) break;
             cell *= 1.25f;
         }
         const int n_cells = nx * ny * nz;
-        const float ox = (float)(-0.5 * ext[0]) - 1e-3f, oy = (float)(-0.5 * ext[1]) - 1e-3f, oz = (float)(-0.5 * ext[2]) - 1e-3f;
-        const int off_cellatoms = off_cellstart + (int)align16(2 * (int64_t)(n_cells + 1));
+        ox = (float)(-0.5 * ext[0]) - 1e-3f;
+        oy = (float)(-0.5 * ext[1]) - 1e-3f;
+        oz = (float)(-0.5 * ext[2]) - 1e-3f;
+        off_cellatoms = off_cellstart + (int)align16(2 * (int64_t)(n_cells + 1));
         uint16_t *cell_start = reinterpret_cast<uint16_t *>(blob + off_cellstart);
         uint16_t *cell_atoms = reinterpret_cast<uint16_t *>(blob + off_cellatoms);
         auto cell_of = [&](int i) {
@@ -286,6 +291,7 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
         }
         __syncthreads();
 
+        }
         if (tid == 0) {
             BlobHeader h;
             h.n_kept = n_kept; h.n_res = n_res; h.res_shift = res_shift; h.status = status; h.eps = eps;
@@ -306,12 +312,12 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff,
     }
 }
 
-void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff,
+void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff, bool build_cells,
                     unsigned long long *stats, unsigned long long *bad, int sm_count, cudaStream_t stream)
 {
     if (B.n_structures <= 0) return;
     int grid = B.n_structures < sm_count * 8 ? B.n_structures : sm_count * 8;
-    emm_prepare_kernel<<<grid, kPrepThreads, 0, stream>>>(L, B, cutoff, stats, bad);
+    emm_prepare_kernel<<<grid, kPrepThreads, 0, stream>>>(L, B, cutoff, build_cells ? 1 : 0, stats, bad);
 }
 
 }  // namespace emm
