@@ -175,6 +175,31 @@ __device__ __forceinline__ double pair_delta(const DevLibrary &L, int a0, int k,
 }
 
 // Cyclic Jacobi on a symmetric 4x4 (fully unrolled so the matrices stay in registers).
+// The scalar part of one Jacobi rotation (divisions and square roots are long software sequences:
+// kept out of line so the six unrolled rotations of jacobi4 share one copy).  Returns false when the
+// off-diagonal element is negligible and is simply zeroed; otherwise s, tau and h = t * apq.
+__device__ __noinline__ bool jacobi_rotation(double apq, double app, double aqq, int sweep, double *s_out,
+                                             double *tau_out, double *h_out)
+{
+    const double g = DMUL(100.0, fabs(apq));
+    if (sweep > 3 && DADD(fabs(app), g) == fabs(app) && DADD(fabs(aqq), g) == fabs(aqq)) return false;
+    double h = DSUB(aqq, app);
+    double t;
+    if (DADD(fabs(h), g) == fabs(h)) {
+        t = DDIV(apq, h);
+    } else {
+        const double theta = DDIV(DMUL(0.5, h), apq);
+        t = DDIV(1.0, DADD(fabs(theta), DSQRT(DADD(1.0, DMUL(theta, theta)))));
+        if (theta < 0.0) t = -t;
+    }
+    const double c = DDIV(1.0, DSQRT(DADD(1.0, DMUL(t, t))));
+    const double s = DMUL(t, c);
+    *s_out = s;
+    *tau_out = DDIV(s, DADD(1.0, c));
+    *h_out = DMUL(t, apq);
+    return true;
+}
+
 __device__ __forceinline__ void jacobi4(double (&a)[4][4], double (&v)[4][4])
 {
 #pragma unroll
@@ -194,25 +219,11 @@ __device__ __forceinline__ void jacobi4(double (&a)[4][4], double (&v)[4][4])
             for (int q = p + 1; q < 4; ++q) {
                 const double apq = a[p][q];
                 if (apq != 0.0) {
-                    const double g = DMUL(100.0, fabs(apq));
-                    if (sweep > 3 && DADD(fabs(a[p][p]), g) == fabs(a[p][p]) &&
-                        DADD(fabs(a[q][q]), g) == fabs(a[q][q])) {
+                    double s, tau, h;
+                    if (!jacobi_rotation(apq, a[p][p], a[q][q], sweep, &s, &tau, &h)) {
                         a[p][q] = 0.0;
                         a[q][p] = 0.0;
                     } else {
-                        double h = DSUB(a[q][q], a[p][p]);
-                        double t;
-                        if (DADD(fabs(h), g) == fabs(h)) {
-                            t = DDIV(apq, h);
-                        } else {
-                            const double theta = DDIV(DMUL(0.5, h), apq);
-                            t = DDIV(1.0, DADD(fabs(theta), DSQRT(DADD(1.0, DMUL(theta, theta)))));
-                            if (theta < 0.0) t = -t;
-                        }
-                        const double c = DDIV(1.0, DSQRT(DADD(1.0, DMUL(t, t))));
-                        const double s = DMUL(t, c);
-                        const double tau = DDIV(s, DADD(1.0, c));
-                        h = DMUL(t, apq);
                         a[p][p] = DSUB(a[p][p], h);
                         a[q][q] = DADD(a[q][q], h);
                         a[p][q] = 0.0;
