@@ -310,3 +310,33 @@ def test_pack_files_coordinates_are_python_floats(tmp_path, active_templates):
     assert batch.xyz.tobytes() == want.tobytes()
     want_bf = np.asarray([float(l[60:66]) if l[60:66].strip() else 0.0 for l in lines]).astype(np.float32)
     assert batch.bfactor.tobytes() == want_bf.tobytes()
+
+
+def test_leader_order_is_a_valid_plan(active_templates):
+    """The expected-work leader order is a permutation of the residue groups; plans stay valid
+    (leaders before the atoms that depend on them, anchors earlier than their position)."""
+    sample = active_templates[::40]
+    from helpers import default_distances
+    dist = default_distances(sample)
+    new = CompiledLibrary(sample, 2.0, dist, dist)
+    old = CompiledLibrary(sample, 2.0, dist, dist, plan_order="leaders_first_greedy")
+    changed = 0
+    for lib in (new, old):
+        for t in range(len(sample)):
+            a0, a1 = int(lib.atom_off[t]), int(lib.atom_off[t + 1])
+            order = lib.plan_atom[a0:a1].tolist()
+            assert sorted(order) == list(range(a1 - a0))
+            src, anchor = lib.plan_src[a0:a1], lib.plan_anchor[a0:a1]
+            assert src[0] < 0
+            n_leaders = int((src < 0).sum())
+            assert all(s < 0 for s in src[:n_leaders]) and all(0 <= s < n_leaders for s in src[n_leaders:])
+            assert all(int(anchor[k]) < k for k in range(1, a1 - a0))
+    for t in range(len(sample)):
+        a0, a1 = int(new.atom_off[t]), int(new.atom_off[t + 1])
+        changed += not np.array_equal(new.plan_atom[a0:a1], old.plan_atom[a0:a1])
+        # same leaders, possibly another order
+        n_leaders = int((new.plan_src[a0:a1] < 0).sum())
+        assert sorted(new.plan_atom[a0:a0 + n_leaders].tolist()) == sorted(old.plan_atom[a0:a0 + n_leaders].tolist())
+    assert changed > 0
+    with pytest.raises(ValueError):
+        CompiledLibrary(sample[:2], 2.0, 1.5, 1.5, plan_order="alphabetical")
