@@ -35,7 +35,7 @@ def test_product_path_never_touches_the_oracle():
     """No import, include, link or dlopen of anything under oracle/ from the product package."""
     pkg = ROOT / "enzymm_b200"
     for path in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
-        text = path.read_text() if path.suffix in (".py", ".cu", ".cuh") or path.name == "Makefile" else ""
+        text = path.read_text() if path.suffix in (".py", ".cu", ".cuh", ".cpp", ".h") or path.name == "Makefile" else ""
         assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), path
         assert not re.search(r"#include\s*[\"<][^\">]*oracle", text), path
         assert "libjess_oracle" not in text, path
@@ -46,3 +46,12 @@ def test_no_cpu_fallback(active_templates):
     with pytest.raises(EngineError) as info:
         Engine(CompiledLibrary(active_templates[:3], 2.0, 1.5, 1.5))
     assert info.value.status == -3
+
+
+@pytest.mark.skipif(load_cdll().emm_device_count() > 0, reason="only meaningful without a GPU")
+def test_stream_entry_point_without_gpu():
+    lib = load_cdll()
+    stream = ctypes.c_void_p()
+    assert lib.emm_stream_create(ctypes.c_int(0), ctypes.byref(stream)) == -3
+    assert not stream.value
+    assert lib.emm_stream_destroy(ctypes.c_int(0), ctypes.c_void_p()) == 0
