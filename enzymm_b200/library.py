@@ -446,6 +446,43 @@ class CompiledLibrary:
             classes[i] = self.class_of(res, name)
         return classes[inverse]
 
+    # ---- vectorised classification of packed atom kinds ----------------------------------------
+    _HASH_BITS = 16
+    _HASH_MULT = np.uint64(0x9E3779B97F4A7C15)
+
+    def classify_keys(self, keys: np.ndarray) -> np.ndarray:
+        """Typing classes for atom kinds packed as ``resname_u32 << 32 | name_u32`` (the bytes of
+        the blank-stripped names, little endian).  A 64 K-slot hash table (kind -> class) answers
+        with two gathers; kinds it has not seen, or that lost their slot to another kind, are
+        resolved through ``class_of``."""
+        table = self.__dict__.get("_kind_table")
+        if table is None:
+            size = 1 << self._HASH_BITS
+            table = self.__dict__["_kind_table"] = (np.full(size, np.uint64(0xFFFFFFFFFFFFFFFF)), np.zeros(size, np.uint16), {})
+        slot_key, slot_class, overflow = table
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        slots = ((keys * self._HASH_MULT) >> np.uint64(64 - self._HASH_BITS)).astype(np.intp)
+        out = slot_class[slots]
+        miss = slot_key[slots] != keys
+        if miss.any():
+            where = np.nonzero(miss)[0]
+            missing, inverse = np.unique(keys[where], return_inverse=True)
+            resolved = np.empty(len(missing), dtype=np.uint16)
+            with _CLASS_LOCK:
+                for i, k in enumerate(missing.tolist()):
+                    c = overflow.get(k)
+                    if c is None:
+                        text = lambda v: int(v).to_bytes(4, "little").rstrip(b"\0").decode("ascii", "replace")
+                        c = self.class_of(text(k >> 32), text(k & 0xFFFFFFFF))
+                        slot = ((k * int(self._HASH_MULT)) & 0xFFFFFFFFFFFFFFFF) >> (64 - self._HASH_BITS)
+                        if slot_key[slot] == np.uint64(0xFFFFFFFFFFFFFFFF):
+                            slot_key[slot], slot_class[slot] = np.uint64(k), c
+                        else:
+                            overflow[k] = c          # slot taken by another kind: answered from here
+                    resolved[i] = c
+            out[where] = resolved[inverse]
+        return out
+
     @property
     def n_classes(self) -> int:
         return len(self._columns)
@@ -509,7 +546,7 @@ class CompiledLibrary:
             return self
         self = cls(templates, rmsd_threshold, distance_cutoff, max_dynamic_distance, plan_order=plan_order)
         cache_dir.mkdir(parents=True, exist_ok=True)
-        state = {k: v for k, v in self.__dict__.items() if k != "templates"}
+        state = {k: v for k, v in self.__dict__.items() if k not in ("templates", "_kind_table")}
         tmp = path.with_suffix(".tmp")
         with open(tmp, "wb") as handle:
             pickle.dump(state, handle, protocol=pickle.HIGHEST_PROTOCOL)

@@ -56,9 +56,12 @@ def residue_ordinals(chain: np.ndarray, resnum: np.ndarray):
 
 
 def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
-                   with_chain: bool = True) -> PackedBatch:
-    """Concatenate molecules into one ``PackedBatch`` (classes come from ``library.classify``)."""
-    sizes = [len(m) for m in molecules]
+                   with_chain: bool = True, block: int = 1024) -> PackedBatch:
+    """Concatenate molecules into one ``PackedBatch``.  Vectorised over blocks of molecules: atom
+    kinds (residue name, atom name) are compared as packed integers and classified once per
+    distinct kind (``library.class_of``); residue ordinals come from one run-length pass.  A block
+    holding a molecule with a split residue goes through the per-molecule path, which reorders."""
+    sizes = np.asarray([len(m) for m in molecules], dtype=np.int64)
     atom_off = np.zeros(len(molecules) + 1, dtype=np.int64)
     np.cumsum(sizes, out=atom_off[1:])
     total = int(atom_off[-1])
@@ -68,7 +71,45 @@ def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
     bfactor = np.empty(total, dtype=np.float32)
     chain = np.empty(total, dtype=np.uint16)
     atom_id: Optional[np.ndarray] = None
-    for i, m in enumerate(molecules):
+    for b0 in range(0, len(molecules), block):
+        mols = molecules[b0:b0 + block]
+        lo, hi = int(atom_off[b0]), int(atom_off[b0 + len(mols)])
+        if hi == lo:
+            continue
+        cat = lambda f: np.concatenate([f(m) for m in mols])
+        res32 = cat(lambda m: m._cols.packed_u32("residue_name"))
+        name32 = cat(lambda m: m._cols.packed_u32("name"))
+        codes = cat(lambda m: m._cols.packed_u32("chain_id")).astype(np.uint16)
+        resnum = cat(lambda m: m.column("residue_number"))
+        bsizes = sizes[b0:b0 + len(mols)]
+        # residue ordinals: runs of equal (molecule, chain, residue number)
+        mol_idx = np.repeat(np.arange(len(mols), dtype=np.int64), bsizes)
+        rkey = (mol_idx << 48) | (codes.astype(np.int64) << 32) | (resnum.astype(np.int64) & 0xFFFFFFFF)
+        change = np.empty(hi - lo, dtype=bool)
+        change[0] = True
+        np.not_equal(rkey[1:], rkey[:-1], out=change[1:])
+        starts = rkey[change]
+        if len(np.unique(starts)) != len(starts):          # some residue is split: reorder per molecule
+            atom_id = _pack_block_per_molecule(mols, b0, atom_off, sizes, library, xyz, klass, residue, bfactor, chain,
+                                               atom_id, total)
+            continue
+        runs = np.cumsum(change) - 1
+        first = runs[(atom_off[b0:b0 + len(mols)] - lo)[bsizes > 0]]
+        residue[lo:hi] = runs - np.repeat(first, bsizes[bsizes > 0])
+        # typing classes: one class_of per distinct atom kind of the block
+        key = (res32.astype(np.uint64) << np.uint64(32)) | name32.astype(np.uint64)
+        klass[lo:hi] = library.classify_keys(key)
+        chain[lo:hi] = codes
+        bfactor[lo:hi] = cat(lambda m: m.column("temperature_factor"))
+        xyz[lo:hi] = cat(lambda m: m.xyz)
+        if atom_id is not None:
+            atom_id[lo:hi] = np.arange(hi - lo, dtype=np.int64) - np.repeat(atom_off[b0:b0 + len(mols)] - lo, bsizes)
+    return PackedBatch(atom_off, xyz, klass, residue, bfactor, chain if with_chain else None, atom_id)
+
+
+def _pack_block_per_molecule(mols, b0, atom_off, sizes, library, xyz, klass, residue, bfactor, chain, atom_id, total):
+    """Per-molecule packing (handles split residues by a stable regrouping + ``atom_id``)."""
+    for i, m in enumerate(mols, start=b0):
         lo, hi = int(atom_off[i]), int(atom_off[i + 1])
         if hi == lo:
             continue
@@ -91,7 +132,7 @@ def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
         residue[lo:hi] = ordinal
         bfactor[lo:hi] = bf
         chain[lo:hi] = codes
-    return PackedBatch(atom_off, xyz, klass, residue, bfactor, chain if with_chain else None, atom_id)
+    return atom_id
 
 
 class _PdbPacked(ctypes.Structure):       # struct emm_pdb_packed

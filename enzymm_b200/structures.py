@@ -105,6 +105,75 @@ _COLUMNS = (
 )
 
 
+_STR_WIDTH = {"name": 4, "altloc": 1, "residue_name": 4, "chain_id": 2, "insertion_code": 1, "segment": 4, "element": 2}
+
+
+class _Columns(dict):
+    """Column store of a ``Molecule``.  String columns that arrive from the native reader stay
+    fixed-width byte matrices (``raw[name]``: uint8 ``[n, width]``, blank-stripped, NUL padded) and
+    become NumPy unicode arrays only when somebody asks for them: a screening run touches the
+    strings of a handful of matched atoms, not of every atom it read."""
+
+    __slots__ = ("raw",)
+
+    def __init__(self, converted=(), raw=None):
+        super().__init__(converted)
+        self.raw = dict(raw or {})
+
+    def __missing__(self, key):
+        r = self.raw.get(key)
+        if r is None:
+            raise KeyError(key)
+        w = r.shape[1]
+        arr = np.ascontiguousarray(r).reshape(-1).view(f"S{w}").astype(f"U{w}") if len(r) else np.zeros(0, dtype=f"U{w}")
+        self[key] = arr
+        return arr
+
+    def names(self):
+        return [k for k, _ in _COLUMNS if k in self or k in self.raw]
+
+    def take(self, keep, copy: bool = False) -> "_Columns":
+        pick = (lambda v: v[keep].copy()) if copy else (lambda v: v[keep])
+        return _Columns({k: pick(v) for k, v in dict.items(self)}, {k: pick(v) for k, v in self.raw.items()})
+
+    def text_at(self, key: str, i: int) -> str:
+        """One string cell without converting the column."""
+        if key in self:
+            return str(dict.__getitem__(self, key)[i])
+        return bytes(self.raw[key][i]).rstrip(b"\0").decode("ascii", "replace")
+
+    def canonical_bytes(self, key: str) -> bytes:
+        """Representation-independent bytes of a column (for hashing / equality)."""
+        w = _STR_WIDTH.get(key)
+        if w is None:
+            return dict.__getitem__(self, key).tobytes()
+        if key in self.raw:
+            return np.ascontiguousarray(self.raw[key]).tobytes()
+        arr = dict.__getitem__(self, key)
+        return np.char.encode(arr, "ascii", "replace").astype(f"S{w}").tobytes() if len(arr) else b""
+
+    def packed_u32(self, key: str) -> np.ndarray:
+        """String column as one little-endian uint32 per cell (bytes of the blank-stripped text)."""
+        w = _STR_WIDTH[key]
+        if key in self.raw:
+            r = self.raw[key]
+            out = np.zeros(len(r), dtype=np.uint32)
+            for j in range(w):
+                out |= r[:, j].astype(np.uint32) << np.uint32(8 * j)
+            return out
+        arr = dict.__getitem__(self, key)
+        if not len(arr):
+            return np.zeros(0, dtype=np.uint32)
+        width = arr.dtype.itemsize // 4
+        code = np.ascontiguousarray(arr).view(np.uint32).reshape(len(arr), width)
+        if (code > 255).any():
+            code = np.where(code > 255, ord("?"), code)
+        out = np.zeros(len(arr), dtype=np.uint32)
+        for j in range(min(w, width)):
+            out |= code[:, j].astype(np.uint32) << np.uint32(8 * j)
+        return out
+
+
 def _parse_pdb_text(lines: Iterable[str]):
     """Fixed-column PDB reader (ATOM/HETATM up to first ENDMDL)."""
     cols = {k: [] for k, _ in _COLUMNS}
@@ -189,17 +258,11 @@ def _fixed_to_str(raw: np.ndarray, width: int) -> np.ndarray:
 
 
 def _columns_from_native(n, serial, name, altloc, resname, chain, resnum, icode, occ, bfac, segment, element, charge):
-    alt = altloc.view("S1")
-    ic = icode.view("S1")
-    return {
-        "serial": serial, "name": _fixed_to_str(name, 4).astype(_STR4),
-        "altloc": alt.astype("U1") if n else np.zeros(0, dtype="U1"),
-        "residue_name": _fixed_to_str(resname, 4).astype(_STR4), "chain_id": _fixed_to_str(chain, 2).astype("U2"),
-        "residue_number": resnum,
-        "insertion_code": ic.astype("U1") if n else np.zeros(0, dtype="U1"),
-        "occupancy": occ, "temperature_factor": bfac, "segment": _fixed_to_str(segment, 4).astype(_STR4),
-        "element": _fixed_to_str(element, 2).astype("U2"), "charge": charge,
-    }
+    raw = {"name": name.reshape(-1, 4), "altloc": altloc.reshape(-1, 1), "residue_name": resname.reshape(-1, 4),
+           "chain_id": chain.reshape(-1, 2), "insertion_code": icode.reshape(-1, 1), "segment": segment.reshape(-1, 4),
+           "element": element.reshape(-1, 2)}
+    return _Columns({"serial": serial, "residue_number": resnum, "occupancy": occ, "temperature_factor": bfac,
+                     "charge": charge}, raw)
 
 
 def _parse_pdb_native(data: bytes):
@@ -241,10 +304,10 @@ class Molecule:
     def __init__(self, atoms: Sequence[Atom] = (), id: Optional[str] = None):
         self.id = id
         n = len(atoms)
-        self._cols = {
+        self._cols = _Columns({
             k: np.asarray([getattr(a, k) for a in atoms], dtype=dt) if n else np.zeros(0, dtype=dt)
             for k, dt in _COLUMNS
-        }
+        })
         self.xyz = np.asarray([(a.x, a.y, a.z) for a in atoms], dtype=np.float64).reshape(n, 3)
         self._digest = None
         self._atoms = None
@@ -254,7 +317,7 @@ class Molecule:
     def _from_columns(cls, cols, xyz, id) -> "Molecule":
         self = cls.__new__(cls)
         self.id = id
-        self._cols = cols
+        self._cols = cols if isinstance(cols, _Columns) else _Columns(cols)
         self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
         self._digest = None
         self._atoms = None
@@ -285,11 +348,10 @@ class Molecule:
         return self.select(keep)
 
     def select(self, keep: np.ndarray) -> "Molecule":
-        cols = {k: v[keep] for k, v in self._cols.items()}
-        return Molecule._from_columns(cols, self.xyz[keep], self.id)
+        return Molecule._from_columns(self._cols.take(keep), self.xyz[keep], self.id)
 
     def copy(self) -> "Molecule":
-        return Molecule._from_columns({k: v.copy() for k, v in self._cols.items()}, self.xyz.copy(), self.id)
+        return Molecule._from_columns(self._cols.take(slice(None), copy=True), self.xyz.copy(), self.id)
 
     def with_xyz(self, xyz: np.ndarray) -> "Molecule":
         """Same atoms, other coordinates (used for ``Hit.molecule(transform=True)``)."""
@@ -308,12 +370,12 @@ class Molecule:
         c = self._cols
         x, y, z = self.xyz[i]
         return Atom(
-            serial=c["serial"][i], name=str(c["name"][i]), altloc=str(c["altloc"][i]),
-            residue_name=str(c["residue_name"][i]), chain_id=str(c["chain_id"][i]),
-            residue_number=c["residue_number"][i], insertion_code=str(c["insertion_code"][i]),
+            serial=c["serial"][i], name=c.text_at("name", i), altloc=c.text_at("altloc", i),
+            residue_name=c.text_at("residue_name", i), chain_id=c.text_at("chain_id", i),
+            residue_number=c["residue_number"][i], insertion_code=c.text_at("insertion_code", i),
             x=x, y=y, z=z, occupancy=c["occupancy"][i],
-            temperature_factor=c["temperature_factor"][i], segment=str(c["segment"][i]),
-            element=str(c["element"][i]), charge=c["charge"][i],
+            temperature_factor=c["temperature_factor"][i], segment=c.text_at("segment", i),
+            element=c.text_at("element", i), charge=c["charge"][i],
         )
 
     def __getitem__(self, i):
@@ -339,7 +401,7 @@ class Molecule:
             h.update(repr(self.id).encode())
             h.update(self.xyz.tobytes())
             for k, _ in _COLUMNS:
-                h.update(self._cols[k].tobytes())
+                h.update(self._cols.canonical_bytes(k))
             self._digest = h.digest()
         return self._digest
 
@@ -405,5 +467,5 @@ def load_many(paths: Sequence[Union[str, os.PathLike]], ids: Optional[Sequence[O
         lo, hi = int(off[i]), int(off[i + 1])
         hid = bytes(headers[i]).split(b"\0")[0].decode() or None
         mol_id = ids[i] if ids is not None and ids[i] is not None else hid
-        out.append(Molecule._from_columns({k: v[lo:hi] for k, v in cols.items()}, xyz[lo:hi], mol_id))
+        out.append(Molecule._from_columns(cols.take(slice(lo, hi)), xyz[lo:hi], mol_id))
     return out
