@@ -62,6 +62,16 @@ def main():
             passing += int(((records["flags"] & 4) != 0).sum())
         dt = time.perf_counter() - t0
         print(f"scan_files: {n / dt:.0f} files/s end to end, {hits} hits, {passing} pass the filter")
+    # the reference-shaped path: Molecule objects in, {Molecule: [Match]} out
+    sample = paths[:min(n, 2048)]
+    t0 = time.perf_counter()
+    molecules = jess_run.load_molecules(sample)
+    t1 = time.perf_counter()
+    matches = matcher.run(molecules)
+    t2 = time.perf_counter()
+    n_matches = sum(len(v) for v in matches.values())
+    print(f"Matcher.run on Molecule objects: load_molecules {len(sample) / (t1 - t0):.0f} files/s, run (pack + search + "
+          f"{n_matches} Match objects) {len(sample) / (t2 - t1):.0f} molecules/s, together {len(sample) / (t2 - t0):.0f}/s")
     for p in paths:
         os.unlink(p)
     os.rmdir(d)
