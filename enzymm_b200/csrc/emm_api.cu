@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <map>
 #include <mutex>
 #include <string>
@@ -488,16 +490,36 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     s->h_ids.clear();
     const uint16_t *cl = lib->class_leaders.data();
     const size_t n_class = lib->class_leaders.size();
+    // exact size of every structure's leader lists (before masking): one table lookup per atom, on a
+    // few threads for large batches (this loop is host time inside the end-to-end path)
+    std::vector<int64_t> entries_of((size_t)n, 0);
+    std::atomic<int> bad_input(0);
+    {
+        auto count = [&](int lo, int hi) {
+            for (int i = lo; i < hi; ++i) {
+                const int64_t a0 = b->atom_off[i], a1 = b->atom_off[i + 1];
+                if (a1 < a0) { bad_input.store(1); return; }
+                int64_t entries = 0;
+                for (int64_t a = a0; a < a1; ++a) {
+                    const uint16_t k = b->klass[a];
+                    if (k >= n_class) { bad_input.store(2); return; }
+                    entries += cl[k];
+                }
+                entries_of[(size_t)i] = entries;
+            }
+        };
+        const int n_threads = b->n_atoms > (int64_t)2000000 ? std::min(4, std::max(1, (int)std::thread::hardware_concurrency())) : 1;
+        std::vector<std::thread> pool;
+        const int per = (n + n_threads - 1) / n_threads;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(count, std::min(n, t * per), std::min(n, (t + 1) * per));
+        count(0, std::min(n, per));
+        for (auto &th : pool) th.join();
+    }
+    if (bad_input.load() == 1) return fail(EMM_ERR_INVALID, "atom_off must be non-decreasing");
+    if (bad_input.load() == 2) return fail(EMM_ERR_INVALID, "typing class out of range");
     for (int i = 0; i < n; ++i) {
         const int64_t a0 = b->atom_off[i], a1 = b->atom_off[i + 1];
-        if (a1 < a0) return fail(EMM_ERR_INVALID, "atom_off must be non-decreasing");
-        int64_t entries = 0;   // exact size of this structure's leader lists (before masking)
-        for (int64_t a = a0; a < a1; ++a) {
-            const uint16_t k = b->klass[a];
-            if (k >= n_class) return fail(EMM_ERR_INVALID, "typing class out of range");
-            entries += cl[k];
-        }
-        const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries);
+        const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries_of[(size_t)i]);
         s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + bytes;
         const int64_t staged = bytes - align16(4 * (a1 - a0)) - align16(2 * (int64_t)(kMaxCells + 1)) - 2 * align16(2 * (a1 - a0));
         if (((staged + 1023) & ~int64_t(1023)) <= stage_cap) {
@@ -718,9 +740,18 @@ int emm_session_download(emm_session *s, emm_hit *hits, int64_t capacity, int64_
         if (!hits) return fail(EMM_ERR_INVALID, "hits is null");
         CUDA_TRY(cudaMemcpyAsync(hits, s->d_hits, sizeof(emm_hit) * (size_t)count, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        std::sort(hits, hits + count, [](const emm_hit &a, const emm_hit &b) {
-            return a.structure != b.structure ? a.structure < b.structure : a.template_index < b.template_index;
-        });
+        // sort by (structure, template): order 12-byte keys, then move every 280-byte record once
+        if (count > 0xFFFFFFFFull) return fail(EMM_ERR_CAPACITY, "more than 2^32 hits in one batch");
+        std::vector<std::pair<uint64_t, uint32_t>> keys((size_t)count);
+        for (size_t i = 0; i < (size_t)count; ++i)
+            keys[i] = {((uint64_t)(uint32_t)hits[i].structure << 32) | (uint32_t)hits[i].template_index, (uint32_t)i};
+        std::sort(keys.begin(), keys.end());
+        bool ordered = true;
+        for (size_t i = 0; i < (size_t)count && ordered; ++i) ordered = keys[i].second == i;
+        if (!ordered) {
+            std::vector<emm_hit> tmp(hits, hits + count);
+            for (size_t i = 0; i < (size_t)count; ++i) hits[i] = tmp[keys[i].second];
+        }
     }
     if (bad) return fail(EMM_ERR_INPUT, "a structure violates the input contract (residue ordinals must be "
                                         "non-decreasing and at most 65535 atoms may survive masking)");
