@@ -55,3 +55,17 @@ def test_stream_entry_point_without_gpu():
     assert lib.emm_stream_create(ctypes.c_int(0), ctypes.byref(stream)) == -3
     assert not stream.value
     assert lib.emm_stream_destroy(ctypes.c_int(0), ctypes.c_void_p()) == 0
+
+
+def test_library_is_sm100a_with_tma_staging():
+    """The shipped shared library holds sm_100a SASS and the search kernel stages blobs with the
+    TMA bulk copy (UBLKCP + mbarrier transaction waits), not with per-thread loads."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not shutil.which(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", str(library_path())], capture_output=True, text=True, timeout=300).stdout
+    assert "arch = sm_100a" in sass and "arch = sm_90" not in sass
+    assert "emm_search_kernel" in sass and "emm_prepare_kernel" in sass
+    assert "UBLKCP.S.G" in sass and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64" in sass
