@@ -364,6 +364,7 @@ class Matcher:
                 self.verbose_print([t.id for t in small])
         self._engine: Optional[Engine] = None
         self._groups: List[Tuple[int, int, int]] = []
+        self._scan_lanes = None
         self.hits_per_structure = 64          # initial hit-buffer sizing; grown on demand
         self._hit_floor = 1024
 
@@ -472,7 +473,9 @@ class Matcher:
         chunks = [paths[i:i + chunk_size] for i in range(0, len(paths), chunk_size)]
         if not chunks:
             return
-        lanes: List[list] = [[None, engine.new_stream()], [None, engine.new_stream()]]   # [session, stream]
+        if self._scan_lanes is None:        # [session, stream] x 2, kept for the next call: no reallocation per scan
+            self._scan_lanes = [[None, engine.new_stream()], [None, engine.new_stream()]]
+        lanes = self._scan_lanes
 
         def collect(lane, chunk, ids, batch):
             try:
@@ -508,10 +511,31 @@ class Matcher:
                 while in_flight:
                     yield collect(*in_flight.popleft())
         finally:
-            for sess, stream in lanes:          # destroying a session waits for its device work
+            while in_flight:                    # generator abandoned early: let the device finish, drop the hits
+                lane = in_flight.popleft()[0]
+                try:
+                    lane[0].download(stream=lane[1])
+                except EngineError:
+                    pass
+
+    def close(self) -> None:
+        """Release the device sessions, streams and library of this matcher."""
+        engine = self._engine
+        if self._scan_lanes is not None and engine is not None:
+            for sess, stream in self._scan_lanes:       # destroying a session waits for its device work
                 if sess is not None:
                     sess.close()
                 engine.free_stream(stream)
+        self._scan_lanes = None
+        if engine is not None:
+            engine.close()
+            self._engine = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def matches_for(self, molecule: Molecule, records: np.ndarray) -> List[Match]:
         """``Match`` objects for the hit records of one structure (``records`` = the rows of a
