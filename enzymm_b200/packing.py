@@ -77,9 +77,18 @@ def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
         if hi == lo:
             continue
         cat = lambda f: np.concatenate([f(m) for m in mols])
-        res32 = cat(lambda m: m._cols.packed_u32("residue_name"))
-        name32 = cat(lambda m: m._cols.packed_u32("name"))
-        codes = cat(lambda m: m._cols.packed_u32("chain_id")).astype(np.uint16)
+
+        def packed(column: str, width: int) -> np.ndarray:
+            """Text column of the block as integers: one view of the concatenated raw bytes when every
+            molecule still holds them (native reader), else per-molecule conversion."""
+            if all(column in m._cols.raw for m in mols):
+                raw = np.ascontiguousarray(np.concatenate([m._cols.raw[column] for m in mols]))
+                return raw.view("<u4" if width == 4 else "<u2").reshape(-1)
+            return cat(lambda m: m._cols.packed_u32(column))
+
+        res32 = packed("residue_name", 4)
+        name32 = packed("name", 4)
+        codes = packed("chain_id", 2).astype(np.uint16)
         resnum = cat(lambda m: m.column("residue_number"))
         bsizes = sizes[b0:b0 + len(mols)]
         # residue ordinals: runs of equal (molecule, chain, residue number)
