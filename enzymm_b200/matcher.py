@@ -363,6 +363,7 @@ class Matcher:
                 self.verbose_print("The templates with the following ids are too small:")
                 self.verbose_print([t.id for t in small])
         self._engine: Optional[Engine] = None
+        self._compiled: Optional[CompiledLibrary] = None
         self._groups: List[Tuple[int, int, int]] = []
         self._scan_lanes = None
         self.hits_per_structure = 64          # initial hit-buffer sizing; grown on demand
@@ -399,10 +400,10 @@ class Matcher:
     def _active_sizes(self) -> List[int]:
         return [s for s in self.template_effective_sizes if s >= 3 or self.match_small_templates]
 
-    def _ensure_engine(self) -> Engine:
-        """Compile every searched size group into ONE device library (size-descending, caller
-        order inside a group) with per-template thresholds."""
-        if self._engine is None:
+    def _compile(self) -> CompiledLibrary:
+        """Every searched size group in ONE compiled library (size-descending, caller order inside a
+        group) with per-template thresholds.  Host work only: no device is touched."""
+        if self._compiled is None:
             ordered: List[Template] = []
             rmsd, dist, dyn = [], [], []
             self._groups = []
@@ -417,7 +418,12 @@ class Matcher:
             if not ordered:
                 raise ValueError("no templates to search with")
             self._ordered = ordered
-            self._engine = Engine(CompiledLibrary(ordered, rmsd, dist, dyn), self.device)
+            self._compiled = CompiledLibrary(ordered, rmsd, dist, dyn)
+        return self._compiled
+
+    def _ensure_engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self._compile(), self.device)
         return self._engine
 
     def _submit(self, session, batch, stream: int = 0) -> None:

@@ -340,3 +340,69 @@ def test_leader_order_is_a_valid_plan(active_templates):
     assert changed > 0
     with pytest.raises(ValueError):
         CompiledLibrary(sample[:2], 2.0, 1.5, 1.5, plan_order="alphabetical")
+
+
+def _oracle_records(matcher, molecules):
+    """Hit records as the device would return them, computed by the CPU oracle (test infrastructure):
+    lets the Matcher's host logic -- size groups, completeness, filtering, ordering -- run without a GPU."""
+    import oracle
+    from enzymm_b200.engine import HIT_DTYPE, HIT_NO_MODEL, HIT_ORIENTED, HIT_PASS
+    matcher._compile()
+    rows = []
+    for size, lo, hi in matcher._groups:
+        group = matcher._ordered[lo:hi]
+        rmsd, dist, dyn = matcher._get_jess_parameters(size)
+        per_mol = oracle.query(molecules, oracle.OracleTemplates(group), rmsd, dist, dyn, max_candidates=10000,
+                               ignore_chain=True, threads=4)
+        for mi, hits in enumerate(per_mol):
+            for h in hits:
+                t = group[h.template_index]
+                rec = np.zeros((), dtype=HIT_DTYPE)
+                rec["structure"], rec["template_index"] = mi, lo + h.template_index
+                rec["n_complete"], rec["n_atoms"] = h.n_complete, len(h.atoms)
+                rec["rmsd"], rec["rot"], rec["qbar"], rec["tbar"] = h.rmsd, h.rot.reshape(9), h.qbar, h.tbar
+                rec["atoms"][:len(h.atoms)] = h.atoms
+                flags = 0
+                if getattr(t, "residues", None):
+                    orient = oracle.orientation(t, h.transform(molecules[mi].xyz[h.atoms]))
+                    rec["orientation"] = orient
+                    flags |= HIT_ORIENTED
+                    try:
+                        if oracle.predicted_correct(t.effective_size, dist, h.rmsd, orient):
+                            flags |= HIT_PASS
+                    except KeyError:
+                        flags |= HIT_NO_MODEL
+                rec["flags"] = flags
+                rows.append(rec)
+    records = np.array(rows, dtype=HIT_DTYPE) if rows else np.zeros(0, dtype=HIT_DTYPE)
+    return records[np.lexsort((records["template_index"], records["structure"]))]
+
+
+def test_matcher_host_logic_on_oracle_records(mol_1amy):
+    """Reference ``TestMatcher`` expectations through ``Matcher._assemble`` with oracle-computed
+    records: grouping by size, completeness before filtering, filter verdicts, result order."""
+    from enzymm_b200 import jess_run
+    from enzymm_b200.templates import load_templates
+    from helpers import oracle_matcher_run
+    mol_af = Molecule.load(GOLDEN / "AF-P0DUB6-F1-model_v4.pdb")
+    res5 = list(load_templates(subset="5_residues/results/csa3d_0285/"))
+    res4 = list(load_templates(subset="4_residues/results/csa3d_0285/"))
+    res3 = list(load_templates(subset="3_residues/results/csa3d_0344/"))
+    molecules = [mol_1amy, mol_af]
+    for kwargs in (dict(), dict(filter_matches=False)):
+        matcher = jess_run.Matcher(templates=res5 + res4 + res3, **kwargs)
+        got = matcher._assemble(_oracle_records(matcher, molecules), molecules)
+        want = oracle_matcher_run(res5 + res4 + res3, molecules, **kwargs)
+        assert [molecules.index(k) for k in got] == list(want)
+        for mi, expect in want.items():
+            mine = got[molecules[mi]]
+            assert [m.hit.template.id for m in mine] == [m.template.id for m in expect]
+            assert [m.complete for m in mine] == [m.complete for m in expect]
+            assert [m.hit.atom_indices for m in mine] == [m.hit.atoms for m in expect]
+            for m in mine:
+                assert m.predicted_correct == m.hit.device_pass          # reference formula vs record flag
+                assert m.orientation == pytest.approx(m.hit.orientation, abs=1e-9)
+    m1 = jess_run.Matcher(templates=res5 + res4)
+    out = m1._assemble(_oracle_records(m1, molecules), molecules)
+    assert len(out[mol_1amy]) == 2 and len(out[mol_af]) == 2           # reference test_matcher.py counts
+    assert [m.query_residue_count for m in out[mol_af]] == [511, 511]
