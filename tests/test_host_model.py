@@ -406,3 +406,18 @@ def test_matcher_host_logic_on_oracle_records(mol_1amy):
     out = m1._assemble(_oracle_records(m1, molecules), molecules)
     assert len(out[mol_1amy]) == 2 and len(out[mol_af]) == 2           # reference test_matcher.py counts
     assert [m.query_residue_count for m in out[mol_af]] == [511, 511]
+
+
+def test_pack_files_columns_outlive_the_batch(active_templates):
+    """The packed columns are views of native buffers; the buffers live as long as any view does."""
+    import gc
+    from enzymm_b200.packing import pack_files
+    lib = CompiledLibrary(active_templates[:5], 2.0, 1.5, 1.5)
+    batch, _ = pack_files([GOLDEN / "1AMY.pdb"] * 4, lib, threads=2)
+    xyz, klass = batch.xyz, batch.klass
+    want_sum, want_classes = float(xyz.sum()), klass.copy()
+    del batch
+    gc.collect()
+    junk = [np.ones(1 << 20) for _ in range(8)]          # churn the allocator
+    assert float(xyz.sum()) == want_sum and np.array_equal(klass, want_classes)
+    del junk
