@@ -183,6 +183,7 @@ def cpu_oracle_rate(workload, n_structures: int, threads: int):
     t0 = time.perf_counter()
     raw = oracle.query_raw(mols, ot, 2.0, dist, dist, max_candidates=10000, ignore_chain=True, threads=threads)
     dt = time.perf_counter() - t0
+    cpu_oracle_rate.evals_per_structure = float(raw["dist_evals"].sum()) / max(n_structures, 1)
     return n_structures / dt, dt, int(raw["found"].sum())
 
 
@@ -387,6 +388,13 @@ def run_b200(args, rank, local_rank, world):
         probe_rate, _, _ = cpu_oracle_rate(workload, min(threads, host.n_structures), threads)
         sample = int(min(max(threads, probe_rate * 15.0), 512, host.n_structures))
         rate, dt, _ = cpu_oracle_rate(workload, sample, threads)
+        # SURVEY 8(d) issue metric: pairwise-distance evaluations of the canonical (oracle) search x 9
+        # thread-instructions / (SMs x 4 schedulers x 32 lanes x SM clock)
+        evals = getattr(cpu_oracle_rate, "evals_per_structure", None)
+        if evals and line.get("roofline_issue"):
+            lanes_per_s = line["roofline_issue"]["peak"] * 1e9 * 32
+            line["roofline_issue"]["canonical_evals_per_structure"] = evals
+            line["roofline_issue"]["canonical_frac"] = evals * 9.0 * value / lanes_per_s
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"first {sample} structures of the same batch x 6780 templates, {dt:.1f} s "
                                           "(CPU restatement of Jess, not PyJess)"}
