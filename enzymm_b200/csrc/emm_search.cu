@@ -5,9 +5,9 @@
 // (reference enzymm/jess_run.py:785-843, 298-346, 425-478).
 //
 // Mapping.  Persistent CTAs (one per SM, kSearchWarps = 24 warps).  A work item is (structure,
-// template chunk): the CTA stages the structure blob into shared memory with one TMA bulk copy
-// (cp.async.bulk + mbarrier), then each WARP
-// pulls templates off a shared counter and runs a warp-synchronous depth-first search:
+// phase of the cost-ordered template schedule): the CTA stages the structure blob into shared
+// memory with one TMA bulk copy (cp.async.bulk + mbarrier), then each WARP pulls templates off a
+// shared counter and runs a warp-synchronous depth-first search (entered directly at level 1):
 //
 //   * level k places plan position k of the template.  Partial assignments live in per-level
 //     shared-memory queues as 4-byte (parent slot, atom) entries -- a trie, so a partial costs
