@@ -149,8 +149,7 @@ class _Columns(dict):
             return dict.__getitem__(self, key).tobytes()
         if key in self.raw:
             return np.ascontiguousarray(self.raw[key]).tobytes()
-        arr = dict.__getitem__(self, key)
-        return np.char.encode(arr, "ascii", "replace").astype(f"S{w}").tobytes() if len(arr) else b""
+        return self.packed_u32(key).astype({4: "<u4", 2: "<u2", 1: "u1"}[w]).tobytes()
 
     def packed_u32(self, key: str) -> np.ndarray:
         """String column as one little-endian uint32 per cell (bytes of the blank-stripped text)."""
