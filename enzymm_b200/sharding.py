@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "merge_hits", "gather_hits"]
+__all__ = ["shard_bounds", "merge_hits", "gather_hits", "ChunkQueue"]
 
 
 def shard_bounds(n_items: int, world_size: int, rank: int, align: int = 1) -> Tuple[int, int]:
@@ -25,6 +25,43 @@ def shard_bounds(n_items: int, world_size: int, rank: int, align: int = 1) -> Tu
     lo_u = rank * base + min(rank, extra)
     hi_u = lo_u + base + (1 if rank < extra else 0)
     return min(lo_u * align, n_items), min(hi_u * align, n_items)
+
+
+class ChunkQueue:
+    """Dynamic hand-out of structure chunks to ranks (for corpora whose structures
+    differ widely in cost a static block per rank leaves GPUs idle).  The queue is one counter in
+    the process group's key-value store -- host side only, nothing on the data path: every rank
+    calls ``next()`` until it returns None and searches chunk ``[lo, hi)`` of the corpus each time.
+    Without an initialised process group it simply enumerates the chunks."""
+
+    def __init__(self, n_items: int, chunk: int, name: str = "emm_chunk_queue"):
+        if chunk <= 0:
+            raise ValueError("chunk must be positive")
+        self.n_items, self.chunk = int(n_items), int(chunk)
+        self.n_chunks = (self.n_items + self.chunk - 1) // self.chunk
+        self._key = name
+        self._local = 0
+        self._store = None
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._store = dist.distributed_c10d._get_default_store()
+
+    def next(self) -> Optional[Tuple[int, int]]:
+        if self._store is not None:
+            index = int(self._store.add(self._key, 1)) - 1
+        else:
+            index, self._local = self._local, self._local + 1
+        if index >= self.n_chunks:
+            return None
+        lo = index * self.chunk
+        return lo, min(lo + self.chunk, self.n_items)
+
+    def __iter__(self):
+        while True:
+            span = self.next()
+            if span is None:
+                return
+            yield span
 
 
 def merge_hits(parts: Sequence[Tuple[int, np.ndarray]]) -> np.ndarray:

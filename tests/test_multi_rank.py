@@ -78,3 +78,46 @@ def test_two_rank_gather_equals_single_process():
     want = merge_hits([(0, _oracle_hits(templates, mols))])
     assert len(want) > 0
     assert got == want.tobytes()
+
+
+def _queue_worker(rank: int, world: int, port: int, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from enzymm_b200.sharding import ChunkQueue
+        templates, mols = _inputs()
+        parts = []
+        for lo, hi in ChunkQueue(len(mols), chunk=2):          # chunks handed out first come, first served
+            parts.append((lo, _oracle_hits(templates, mols[lo:hi])))
+        mine = merge_hits(parts) if parts else np.zeros(0, dtype=HIT_DTYPE)
+        merged = gather_hits(0, mine)                           # already rebased to corpus indices
+        spans = [None] * world
+        dist.all_gather_object(spans, [p[0] for p in parts])
+        dist.barrier()
+        if rank == 0:
+            queue.put((merged.tobytes(), spans))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dynamic_chunk_queue_covers_every_structure_once():
+    from enzymm_b200.sharding import ChunkQueue
+    assert list(ChunkQueue(5, 2)) == [(0, 2), (2, 4), (4, 5)] and list(ChunkQueue(0, 4)) == []
+    with pytest.raises(ValueError):
+        ChunkQueue(4, 0)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_queue_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, spans = queue.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(lo for part in spans for lo in part) == [0, 2, 4]      # every chunk exactly once
+    templates, mols = _inputs()
+    want = merge_hits([(0, _oracle_hits(templates, mols))])
+    assert got == want.tobytes()
