@@ -460,7 +460,7 @@ class Matcher:
                 self.hits_per_structure = max(self.hits_per_structure, capacity // max(batch.n_structures, 1))
         raise EngineError(-4, "hit buffer kept overflowing")
 
-    def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0):
+    def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0, queue=None):
         """Screen PDB files without building ``Molecule`` objects: a generator of
         ``(chunk_paths, header_ids, records)`` per chunk of ``chunk_size`` files, ``records`` being the
         hit records of the chunk (``structure`` indexes ``chunk_paths``; ``flags & 4`` = passes the
@@ -468,7 +468,9 @@ class Matcher:
         (``packing.pack_files``) on a background thread; the packed chunk crosses PCIe on one CUDA
         stream while the previous chunk is searched on another (two device sessions).
         ``matches_for`` turns the records of one file into the ``Match`` objects ``run`` would have
-        returned for it."""
+        returned for it.  With ``queue`` (a ``sharding.ChunkQueue`` over ``len(paths)``) the chunks
+        are not taken in order but pulled from the queue, which several ranks -- one per GPU --
+        share: each file is searched by exactly one of them."""
         import concurrent.futures
         from .engine import Session
         from .packing import pack_files
@@ -476,8 +478,10 @@ class Matcher:
             return
         engine = self._ensure_engine()
         paths = [os.fspath(p) for p in paths]
-        chunks = [paths[i:i + chunk_size] for i in range(0, len(paths), chunk_size)]
-        if not chunks:
+        spans = iter(queue) if queue is not None else iter([(i, min(i + chunk_size, len(paths)))
+                                                             for i in range(0, len(paths), chunk_size)])
+        first = next(spans, None)
+        if first is None:
             return
         if self._scan_lanes is None:        # [session, stream] x 2, kept for the next call: no reallocation per scan
             self._scan_lanes = [[None, engine.new_stream()], [None, engine.new_stream()]]
@@ -494,11 +498,19 @@ class Matcher:
         in_flight: collections.deque = collections.deque()      # (lane, chunk paths, ids, batch)
         try:
             with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-                pending = pool.submit(pack_files, chunks[0], engine.compiled, True, threads)
-                for ci, chunk in enumerate(chunks):
+                chunk = paths[first[0]:first[1]]
+                pending = pool.submit(pack_files, chunk, engine.compiled, True, threads)
+                ci = -1
+                while pending is not None:
+                    ci += 1
                     batch, ids = pending.result()
-                    pending = (pool.submit(pack_files, chunks[ci + 1], engine.compiled, True, threads)
-                               if ci + 1 < len(chunks) else None)
+                    this_chunk = chunk
+                    span = next(spans, None)
+                    if span is not None:
+                        chunk = paths[span[0]:span[1]]
+                        pending = pool.submit(pack_files, chunk, engine.compiled, True, threads)
+                    else:
+                        pending = None
                     lane = lanes[ci % 2]
                     sess = lane[0]
                     need_hits = self._hit_capacity(batch.n_structures)
@@ -511,7 +523,7 @@ class Matcher:
                                                  grow(batch.n_atoms, sess.max_atoms if sess else 0),
                                                  grow(batch.n_structures, sess.max_structures if sess else 0), need_hits)
                     self._submit(sess, batch, stream=lane[1])
-                    in_flight.append((lane, chunk, ids, batch))
+                    in_flight.append((lane, this_chunk, ids, batch))
                     if len(in_flight) == 2:
                         yield collect(*in_flight.popleft())
                 while in_flight:

@@ -604,6 +604,11 @@ def test_scan_files_equals_matcher_run(tmp_path, active_templates):
                 assert [m.complete for m in got] == [m.complete for m in expect]
             seen += len(chunk_paths)
         assert seen == len(paths)
+        # the same chunks pulled from a (here: single-process) ChunkQueue give the same records
+        from enzymm_b200.sharding import ChunkQueue
+        plain = [r for _, _, r in matcher.scan_files(paths, chunk_size=3, threads=2)]
+        queued = [r for _, _, r in matcher.scan_files(paths, threads=2, queue=ChunkQueue(len(paths), 3))]
+        assert len(plain) == len(queued) == 3 and all(a.tobytes() == b.tobytes() for a, b in zip(plain, queued))
 
 
 def test_matcher_grows_its_hit_buffer(tmp_path, active_templates, mol_1amy, mol_af):
