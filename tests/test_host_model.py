@@ -421,3 +421,14 @@ def test_pack_files_columns_outlive_the_batch(active_templates):
     junk = [np.ones(1 << 20) for _ in range(8)]          # churn the allocator
     assert float(xyz.sum()) == want_sum and np.array_equal(klass, want_classes)
     del junk
+
+
+def test_rank_order_reference_vectors():
+    """``utils.ranked_argsort`` known answers (reference tests/test_utils.py:10-15); feeds
+    ``Match.preserved_resid_order``."""
+    from enzymm_b200.templates import rank_order
+    assert rank_order([0, 4, 8, 6]) == [1, 2, 4, 3]
+    assert rank_order([2, 3, 20, 9]) == [1, 2, 4, 3]
+    assert rank_order([-3, 3, 20, 9]) == [1, 2, 4, 3]
+    assert rank_order([2, 3, 20, 20, 9]) == [1, 2, 4, 4, 3]
+    assert rank_order([2, 20, 3, 20, 9]) == [1, 4, 2, 4, 3]
