@@ -432,3 +432,31 @@ def test_rank_order_reference_vectors():
     assert rank_order([-3, 3, 20, 9]) == [1, 2, 4, 3]
     assert rank_order([2, 3, 20, 20, 9]) == [1, 2, 4, 4, 3]
     assert rank_order([2, 20, 3, 20, 9]) == [1, 4, 2, 4, 3]
+
+
+def test_vec3_reference_vectors():
+    """Known answers of the reference's ``TestVec3`` (tests/test_template.py:55-167)."""
+    vec1, vec2, vec3 = Vec3(1, 2, 3), Vec3(-0.275, 2.8, 0.837), Vec3(0, 0, 0)
+    vec4, vec5 = Vec3(1.00000000001, 0, 0), Vec3(-1, 0, 0)
+    vec6 = Vec3(-0.43667809853452577, 0.6652199071133453, 0.6056357927338702)
+    vec7 = Vec3(-0.4366780985345203, 0.6652199071133459, 0.6056357927338736)
+    notavec = (0, 3, 5)
+    assert (vec1.x, vec1.y, vec1.z) == (1.0, 2.0, 3.0) and (vec2.x, vec2.y, vec2.z) == (-0.275, 2.8, 0.837)
+    assert vec1.norm == math.sqrt(14) and vec3.norm == 0.0
+    n = vec1.normalize()
+    assert (n.x, n.y, n.z) == (1 / math.sqrt(14), 2 / math.sqrt(14), 3 / math.sqrt(14)) and vec3.normalize() == vec3
+    for got, want in (((vec1 + vec2), (0.725, 4.8, 3.837)), ((vec1 + 5), (6, 7, 8)), ((vec1 - vec2), (1.275, -0.8, 2.163)),
+                      ((vec1 - 5), (-4, -3, -2)), ((vec1 / vec2), (-3.6363636, 0.7142857, 3.58422939)),
+                      ((vec1 / 2), (0.5, 1, 1.5))):
+        assert (got.x, got.y, got.z) == pytest.approx(want, abs=5e-8)
+    assert vec1 + vec3 == vec1 and vec1 - vec3 == vec1
+    with pytest.raises(ZeroDivisionError):
+        vec1 / vec3
+    for op in (lambda: vec1 + notavec, lambda: vec1 - notavec, lambda: vec1 / notavec, lambda: vec1 @ notavec):
+        with pytest.raises(TypeError):
+            op()
+    assert vec1 @ vec3 == 0 and vec1 @ vec2 == pytest.approx(7.836)
+    assert vec1.normalize() @ vec2.normalize() == pytest.approx(0.713465, abs=5e-7)
+    assert vec1.angle_to(vec2) == pytest.approx(math.acos(0.713465), abs=5e-7)
+    assert vec4.angle_to(vec4) == pytest.approx(0, abs=1e-7) and vec4.angle_to(vec5) == pytest.approx(math.pi, abs=1e-7)
+    assert vec6.angle_to(vec7) == pytest.approx(0, abs=1e-7)          # cosine rounds above 1: clamped, not a math error
