@@ -460,3 +460,22 @@ def test_vec3_reference_vectors():
     assert vec1.angle_to(vec2) == pytest.approx(math.acos(0.713465), abs=5e-7)
     assert vec4.angle_to(vec4) == pytest.approx(0, abs=1e-7) and vec4.angle_to(vec5) == pytest.approx(math.pi, abs=1e-7)
     assert vec6.angle_to(vec7) == pytest.approx(0, abs=1e-7)          # cosine rounds above 1: clamped, not a math error
+
+
+def test_residue_reference_attributes(all_templates):
+    """Reference ``TestResidue.test_attributes`` (tests/test_template.py:709-754): residue typing and
+    the orientation vectors the device filter is fed with (GLU: C -> midpoint of the Os; HIS: CG -> ND1)."""
+    from enzymm_b200.templates import check_template
+    t = next(t for t in all_templates
+             if t.pdb_id == "1b74" and len(t.residues) == 6 and t.residues[0].residue_number == 147
+             and t.cluster is not None and (t.cluster.id, t.cluster.member, t.cluster.size) == (1, 1, 1))
+    r1, r2 = t.residues[0], t.residues[1]
+    assert (r1.residue_name, r1.allowed_residues, r1.match_mode, r1.backbone, r1.residue_number, r1.chain_id) == \
+           ("GLU", "E", 3, False, 147, "A")
+    v = r1.orientation_vector
+    assert (v.x, v.y, v.z) == pytest.approx((-0.125, -0.347499999, 0.45599999), abs=5e-8)
+    assert r1.orientation_vector_indices == (0, 9)
+    v = r2.orientation_vector
+    assert (v.x, v.y, v.z) == pytest.approx((1.079, -0.638, 0.57), abs=5e-8)
+    assert r2.orientation_vector_indices == (0, 1)
+    assert check_template(t, warn=False) is True and check_template(t, warn=True) is True
