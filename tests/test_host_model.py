@@ -479,3 +479,42 @@ def test_residue_reference_attributes(all_templates):
     assert (v.x, v.y, v.z) == pytest.approx((1.079, -0.638, 0.57), abs=5e-8)
     assert r2.orientation_vector_indices == (0, 1)
     assert check_template(t, warn=False) is True and check_template(t, warn=True) is True
+
+
+def test_template_reference_good_loads():
+    """Reference ``TestTemplate.test_good_loads`` / ``test_copy`` / ``test_template_non_equality``
+    (tests/test_template.py:335-440) on the same two shipped templates."""
+    from enzymm_b200.templates import iter_bundle
+    texts = {name: text for name, text in iter_bundle() if "1b74_A147-AA180-AA70-AA178-AA8-AA7" in name
+             or "csa3d_0011.cluster_1_1_3.1qum_D145" in name}
+    text1 = next(v for k, v in texts.items() if "6_residues/results/csa3d_0001/csa3d_0001.cluster_1_1_1.1b74" in k)
+    text2 = next(v for k, v in texts.items() if "4_residues/results/csa3d_0011/csa3d_0011.cluster_1_1_3.1qum" in k)
+    t1 = Template.loads(text1, warn=True)
+    t1_with_id = Template.loads(text1, id="hello_world", warn=True)
+    t2 = Template.loads(text2, id="hello_world", warn=True)
+    want1 = dict(pdb_id="1b74", template_id_string="1b74_A147-AA180-AA70-AA178-AA8-AA7", mcsa_id=1, uniprot_id="P56868",
+                 organism="Aquifex pyrophilus", organism_id="2714", resolution=2.3, experimental_method="X-ray diffraction",
+                 ec=("5.1.1.3",), represented_sites=2, enzyme_discription="GLUTAMATE RACEMASE (E.C.5.1.1.3)",
+                 effective_size=6, dimension=6, multimeric=True, relative_order=[0], cath=("3.40.50.1860",))
+    want2 = dict(pdb_id="1qum", id="hello_world",
+                 template_id_string="1qum_D145-D109-D37-D72-D69-D229-D182-D231-D261-D216-D179", mcsa_id=11, uniprot_id=None,
+                 organism="Escherichia coli", organism_id="562", resolution=1.55, experimental_method="X-ray diffraction",
+                 ec=("3.1.21.2",), represented_sites=1, enzyme_discription="ENDONUCLEASE IV (E.C.3.1.21.2)/DNA",
+                 dimension=4, effective_size=4, multimeric=False, relative_order=[2, 1, 4, 3], cath=("3.20.20.150",))
+    for t, want in ((t1, want1), (t2, want2)):
+        for key, value in want.items():
+            assert getattr(t, key) == value, (key, getattr(t, key), value)
+    assert (t1.cluster.id, t1.cluster.member, t1.cluster.size) == (1, 1, 1) and len(t1.residues) == 6
+    assert (t2.cluster.id, t2.cluster.member, t2.cluster.size) == (1, 1, 3) and len(t2.residues) == 4
+    c = t1.copy()
+    assert c == t1 and list(c) == list(t1) and hash(c) == hash(t1) and c.cluster == t1.cluster
+    assert t1 != t1_with_id and t1 != t2
+
+
+def test_cluster_reference():
+    """Reference ``TestCluster`` (tests/test_template.py:165-178)."""
+    from enzymm_b200.templates import Cluster
+    with pytest.raises(ValueError):
+        Cluster(1, 2, 1)                       # member index beyond the cluster size
+    c = Cluster(3, 1, 2)
+    assert (c.id, c.member, c.size) == (3, 1, 2)
