@@ -518,3 +518,68 @@ def test_cluster_reference():
         Cluster(1, 2, 1)                       # member index beyond the cluster size
     c = Cluster(3, 1, 2)
     assert (c.id, c.member, c.size) == (3, 1, 2)
+
+
+def _oracle_hit_record(template, molecule, rmsd, dist, dyn):
+    """One device-shaped hit record computed by the oracle (test infrastructure only)."""
+    import oracle
+    from enzymm_b200.engine import HIT_DTYPE, HIT_NO_MODEL, HIT_ORIENTED, HIT_PASS
+    (h,) = oracle.query([molecule], oracle.OracleTemplates([template]), rmsd, dist, dyn, max_candidates=10000,
+                        ignore_chain=True)[0]
+    rec = np.zeros((), dtype=HIT_DTYPE)
+    rec["n_complete"], rec["n_atoms"] = h.n_complete, len(h.atoms)
+    rec["rmsd"], rec["rot"], rec["qbar"], rec["tbar"] = h.rmsd, h.rot.reshape(9), h.qbar, h.tbar
+    rec["atoms"][:len(h.atoms)] = h.atoms
+    rec["orientation"] = oracle.orientation(template, h.transform(molecule.xyz[h.atoms]))
+    try:
+        verdict = HIT_PASS if oracle.predicted_correct(template.effective_size, dist, h.rmsd, float(rec["orientation"])) else 0
+    except KeyError:                 # no logistic models for this distance (jess_run.py:339-342)
+        verdict = HIT_NO_MODEL
+    rec["flags"] = HIT_ORIENTED | verdict
+    return rec
+
+
+def test_match_and_writers_on_oracle_records(mol_1amy):
+    """The reference's ``TestMatch`` known answers and golden files (tests/test_jess_run.py:61-179)
+    through the product's ``Hit`` / ``Match`` host code, fed with oracle-computed records (no GPU)."""
+    import io
+    from enzymm_b200 import jess_run
+    from enzymm_b200.pyjess_api import Hit
+    from test_oracle_golden import T1_PATH, T2_PATH, bundle_templates
+    t1, t2 = bundle_templates([T1_PATH, T2_PATH])
+    match1 = jess_run.Match(hit=Hit(_oracle_hit_record(t1, mol_1amy, 2, 1.5, 1.5), t1, mol_1amy), pairwise_distance=1.5,
+                            complete=True, index=0)
+    assert match1.hit.molecule().id == "1AMY" and match1.index == 0
+    assert match1.query_atom_count == 3339 and match1.query_residue_count == 403
+    assert match1.hit.rmsd == pytest.approx(0.32093143, abs=5e-8)
+    assert match1.orientation == pytest.approx(0.15327054322, abs=5e-8)
+    expected = [(0.2290067979141952, -0.3853409610281773, 0.377114677867322),
+                (0.4249816660862038, -0.21966898402981627, -0.3540863184957992),
+                (0.45459385444007694, -0.34869961601989985, 0.10687378206512577),
+                (-0.8733960645698886, 0.2563504028143271, -0.9840695023070225),
+                (-0.510183600042339, -0.1958417994791759, 0.18963368325429997)]
+    assert [(v.x, v.y, v.z) for v in match1.match_vector_list] == [pytest.approx(e, rel=1e-9, abs=1e-9) for e in expected]
+    assert match1.template_vector_list == [r.orientation_vector for r in t1.residues]
+    assert match1.preserved_resid_order is True and match1.multimeric is False and match1.complete is True
+    assert match1.matched_residues == [("GLU", "A", "204"), ("ASP", "A", "87"), ("ASP", "A", "179"),
+                                       ("HIS", "A", "288"), ("ASP", "A", "289")]
+    assert match1.predicted_correct is True and match1.hit.device_pass
+    match2 = jess_run.Match(hit=Hit(_oracle_hit_record(t2, mol_1amy, 2, 1, 1), t2, mol_1amy))
+    assert match2.hit.rmsd == pytest.approx(1.7353479120, abs=5e-8)
+    assert match2.orientation == pytest.approx(1.6503123465442575, abs=1e-9)
+    assert match2.preserved_resid_order is False and match2.complete is False and match2.multimeric is False
+    assert match2.matched_residues == [("TRP", "A", "38"), ("HIS", "A", "288"), ("ASP", "A", "289")]
+    # writers: byte parity with the reference's golden files
+    for name, kwargs in (("1AMY_matches_no_query.pdb", dict(transform=False, include_query=False)),
+                         ("1AMY_matches_query_included.pdb", dict(transform=False, include_query=True)),
+                         ("1AMY_matches_template.pdb", dict(transform=True, include_query=False))):
+        buffer = io.StringIO()
+        match1.dump2pdb(buffer, **kwargs)
+        assert buffer.getvalue() == (GOLDEN / name).read_text(), name
+    got_header, got_row = [l.split("\t") for l in match1.dumps(header=True).splitlines()]
+    want_header, want_row = [l.split("\t") for l in (GOLDEN / "results.tsv").read_text().splitlines()]
+    assert got_header == want_header
+    skip = {"log_evalue", "number_of_mutated_residues", "number_of_side_chain_residues_(template,reference)",
+            "number_of_metal_ligands_(template,reference)", "number_of_ptm_residues_(template, reference)",
+            "total_reference_residues"}
+    assert [(c, g) for c, g, w in zip(want_header, got_row, want_row) if c not in skip and g != w] == []
