@@ -583,3 +583,26 @@ def test_match_and_writers_on_oracle_records(mol_1amy):
             "number_of_metal_ligands_(template,reference)", "number_of_ptm_residues_(template, reference)",
             "total_reference_residues"}
     assert [(c, g) for c, g, w in zip(want_header, got_row, want_row) if c not in skip and g != w] == []
+
+
+def test_remark_annotation_parsing_reference():
+    """Reference ``test_annotation_parsing`` (tests/test_template.py:509-541) on the REMARK handlers."""
+    from enzymm_b200 import templates as T
+    h = T._REMARK_HANDLERS
+    for tag, token in (("PDB_ID", "abcde"), ("UNIPROT_ID", "abcde"), ("MCSA_ID", "abcde"), ("CLUSTER", "abcde"),
+                       ("CLUSTER", "ab_cd_e"), ("RESOLUTION", "abcde"), ("REPRESENTING", "abcde")):
+        with pytest.raises(ValueError):
+            h[tag]([0, 1, token], {}, True)
+    for token in ("1.1.1", "8.1.1.1"):
+        with pytest.raises(ValueError):
+            h["EC"]([0, 1, token], {"ec": []}, True)
+    with pytest.warns(Warning):
+        meta = {"ec": []}
+        h["EC"]([0, 1, "1.1.1.n1"], meta, True)
+    assert meta["ec"] == ["1.1.1.n1"]
+    with pytest.raises(ValueError):
+        h["CATH"]([0, 1, "1.1.1.n1"], {"cath": []}, True)
+    for token in ("1.1.1.1", "1.1.1800.1"):
+        meta = {"cath": []}
+        h["CATH"]([0, 1, token], meta, True)
+        assert meta["cath"] == [token]
