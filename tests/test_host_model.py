@@ -83,6 +83,11 @@ def test_bad_templates():
     Template.loads((bad / "new_remark.pdb").read_text())
     with pytest.raises(NotADirectoryError):
         list(load_templates("/some/bogus/folder"))
+    with pytest.raises(NotADirectoryError):
+        list(load_templates(bad / "pdb_id_none.pdb"))       # a file, not a folder (test_template.py:23-28)
+    with pytest.raises(IndexError):
+        Template.loads((bad / "missing_cluster_annotation.pdb").read_text(), warn=True)
+    assert Template.loads((bad / "pdb_id_none.pdb").read_text(), warn=True).pdb_id is None
     with pytest.raises(ValueError):
         list(load_templates(GOLDEN))           # a folder of non-template .pdb files
 
