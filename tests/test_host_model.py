@@ -611,3 +611,30 @@ def test_remark_annotation_parsing_reference():
         meta = {"cath": []}
         h["CATH"]([0, 1, token], meta, True)
         assert meta["cath"] == [token]
+
+
+def test_matcher_init_reference():
+    """Reference ``TestMatcher.test_init`` (tests/test_jess_run.py:278-299): defaults, size detection,
+    cpu counts, duplicate detection -- none of it needs a device."""
+    import os
+    from enzymm_b200 import jess_run
+    from enzymm_b200.templates import load_templates
+    res5 = list(load_templates(subset="5_residues/results/csa3d_0285/"))
+    res4 = list(load_templates(subset="4_residues/results/csa3d_0285/"))
+    res3 = list(load_templates(subset="3_residues/results/csa3d_0344/"))
+    defaults = {3: {"rmsd": 2, "distance": 0.9, "max_dynamic_distance": 0.9},
+                4: {"rmsd": 2, "distance": 1.7, "max_dynamic_distance": 1.7},
+                5: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0},
+                6: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0},
+                7: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0},
+                8: {"rmsd": 2, "distance": 2.0, "max_dynamic_distance": 2.0}}
+    m1 = jess_run.Matcher(templates=res5 + res4, cpus=2, warn=True)
+    m2 = jess_run.Matcher(templates=res5 + res4, skip_smaller_hits=True)
+    with pytest.warns(Warning):
+        m3 = jess_run.Matcher(templates=res5 + res4 + res3, match_small_templates=True, warn=True, cpus=-1)
+    available = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    assert m1.jess_params == defaults and m1.template_effective_sizes == [5, 4]
+    assert m1.cpus == 2 and m2.cpus == available and m3.cpus == max(1, available - 1)
+    with pytest.raises(ValueError):
+        jess_run.Matcher(templates=res5 + res5)
+    assert m1.run([]) == {} and m1._engine is None          # nothing to search: no device touched
