@@ -34,6 +34,7 @@ static thread_local std::string g_error;
 // Largest dynamic shared-memory size the search kernels have been opted into, per device (the
 // attribute is per function and device, shared by every library handle of the process).
 static size_t g_configured_smem[64] = {0};
+static std::mutex g_config_mutex;      // sessions of one device may be driven from different host threads
 
 static int fail(emm_status st, const std::string &msg)
 {
@@ -668,9 +669,12 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
         const int cap = staged ? (int)((s->max_staged + 1023) & ~int64_t(1023)) : 0;
         P.blob_cap = cap;
         const size_t smem = search_smem_bytes(cap, P.levels);
-        if (lib->device >= 64 || smem > g_configured_smem[lib->device]) {   // raise only; never per launch
-            CUDA_TRY(configure_search((int)smem));
-            if (lib->device < 64) g_configured_smem[lib->device] = smem;
+        {
+            std::lock_guard<std::mutex> guard(g_config_mutex);
+            if (lib->device >= 64 || smem > g_configured_smem[lib->device]) {   // raise only; never per launch
+                CUDA_TRY(configure_search((int)smem));
+                if (lib->device < 64) g_configured_smem[lib->device] = smem;
+            }
         }
         CUDA_TRY(cudaMemsetAsync(s->d_work, 0, 4, stream));
         cudaEvent_t e0, e1;
