@@ -101,91 +101,6 @@ inline bool parse_real(const char *line, int64_t len, int a, int b, double *out,
     return *end == 0;
 }
 
-struct Columns {
-    int32_t *serial; char *name; char *altloc; char *resname; char *chain; int32_t *resnum; char *icode;
-    double *xyz; double *occupancy; double *bfactor; char *segment; char *element; int8_t *charge;
-};
-
-int64_t count_atoms(const char *text, int64_t len)
-{
-    int64_t n = 0, pos = 0;
-    while (pos < len) {
-        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
-        const int64_t end = nl ? nl - text : len;
-        const char *line = text + pos;
-        const int64_t ll = end - pos;
-        if (is_coord_record(line, ll)) ++n;
-        else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) break;
-        pos = end + 1;
-    }
-    return n;
-}
-
-// returns atoms parsed, or -1 (t_error set)
-int64_t parse_into(const char *text, int64_t len, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
-{
-    int64_t n = 0, pos = 0;
-    bool have_header = false;
-    memset(header_id, 0, 5);
-    while (pos < len) {
-        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
-        const int64_t end = nl ? nl - text : len;
-        const char *line = text + pos;
-        int64_t ll = end - pos;
-        while (ll > 0 && line[ll - 1] == '\r') --ll;
-        if (is_coord_record(line, ll)) {
-            if (n >= capacity) { t_error = "atom capacity exceeded"; return -1; }
-            const int64_t i = base + n;
-            double x, y, z;
-            if (ll < 54 || !parse_int(line, ll, 6, 11, c.serial + i) || !parse_int(line, ll, 22, 26, c.resnum + i) ||
-                !parse_real(line, ll, 30, 38, &x, false) || !parse_real(line, ll, 38, 46, &y, false) ||
-                !parse_real(line, ll, 46, 54, &z, false) || !parse_real(line, ll, 54, 60, c.occupancy + i, true) ||
-                !parse_real(line, ll, 60, 66, c.bfactor + i, true)) {
-                t_error = "malformed PDB coordinate record: " + std::string(line, (size_t)std::min<int64_t>(ll, 80));
-                return -1;
-            }
-            c.xyz[3 * i] = x; c.xyz[3 * i + 1] = y; c.xyz[3 * i + 2] = z;
-            field(line, ll, 12, 16, c.name + 4 * i, 4);
-            c.altloc[i] = ll > 16 ? line[16] : ' ';
-            field(line, ll, 17, 20, c.resname + 4 * i, 4);
-            field(line, ll, 20, 22, c.chain + 2 * i, 2);
-            c.icode[i] = ll > 26 ? line[26] : ' ';
-            field(line, ll, 72, 76, c.segment + 4 * i, 4);
-            field(line, ll, 76, 78, c.element + 2 * i, 2);
-            char chg[3];
-            field(line, ll, 78, 80, chg, 2);
-            chg[2] = 0;
-            int8_t q = 0;
-            if (chg[0] >= '0' && chg[0] <= '9') q = (int8_t)((chg[0] - '0') * ((chg[1] == '-') ? -1 : 1));
-            c.charge[i] = q;
-            ++n;
-        } else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) {
-            break;
-        } else if (!have_header && ll >= 6 && memcmp(line, "HEADER", 6) == 0) {
-            have_header = true;
-            char id[5];
-            field(line, ll, 62, 66, id, 4);
-            id[4] = 0;
-            memcpy(header_id, id, 5);
-        }
-        pos = end + 1;
-    }
-    return n;
-}
-
-// ---- files -> emm_batch columns -------------------------------------------------------------------
-
-// blank-stripped field of width w (<= 4) as little-endian bytes, NUL padded: the same bytes field() yields
-inline uint32_t strip_field(const char *p, int w)
-{
-    int lo = 0, hi = w;
-    while (lo < hi && (p[lo] == ' ' || p[lo] == '\t')) ++lo;
-    while (hi > lo && (p[hi - 1] == ' ' || p[hi - 1] == '\t' || p[hi - 1] == '\r')) --hi;
-    uint32_t v = 0;
-    for (int i = 0; lo + i < hi; ++i) v |= (uint32_t)(unsigned char)p[lo + i] << (8 * i);
-    return v;
-}
-
 inline bool fast_int(const char *p, const char *e, int32_t *out)
 {
     while (p < e && *p == ' ') ++p;
@@ -241,6 +156,94 @@ inline bool real_layout(const char *p, double *out)
     const double v = (double)(ip * mul + frac) / div;
     *out = neg ? -v : v;
     return true;
+}
+
+struct Columns {
+    int32_t *serial; char *name; char *altloc; char *resname; char *chain; int32_t *resnum; char *icode;
+    double *xyz; double *occupancy; double *bfactor; char *segment; char *element; int8_t *charge;
+};
+
+int64_t count_atoms(const char *text, int64_t len)
+{
+    int64_t n = 0, pos = 0;
+    while (pos < len) {
+        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
+        const int64_t end = nl ? nl - text : len;
+        const char *line = text + pos;
+        const int64_t ll = end - pos;
+        if (is_coord_record(line, ll)) ++n;
+        else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) break;
+        pos = end + 1;
+    }
+    return n;
+}
+
+// returns atoms parsed, or -1 (t_error set)
+int64_t parse_into(const char *text, int64_t len, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
+{
+    int64_t n = 0, pos = 0;
+    bool have_header = false;
+    memset(header_id, 0, 5);
+    while (pos < len) {
+        const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
+        const int64_t end = nl ? nl - text : len;
+        const char *line = text + pos;
+        int64_t ll = end - pos;
+        while (ll > 0 && line[ll - 1] == '\r') --ll;
+        if (is_coord_record(line, ll)) {
+            if (n >= capacity) { t_error = "atom capacity exceeded"; return -1; }
+            const int64_t i = base + n;
+            double x, y, z;
+            const bool wide = ll >= 66;
+            if (ll < 54 || !int_field(line, ll, 6, 11, c.serial + i) || !int_field(line, ll, 22, 26, c.resnum + i) ||
+                !(real_layout<8, 3>(line + 30, &x) || parse_real(line, ll, 30, 38, &x, false)) ||
+                !(real_layout<8, 3>(line + 38, &y) || parse_real(line, ll, 38, 46, &y, false)) ||
+                !(real_layout<8, 3>(line + 46, &z) || parse_real(line, ll, 46, 54, &z, false)) ||
+                !((wide && real_layout<6, 2>(line + 54, c.occupancy + i)) || parse_real(line, ll, 54, 60, c.occupancy + i, true)) ||
+                !((wide && real_layout<6, 2>(line + 60, c.bfactor + i)) || parse_real(line, ll, 60, 66, c.bfactor + i, true))) {
+                t_error = "malformed PDB coordinate record: " + std::string(line, (size_t)std::min<int64_t>(ll, 80));
+                return -1;
+            }
+            c.xyz[3 * i] = x; c.xyz[3 * i + 1] = y; c.xyz[3 * i + 2] = z;
+            field(line, ll, 12, 16, c.name + 4 * i, 4);
+            c.altloc[i] = ll > 16 ? line[16] : ' ';
+            field(line, ll, 17, 20, c.resname + 4 * i, 4);
+            field(line, ll, 20, 22, c.chain + 2 * i, 2);
+            c.icode[i] = ll > 26 ? line[26] : ' ';
+            field(line, ll, 72, 76, c.segment + 4 * i, 4);
+            field(line, ll, 76, 78, c.element + 2 * i, 2);
+            char chg[3];
+            field(line, ll, 78, 80, chg, 2);
+            chg[2] = 0;
+            int8_t q = 0;
+            if (chg[0] >= '0' && chg[0] <= '9') q = (int8_t)((chg[0] - '0') * ((chg[1] == '-') ? -1 : 1));
+            c.charge[i] = q;
+            ++n;
+        } else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) {
+            break;
+        } else if (!have_header && ll >= 6 && memcmp(line, "HEADER", 6) == 0) {
+            have_header = true;
+            char id[5];
+            field(line, ll, 62, 66, id, 4);
+            id[4] = 0;
+            memcpy(header_id, id, 5);
+        }
+        pos = end + 1;
+    }
+    return n;
+}
+
+// ---- files -> emm_batch columns -------------------------------------------------------------------
+
+// blank-stripped field of width w (<= 4) as little-endian bytes, NUL padded: the same bytes field() yields
+inline uint32_t strip_field(const char *p, int w)
+{
+    int lo = 0, hi = w;
+    while (lo < hi && (p[lo] == ' ' || p[lo] == '\t')) ++lo;
+    while (hi > lo && (p[hi - 1] == ' ' || p[hi - 1] == '\t' || p[hi - 1] == '\r')) --hi;
+    uint32_t v = 0;
+    for (int i = 0; lo + i < hi; ++i) v |= (uint32_t)(unsigned char)p[lo + i] << (8 * i);
+    return v;
 }
 
 struct PackedCols {

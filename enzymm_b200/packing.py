@@ -14,7 +14,7 @@ import numpy as np
 
 from .engine import PackedBatch
 from .library import CompiledLibrary
-from .structures import Molecule, _native_lib
+from .structures import Molecule, _NativeBatch, _native_lib, _native_view
 
 __all__ = ["residue_ordinals", "pack_molecules", "pack_files", "chain_codes"]
 
@@ -150,18 +150,6 @@ class _PdbPacked(ctypes.Structure):       # struct emm_pdb_packed
                [("n_kinds", ctypes.c_int32), ("kind_names", ctypes.c_void_p), ("header_id", ctypes.c_void_p)]
 
 
-class _NativeBatch:
-    """Owns one ``emm_pdb_batch`` handle; freed when the last array viewing it goes away."""
-
-    def __init__(self, lib, handle):
-        self._lib, self._handle = lib, handle
-
-    def __del__(self):
-        if self._handle:
-            self._lib.emm_pdb_batch_free(self._handle)
-            self._handle = None
-
-
 def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrary, with_chain: bool = True,
                threads: int = 0) -> Tuple[PackedBatch, List[Optional[str]]]:
     """PDB files -> ``PackedBatch`` on the native thread pool (``emm_pdb_pack_files``), without
@@ -187,12 +175,7 @@ def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrar
         raise RuntimeError("emm_pdb_batch_packed failed")
     n, nf = c.n_atoms, c.n_files
 
-    def grab(ptr, dtype, count):
-        if count == 0 or not ptr:
-            return np.zeros(0, dtype=dtype)
-        buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
-        buf._owner = owner                   # array -> memoryview -> buf -> owner keeps the batch alive
-        return np.frombuffer(buf, dtype=dtype, count=count)
+    grab = lambda ptr, dtype, count: _native_view(owner, ptr, dtype, count)
 
     names = grab(c.kind_names, np.uint8, 8 * c.n_kinds).reshape(-1, 8)
     class_of_kind = np.zeros(max(len(names), 1), dtype=np.uint16)

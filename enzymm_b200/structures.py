@@ -244,6 +244,27 @@ def _native_lib():
     return _native
 
 
+class _NativeBatch:
+    """Owns one ``emm_pdb_batch`` handle; freed when the last array viewing it goes away."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._handle = lib, handle
+
+    def __del__(self):
+        if self._handle:
+            self._lib.emm_pdb_batch_free(self._handle)
+            self._handle = None
+
+
+def _native_view(owner: "_NativeBatch", ptr, dtype, count: int) -> np.ndarray:
+    """NumPy view of ``count`` items at ``ptr`` inside a native batch (array -> buffer -> owner keeps it alive)."""
+    if count == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
 class _PdbColumns(ctypes.Structure):
     _fields_ = [("n_files", ctypes.c_int32), ("n_atoms", ctypes.c_int64), ("atom_off", ctypes.c_void_p)] + \
                [(k, ctypes.c_void_p) for k in ("serial", "name", "altloc", "resname", "chain", "resnum", "icode",
@@ -440,27 +461,19 @@ def load_many(paths: Sequence[Union[str, os.PathLike]], ids: Optional[Sequence[O
     rc = lib.emm_pdb_load_files(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.byref(handle))
     if rc != 0:
         raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
-    try:
-        c = _PdbColumns()
-        lib.emm_pdb_batch_columns(handle, ctypes.byref(c))
-        n, nf = c.n_atoms, c.n_files
-
-        def grab(ptr, dtype, count):
-            if count == 0:
-                return np.zeros(0, dtype=dtype)
-            buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
-            return np.frombuffer(buf, dtype=dtype, count=count).copy()
-
-        off = grab(c.atom_off, np.int64, nf + 1)
-        cols = _columns_from_native(
-            n, grab(c.serial, np.int32, n), grab(c.name, np.uint8, 4 * n), grab(c.altloc, np.uint8, n),
-            grab(c.resname, np.uint8, 4 * n), grab(c.chain, np.uint8, 2 * n), grab(c.resnum, np.int32, n),
-            grab(c.icode, np.uint8, n), grab(c.occupancy, np.float64, n), grab(c.bfactor, np.float64, n),
-            grab(c.segment, np.uint8, 4 * n), grab(c.element, np.uint8, 2 * n), grab(c.charge, np.int8, n))
-        xyz = grab(c.xyz, np.float64, 3 * n).reshape(n, 3)
-        headers = grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5)
-    finally:
-        lib.emm_pdb_batch_free(handle)
+    owner = _NativeBatch(lib, handle)       # columns stay views of the native buffers: no copies
+    c = _PdbColumns()
+    lib.emm_pdb_batch_columns(handle, ctypes.byref(c))
+    n, nf = c.n_atoms, c.n_files
+    grab = lambda ptr, dtype, count: _native_view(owner, ptr, dtype, count)
+    off = grab(c.atom_off, np.int64, nf + 1)
+    cols = _columns_from_native(
+        n, grab(c.serial, np.int32, n), grab(c.name, np.uint8, 4 * n), grab(c.altloc, np.uint8, n),
+        grab(c.resname, np.uint8, 4 * n), grab(c.chain, np.uint8, 2 * n), grab(c.resnum, np.int32, n),
+        grab(c.icode, np.uint8, n), grab(c.occupancy, np.float64, n), grab(c.bfactor, np.float64, n),
+        grab(c.segment, np.uint8, 4 * n), grab(c.element, np.uint8, 2 * n), grab(c.charge, np.int8, n))
+    xyz = grab(c.xyz, np.float64, 3 * n).reshape(n, 3)
+    headers = grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5)
     out = []
     for i in range(nf):
         lo, hi = int(off[i]), int(off[i + 1])

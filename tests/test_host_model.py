@@ -315,6 +315,11 @@ def test_pack_files_coordinates_are_python_floats(tmp_path, active_templates):
     assert batch.xyz.tobytes() == want.tobytes()
     want_bf = np.asarray([float(l[60:66]) if l[60:66].strip() else 0.0 for l in lines]).astype(np.float32)
     assert batch.bfactor.tobytes() == want_bf.tobytes()
+    from enzymm_b200.structures import load_many
+    (mol,) = load_many([path])                       # the Molecule reader shares the number paths
+    assert mol.xyz.tobytes() == want.tobytes()
+    assert mol.column("temperature_factor").astype(np.float32).tobytes() == want_bf.tobytes()
+    assert Molecule.load(path).xyz.tobytes() == want.tobytes()
 
 
 def test_leader_order_is_a_valid_plan(active_templates):
