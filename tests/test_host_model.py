@@ -643,3 +643,71 @@ def test_matcher_init_reference():
     with pytest.raises(ValueError):
         jess_run.Matcher(templates=res5 + res5)
     assert m1.run([]) == {} and m1._engine is None          # nothing to search: no device touched
+
+
+def _random_pdb_text(rng) -> str:
+    """A syntactically valid but unruly PDB file: odd chain ids, negative residue numbers, split
+    residues, HETATM records, blank or missing B-factors, short lines, CRLF line ends, a second model."""
+    names = ["N", "CA", "C", "O", "CB", "CG", "OD1", "ND2", "OG", "SG", "NE2", "ZN", "OXT", "H1"]
+    residues = ["ALA", "ASP", "HIS", "SER", "CYS", "GLU", "HOH", "MSE", "ZN", "UNK", "A"]
+    chains = ["A", "B", " ", "AA", "1", "z"]
+    lines, serial = ["HEADER    TEST" + " " * 48 + "1ABC"], 1
+    blocks = []
+    for _ in range(int(rng.integers(1, 40))):
+        chain, resname, resnum = chains[rng.integers(len(chains))], residues[rng.integers(len(residues))], int(rng.integers(-20, 400))
+        block = []
+        for name in rng.choice(names, size=int(rng.integers(1, 8)), replace=False):
+            x, y, z = rng.uniform(-99, 999, 3)
+            rec = "HETATM" if resname in ("HOH", "ZN", "MSE") and rng.random() < 0.7 else "ATOM  "
+            core = f"{rec}{serial % 100000:5d} {name:<4s}{' ' if rng.random() < 0.9 else 'B'}{resname:>3s}{chain:>2s}{resnum:4d}" \
+                   f"{' ' if rng.random() < 0.95 else 'A'}   {x:8.3f}{y:8.3f}{z:8.3f}"
+            tail = rng.integers(4)
+            if tail == 0:
+                line = core                                             # stops after z
+            elif tail == 1:
+                line = core + f"{rng.uniform(0, 1):6.2f}"              # occupancy only
+            elif tail == 2:
+                line = core + f"{rng.uniform(0, 1):6.2f}{rng.uniform(0, 99):6.2f}"
+            else:
+                line = (core + f"{1.0:6.2f}{rng.uniform(0, 99):6.2f}").ljust(76) + f"{name[0]:>2s}" + ("1-" if rng.random() < 0.1 else "  ")
+            block.append(line)
+            serial += 1
+        blocks.append(block)
+    if len(blocks) > 3 and rng.random() < 0.5:                          # split one residue around another
+        first = blocks[0]
+        if len(first) > 1:
+            blocks[0], extra = first[:1], first[1:]
+            blocks.insert(2, extra)
+    for block in blocks:
+        lines.extend(block)
+        if rng.random() < 0.1:
+            lines.append("TER")
+    if rng.random() < 0.3:
+        lines += ["ENDMDL", "MODEL        2", "ATOM      1  N   ALA A   1       0.000   0.000   0.000  1.00  0.00           N", "ENDMDL"]
+    lines.append("END")
+    return ("\r\n" if rng.random() < 0.2 else "\n").join(lines) + "\n"
+
+
+def test_ingest_paths_agree_on_unruly_files(tmp_path, active_templates):
+    """Three readers, one answer: native packer == native Molecule reader + ``pack_molecules`` ==
+    pure-Python parser + ``pack_molecules``, on randomly generated awkward-but-valid files."""
+    from enzymm_b200.packing import pack_files
+    from enzymm_b200.structures import _parse_pdb_text, load_many
+    lib = CompiledLibrary(active_templates[::60], 2.0, 1.5, 1.5)
+    rng = np.random.default_rng(20230210)
+    paths = []
+    for i in range(40):
+        p = tmp_path / f"unruly_{i}.pdb"
+        p.write_bytes(_random_pdb_text(rng).encode())
+        paths.append(p)
+    native, ids = pack_files(paths, lib, threads=3)
+    through_molecules = pack_molecules(load_many(paths, threads=2), lib)
+    python_mols = []
+    for p in paths:
+        cols, xyz, hid = _parse_pdb_text(p.read_bytes().decode().splitlines(True))
+        python_mols.append(Molecule._from_columns(cols, xyz, hid))
+    through_python = pack_molecules(python_mols, lib)
+    _assert_batches_equal(native, through_molecules)
+    _assert_batches_equal(native, through_python)
+    assert ids == [m.id for m in python_mols] == ["1ABC"] * len(paths)
+    assert [m == n for m, n in zip(load_many(paths), python_mols)] == [True] * len(paths)
