@@ -579,6 +579,67 @@ int emm_pdb_batch_columns(const emm_pdb_batch *b, emm_pdb_columns *out)
     return EMM_OK;
 }
 
+// Blocks (one per structure, already parsed) -> the batch columns: offsets, the merged kind table
+// (structure order: deterministic whatever the thread count) and a parallel copy into place.
+static void finish_packed(emm_pdb_batch *b, std::vector<FileBlock> &blocks, int n_threads)
+{
+    const size_t nf = blocks.size();
+    const int n_files = (int)nf;
+    auto run_pool = [&](auto &&work) {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    };
+    b->atom_off.assign(nf + 1, 0);
+    bool any_split = false;
+    for (size_t i = 0; i < nf; ++i) {
+        b->atom_off[i + 1] = b->atom_off[i] + blocks[i].n;
+        any_split = any_split || blocks[i].split;
+    }
+    const size_t n = (size_t)b->atom_off[nf];
+    b->n_atoms = (int64_t)n;
+    b->pxyz.resize(3 * n); b->kind.resize(n); b->residue.resize(n); b->bfactor32.resize(n); b->chain16.resize(n);
+    b->has_atom_id = any_split;
+    if (any_split) b->atom_id.resize(n);
+    // merge the per-file kind lists in file order (deterministic whatever the thread count)
+    KindTable global;
+    std::vector<std::vector<uint32_t>> remap(nf);
+    for (size_t f = 0; f < nf; ++f) {
+        remap[f].resize(blocks[f].kinds.size());
+        for (size_t j = 0; j < blocks[f].kinds.size(); ++j) remap[f][j] = global.lookup(blocks[f].kinds[j]);
+    }
+    b->kind_names.assign(8 * global.keys.size(), 0);
+    for (size_t j = 0; j < global.keys.size(); ++j) memcpy(&b->kind_names[8 * j], &global.keys[j], 8);
+    // pass 2: blocks -> their place in the batch columns (first touch of those pages, in parallel)
+    {
+        std::atomic<int> next(0);
+        emm_pdb_batch *bp = b;
+        run_pool([&]() {
+            for (int i; (i = next.fetch_add(1)) < n_files;) {
+                const size_t f = (size_t)i;
+                FileBlock &blk = blocks[f];
+                const size_t lo = (size_t)bp->atom_off[f], cnt = (size_t)blk.n;
+                if (cnt) {
+                    memcpy(bp->pxyz.data() + 3 * lo, blk.xyz, cnt * 3 * sizeof(double));
+                    memcpy(bp->residue.data() + lo, blk.residue, cnt * sizeof(int32_t));
+                    memcpy(bp->bfactor32.data() + lo, blk.bfactor, cnt * sizeof(float));
+                    memcpy(bp->chain16.data() + lo, blk.chain, cnt * sizeof(uint16_t));
+                    const std::vector<uint32_t> &m = remap[f];
+                    uint32_t *kd = bp->kind.data() + lo;
+                    for (size_t a = 0; a < cnt; ++a) kd[a] = m[blk.kind[a]];
+                    if (bp->has_atom_id) {
+                        int32_t *ad = bp->atom_id.data() + lo;
+                        if (blk.split) memcpy(ad, blk.atom_id.get(), cnt * sizeof(int32_t));
+                        else for (size_t a = 0; a < cnt; ++a) ad[a] = (int32_t)a;
+                    }
+                }
+                blk.release();
+            }
+        });
+    }
+}
+
 int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out)
 {
     if (!paths || !out || n_files < 0) return EMM_ERR_INVALID;
@@ -634,53 +695,76 @@ int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_thre
             else t_error = std::string(e == 1 ? "cannot open " : "cannot read ") + paths[i];
             return e == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
         }
-    b->atom_off.assign(nf + 1, 0);
-    bool any_split = false;
-    for (size_t i = 0; i < nf; ++i) {
-        b->atom_off[i + 1] = b->atom_off[i] + blocks[i].n;
-        any_split = any_split || blocks[i].split;
-    }
-    const size_t n = (size_t)b->atom_off[nf];
-    b->n_atoms = (int64_t)n;
-    b->pxyz.resize(3 * n); b->kind.resize(n); b->residue.resize(n); b->bfactor32.resize(n); b->chain16.resize(n);
-    b->has_atom_id = any_split;
-    if (any_split) b->atom_id.resize(n);
-    // merge the per-file kind lists in file order (deterministic whatever the thread count)
-    KindTable global;
-    std::vector<std::vector<uint32_t>> remap(nf);
-    for (size_t f = 0; f < nf; ++f) {
-        remap[f].resize(blocks[f].kinds.size());
-        for (size_t j = 0; j < blocks[f].kinds.size(); ++j) remap[f][j] = global.lookup(blocks[f].kinds[j]);
-    }
-    b->kind_names.assign(8 * global.keys.size(), 0);
-    for (size_t j = 0; j < global.keys.size(); ++j) memcpy(&b->kind_names[8 * j], &global.keys[j], 8);
-    // pass 2: blocks -> their place in the batch columns (first touch of those pages, in parallel)
+    finish_packed(b.get(), blocks, n_threads);
+    *out = b.release();
+    return EMM_OK;
+}
+
+int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *const *name4,
+                     const uint8_t *const *resname4, const uint8_t *const *chain2, const int32_t *const *resnum,
+                     const double *const *xyz, const double *const *bfactor, int32_t n_threads, emm_pdb_batch **out)
+{
+    if (!out || n_structures < 0 || (n_structures > 0 && (!sizes || !name4 || !resname4 || !chain2 || !resnum || !xyz || !bfactor)))
+        return EMM_ERR_INVALID;
+    *out = nullptr;
+    std::unique_ptr<emm_pdb_batch> b(new emm_pdb_batch());
+    b->n_files = n_structures;
+    b->packed = true;
+    const size_t nf = (size_t)n_structures;
+    if (n_threads < 1) n_threads = 1;
+    n_threads = std::min<int32_t>(n_threads, std::max(n_structures, 1));
+    b->n_threads = n_threads;
+    b->header_id.assign(5 * nf, 0);
+    std::vector<FileBlock> blocks(nf);
     {
         std::atomic<int> next(0);
-        emm_pdb_batch *bp = b.get();
-        run_pool([&]() {
-            for (int i; (i = next.fetch_add(1)) < n_files;) {
+        auto work = [&]() {
+            KindTable kinds;
+            std::vector<uint64_t> run_keys;
+            for (int i; (i = next.fetch_add(1)) < n_structures;) {
                 const size_t f = (size_t)i;
+                const int64_t n = sizes[f];
                 FileBlock &blk = blocks[f];
-                const size_t lo = (size_t)bp->atom_off[f], cnt = (size_t)blk.n;
-                if (cnt) {
-                    memcpy(bp->pxyz.data() + 3 * lo, blk.xyz, cnt * 3 * sizeof(double));
-                    memcpy(bp->residue.data() + lo, blk.residue, cnt * sizeof(int32_t));
-                    memcpy(bp->bfactor32.data() + lo, blk.bfactor, cnt * sizeof(float));
-                    memcpy(bp->chain16.data() + lo, blk.chain, cnt * sizeof(uint16_t));
-                    const std::vector<uint32_t> &m = remap[f];
-                    uint32_t *kd = bp->kind.data() + lo;
-                    for (size_t a = 0; a < cnt; ++a) kd[a] = m[blk.kind[a]];
-                    if (bp->has_atom_id) {
-                        int32_t *ad = bp->atom_id.data() + lo;
-                        if (blk.split) memcpy(ad, blk.atom_id.get(), cnt * sizeof(int32_t));
-                        else for (size_t a = 0; a < cnt; ++a) ad[a] = (int32_t)a;
-                    }
+                blk.allocate(n);
+                kinds.clear();
+                run_keys.clear();
+                uint64_t prev_kind = ~0ull, prev_res = ~0ull;
+                uint32_t prev_kind_idx = 0;
+                int32_t run = -1;
+                const uint8_t *nm = name4[f], *rn = resname4[f], *ch = chain2[f];
+                for (int64_t a = 0; a < n; ++a) {
+                    uint32_t name, res;
+                    uint16_t chain;
+                    memcpy(&name, nm + 4 * a, 4);
+                    memcpy(&res, rn + 4 * a, 4);
+                    memcpy(&chain, ch + 2 * a, 2);
+                    const uint64_t kkey = (uint64_t)res | ((uint64_t)name << 32);
+                    if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
+                    blk.kind[a] = prev_kind_idx;
+                    blk.chain[a] = chain;
+                    const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum[f][a];
+                    if (rkey != prev_res || run < 0) { prev_res = rkey; ++run; run_keys.push_back(rkey); }
+                    blk.residue[a] = run;
+                    blk.bfactor[a] = (float)bfactor[f][a];
                 }
-                blk.release();
+                if (n) memcpy(blk.xyz, xyz[f], (size_t)n * 3 * sizeof(double));
+                blk.kinds = kinds.keys;
+                std::vector<uint64_t> sorted(run_keys);
+                std::sort(sorted.begin(), sorted.end());
+                blk.split = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+                if (blk.split) {
+                    blk.atom_id.reset(new int32_t[(size_t)std::max<int64_t>(n, 1)]);
+                    const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
+                    regroup_file(c, 0, n, run_keys, blk.atom_id.get());
+                }
             }
-        });
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
     }
+    finish_packed(b.get(), blocks, n_threads);
     *out = b.release();
     return EMM_OK;
 }

@@ -14,7 +14,7 @@ import numpy as np
 
 from .engine import PackedBatch
 from .library import CompiledLibrary
-from .structures import Molecule, _NativeBatch, _native_lib, _native_view
+from .structures import Molecule, _Columns, _NativeBatch, _native_lib, _native_view
 
 __all__ = ["residue_ordinals", "pack_molecules", "pack_files", "chain_codes"]
 
@@ -61,6 +61,9 @@ def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
     kinds (residue name, atom name) are compared as packed integers and classified once per
     distinct kind (``library.class_of``); residue ordinals come from one run-length pass.  A block
     holding a molecule with a split residue goes through the per-molecule path, which reorders."""
+    if molecules and all(isinstance(m._cols, _Columns) and {"name", "residue_name", "chain_id"} <= set(m._cols.raw)
+                         for m in molecules):
+        return _pack_molecules_native(molecules, library, with_chain)
     sizes = np.asarray([len(m) for m in molecules], dtype=np.int64)
     atom_off = np.zeros(len(molecules) + 1, dtype=np.int64)
     np.cumsum(sizes, out=atom_off[1:])
@@ -116,6 +119,35 @@ def pack_molecules(molecules: Sequence[Molecule], library: CompiledLibrary,
     return PackedBatch(atom_off, xyz, klass, residue, bfactor, chain if with_chain else None, atom_id)
 
 
+def _pack_molecules_native(molecules: Sequence[Molecule], library: CompiledLibrary, with_chain: bool) -> PackedBatch:
+    """Molecules that still hold their raw name bytes (native reader) are packed by
+    ``emm_pack_columns`` on the native thread pool: same result as the NumPy path below."""
+    lib = _native_lib()
+    n = len(molecules)
+    keep = []                                  # contiguous arrays the pointers refer to, kept alive for the call
+
+    def pointers(get, dtype):
+        out = (ctypes.c_void_p * n)()
+        for i, m in enumerate(molecules):
+            arr = np.ascontiguousarray(get(m), dtype=dtype)
+            keep.append(arr)
+            out[i] = arr.ctypes.data
+        return out
+
+    sizes = np.asarray([len(m) for m in molecules], dtype=np.int64)
+    handle = ctypes.c_void_p()
+    n_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rc = lib.emm_pack_columns(
+        ctypes.c_int32(n), sizes.ctypes.data_as(ctypes.c_void_p),
+        pointers(lambda m: m._cols.raw["name"], np.uint8), pointers(lambda m: m._cols.raw["residue_name"], np.uint8),
+        pointers(lambda m: m._cols.raw["chain_id"], np.uint8), pointers(lambda m: m.column("residue_number"), np.int32),
+        pointers(lambda m: m.xyz, np.float64), pointers(lambda m: m.column("temperature_factor"), np.float64),
+        ctypes.c_int32(n_threads), ctypes.byref(handle))
+    if rc != 0:
+        raise RuntimeError(f"emm_pack_columns failed ({rc})")
+    return _packed_from_handle(lib, handle, library, with_chain)[0]
+
+
 def _pack_block_per_molecule(mols, b0, atom_off, sizes, library, xyz, klass, residue, bfactor, chain, atom_id, total):
     """Per-molecule packing (handles split residues by a stable regrouping + ``atom_id``)."""
     for i, m in enumerate(mols, start=b0):
@@ -169,6 +201,12 @@ def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrar
     rc = lib.emm_pdb_pack_files(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.byref(handle))
     if rc != 0:
         raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
+    return _packed_from_handle(lib, handle, library, with_chain)
+
+
+def _packed_from_handle(lib, handle, library: CompiledLibrary, with_chain: bool):
+    """``(PackedBatch, header ids)`` from a native packed batch: classify its atom kinds through
+    ``library`` and wrap the columns without copying them."""
     owner = _NativeBatch(lib, handle)       # the big columns stay views of the native buffers
     c = _PdbPacked()
     if lib.emm_pdb_batch_packed(handle, ctypes.byref(c)) != 0:

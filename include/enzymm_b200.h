@@ -276,6 +276,12 @@ typedef struct emm_pdb_packed {
 } emm_pdb_packed;
 int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
 int emm_pdb_batch_packed(const emm_pdb_batch *batch, emm_pdb_packed *out);
+/* The same packing from per-structure columns that are already in memory (what Matcher.run has after
+ * Molecule.load, jess_run.py:538-548): name4 / resname4 / chain2 are blank-stripped NUL-padded fixed
+ * width bytes ([n][4], [n][4], [n][2]) per structure.  Result: as emm_pdb_pack_files. */
+int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *const *name4,
+                     const uint8_t *const *resname4, const uint8_t *const *chain2, const int32_t *const *resnum,
+                     const double *const *xyz, const double *const *bfactor, int32_t n_threads, emm_pdb_batch **out);
 /* klass[a] = class_of_kind[kind[a]] for every atom, on the batch's thread pool */
 int emm_pdb_batch_classify(emm_pdb_batch *batch, const uint16_t *class_of_kind, int32_t n_kinds);
 

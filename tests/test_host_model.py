@@ -711,3 +711,27 @@ def test_ingest_paths_agree_on_unruly_files(tmp_path, active_templates):
     _assert_batches_equal(native, through_python)
     assert ids == [m.id for m in python_mols] == ["1ABC"] * len(paths)
     assert [m == n for m, n in zip(load_many(paths), python_mols)] == [True] * len(paths)
+
+
+def test_native_and_numpy_pack_molecules_agree(tmp_path, active_templates, mol_1amy):
+    """``pack_molecules`` takes the native route for molecules that still hold raw name bytes and the
+    NumPy route otherwise: same batch, including masked molecules, an empty one and a split residue."""
+    from enzymm_b200.structures import _COLUMNS, load_many
+    lib = CompiledLibrary(active_templates[::50], 2.0, 1.5, 1.5)
+    lines = [l for l in (GOLDEN / "1AMY.pdb").read_text().splitlines() if l.startswith(("ATOM", "HETATM"))]
+    first = [l for l in lines if int(l[22:26]) == 1]
+    split = tmp_path / "split.pdb"
+    split.write_text("\n".join(first[:3] + [l for l in lines if 1 < int(l[22:26]) <= 3] + first[3:] + lines[40:120]) + "\n")
+    empty = tmp_path / "empty.pdb"
+    empty.write_text("END\n")
+    native_mols = load_many([GOLDEN / "1AMY.pdb", split, empty, GOLDEN / "AF-P0DUB6-F1-model_v4.pdb"])
+    native_mols.append(native_mols[3].conserved(80))
+    native_mols.append(native_mols[0][10:500])
+    assert all(m._cols.raw for m in native_mols)
+    plain = [Molecule._from_columns({k: m.column(k) for k, _ in _COLUMNS}, m.xyz, m.id) for m in native_mols]
+    assert not any(m._cols.raw for m in plain) and plain == native_mols
+    for with_chain in (True, False):
+        _assert_batches_equal(pack_molecules(native_mols, lib, with_chain=with_chain),
+                              pack_molecules(plain, lib, with_chain=with_chain))
+    mixed = [native_mols[0], plain[1], native_mols[3]]           # one plain molecule: the NumPy route for all
+    _assert_batches_equal(pack_molecules(mixed, lib), pack_molecules([plain[0], plain[1], plain[3]], lib))
