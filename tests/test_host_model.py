@@ -735,3 +735,26 @@ def test_native_and_numpy_pack_molecules_agree(tmp_path, active_templates, mol_1
                               pack_molecules(plain, lib, with_chain=with_chain))
     mixed = [native_mols[0], plain[1], native_mols[3]]           # one plain molecule: the NumPy route for all
     _assert_batches_equal(pack_molecules(mixed, lib), pack_molecules([plain[0], plain[1], plain[3]], lib))
+
+
+def test_classify_keys_including_slot_collisions(active_templates):
+    """The vectorised kind -> class lookup equals ``class_of`` kind by kind, also when the hash table
+    is so small that most kinds lose their slot and are answered from the overflow map."""
+    from enzymm_b200.chem import RESIDUE_ATOMS
+    kinds = [(res, name) for res, names in RESIDUE_ATOMS.items() for name in names] + [("HOH", "O"), ("ZN", "ZN"), ("XYZ", "Q1")]
+
+    def key_of(res, name):
+        pack = lambda text: int.from_bytes(text.encode().ljust(4, bytes(1)), "little")
+        return (pack(res) << 32) | pack(name)
+
+    rng = np.random.default_rng(3)
+    picks = rng.integers(0, len(kinds), 5000)
+    keys = np.asarray([key_of(*kinds[i]) for i in picks], dtype=np.uint64)
+    for bits in (16, 3):
+        lib = CompiledLibrary(active_templates[::80], 2.0, 1.5, 1.5)
+        lib._HASH_BITS = bits
+        want = np.asarray([lib.class_of(*kinds[i]) for i in picks], dtype=np.uint16)
+        for _ in range(2):                       # second call: everything answered from the table / overflow map
+            assert np.array_equal(lib.classify_keys(keys), want)
+        if bits == 3:
+            assert len(lib._kind_table[2]) > 0   # the overflow map really was used
