@@ -758,3 +758,30 @@ def test_classify_keys_including_slot_collisions(active_templates):
             assert np.array_equal(lib.classify_keys(keys), want)
         if bits == 3:
             assert len(lib._kind_table[2]) > 0   # the overflow map really was used
+
+
+def test_residue_ordinals_against_a_plain_python_reference():
+    """Residues are numbered by first appearance of (chain, residue number); split residues are
+    regrouped by a stable sort.  Checked against a dictionary-based restatement on random inputs."""
+    rng = np.random.default_rng(11)
+    for trial in range(200):
+        n = int(rng.integers(1, 60))
+        chain = rng.integers(0, 3, n).astype(np.uint16)
+        resnum = rng.integers(-3, 6, n).astype(np.int32)
+        if trial % 2:                                   # mostly contiguous residues, as in real files
+            order = np.lexsort((resnum, chain))
+            chain, resnum = chain[order], resnum[order]
+        first_seen = {}
+        want = []
+        for c, r in zip(chain.tolist(), resnum.tolist()):
+            want.append(first_seen.setdefault((c, r), len(first_seen)))
+        contiguous = all(want[i] >= want[i - 1] for i in range(1, n))
+        ordinal, order = residue_ordinals(chain, resnum)
+        if contiguous:
+            assert order is None and ordinal.tolist() == want
+        else:
+            assert order is not None and sorted(order.tolist()) == list(range(n))
+            assert ordinal.tolist() == sorted(want)                         # grouped, first-appearance numbering
+            assert [want[i] for i in order.tolist()] == ordinal.tolist()    # the permutation realises it
+            for a, b in zip(order.tolist(), order.tolist()[1:]):            # stable inside a residue
+                assert want[a] != want[b] or a < b
