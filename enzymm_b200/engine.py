@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 from pathlib import Path
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 

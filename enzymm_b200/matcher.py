@@ -24,7 +24,6 @@ from __future__ import annotations
 import collections
 import csv
 import io
-import itertools
 import math
 import os
 import sys
@@ -32,7 +31,7 @@ import warnings
 from dataclasses import dataclass, field
 from functools import cached_property
 from pathlib import Path
-from typing import ClassVar, Dict, IO, Iterable, List, Optional, Sequence, Tuple
+from typing import ClassVar, Dict, IO, List, Optional, Sequence, Tuple
 
 import numpy as np
 

@@ -17,8 +17,7 @@ from typing import Iterator, List, Optional, Sequence
 import numpy as np
 
 from . import __version__  # noqa: F401  (pyjess.__version__ is printed at jess_run.py:659)
-from .engine import (Engine, HIT_BORDERLINE, HIT_NO_MODEL, HIT_ORIENTED, HIT_OVERFLOW, HIT_PASS,
-                     PackedBatch)
+from .engine import Engine, HIT_BORDERLINE, HIT_NO_MODEL, HIT_OVERFLOW, HIT_PASS
 from .library import CompiledLibrary
 from .packing import pack_molecules
 from .structures import Atom, Molecule

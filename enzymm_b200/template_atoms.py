@@ -11,7 +11,7 @@ residue one-letter codes, 61-66 distance weight.
 """
 from __future__ import annotations
 
-from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+from typing import Iterable, Iterator, Optional, Sequence, Tuple
 
 __all__ = ["TemplateAtom", "JessTemplate", "ONE_TO_THREE"]
 
