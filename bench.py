@@ -142,16 +142,35 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def kernel_stamp() -> str:
+    """SHA-256 over the sources and build flags of the search kernel; ``profiles/roofline_traffic.json``
+    carries the stamp of the build its ncu counters were captured from (``tools/roofline_stamp.py``)."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = ROOT / "enzymm_b200" / "csrc"
+    for name in ("emm_search.cu", "emm_device.cuh", "Makefile"):
+        h.update((csrc / name).read_bytes())
+    return h.hexdigest()
+
+
+def committed_counters():
+    """ncu counters of the search kernel from the committed ``--set full`` capture, or (None, why)
+    when the file is missing or was captured from another build of the kernel (stale)."""
+    path = ROOT / "profiles" / "roofline_traffic.json"
+    try:
+        data = json.loads(path.read_text())
+    except Exception:
+        return None, "profiles/roofline_traffic.json missing"
+    if data.get("kernel_sha256") != kernel_stamp():
+        return None, "stale: profiles/roofline_traffic.json was captured from another build of emm_search.cu"
+    return data, None
+
+
 def committed_traffic_bytes(n_structures: int):
     """dram__bytes_read+write of the search kernel per launch, from the committed ncu --set full
     capture (taken at a smaller batch; scaled per structure to this launch's batch)."""
-    path = ROOT / "profiles" / "roofline_traffic.json"
-    if path.exists():
-        try:
-            return int(json.loads(path.read_text())["search_kernel_dram_bytes_per_structure"] * n_structures)
-        except Exception:
-            return None
-    return None
+    data, _ = committed_counters()
+    return None if data is None else int(data["search_kernel_dram_bytes_per_structure"] * n_structures)
 
 
 def committed_issue_figure(pairs_per_launch: float, kernel_ms: float, sm_mhz):
@@ -159,16 +178,19 @@ def committed_issue_figure(pairs_per_launch: float, kernel_ms: float, sm_mhz):
     instructions per (template, structure) pair from the committed ncu capture x the pairs of this
     launch / the kernel time measured here, against one warp instruction per SM sub-partition per
     clock (SMs x 4 x SM clock).  Extra information next to the HBM roofline the contract asks for."""
-    path = ROOT / "profiles" / "roofline_traffic.json"
+    data, why = committed_counters()
+    if data is None:
+        return {"bound": "issue", "achieved": None, "frac": None, "stale": True, "note": why}
     try:
-        per_pair = float(json.loads(path.read_text())["search_kernel_warp_instructions_per_pair"])
+        per_pair = float(data["search_kernel_warp_instructions_per_pair"])
         import torch
         sms = torch.cuda.get_device_properties(0).multi_processor_count
         mhz = float(sm_mhz or 1965.0)
         achieved = per_pair * pairs_per_launch / (kernel_ms / 1000.0) / 1e9
         peak = sms * 4 * mhz * 1e6 / 1e9
         return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
-                "warp_inst_per_pair": per_pair, "source": "profiles/roofline_traffic.json (ncu smsp__inst_executed.sum)"}
+                "warp_inst_per_pair": per_pair, "stale": False,
+                "source": "profiles/roofline_traffic.json (ncu smsp__inst_executed.sum, same kernel build)"}
     except Exception:
         return None
 
@@ -184,7 +206,42 @@ def cpu_oracle_rate(workload, n_structures: int, threads: int):
     raw = oracle.query_raw(mols, ot, 2.0, dist, dist, max_candidates=10000, ignore_chain=True, threads=threads)
     dt = time.perf_counter() - t0
     cpu_oracle_rate.evals_per_structure = float(raw["dist_evals"].sum()) / max(n_structures, 1)
+    cpu_oracle_rate.raw = raw
+    cpu_oracle_rate.molecules = mols
     return n_structures / dt, dt, int(raw["found"].sum())
+
+
+def parity_against_oracle(hits, raw, molecules, templates):
+    """Outside the timed region: the GPU hits of the structures the CPU baseline just searched,
+    compared with the oracle's -- hit set, matched atoms in template order, RMSD bit for bit,
+    complete-assignment counts, orientation (1e-4) and the filter verdict of every hit."""
+    import oracle
+    from enzymm_b200.engine import HIT_PASS
+    n = raw.shape[0]
+    mine = hits[hits["structure"] < n]
+    want = {(int(s), int(t)) for s, t in zip(*np.nonzero(raw["found"]))}
+    got = {}
+    for h in mine:
+        got[(int(h["structure"]), int(h["template_index"]))] = h
+    mismatches = len(want ^ set(got))
+    worst_orient = 0.0
+    for key in want & set(got):
+        s, t = key
+        h, r = got[key], raw[s, t]
+        m = int(h["n_atoms"])
+        ok = (m == len(templates[t]) and h["atoms"][:m].tolist() == r["atoms"][:m].tolist()
+              and float(h["rmsd"]) == float(r["rmsd"]) and int(h["n_complete"]) == int(r["n_complete"]))
+        if ok:
+            moved = (molecules[s].xyz[r["atoms"][:m]] - r["qbar"]) @ r["rot"].reshape(3, 3).T + r["tbar"]
+            orient = oracle.orientation(templates[t], moved)
+            worst_orient = max(worst_orient, abs(orient - float(h["orientation"])))
+            dist = DEFAULT_DIST[min(templates[t].effective_size, 8)]
+            verdict = oracle.predicted_correct(templates[t].effective_size, dist, float(r["rmsd"]), orient)
+            ok = abs(orient - float(h["orientation"])) <= 1e-4 and verdict == bool(int(h["flags"]) & HIT_PASS)
+        mismatches += 0 if ok else 1
+    return {"structures": int(n), "pairs": int(n) * len(templates), "hits_oracle": len(want), "hits_gpu": len(got),
+            "mismatches": int(mismatches), "max_orientation_diff": worst_orient,
+            "checked": "hit set, atoms, rmsd ==, n_complete ==, orientation <= 1e-4, filter verdict"}
 
 
 def host_threads() -> int:
@@ -398,10 +455,14 @@ def run_b200(args, rank, local_rank, world):
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"first {sample} structures of the same batch x 6780 templates, {dt:.1f} s "
                                           "(CPU restatement of Jess, not PyJess)"}
+        # the oracle's hits of that sample vs the GPU's hits of the same structures
+        line["parity"] = parity_against_oracle(hits, cpu_oracle_rate.raw, cpu_oracle_rate.molecules, templates)
     print(json.dumps(line), flush=True)
     engine.close()
     if world > 1:
         dist.destroy_process_group()
+    if line.get("parity", {}).get("mismatches"):
+        sys.exit(f"PARITY FAILURE: {line['parity']}")
 
 
 def main():

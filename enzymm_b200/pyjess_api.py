@@ -11,6 +11,7 @@ There is no CPU path: constructing the engine without the CUDA library or a GPU 
 from __future__ import annotations
 
 import math
+import threading
 from collections import OrderedDict
 from typing import Iterator, List, Optional, Sequence
 
@@ -129,25 +130,77 @@ class Query:
         return hit
 
 
-_ENGINE_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
-_ENGINE_CACHE_SIZE = 4
+class _EngineEntry:
+    """One cached engine: its own compiled library, device tables, session and lock."""
+
+    __slots__ = ("engine", "templates", "lock", "users", "evicted")
+
+    def __init__(self, engine: Engine, templates: Sequence[Template]):
+        self.engine = engine
+        self.templates = list(templates)     # keeps the templates alive so their ids stay unique
+        self.lock = threading.Lock()         # one query at a time per engine (its session is not re-entrant)
+        self.users = 0
+        self.evicted = False
 
 
-def _engine_for(templates: Sequence[Template], device: int) -> Engine:
-    """EnzyMM rebuilds ``Jess(templates)`` on every call (jess_run.py:800); compiling and
-    uploading a library per call would dominate, so engines are cached by template identity."""
-    key = (device, tuple(id(t) for t in templates))
-    entry = _ENGINE_CACHE.get(key)
-    if entry is not None:
-        _ENGINE_CACHE.move_to_end(key)
-        return entry[0]
-    compiled = CompiledLibrary(templates, 2.0, 2.0, 2.0)
-    engine = Engine(compiled, device)
-    _ENGINE_CACHE[key] = (engine, list(templates))   # keep templates alive so ids stay unique
-    while len(_ENGINE_CACHE) > _ENGINE_CACHE_SIZE:
-        _, (old, _) = _ENGINE_CACHE.popitem(last=False)
-        old.close()
-    return engine
+_ENGINE_CACHE: "OrderedDict[tuple, _EngineEntry]" = OrderedDict()
+_ENGINE_CACHE_SIZE = 16
+_CACHE_LOCK = threading.Lock()
+
+
+def _acquire_engine(templates: Sequence[Template], device: int, rmsd_threshold: float, distance_cutoff: float,
+                    max_dynamic_distance: float) -> _EngineEntry:
+    """EnzyMM rebuilds ``Jess(templates)`` on every call (jess_run.py:800) and calls ``query`` from a
+    ``ThreadPool`` (jess_run.py:919-921, 976-978); compiling and uploading a library per call would
+    dominate, so engines are cached -- keyed by template identity AND the threshold triple, so a
+    cached engine's device tables are never rewritten by a query and concurrent calls with other
+    thresholds (other size groups) get their own engine."""
+    key = (device, tuple(id(t) for t in templates), float(rmsd_threshold), str(distance_cutoff),
+           float(max_dynamic_distance))
+    with _CACHE_LOCK:
+        entry = _ENGINE_CACHE.get(key)
+        if entry is not None:
+            _ENGINE_CACHE.move_to_end(key)
+        else:
+            compiled = CompiledLibrary(templates, rmsd_threshold, distance_cutoff, max_dynamic_distance)
+            entry = _ENGINE_CACHE[key] = _EngineEntry(Engine(compiled, device), templates)
+            while len(_ENGINE_CACHE) > _ENGINE_CACHE_SIZE:
+                _, old = _ENGINE_CACHE.popitem(last=False)
+                old.evicted = True
+                if old.users == 0:
+                    old.engine.close()
+        entry.users += 1
+        return entry
+
+
+def _release_engine(entry: _EngineEntry) -> None:
+    with _CACHE_LOCK:
+        entry.users -= 1
+        if entry.evicted and entry.users == 0:    # evicted while in use: the last user closes it
+            entry.engine.close()
+
+
+def clear_engine_cache() -> None:
+    """Release every cached engine (device libraries and sessions) that is not in use."""
+    with _CACHE_LOCK:
+        while _ENGINE_CACHE:
+            _, old = _ENGINE_CACHE.popitem(last=False)
+            old.evicted = True
+            if old.users == 0:
+                old.engine.close()
+
+
+def _device_query(templates: Sequence[Template], device: int, molecule: Molecule, rmsd_threshold: float,
+                  distance_cutoff: float, max_dynamic_distance: float, max_candidates: int,
+                  ignore_chain: bool) -> np.ndarray:
+    """Hit records of one molecule against ``templates`` (re-entrant: safe to call from many threads)."""
+    entry = _acquire_engine(templates, device, rmsd_threshold, distance_cutoff, max_dynamic_distance)
+    try:
+        with entry.lock:
+            batch = pack_molecules([molecule], entry.engine.compiled)
+            return entry.engine.query(batch, max_candidates=max_candidates, ignore_chain=ignore_chain)
+    finally:
+        _release_engine(entry)
 
 
 class Jess:
@@ -178,13 +231,10 @@ class Jess:
                 "enzymm_b200 implements best_match=True only (the mode EnzyMM uses, jess_run.py:809)")
         hits: List[Hit] = []
         if self._templates and len(molecule):
-            engine = _engine_for(self._templates, self._device)
-            engine.compiled.set_thresholds(rmsd_threshold, distance_cutoff, max_dynamic_distance)
-            engine.device_library.push_thresholds()
-            batch = pack_molecules([molecule], engine.compiled)
             # pyjess's own default when max_candidates is None is 1000 (comment at jess_run.py:796)
             cap = 1000 if max_candidates is None else int(max_candidates)
-            records = engine.query(batch, max_candidates=cap, ignore_chain=ignore_chain)
+            records = _device_query(self._templates, self._device, molecule, rmsd_threshold, distance_cutoff,
+                                    max_dynamic_distance, cap, ignore_chain)
             hits = [Hit(r, self._templates[int(r["template_index"])], molecule) for r in records]
         return Query(hits, molecule, rmsd_threshold, distance_cutoff, max_dynamic_distance,
                      max_candidates, best_match, ignore_chain)
