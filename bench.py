@@ -449,7 +449,9 @@ def run_b200(args, rank, local_rank, world):
         # thread-instructions / (SMs x 4 schedulers x 32 lanes x SM clock)
         evals = getattr(cpu_oracle_rate, "evals_per_structure", None)
         if evals and line.get("roofline_issue"):
-            lanes_per_s = line["roofline_issue"]["peak"] * 1e9 * 32
+            # the peak needs no ncu capture: SMs x 4 schedulers x SM clock (x 32 lanes)
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            lanes_per_s = sms * 4 * float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 * 32
             line["roofline_issue"]["canonical_evals_per_structure"] = evals
             line["roofline_issue"]["canonical_frac"] = evals * 9.0 * value / lanes_per_s
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",

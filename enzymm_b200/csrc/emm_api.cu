@@ -96,6 +96,7 @@ struct emm_session {
     int *d_any = nullptr, *d_pass = nullptr;
     unsigned char *d_skip = nullptr;
     int *d_ids = nullptr;          // structures that can be staged first, then the ones too large for shared memory
+    int32_t *d_status = nullptr;   // per structure: BlobHeader.status written by the prepare kernel
     unsigned long long *d_stats = nullptr;
     // current batch
     int32_t n_structures = 0;
@@ -216,6 +217,7 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
     if (desc->n_templates <= 0 || desc->n_atoms <= 0) return fail(EMM_ERR_INVALID, "empty template library");
     if (desc->n_leader <= 0 || desc->n_leader > 1023) return fail(EMM_ERR_INVALID, "n_leader must be in 1..1023");
     if (desc->class_words <= 0 || desc->n_ttype <= 0) return fail(EMM_ERR_INVALID, "empty compat matrix");
+    if (desc->class_words > (1 << kClassBits) / 32) return fail(EMM_ERR_INVALID, "more than 1024 typing classes");
 
     // validate the search plans on the host: the kernels trust them
     int max_m = 0;
@@ -262,7 +264,7 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
     d.n_atoms = desc->n_atoms;
     d.n_ttype = desc->n_ttype;
     d.class_words = desc->class_words;
-    d.class_words_cap = std::max(desc->class_words, 32);   // room for 1024 classes without re-allocation
+    d.class_words_cap = (1 << kClassBits) / 32;            // room for all 1024 classes without re-allocation
     d.n_leader = desc->n_leader;
     d.max_tpl_atoms = max_m;
     d.n_lr = desc->n_lr;
@@ -446,6 +448,7 @@ int emm_session_create(emm_library *lib, int64_t max_atoms, int32_t max_structur
     ALLOC(s->d_pass, 4 * (size_t)max_structures);
     ALLOC(s->d_skip, (size_t)max_structures);
     ALLOC(s->d_ids, 4 * (size_t)max_structures);
+    ALLOC(s->d_status, 4 * (size_t)max_structures);
     ALLOC(s->d_stats, 8 * 136);
     s->blob_capacity = 64 * max_atoms + (1024 + 4 * (int64_t)lib->d.n_leader) * max_structures;   // grown on demand at upload
     ALLOC(s->d_blob, s->blob_capacity);
@@ -454,6 +457,7 @@ int emm_session_create(emm_library *lib, int64_t max_atoms, int32_t max_structur
     cudaMemset(s->d_stats, 0, 8 * 136);
     cudaMemset(s->d_any, 0, 4 * (size_t)max_structures);
     cudaMemset(s->d_pass, 0, 4 * (size_t)max_structures);
+    cudaMemset(s->d_status, 0, 4 * (size_t)max_structures);
     *out = s;
     return EMM_OK;
 }
@@ -464,7 +468,7 @@ void emm_session_destroy(emm_session *s)
     cudaSetDevice(s->lib->device);
     void *ptrs[] = {s->d_atom_off, s->d_xyz, s->d_klass, s->d_residue, s->d_bfactor, s->d_chain, s->d_atom_id,
                     s->d_blob, s->d_blob_off, s->d_hits, s->d_hit_count, s->d_work, s->d_any, s->d_pass,
-                    s->d_skip, s->d_stats, s->d_ids};
+                    s->d_skip, s->d_stats, s->d_ids, s->d_status};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : s->ev_prepare) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : s->ev_search) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -520,10 +524,11 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     if (bad_input.load() == 2) return fail(EMM_ERR_INVALID, "typing class out of range");
     for (int i = 0; i < n; ++i) {
         const int64_t a0 = b->atom_off[i], a1 = b->atom_off[i + 1];
-        const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries_of[(size_t)i]);
+        int64_t staged = 0;
+        const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries_of[(size_t)i], &staged);
+        if (bytes >= (int64_t)1 << 31) return fail(EMM_ERR_INPUT, "a structure is too large: its blob would exceed 2 GiB");
         s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + bytes;
-        const int64_t staged = bytes - align16(4 * (a1 - a0)) - align16(2 * (int64_t)(kMaxCells + 1)) - 2 * align16(2 * (a1 - a0));
-        if (((staged + 1023) & ~int64_t(1023)) <= stage_cap) {
+        if (!is_wide(a1 - a0) && ((staged + 1023) & ~int64_t(1023)) <= stage_cap) {
             max_staged = std::max(max_staged, staged);
             s->h_ids.push_back(i);
         } else {
@@ -598,6 +603,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     B.atom_id = s->has_atom_id ? s->d_atom_id : nullptr;
     B.blob = s->d_blob;
     B.blob_off = s->d_blob_off;
+    B.status = s->d_status;
 
     const float cutoff = q->conservation_cutoff > 0.f ? q->conservation_cutoff : 0.f;
     if (cutoff > 0.f && !s->has_bfactor) return fail(EMM_ERR_INVALID, "conservation_cutoff needs the bfactor column");
@@ -757,8 +763,21 @@ int emm_session_download(emm_session *s, emm_hit *hits, int64_t capacity, int64_
             for (size_t i = 0; i < (size_t)count; ++i) hits[i] = tmp[keys[i].second];
         }
     }
+    // Loud, but not fatal for the rest of the batch: the hits of every other structure were delivered
+    // above; emm_session_structure_status names the offenders.
     if (bad) return fail(EMM_ERR_INPUT, "a structure violates the input contract (residue ordinals must be "
-                                        "non-decreasing and at most 65535 atoms may survive masking)");
+                                        "non-decreasing, at most 4194303 kept atoms, at most 1023 kept atoms per "
+                                        "residue): its search was skipped; see emm_session_structure_status");
+    return EMM_OK;
+}
+
+int emm_session_structure_status(emm_session *s, int32_t *status, int32_t capacity)
+{
+    if (!s || !status || capacity < s->n_structures) return fail(EMM_ERR_INVALID, "status buffer too small");
+    CUDA_TRY(cudaSetDevice(s->lib->device));
+    if (!s->prepared) return fail(EMM_ERR_INVALID, "no prepared batch: call emm_session_run first");
+    if (s->n_structures > 0)
+        CUDA_TRY(cudaMemcpy(status, s->d_status, 4 * (size_t)s->n_structures, cudaMemcpyDeviceToHost));
     return EMM_OK;
 }
 

@@ -84,29 +84,45 @@ struct DevBatch {
     const int32_t *atom_id;  // may be null
     unsigned char *blob;     // all structure blobs
     const int64_t *blob_off; // [n_structures+1]
+    int32_t *status;         // [n_structures] BlobHeader.status of every structure, written by prepare
 };
 
 constexpr int kMaxCells = 4096;        // uniform-grid cells per structure (cell edge grows to fit)
 constexpr float kMinCell = 6.0f;       // cell edge in Angstrom for ordinary structures
+
+// Atom ids.  A queue entry of the search packs (flags, parent slot, atom) into 32 bits with 22 bits
+// for the atom, and an atom record packs (residue, typing class) into 32 bits with 22 bits for the
+// residue and 10 for the class, so a structure may keep up to 4 194 303 atoms in as many residues
+// (the largest PDB / mmCIF assemblies are well below that).  Index arrays inside the blob (residue
+// starts, leader lists, cell list) are 16-bit for structures of at most 65 535 input atoms -- every
+// structure that can be staged into shared memory -- and 32-bit ("wide") above.
+constexpr int kAtomBits = 22;
+constexpr uint32_t kAtomMask = (1u << kAtomBits) - 1u;
+constexpr int kClassBits = 10;                         // typing classes per library: at most 1024
+constexpr uint32_t kClassMask = (1u << kClassBits) - 1u;
+constexpr int kMaxResidueAtoms = 1023;                 // kept atoms of one residue (10-bit span length)
+constexpr int64_t kNarrowAtoms = 65535;
+__host__ __device__ constexpr bool is_wide(int64_t n_input_atoms) { return n_input_atoms > kNarrowAtoms; }
 
 // Blob header (128 bytes).  All off_* are byte offsets from the blob base, 16-byte aligned.
 struct BlobHeader {
     int32_t n_kept;        // atoms kept (mask + class != 0), local ids 0..n_kept-1 in input order
     int32_t n_res;         // residues holding at least one kept atom
     int32_t res_shift;     // log2 of res_stride, res_stride = pow2 >= largest residue
-    int32_t status;        // 0 ok, 1 residue order violated, 2 too many atoms for 16-bit ids
+    int32_t status;        // 0 ok, 1 residue order violated, 2 too many atoms kept, 3 residue too large
     float eps;             // FP32 guard band (Angstrom) for this structure
     int32_t staged_bytes;  // prefix of the blob the search kernel stages into shared memory
-    int32_t off_atom;      // float4[n_kept] atom records: centred x, y, z; w = bits (res_of << 16 | klass)
-    int32_t reserved[4];
-    int32_t off_resstart;  // uint16 res_start[n_res+1]
+    int32_t off_atom;      // float4[n_kept] atom records: centred x, y, z; w = bits (res_of << 10 | klass)
+    int32_t wide;          // 1: res_start / lead / cell arrays hold 32-bit entries, 0: 16-bit
+    int32_t reserved[3];
+    int32_t off_resstart;  // idx res_start[n_res+1]
     int32_t off_leadoff;   // uint32 lead_off[n_leader+1]
-    int32_t off_lead;      // uint16 lead[...]
+    int32_t off_lead;      // idx lead[...]
     int32_t off_orig;      // int32 orig[n_kept]: position of the atom inside its structure (NOT staged)
     // uniform grid over the kept atoms (cell list): cell c = (iz*ny + iy)*nx + ix holds
     // cell_atoms[cell_start[c] .. cell_start[c+1]) in ascending atom order
-    int32_t off_cellstart; // uint16 cell_start[nx*ny*nz + 1]
-    int32_t off_cellatoms; // uint16 cell_atoms[n_kept]
+    int32_t off_cellstart; // idx cell_start[nx*ny*nz + 1]
+    int32_t off_cellatoms; // idx cell_atoms[n_kept]
     int32_t nx, ny, nz;
     float cell;            // cell edge
     float ox, oy, oz;      // grid origin in centred coordinates
@@ -147,15 +163,18 @@ struct SearchOut {
 inline __host__ __device__ int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
 
 // Size of a structure blob for n input atoms whose leader lists hold lead_entries entries in
-// total (the host computes this exactly at upload, so blobs are laid out without a size pass).
-inline __host__ __device__ int64_t blob_bytes(int64_t n, int n_leader, int64_t lead_entries)
+// total (the host computes this exactly at upload, so blobs are laid out without a size pass);
+// *staged_bound = upper bound of the prefix the search kernel stages (header .. leader lists).
+inline __host__ __device__ int64_t blob_bytes(int64_t n, int n_leader, int64_t lead_entries, int64_t *staged_bound = nullptr)
 {
+    const int64_t ib = is_wide(n) ? 4 : 2;   // bytes per index entry
     int64_t b = sizeof(BlobHeader);
     b += 16 * n;                             // atom records (x, y, z, res_of | klass)
-    b += align16(2 * (n + 1));               // res_start
+    b += align16(ib * (n + 1));              // res_start
     b += align16(4 * (int64_t)(n_leader + 1));
-    b += align16(2 * lead_entries);
-    b += align16(2 * (int64_t)(kMaxCells + 1)) + align16(2 * n);   // cell_start, cell_atoms
+    b += align16(ib * lead_entries);
+    if (staged_bound) *staged_bound = b;
+    b += align16(ib * (int64_t)(kMaxCells + 1)) + align16(ib * n);   // cell_start, cell_atoms
     b += align16(2 * n);                     // compact klass copy (prepare-kernel scratch, not staged)
     b += align16(4 * n);                     // orig
     return b;

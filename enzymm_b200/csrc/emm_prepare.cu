@@ -39,6 +39,18 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int *warp_tot, in
     return before + warp_excl_prefix(b, lane);
 }
 
+// Index arrays of a blob hold 16-bit entries, or 32-bit ones for "wide" structures (> 65 535 atoms).
+__device__ __forceinline__ void put_idx(void *base, bool wide, int64_t i, unsigned v)
+{
+    if (wide) reinterpret_cast<uint32_t *>(base)[i] = v;
+    else reinterpret_cast<uint16_t *>(base)[i] = (uint16_t)v;
+}
+
+__device__ __forceinline__ unsigned get_idx(const void *base, bool wide, int64_t i)
+{
+    return wide ? reinterpret_cast<const uint32_t *>(base)[i] : (unsigned)reinterpret_cast<const uint16_t *>(base)[i];
+}
+
 __device__ __forceinline__ double block_reduce_minmax(double v, bool is_max, double *scratch)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -102,7 +114,9 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
         }
         __syncthreads();
         int status = 0;
-        if (n_kept > 65535) { status = 2; n_kept = 0; }
+        const bool wide = is_wide(N);
+        const int ib = wide ? 4 : 2;
+        if (n_kept > (int)kAtomMask) { status = 2; n_kept = 0; }
 
         // ---- pass B: bounding box -> centre, extent, guard band ---------------------------------
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -124,12 +138,12 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
         const float eps = (float)(64.0 * 5.9604644775390625e-08 * fmax(half, 16.0) + 1e-5);
 
         // ---- layout of the staged part ------------------------------------------------------------
-        // one 16-byte record per atom -- x, y, z and (res_of << 16 | klass) in w -- so that the search
+        // one 16-byte record per atom -- x, y, z and (res_of << 10 | klass) in w -- so that the search
         // kernel gets everything it needs about an atom with one 128-bit shared-memory load
         const int off_atom = (int)sizeof(BlobHeader);
         const int off_resstart = off_atom + 16 * n_kept;
         float4 *atoms = reinterpret_cast<float4 *>(blob + off_atom);
-        uint16_t *res_start = reinterpret_cast<uint16_t *>(blob + off_resstart);
+        void *res_start = blob + off_resstart;
 
         // ---- pass C: coordinates, classes, residue CSR ---------------------------------------------
         int n_res = 0;
@@ -154,29 +168,30 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
                 const int rid = n_res + pre + (starts ? 1 : 0) - 1;
                 const double *p = xyz + 3 * (int64_t)a;
                 atoms[i] = make_float4((float)(p[0] - ctr[0]), (float)(p[1] - ctr[1]), (float)(p[2] - ctr[2]),
-                                       __uint_as_float(((uint32_t)rid << 16) | (uint32_t)klass_in[a]));
+                                       __uint_as_float(((uint32_t)rid << kClassBits) | ((uint32_t)klass_in[a] & kClassMask)));
                 bklass[i] = klass_in[a];
-                if (starts) res_start[rid] = (uint16_t)i;
+                if (starts) put_idx(res_start, wide, rid, (unsigned)i);
             }
             n_res += tot;
         }
         __syncthreads();
-        if (tid == 0) res_start[n_res] = (uint16_t)n_kept;
+        if (tid == 0) put_idx(res_start, wide, n_res, (unsigned)n_kept);
         __syncthreads();
         if (s_bad) status = 1;
         int local_max = 0;
         for (int r = tid; r < n_res; r += kPrepThreads)
-            local_max = max(local_max, (int)res_start[r + 1] - (int)res_start[r]);
+            local_max = max(local_max, (int)get_idx(res_start, wide, r + 1) - (int)get_idx(res_start, wide, r));
         if (local_max) atomicMax(&s_maxres, local_max);
         __syncthreads();
+        if (s_maxres > kMaxResidueAtoms && status == 0) status = 3;
         int res_shift = 0;
         while ((1 << res_shift) < s_maxres) ++res_shift;
 
         // ---- pass D: leader candidate lists -----------------------------------------------------------
-        const int off_leadoff = off_resstart + (int)align16(2 * (int64_t)(n_res + 1));
+        const int off_leadoff = off_resstart + (int)align16(ib * (int64_t)(n_res + 1));
         const int off_lead = off_leadoff + (int)align16(4 * (int64_t)(L.n_leader + 1));
         uint32_t *lead_off = reinterpret_cast<uint32_t *>(blob + off_leadoff);
-        uint16_t *lead = reinterpret_cast<uint16_t *>(blob + off_lead);
+        void *lead = blob + off_lead;
         // Counts: a class histogram of the kept atoms, then per list the sum over its classes.
         const int n_class = L.class_words * 32, mw = L.mask_words;
         for (int c = tid; c < n_class; c += kPrepThreads) s_hist[c] = 0;
@@ -231,7 +246,7 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
                     for (int j = 0; j < 4; ++j) {
                         const bool ok = (mine >> (8 * j)) & 1u;
                         const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                        if (ok) lead[pos[wd][j] + warp_excl_prefix(bal, lane)] = (uint16_t)i;
+                        if (ok) put_idx(lead, wide, pos[wd][j] + warp_excl_prefix(bal, lane), (unsigned)i);
                         pos[wd][j] += __popc(bal);
                     }
                 }
@@ -242,7 +257,7 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
         // ---- pass E: uniform grid (cell list) over the kept atoms -------------------------------------
         // Counting sort by cell; atoms inside a cell end up in ascending order, so the layout is
         // deterministic.  The cell edge grows until the grid has at most kMaxCells cells.
-        const int off_cellstart = (int)align16(off_lead + 2 * (int64_t)s_lead_cnt[L.n_leader]);
+        const int off_cellstart = (int)align16(off_lead + ib * (int64_t)s_lead_cnt[L.n_leader]);
         float cell = kMinCell;
         int nx = 0, ny = 0, nz = 0;
         float ox = 0.f, oy = 0.f, oz = 0.f;
@@ -257,9 +272,9 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
         ox = (float)(-0.5 * ext[0]) - 1e-3f;
         oy = (float)(-0.5 * ext[1]) - 1e-3f;
         oz = (float)(-0.5 * ext[2]) - 1e-3f;
-        off_cellatoms = off_cellstart + (int)align16(2 * (int64_t)(n_cells + 1));
-        uint16_t *cell_start = reinterpret_cast<uint16_t *>(blob + off_cellstart);
-        uint16_t *cell_atoms = reinterpret_cast<uint16_t *>(blob + off_cellatoms);
+        off_cellatoms = off_cellstart + (int)align16(ib * (int64_t)(n_cells + 1));
+        void *cell_start = blob + off_cellstart;
+        void *cell_atoms = blob + off_cellatoms;
         auto cell_of = [&](int i) {
             const float4 p = atoms[i];
             const int ix = min(nx - 1, max(0, (int)((p.x - ox) / cell)));
@@ -273,20 +288,20 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
         __syncthreads();
         if (tid == 0) {
             int run = 0;
-            for (int c = 0; c < n_cells; ++c) { const int cnt = s_cell[c]; s_cell[c] = run; cell_start[c] = (uint16_t)run; run += cnt; }
+            for (int c = 0; c < n_cells; ++c) { const int cnt = s_cell[c]; s_cell[c] = run; put_idx(cell_start, wide, c, (unsigned)run); run += cnt; }
             s_cell[n_cells] = run;
-            cell_start[n_cells] = (uint16_t)run;
+            put_idx(cell_start, wide, n_cells, (unsigned)run);
         }
         __syncthreads();
-        for (int i = tid; i < n_kept; i += kPrepThreads) cell_atoms[atomicAdd(&s_cell[cell_of(i)], 1)] = (uint16_t)i;
+        for (int i = tid; i < n_kept; i += kPrepThreads) put_idx(cell_atoms, wide, atomicAdd(&s_cell[cell_of(i)], 1), (unsigned)i);
         __syncthreads();
         for (int c = tid; c < n_cells; c += kPrepThreads) {      // insertion sort inside each (small) cell
-            const int b0 = cell_start[c], b1 = cell_start[c + 1];
+            const int b0 = (int)get_idx(cell_start, wide, c), b1 = (int)get_idx(cell_start, wide, c + 1);
             for (int i = b0 + 1; i < b1; ++i) {
-                const uint16_t v = cell_atoms[i];
+                const unsigned v = get_idx(cell_atoms, wide, i);
                 int j = i - 1;
-                while (j >= b0 && cell_atoms[j] > v) { cell_atoms[j + 1] = cell_atoms[j]; --j; }
-                cell_atoms[j + 1] = v;
+                while (j >= b0 && get_idx(cell_atoms, wide, j) > v) { put_idx(cell_atoms, wide, j + 1, get_idx(cell_atoms, wide, j)); --j; }
+                put_idx(cell_atoms, wide, j + 1, v);
             }
         }
         __syncthreads();
@@ -301,11 +316,13 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
             h.cell = cell; h.ox = ox; h.oy = oy; h.oz = oz;
             for (int i = 0; i < 8; ++i) h.pad[i] = 0;
             h.off_atom = off_atom;
-            for (int i = 0; i < 4; ++i) h.reserved[i] = 0;
+            h.wide = wide ? 1 : 0;
+            for (int i = 0; i < 3; ++i) h.reserved[i] = 0;
             h.off_resstart = off_resstart; h.off_leadoff = off_leadoff;
             h.off_lead = off_lead; h.off_orig = off_orig;
             *reinterpret_cast<BlobHeader *>(blob) = h;
             if (stats) atomicAdd(stats + 5, (unsigned long long)n_kept);
+            if (B.status) B.status[s] = status;
             if (status != 0 && bad) atomicAdd(bad, 1ull);
         }
         __syncthreads();

@@ -48,8 +48,14 @@ namespace emm {
 #define DSQRT(a) __dsqrt_rn((a))
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr uint32_t kEntryValid = 1u << 24;   // entry passed validation
-constexpr uint32_t kEntryDead = 1u << 25;    // entry failed validation
+// Queue entry: atom (22 bits) | parent slot (8 bits) << 22 | flags.
+constexpr uint32_t kEntryValid = 1u << 30;   // entry passed validation
+constexpr uint32_t kEntryDead = 1u << 31;    // entry failed validation
+__device__ __forceinline__ int entry_atom(uint32_t e) { return (int)(e & kAtomMask); }
+__device__ __forceinline__ int entry_parent(uint32_t e) { return (int)((e >> kAtomBits) & 0xffu); }
+__device__ __forceinline__ uint32_t make_entry(int parent, int atom) { return ((uint32_t)parent << kAtomBits) | (uint32_t)atom; }
+// same-residue payload of an anchor: first atom of the residue | atoms in it << 22
+__device__ __forceinline__ int span_payload(int first, int count) { return first | (count << kAtomBits); }
 
 struct WarpState {
     int n[kMaxAtoms + 1];        // entries queued per level
@@ -64,7 +70,7 @@ struct WarpState {
     unsigned long long n_complete;
     int best_valid;
     int overflow;
-    uint16_t best_asg[kMaxAtoms];
+    uint32_t best_asg[kMaxAtoms];
 };
 
 // Dynamic shared memory: [staged blob][per-warp queues][per-warp state].
@@ -78,7 +84,8 @@ struct Blob {
     const uint16_t *chain;    // may be null
     const int32_t *atom_id;   // may be null
     // uniform grid (cell list) of the structure, see BlobHeader; read in place from global memory
-    const uint16_t *cell_start, *cell_atoms;
+    const void *cell_start, *cell_atoms;
+    int wide;                 // 32-bit entries in cell_start / cell_atoms (and res_start / lead)
     int nx, ny, nz;
     float cell, ox, oy, oz;
 };
@@ -91,6 +98,7 @@ struct View {
     const unsigned char *gbase;
     int off_atom, off_resstart, off_leadoff, off_lead;
     int res_shift;
+    bool wide;                // index arrays hold 32-bit entries (never the case for a staged blob)
     float eps;
     template <typename T>
     __device__ __forceinline__ T ld(int byte_off) const
@@ -98,14 +106,25 @@ struct View {
         if (kStaged) return *reinterpret_cast<const T *>(g_smem + byte_off);
         return __ldg(reinterpret_cast<const T *>(gbase + byte_off));
     }
-    // atom record: centred x, y, z and (res_of << 16 | klass) as the bits of w -- one 128-bit load
+    // atom record: centred x, y, z and (res_of << 10 | klass) as the bits of w -- one 128-bit load
     __device__ __forceinline__ float4 atom(int i) const { return ld<float4>(off_atom + 16 * i); }
-    static __device__ __forceinline__ unsigned klass_of(const float4 &p) { return __float_as_uint(p.w) & 0xffffu; }
-    static __device__ __forceinline__ int res_of(const float4 &p) { return (int)(__float_as_uint(p.w) >> 16); }
-    __device__ __forceinline__ int res_start(int r) const { return ld<uint16_t>(off_resstart + 2 * r); }
+    static __device__ __forceinline__ unsigned klass_of(const float4 &p) { return __float_as_uint(p.w) & kClassMask; }
+    static __device__ __forceinline__ int res_of(const float4 &p) { return (int)(__float_as_uint(p.w) >> kClassBits); }
+    __device__ __forceinline__ int idx(int off, int i) const
+    {
+        if (!kStaged && wide) return (int)ld<uint32_t>(off + 4 * i);
+        return ld<uint16_t>(off + 2 * i);
+    }
+    __device__ __forceinline__ int res_start(int r) const { return idx(off_resstart, r); }
     __device__ __forceinline__ int lead_off(int l) const { return (int)ld<uint32_t>(off_leadoff + 4 * l); }
-    __device__ __forceinline__ int lead(int i) const { return ld<uint16_t>(off_lead + 2 * i); }
+    __device__ __forceinline__ int lead(int i) const { return idx(off_lead, i); }
 };
+
+__device__ __forceinline__ int cell_idx(const void *base, int wide, int i)
+{
+    return wide ? (int)__ldg(reinterpret_cast<const uint32_t *>(base) + i)
+                : (int)__ldg(reinterpret_cast<const uint16_t *>(base) + i);
+}
 
 struct SearchArgs {
     DevLibrary L;
@@ -254,7 +273,7 @@ __device__ __forceinline__ void jacobi4(double (&a)[4][4], double (&v)[4][4])
 // Optimal proper rotation of the matched query atoms onto the template atoms; returns rmsd.
 // asg[i] = local atom id bound to template atom i (template order).
 __device__ double superpose(int m, const double *__restrict__ txyz, const Blob &S,
-                            const uint16_t *asg, double (&rot)[9], double (&qbar)[3],
+                            const uint32_t *asg, double (&rot)[9], double (&qbar)[3],
                             double (&tbar)[3])
 {
     const double inv_m = DDIV(1.0, (double)m);
@@ -425,12 +444,12 @@ __device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S
     const double *txyz = L.xyz + 3 * (int64_t)a0;
     const double thr = L.rmsd_thr[t];
     bool have = (valid >> lane) & 1u;
-    uint16_t asg[kMaxAtoms];
+    uint32_t asg[kMaxAtoms];
     if (have) {
         uint32_t w = Q[queue_off(m) + base + lane];
         for (int pos = m - 1; pos >= 0; --pos) {
-            asg[L.plan_atom[a0 + pos]] = (uint16_t)(w & 0xffffu);
-            if (pos > 0) w = Q[queue_off(pos) + ((w >> 16) & 0xffu)];
+            asg[L.plan_atom[a0 + pos]] = (uint32_t)entry_atom(w);
+            if (pos > 0) w = Q[queue_off(pos) + entry_parent(w)];
         }
         if (!A.P.ignore_chain && S.chain) {
             // template atoms on equal chains <=> query atoms on equal chains (oracle rule 11)
@@ -492,12 +511,12 @@ __device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S
 __device__ __noinline__ bool exact_validate(const DevLibrary &L, const Blob &S, const uint32_t *Q, int a0,
                                             int64_t p0, int k, uint32_t e, double cut, double dyn)
 {
-    const int oa = S.orig[e & 0xffffu];
+    const int oa = S.orig[entry_atom(e)];
     const double *row64 = L.pair_dist + p0 + ((k - 1) * (k - 2)) / 2;
     uint32_t w = e;
     for (int pos = k - 2; pos >= 0; --pos) {
-        w = Q[queue_off(pos + 1) + ((w >> 16) & 0xffu)];
-        const double d = exact_dist(S.xyz64, oa, S.orig[w & 0xffffu]);
+        w = Q[queue_off(pos + 1) + entry_parent(w)];
+        const double d = exact_dist(S.xyz64, oa, S.orig[entry_atom(w)]);
         const double delta = pair_delta(L, a0, k - 1, pos, cut, dyn);
         if (!(fabs(DSUB(d, row64[pos])) <= delta)) return false;
     }
@@ -532,8 +551,8 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
         for (; row < nrows && !full; ++row, ipos = -1) {
             const int iz = iz0 + row / nry, iy = iy0 + row % nry;
             const int c0 = (iz * S.ny + iy) * S.nx + ix0;
-            const int beg = __ldg(S.cell_start + c0);
-            const int end = __ldg(S.cell_start + c0 + ix1 - ix0 + 1);
+            const int beg = cell_idx(S.cell_start, S.wide, c0);
+            const int end = cell_idx(S.cell_start, S.wide, c0 + ix1 - ix0 + 1);
             if (ipos < 0) ipos = beg;
             for (; ipos < end; ipos += 32) {
                 if (n_next >= cap_next) { full = true; break; }
@@ -543,7 +562,7 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
                 int a = 0;
                 float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (alive) {
-                    a = __ldg(S.cell_atoms + i);
+                    a = cell_idx(S.cell_atoms, S.wide, i);
                     p = V.atom(a);
                     const unsigned kl = V.klass_of(p);
                     alive = (__ldg(crow + (kl >> 5)) >> (kl & 31u)) & 1u;
@@ -556,7 +575,7 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
                 const unsigned sv = __ballot_sync(kFull, alive);
                 if (sv) {
                     const int room = cap_next - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
-                    if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)parent << 16) | (uint32_t)a;
+                    if (alive && rank < room) Qn[n_next + rank] = make_entry(parent, a);
                     if (cnt > room) {
                         n_next = cap_next;
                         todo = __ballot_sync(kFull, alive && rank >= room);
@@ -570,6 +589,7 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
         }
         if (full) break;
     }
+    __syncwarp();          // every lane has read the resume point above before lane 0 replaces it
     if (lane == 0) { ws->cur[k] = pidx; ws->cellrow[k] = row; ws->celli[k] = ipos; ws->todo[k] = todo; }
     *n_next_io = n_next;
     *done = !full && pidx >= P;
@@ -607,7 +627,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     uint32_t e = have ? Q[queue_off(k) + base + lane] : kEntryDead;
     bool alive = !(e & kEntryDead);
     const bool check = alive && !(e & kEntryValid);
-    const int a = (int)(e & 0xffffu);
+    const int a = entry_atom(e);
     const int anchor_pos = k < m ? (int)L.plan_anchor[a0 + k] : -1;     // warp-uniform
     const bool dynamic = dyn64 != cut64;
     const float eps = V.eps;
@@ -621,8 +641,8 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     // a chunk that was validated on an earlier visit only needs its anchors again: stop the walk there
     const int stop = __any_sync(kFull, check) ? 0 : (anchor_pos < 0 ? k - 1 : anchor_pos);
     for (int pos = k - 2; pos >= stop; --pos) {
-        w = Q[queue_off(pos + 1) + ((w >> 16) & 0xffu)];
-        const int b = (int)(w & 0xffffu);
+        w = Q[queue_off(pos + 1) + entry_parent(w)];
+        const int b = entry_atom(w);
         const float4 pb = V.atom(b);
         const float xb = pb.x, yb = pb.y, zb = pb.z;
         if (pos == anchor_pos) { ax = xb; ay = yb; az = zb; aatom = b; ares = V.res_of(pb); }
@@ -646,7 +666,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
         int payload = aatom;
         if ((int)L.plan_src[a0 + k] >= 0) {        // same-residue level: the anchor's residue span
             const int rs = V.res_start(ares);
-            payload = rs | ((V.res_start(ares + 1) - rs) << 16);
+            payload = span_payload(rs, V.res_start(ares + 1) - rs);
         }
         const int rank = __popc(valid & ((1u << lane) - 1u));      // anchors are stored compacted
         ws->anchor[rank] = make_float4(ax, ay, az, __int_as_float(payload));
@@ -701,7 +721,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                 int payload = a;
                 if ((int)L.plan_src[a0 + 1] >= 0) {                           // position 1 shares this atom's residue
                     const int r = V.res_of(p), rs = V.res_start(r);
-                    payload = rs | ((V.res_start(r + 1) - rs) << 16);
+                    payload = span_payload(rs, V.res_start(r + 1) - rs);
                 }
                 ws->anchor[lane] = make_float4(p.x, p.y, p.z, __int_as_float(payload));
                 ws->vslot[lane] = (unsigned char)lane;
@@ -760,7 +780,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             // did not fit (0 = all pushed)
             auto push = [&](unsigned sv, bool alive, int a, int parent) -> unsigned {
                 const int room = cap_next - n_next, rank = __popc(sv & lt_mask), cnt = __popc(sv);
-                if (alive && rank < room) Qn[n_next + rank] = ((uint32_t)parent << 16) | (uint32_t)a;
+                if (alive && rank < room) Qn[n_next + rank] = make_entry(parent, a);
                 if (cnt > room) {
                     n_next = cap_next;
                     return __ballot_sync(kFull, alive && rank >= room);
@@ -888,8 +908,8 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
                     bool alive = pidx < P && (todo == 0ull || ((todo >> lane) & 1ull));
                     const float4 an = ws->anchor[alive ? pidx : 0];
                     const int payload = __float_as_int(an.w);
-                    const int a = (payload & 0xffff) + sidx;
-                    alive = alive && sidx < (payload >> 16);
+                    const int a = (payload & (int)kAtomMask) + sidx;
+                    alive = alive && sidx < (int)((unsigned)payload >> kAtomBits);
                     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (alive) {
                         p = V.atom(a);
@@ -945,6 +965,7 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             if (ws->cur[k] >= 0) break;           // the parent still has candidates to try: re-enter it
             if (k == 0) { finished = true; break; }       // the root was expanded completely
             base = ws->n[k] - ws->chunk[k];
+            __syncwarp();                         // every lane has read level k before lane 0 rewrites it above
         }
         if (finished) break;
         entered = false;
@@ -1021,8 +1042,9 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                 s_blob.xyz64 = A.B.xyz + 3 * abase;
                 s_blob.chain = A.B.chain ? A.B.chain + abase : nullptr;
                 s_blob.atom_id = A.B.atom_id ? A.B.atom_id + abase : nullptr;
-                s_blob.cell_start = reinterpret_cast<const uint16_t *>(gblob + hdr.off_cellstart);
-                s_blob.cell_atoms = reinterpret_cast<const uint16_t *>(gblob + hdr.off_cellatoms);
+                s_blob.cell_start = gblob + hdr.off_cellstart;
+                s_blob.cell_atoms = gblob + hdr.off_cellatoms;
+                s_blob.wide = hdr.wide;
                 s_blob.nx = hdr.nx; s_blob.ny = hdr.ny; s_blob.nz = hdr.nz;
                 s_blob.cell = hdr.cell; s_blob.ox = hdr.ox; s_blob.oy = hdr.oy; s_blob.oz = hdr.oz;
             }
@@ -1035,7 +1057,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             V.gbase = gblob;
             V.off_atom = hdr.off_atom;
             V.off_resstart = hdr.off_resstart; V.off_leadoff = hdr.off_leadoff;
-            V.off_lead = hdr.off_lead; V.res_shift = hdr.res_shift; V.eps = hdr.eps;
+            V.off_lead = hdr.off_lead; V.res_shift = hdr.res_shift; V.eps = hdr.eps; V.wide = hdr.wide != 0;
             for (;;) {
                 int t = -1;
                 if (lane == 0) {

@@ -37,9 +37,15 @@ STATS_FIELDS = ("pairs", "sweeps", "dist_evals", "exact_rechecks", "complete", "
 
 
 class EngineError(RuntimeError):
+    """A negative ``emm_status``.  For ``EMM_ERR_INPUT`` raised by a download, ``hits`` holds the hit
+    records of the batch's valid structures (they were searched) and ``bad_structures`` maps the index
+    of every skipped structure to its status (1 residue order, 2 too many atoms, 3 residue too large)."""
+
     def __init__(self, status: int, message: str):
         super().__init__(f"{_STATUS.get(status, status)}: {message}")
         self.status = status
+        self.hits = None
+        self.bad_structures = {}
 
 
 class _LibraryDesc(ctypes.Structure):
@@ -102,6 +108,7 @@ def load_cdll() -> ctypes.CDLL:
         for name in ("emm_abi_version", "emm_hit_size", "emm_device_count", "emm_library_create", "emm_library_set_compat",
                      "emm_library_set_thresholds", "emm_library_set_filter", "emm_session_create", "emm_session_upload",
                      "emm_session_run", "emm_session_download", "emm_session_last_launches",
+                     "emm_session_structure_status",
                      "emm_session_kernel_ms", "emm_session_clear_timings", "emm_session_debug_counters",
                      "emm_stream_create", "emm_stream_destroy",
                      "emm_query_batch"):
@@ -266,11 +273,26 @@ class Session:
         stats = _Stats()
         rc = self._lib.emm_session_download(self.handle, _p(self._hits), ctypes.c_int64(self.hit_capacity),
                                             ctypes.byref(n), ctypes.byref(stats), ctypes.c_void_p(stream))
+        if rc == -5:
+            # structures that break the input contract were skipped; everything else was searched
+            message = self._lib.emm_last_error().decode(errors="replace")
+            exc = EngineError(rc, message)
+            exc.hits = self._hits[:n.value].copy()
+            status = self.structure_status()
+            exc.bad_structures = {int(i): int(status[i]) for i in np.nonzero(status)[0]}
+            raise exc
         _check(rc)
         hits = self._hits[:n.value].copy()
         if with_stats:
             return hits, {k: int(getattr(stats, k)) for k in STATS_FIELDS}
         return hits
+
+    def structure_status(self) -> np.ndarray:
+        """Per-structure outcome of the prepare pass of the uploaded batch (0 = searched)."""
+        n = self._batch.n_structures if self._batch is not None else 0
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        _check(self._lib.emm_session_structure_status(self.handle, _p(out), ctypes.c_int32(len(out))))
+        return out[:n]
 
     @property
     def last_launches(self) -> int:

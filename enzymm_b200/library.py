@@ -19,6 +19,7 @@ from __future__ import annotations
 import hashlib
 import json
 import math
+import os
 import pickle
 import threading
 from pathlib import Path
@@ -515,16 +516,24 @@ class CompiledLibrary:
         return len(self.templates)
 
     # ---- compiled-library cache: compile the 7607-file library once ---------------
-    _CACHE_VERSION = 5
+    _CACHE_VERSION = 6
 
     @staticmethod
     def _digest(templates, rmsd_threshold, distance_cutoff, max_dynamic_distance, plan_order) -> str:
+        """Everything the compiled tables depend on: the template atoms, the per-residue orientation
+        constants EnzyMM derives from them, the thresholds, the plan order, the logistic-model file
+        and the planner's background tables."""
         h = hashlib.blake2b(digest_size=16)
         h.update(repr((CompiledLibrary._CACHE_VERSION, plan_order, np.asarray(rmsd_threshold, dtype=np.float64).tolist(),
                        [str(d) for d in np.atleast_1d(np.asarray(distance_cutoff, dtype=object))],
                        np.asarray(max_dynamic_distance, dtype=np.float64).tolist())).encode())
+        h.update((_DATA / "logistic_regression_models.json").read_bytes())
+        h.update(repr((sorted(BACKGROUND_PERCENT.items()), sorted((k, tuple(v)) for k, v in RESIDUE_ATOMS.items()))).encode())
         for t in templates:
-            h.update(repr((getattr(t, "effective_size", None), [a._key() for a in t])).encode())
+            orient = [(tuple(r.orientation_vector_indices), (r.orientation_vector.x, r.orientation_vector.y,
+                                                             r.orientation_vector.z))
+                      for r in (getattr(t, "residues", None) or [])]
+            h.update(repr((getattr(t, "effective_size", None), [a._key() for a in t], orient)).encode())
         return h.hexdigest()
 
     @classmethod
@@ -538,17 +547,36 @@ class CompiledLibrary:
         path = cache_dir / f"emm_library_{key}.pkl"
         if path.exists():
             with open(path, "rb") as handle:
-                state = pickle.load(handle)
+                state = _TablesUnpickler(handle).load()     # arrays and plain containers only: no code runs
             self = cls.__new__(cls)
             self.__dict__.update(state)
             self.templates = templates
             self.compat_dirty = True
             return self
         self = cls(templates, rmsd_threshold, distance_cutoff, max_dynamic_distance, plan_order=plan_order)
-        cache_dir.mkdir(parents=True, exist_ok=True)
+        cache_dir.mkdir(parents=True, exist_ok=True, mode=0o700)
         state = {k: v for k, v in self.__dict__.items() if k not in ("templates", "_kind_table")}
-        tmp = path.with_suffix(".tmp")
-        with open(tmp, "wb") as handle:
+        tmp = path.with_suffix(f".{os.getpid()}.tmp")
+        with open(os.open(tmp, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600), "wb") as handle:
             pickle.dump(state, handle, protocol=pickle.HIGHEST_PROTOCOL)
         tmp.replace(path)
         return self
+
+
+class _TablesUnpickler(pickle.Unpickler):
+    """Unpickler for the compiled-library cache: NumPy arrays / scalars / dtypes and plain containers
+    only.  A cache file is data written by ``CompiledLibrary.cached``; anything else in it (a global
+    that could run code on load) is refused."""
+
+    _ALLOWED = {
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+        ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy._core.numeric", "_frombuffer"),
+        ("numpy.core.numeric", "_frombuffer"), ("collections", "OrderedDict"), ("builtins", "set"),
+        ("builtins", "frozenset"), ("builtins", "slice"), ("builtins", "bytearray"), ("builtins", "complex"),
+    }
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED or (module == "numpy.dtypes" and name.endswith("DType")):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"compiled-library cache refers to {module}.{name}: refusing to load it")

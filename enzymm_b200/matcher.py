@@ -366,6 +366,7 @@ class Matcher:
         self._groups: List[Tuple[int, int, int]] = []
         self._scan_lanes = None
         self.hits_per_structure = 64          # initial hit-buffer sizing; grown on demand
+        self.skipped_structures: Dict[int, int] = {}   # batch index -> status of structures the device refused
         self._hit_floor = 1024
 
     def verbose_print(self, *args):
@@ -453,6 +454,14 @@ class Matcher:
             try:
                 return session.download()
             except EngineError as exc:
+                if exc.status == -5 and exc.hits is not None:
+                    # structures outside the engine's input contract were skipped on the device; the
+                    # rest of the batch was searched -- keep those results instead of losing the batch
+                    warnings.warn(f"{len(exc.bad_structures)} structure(s) were not searched (index: status "
+                                  f"{exc.bad_structures}; 2 = more than 4194303 atoms, 3 = a residue with more "
+                                  f"than 1023 atoms): {exc}")
+                    self.skipped_structures = dict(exc.bad_structures)
+                    return exc.hits
                 if exc.status != -4:
                     raise
                 capacity = 4 * session.hit_capacity

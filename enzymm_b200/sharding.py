@@ -8,6 +8,7 @@ gather (and for barriers / max-over-ranks timing in ``bench.py``), never inside 
 """
 from __future__ import annotations
 
+import sys
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -32,19 +33,27 @@ class ChunkQueue:
     differ widely in cost a static block per rank leaves GPUs idle).  The queue is one counter in
     the process group's key-value store -- host side only, nothing on the data path: every rank
     calls ``next()`` until it returns None and searches chunk ``[lo, hi)`` of the corpus each time.
-    Without an initialised process group it simply enumerates the chunks."""
+    Without an initialised process group it simply enumerates the chunks.
+
+    Constructing a queue is collective: every rank creates its queues in the same order, and the
+    n-th queue of a job gets its own counter key (``<name>/<n>``), so a second corpus, a second
+    ``scan_files`` call or a retry starts from zero instead of from the exhausted counter of the
+    previous queue."""
+
+    _created = 0            # queues constructed by this process so far (same on every rank)
 
     def __init__(self, n_items: int, chunk: int, name: str = "emm_chunk_queue"):
         if chunk <= 0:
             raise ValueError("chunk must be positive")
         self.n_items, self.chunk = int(n_items), int(chunk)
         self.n_chunks = (self.n_items + self.chunk - 1) // self.chunk
-        self._key = name
         self._local = 0
         self._store = None
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist = sys.modules.get("torch.distributed")     # not imported -> no process group to ask
+        if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self._store = dist.distributed_c10d._get_default_store()
+        ChunkQueue._created += 1
+        self._key = f"{name}/{ChunkQueue._created}"
 
     def next(self) -> Optional[Tuple[int, int]]:
         if self._store is not None:
@@ -81,8 +90,8 @@ def merge_hits(parts: Sequence[Tuple[int, np.ndarray]]) -> np.ndarray:
 def gather_hits(first: int, hits: np.ndarray, dst: int = 0) -> Optional[np.ndarray]:
     """Gather every rank's (first, hits) on ``dst`` and merge; other ranks get None.
     Works without an initialised process group (single process)."""
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    dist = sys.modules.get("torch.distributed")         # not imported -> no process group
+    if dist is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return merge_hits([(first, hits)])
     payload = (int(first), hits)
     gathered: Optional[List] = [None] * dist.get_world_size() if dist.get_rank() == dst else None

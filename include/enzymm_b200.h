@@ -126,7 +126,11 @@ void emm_library_destroy(emm_library *lib);
  *
  * Input contract (violations -> EMM_ERR_INPUT): within one structure `residue` is non-decreasing
  * (atoms of a residue are contiguous; the host reorders odd files and reports original indices
- * through atom_id).  A residue is a distinct (chain_id, residue_number) (SURVEY.md 8c rule 4).
+ * through atom_id); at most 4 194 303 atoms of a structure survive masking and class-0 removal, at
+ * most 1 023 of them in one residue.  A residue is a distinct (chain_id, residue_number) (SURVEY.md
+ * 8c rule 4).  A structure that breaks the contract is skipped, not searched: the batch's other
+ * structures are searched and their hits delivered, emm_session_download still returns EMM_ERR_INPUT
+ * and emm_session_structure_status names the offenders.
  */
 typedef struct emm_batch {
     int32_t n_structures;
@@ -202,6 +206,11 @@ int emm_session_run(emm_session *s, const emm_query_params *params, void *stream
  * Hits come back sorted by (structure, template_index).  stats may be NULL. */
 int emm_session_download(emm_session *s, emm_hit *hits, int64_t capacity, int64_t *n_hits,
                          emm_stats *stats, void *stream);
+
+/* Per-structure outcome of the last prepare pass of the uploaded batch (synchronous; call after
+ * emm_session_download): 0 searched; 1 residue ordinals decrease; 2 too many kept atoms; 3 a residue
+ * keeps more than 1023 atoms.  capacity >= n_structures of the batch. */
+int emm_session_structure_status(emm_session *s, int32_t *status, int32_t capacity);
 
 /* Number of kernel launches issued by the last emm_session_run (for bench accounting). */
 int emm_session_last_launches(const emm_session *s);

@@ -349,6 +349,7 @@ def test_hit_buffer_overflow_is_loud_then_recovers(full_engine, active_templates
 
 
 def test_input_contract_violation_is_loud(full_engine):
+    """Loud: EMM_ERR_INPUT, with the offender named (see also test_refused_structure_does_not_cost_the_batch)."""
     xyz = np.zeros((4, 3))
     bad = PackedBatch(np.array([0, 4]), xyz, np.ones(4, dtype=np.uint16), np.array([0, 1, 0, 1], dtype=np.int32))
     with pytest.raises(EngineError) as info:
@@ -649,3 +650,132 @@ def test_mixed_batch_stages_what_fits(active_templates, mol_1amy, monkeypatch):
             assert mine["rmsd"].tolist() == part["rmsd"].tolist()
     finally:
         eng.close()
+
+
+# ---- BASELINE configs 4 and 5 at their stated parameters ---------------------------------------------
+
+def test_config4_unfiltered_loose_cutoff_full_library(active_templates):
+    """BASELINE config 4 as stated: ``--unfiltered -j 2 3.0 3.0``, ``max_candidates = 10**7``,
+    the full active library x 32 synthetic 400-residue structures, against the oracle: hit set, atoms,
+    RMSD bits and the number of complete assignments of every one of the ~50 k hits (up to ~10^5
+    assignments superposed per pair; no pair may reach the cap)."""
+    chunk = generate_chunk(0, SynthConfig(), active_templates, 32)
+    mols = [chunk.to_molecule(i) for i in range(chunk.n_structures)]
+    eng = Engine(CompiledLibrary(active_templates, 2.0, 3.0, 3.0))
+    try:
+        hits = compare_with_oracle(eng, active_templates, mols, 3.0, rmsd=2.0, max_candidates=10 ** 7)
+    finally:
+        eng.close()
+    assert len(hits) > 1000 * len(mols) // 2 and not (hits["flags"] & HIT_OVERFLOW).any()
+    assert int(hits["n_complete"].max()) > 10000
+    # the same batch through the Matcher front end: --unfiltered keeps every raw hit
+    params = {s: {"rmsd": 2, "distance": 3.0, "max_dynamic_distance": 3.0} for s in range(3, 9)}
+    matcher = jess_run.Matcher(active_templates, jess_params=params, filter_matches=False, max_candidates=10 ** 7)
+    try:
+        got = matcher.run(mols[:4])
+    finally:
+        matcher.close()
+    per_structure = np.bincount(hits["structure"], minlength=len(mols))
+    assert [len(got[m]) for m in mols[:4]] == per_structure[:4].tolist()
+
+
+def test_config5_masked_assemblies_skip_smaller_full_library(active_templates):
+    """BASELINE config 5 as stated: 4 x 400-residue assemblies (chains A-D, ~12.5 k atoms),
+    ``--conservation-cutoff 70`` applied as a real mask, ``--skip-smaller-hits``, full active library x
+    16 assemblies, against the oracle's restatement of ``Matcher.run`` on explicitly masked molecules."""
+    chunk = generate_chunk(0, SynthConfig(n_chains=4), active_templates, 16)
+    mols = [chunk.to_molecule(i) for i in range(chunk.n_structures)]
+    masked = [m.conserved(70) for m in mols]
+    keeps = [np.nonzero(m.column("temperature_factor") >= 70)[0] for m in mols]
+    assert all(len(m) > 9000 for m in mols) and all(0 < len(k) < len(m) for k, m in zip(keeps, mols))
+    matcher = jess_run.Matcher(templates=active_templates, skip_smaller_hits=True, conservation_cutoff=70,
+                               apply_conservation_mask=True)
+    try:
+        got = matcher.run(mols)
+    finally:
+        matcher.close()
+    want = oracle_matcher_run(active_templates, masked, skip_smaller_hits=True, threads=16)
+    assert [mols.index(k) for k in got] == list(want) and len(want) >= 4
+    for mi, wm in want.items():
+        gm = got[mols[mi]]
+        assert [m.hit.template.id for m in gm] == [m.template.id for m in wm]
+        assert [m.hit.atom_indices for m in gm] == [[int(keeps[mi][a]) for a in m.hit.atoms] for m in wm]
+        assert [m.hit.rmsd for m in gm] == [m.hit.rmsd for m in wm]
+        assert [m.complete for m in gm] == [m.complete for m in wm]
+    # and the raw device path on the unmasked assemblies (global-memory search), every size group
+    dist = default_distances(active_templates)
+    eng = Engine(CompiledLibrary(active_templates, 2.0, dist, dist))
+    try:
+        compare_with_oracle(eng, active_templates, mols[:4], dist)
+        compare_with_oracle(eng, active_templates, mols[:4], dist, cutoff=70.0, oracle_molecules=masked[:4],
+                            atom_maps=keeps[:4])
+    finally:
+        eng.close()
+
+
+# ---- structures beyond 65 535 atoms; structures the device refuses -----------------------------------
+
+def _mega_molecule(templates, n_assemblies=8):
+    """One structure of ~100 k atoms: ``n_assemblies`` 4-chain synthetic assemblies on a 95 A lattice,
+    every chain with its own two-letter id."""
+    from enzymm_b200.structures import _COLUMNS
+    chunk = generate_chunk(0, SynthConfig(n_chains=4), templates, n_assemblies)
+    parts = [chunk.to_molecule(i) for i in range(n_assemblies)]
+    cols = {k: np.concatenate([m.column(k) for m in parts]) for k, _ in _COLUMNS}
+    xyz = np.concatenate([m.xyz + 95.0 * np.array([i & 1, (i >> 1) & 1, (i >> 2) & 1]) for i, m in enumerate(parts)])
+    cols["chain_id"] = np.concatenate([np.char.add(m.column("chain_id").astype("U1"), "ABCDEFGH"[i])
+                                       for i, m in enumerate(parts)]).astype("U2")
+    cols["serial"] = (np.arange(len(xyz)) % 99999 + 1).astype(np.int32)
+    return Molecule._from_columns(cols, xyz, "mega")
+
+
+def test_structure_beyond_65535_atoms(active_templates, mol_1amy):
+    """A 100 k-atom assembly (32-bit index arrays in its blob, searched in place) next to an ordinary
+    structure in the same batch: hit set, atoms, RMSD bits and counts equal the oracle's; the reference
+    has no size limit, round 1 refused anything above 65 535 kept atoms."""
+    subset = active_templates[::40]
+    mega = _mega_molecule(subset)
+    assert len(mega) > 100000
+    dist = default_distances(subset)
+    eng = Engine(CompiledLibrary(subset, 2.0, dist, dist))
+    try:
+        hits = compare_with_oracle(eng, subset, [mol_1amy, mega], dist)
+        assert (hits["structure"] == 1).sum() >= 3 and int(hits["atoms"].max()) > 65535
+        cells = eng.query(pack_molecules([mega], eng.compiled), cell_threshold=64)      # wide cell list
+        plain = hits[hits["structure"] == 1]
+        assert np.array_equal(cells["atoms"], plain["atoms"]) and np.array_equal(cells["rmsd"], plain["rmsd"])
+    finally:
+        eng.close()
+    got = jess_run.Matcher(templates=subset).run([mega, mol_1amy])
+    want = oracle_matcher_run(subset, [mega, mol_1amy], threads=2)
+    assert {k.id: [m.hit.atom_indices for m in v] for k, v in got.items()} == \
+           {[mega, mol_1amy][i].id: [m.hit.atoms for m in v] for i, v in want.items()}
+
+
+def test_refused_structure_does_not_cost_the_batch(full_engine, active_templates, mol_1amy, mol_af):
+    """one structure outside the input contract used to fail the whole batch.  Now it is
+    skipped and named; every other structure's hits are delivered (engine: on the exception; Matcher:
+    a warning and the results)."""
+    good = pack_molecules([mol_1amy, mol_af], full_engine.compiled)
+    n1 = len(mol_1amy)
+    # middle structure: residue ordinals that decrease (status 1)
+    atom_off = np.array([0, n1, n1 + 4, n1 + 4 + len(mol_af)])
+    xyz = np.concatenate([good.xyz[:n1], np.zeros((4, 3)), good.xyz[n1:]])
+    klass = np.concatenate([good.klass[:n1], np.ones(4, dtype=np.uint16), good.klass[n1:]])
+    residue = np.concatenate([good.residue[:n1], np.array([0, 1, 0, 1], dtype=np.int32), good.residue[n1:]])
+    batch = PackedBatch(atom_off, xyz, klass, residue)
+    with pytest.raises(EngineError) as info:
+        full_engine.query(batch)
+    exc = info.value
+    assert exc.status == -5 and exc.bad_structures == {1: 1}
+    clean = full_engine.query(good)
+    relabel = exc.hits.copy()
+    relabel["structure"] = np.where(relabel["structure"] == 2, 1, relabel["structure"])
+    assert len(clean) == 13 + 11 and relabel.tobytes() == clean.tobytes()
+    # a residue with more than 1023 kept atoms (status 3)
+    n = 1100
+    blob = PackedBatch(np.array([0, n]), np.random.default_rng(0).normal(size=(n, 3)) * 20,
+                       np.full(n, good.klass[good.klass > 0][0], dtype=np.uint16), np.zeros(n, dtype=np.int32))
+    with pytest.raises(EngineError) as info:
+        full_engine.query(blob)
+    assert info.value.bad_structures == {0: 3} and len(info.value.hits) == 0

@@ -210,6 +210,15 @@ def test_compiled_library_cache(tmp_path, active_templates):
     assert again.templates[0] is subset[0]
     CompiledLibrary.cached(subset, 2.0, 1.5, 1.5, tmp_path)             # other thresholds: a second entry
     assert len(list(tmp_path.glob("emm_library_*.pkl"))) == 2
+    # a cache file is data: one that names a callable is refused instead of executed
+    import pickle
+    from enzymm_b200.library import _TablesUnpickler
+    evil = tmp_path / "evil.pkl"
+    evil.write_bytes(pickle.dumps({"x": print}))
+    with pytest.raises(pickle.UnpicklingError):
+        _TablesUnpickler(evil.open("rb")).load()
+    for path in tmp_path.glob("emm_library_*.pkl"):
+        assert (path.stat().st_mode & 0o077) == 0
 
 
 def test_load_molecules_ids_and_errors(tmp_path):

@@ -89,6 +89,11 @@ def _queue_worker(rank: int, world: int, port: int, queue):
         parts = []
         for lo, hi in ChunkQueue(len(mols), chunk=2):          # chunks handed out first come, first served
             parts.append((lo, _oracle_hits(templates, mols[lo:hi])))
+        # a second queue in the same job starts from zero again (its own counter key)
+        dist.barrier()
+        again = [None] * world
+        dist.all_gather_object(again, [lo for lo, _ in ChunkQueue(len(mols), chunk=3)])
+        assert sorted(lo for part in again for lo in part) == [0, 3], again
         mine = merge_hits(parts) if parts else np.zeros(0, dtype=HIT_DTYPE)
         merged = gather_hits(0, mine)                           # already rebased to corpus indices
         spans = [None] * world
