@@ -244,6 +244,64 @@ def parity_against_oracle(hits, raw, molecules, templates):
             "checked": "hit set, atoms, rmsd ==, n_complete ==, orientation <= 1e-4, filter verdict"}
 
 
+def api_legs(workload, n_files: int, chunk: int = 2048):
+    """What a user of the Python-facing API gets, from PDB FILES on local disk (page cache) to results,
+    on one GPU -- three entry points, each timed end to end on its second call (the first one allocates
+    the device sessions):
+      files_to_hits     Matcher.scan_files(paths): native ingest -> GPU -> emm_hit records
+      files_to_matches  load_molecules(paths) + Matcher.run(molecules): Molecule objects -> {Molecule: [Match]}
+                        (the reference's own call sequence, _cli.py:217-248)
+      files_to_tsv      Matcher.scan_to_tsv(paths, file): the reference's results table (_cli.py:270-316)
+    """
+    import io
+    import shutil
+    import tempfile
+    from enzymm_b200 import jess_run
+    distinct = min(n_files, workload.n_structures, 1024)
+    root = tempfile.mkdtemp(prefix="emm_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        texts = [workload.to_pdb(i).encode() for i in range(distinct)]
+        paths = []
+        for i in range(n_files):
+            path = os.path.join(root, f"s{i:06d}.pdb")
+            with open(path, "wb") as handle:
+                handle.write(texts[i % distinct])
+            paths.append(path)
+        size = sum(len(texts[i % distinct]) for i in range(n_files))
+        matcher = jess_run.Matcher(templates=active_templates())
+        out = {"files": n_files, "distinct_structures": distinct, "pdb_text_bytes": size, "chunk": chunk,
+               "host_threads": host_threads(), "unit": "files/s",
+               "note": "second call of each entry point; files in the page cache; one GPU"}
+        hits = rows = 0
+        for rep in range(2):
+            t0 = time.perf_counter()
+            hits = sum(len(records) for _, _, records in matcher.scan_files(paths, chunk_size=chunk))
+            out["files_to_hits"] = n_files / (time.perf_counter() - t0)
+        sample = paths[:min(n_files, 4096)]
+        for rep in range(2):
+            t0 = time.perf_counter()
+            molecules = jess_run.load_molecules(sample)
+            t1 = time.perf_counter()
+            matches = matcher.run(molecules)
+            t2 = time.perf_counter()
+            out["files_to_matches"] = len(sample) / (t2 - t0)
+            out["files_to_matches_parts"] = {"load_molecules": len(sample) / (t1 - t0), "run": len(sample) / (t2 - t1),
+                                             "files": len(sample), "matches": sum(len(v) for v in matches.values())}
+            del molecules, matches
+        for rep in range(2):
+            sink = io.BytesIO()
+            sink.mode = "wb"
+            t0 = time.perf_counter()
+            rows = matcher.scan_to_tsv(paths, sink, chunk_size=chunk)
+            out["files_to_tsv"] = n_files / (time.perf_counter() - t0)
+            out["tsv_rows"], out["tsv_bytes"] = rows, sink.tell()
+        out["hits"] = hits
+        matcher.close()
+        return out
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def host_threads() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
@@ -403,6 +461,7 @@ def run_b200(args, rank, local_rank, world):
     windows.append((w0, time.time()))
     e2e_ms = max_over_ranks(f0.elapsed_time(f1), "e2e")
     clocks = sampler.stop(windows) if sampler else None
+    second.close()
 
     # ---- sanity outside the timed regions: planted motifs are being found ---------------------------
     found = set(zip(hits["structure"].tolist(), hits["template_index"].tolist()))
@@ -459,12 +518,165 @@ def run_b200(args, rank, local_rank, world):
                                           "(CPU restatement of Jess, not PyJess)"}
         # the oracle's hits of that sample vs the GPU's hits of the same structures
         line["parity"] = parity_against_oracle(hits, cpu_oracle_rate.raw, cpu_oracle_rate.molecules, templates)
+    if world == 1 and args.api_files > 0:
+        engine.close()              # the API legs bring their own Matcher (own device library and sessions)
+        line["e2e_api"] = api_legs(workload, args.api_files)
     print(json.dumps(line), flush=True)
     engine.close()
     if world > 1:
         dist.destroy_process_group()
     if line.get("parity", {}).get("mismatches"):
         sys.exit(f"PARITY FAILURE: {line['parity']}")
+
+
+def run_strong(args, rank, local_rank, world):
+    """BASELINE config 3: ONE list of ``--total`` structures searched by N GPUs with the host merge
+    inside the timed region.  Ranks pull chunks of the list from one counter (``sharding.ChunkQueue``,
+    a key in the process group's store: dynamic hand-out, no data-path collective), every chunk is
+    uploaded from pinned host memory, prepared, searched and its hits read back (two sessions on two
+    streams per rank, as the e2e leg of the weak-scaling bench), and at the end all hit records travel
+    to rank 0 in one NCCL gather and are placed in input order (``sharding.gather_hit_blocks``).
+    Wall clock from a barrier before the first chunk to the merged list on rank 0.
+
+    Host memory: a 10^6-structure list is ~107 GB of SoA columns, so structure i of the list is
+    structure ``i mod D`` of D distinct synthetic structures (``--distinct``, default 16 384 = 1.7 GB
+    of pinned memory per rank) -- the LIST is one million long and every chunk is uploaded, prepared
+    and searched anew; only the host buffers repeat."""
+    import torch
+    import torch.distributed as dist
+    from enzymm_b200.engine import Engine, HIT_DTYPE, PackedBatch, Session
+    from enzymm_b200.library import CompiledLibrary
+    from enzymm_b200.sharding import ChunkQueue, gather_hit_blocks
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    chunk = args.chunk
+    distinct_chunks = max(1, args.distinct // chunk)
+    workers = max(1, host_threads() // max(world, 1))
+    templates = active_templates()
+    dists = [DEFAULT_DIST[min(t.effective_size, 8)] for t in templates]
+    engine = Engine(CompiledLibrary(templates, 2.0, dists, dists), device=local_rank)
+
+    def pinned(a):
+        return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    # distinct chunk c is generated by rank c mod N and broadcast: nobody generates the corpus twice
+    t_gen = time.perf_counter()
+    host_chunks = []
+    for c in range(distinct_chunks):
+        src = c % world
+        cols = None
+        if rank == src:
+            packed = make_workload(c, chunk, args.residues, args.chains, workers).to_packed(engine.compiled)
+            cols = [packed.atom_off, packed.xyz, packed.klass, packed.residue, packed.bfactor]
+        if world > 1:
+            shapes = [[(a.shape, str(a.dtype)) for a in cols]] if rank == src else [None]
+            dist.broadcast_object_list(shapes, src=src)
+            received = []
+            for i, (shape, dtype) in enumerate(shapes[0]):
+                n_bytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                buf = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+                if rank == src:
+                    buf.copy_(torch.from_numpy(np.ascontiguousarray(cols[i]).view(np.uint8).reshape(-1)))
+                dist.broadcast(buf, src=src)
+                received.append(buf.cpu().numpy().view(dtype).reshape(shape))
+            cols = received
+        host_chunks.append(PackedBatch(pinned(cols[0]), pinned(cols[1]), pinned(cols[2]), pinned(cols[3]), pinned(cols[4]),
+                                       None, None))
+    t_gen = time.perf_counter() - t_gen
+    max_atoms = max(b.n_atoms for b in host_chunks)
+    lanes = [(Session(engine.device_library, max_atoms, chunk, 64 * chunk), torch.cuda.Stream().cuda_stream) for _ in range(2)]
+    kwargs = dict(max_candidates=10000, ignore_chain=True, reset=True, force_prepare=True)
+
+    def sweep(n_total):
+        """Search chunks of an n_total-long list until the queue is empty; returns [(first, hits)]."""
+        queue = ChunkQueue(n_total, chunk)
+        spans = iter(queue)
+        blocks, flying = [], []
+
+        def submit(span, lane):
+            sess, st = lanes[lane]
+            batch = host_chunks[(span[0] // chunk) % distinct_chunks]
+            if span[1] - span[0] < batch.n_structures:
+                batch = batch.slice(0, span[1] - span[0])
+            sess.upload(batch, stream=st)
+            sess.run(stream=st, **kwargs)
+            return span, lane
+
+        span = next(spans, None)
+        i = 0
+        while span is not None or flying:
+            if span is not None:
+                flying.append(submit(span, i % 2))
+                i += 1
+                span = next(spans, None)
+            if len(flying) == 2 or span is None:
+                done, lane = flying.pop(0)
+                blocks.append((done[0], lanes[lane][0].download(stream=lanes[lane][1])))
+        return blocks
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 1)):                       # warm-up: a short list through the same code
+        gather_hit_blocks(sweep(2 * world * chunk), HIT_DTYPE, device="cuda" if world > 1 else None)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    times, busy, n_hits = [], [], 0
+    windows = []
+    for _ in range(args.steps):
+        barrier()
+        w0 = time.time()
+        t0 = time.perf_counter()
+        blocks = sweep(args.total)
+        t_search = time.perf_counter() - t0
+        merged = gather_hit_blocks(blocks, HIT_DTYPE, device="cuda" if world > 1 else None)
+        barrier()
+        times.append(time.perf_counter() - t0)
+        windows.append((w0, time.time()))
+        busy.append(t_search)
+        if rank == 0:
+            n_hits = len(merged)
+            order_ok = bool(np.all(np.diff(merged["structure"].astype(np.int64)) >= 0))
+            assert order_ok and int(merged["structure"].max()) < args.total
+        del merged, blocks
+    clocks = sampler.stop(windows) if sampler else None
+    every_busy = [None] * world
+    if world > 1:
+        dist.all_gather_object(every_busy, [round(b, 4) for b in busy])
+    else:
+        every_busy = [[round(b, 4) for b in busy]]
+    if rank == 0:
+        total_s = sum(times)
+        line = base_line(args, world)
+        line.update({
+            "impl": "b200", "scaling": "strong", "value": args.total * args.steps / total_s,
+            "ms_per_step": 1000.0 * total_s / args.steps, "dtype": "f32 (+f64 guard band and superposition)",
+            "config": {"workload": f"ONE list of {args.total} synthetic {args.residues}-residue structures (structure i = distinct "
+                                   f"structure i mod {distinct_chunks * chunk}; planted M-CSA motifs, seed 20230210) x 6780 active "
+                                   f"templates, default --jess thresholds, sharded by query over {world} GPU(s) in chunks of "
+                                   f"{chunk} from one shared counter, hit lists merged on rank 0 in input order (BASELINE config 3)",
+                       "total_structures": args.total, "chunk": chunk, "distinct_structures": distinct_chunks * chunk,
+                       "templates": 6780, "parallelism": f"shard-by-structure x{world}, dynamic chunk queue",
+                       "timed_region": "pinned host buffers -> H2D -> prepare -> search -> hits D2H per chunk, then the "
+                                       "gather of all hit records to rank 0 and their placement in input order; wall clock "
+                                       "between barriers",
+                       "l2": "every chunk (~220 MB) exceeds the 126 MB L2"},
+            "e2e": {"value": args.total * args.steps / total_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(sum(host_chunks[c % distinct_chunks].nbytes() for c in range((args.total + chunk - 1) // chunk))),
+                    "d2h_bytes_per_step": int(n_hits * HIT_DTYPE.itemsize)},
+            "hits_per_step": int(n_hits), "merged_in_input_order": True,
+            "per_rank_search_s": every_busy, "merge_s": [round(t - max(b[i] for b in every_busy), 4) for i, t in enumerate(times)],
+            "clocks": clocks, "generation_s": t_gen, "gpu_launches": int(2 * ((args.total + chunk - 1) // chunk) * args.steps),
+        })
+        print(json.dumps(line), flush=True)
+    for sess, _ in lanes:
+        sess.close()
+    engine.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -478,6 +690,13 @@ def main():
     ap.add_argument("--chains", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=0, help="structures per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="strong: ONE list of --total structures over N GPUs, host merge timed (BASELINE config 3)")
+    ap.add_argument("--total", type=int, default=1000000, help="length of the list in --scaling strong")
+    ap.add_argument("--chunk", type=int, default=2048, help="structures per chunk handed out in --scaling strong")
+    ap.add_argument("--distinct", type=int, default=16384, help="distinct synthetic structures behind the list")
+    ap.add_argument("--api-files", type=int, default=4096,
+                    help="PDB files for the Python-API legs (files -> hits / Match objects / TSV); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -485,6 +704,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.scaling == "strong":
+        run_strong(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 

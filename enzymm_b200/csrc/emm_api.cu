@@ -639,6 +639,8 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     P.skip_mode = q->skip_mode;
     P.levels = lib->d.max_tpl_atoms + 1;
     P.cell_threshold = q->cell_threshold > 0 ? q->cell_threshold : 0;   // opt-in: typed lists measured faster at every tested size
+    P.donate_after = q->donate_after < 0 ? -1 : (q->donate_after > 0 ? q->donate_after : 48);
+    if (const char *env = getenv("EMM_DONATE_AFTER")) P.donate_after = atoi(env);                  // tuning knob
     const int grid = lib->sm_count;
     emm_library::Sched sc;
     if (int rc = get_sched(lib, tb, te, &sc)) return rc;

@@ -148,6 +148,7 @@ struct SearchParams {
     int blob_cap;          // shared-memory bytes available for a staged blob
     int levels;            // queue levels per warp (max template atoms + 1)
     int cell_threshold;    // leader lists at least this long are searched through the cell list
+    int donate_after;      // level entries after which a pair may hand subtrees to idle warps; < 0: never
 };
 
 struct SearchOut {

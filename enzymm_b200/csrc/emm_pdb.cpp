@@ -281,12 +281,42 @@ struct KindTable {
     }
 };
 
+// Residue names Match.query_residue_count counts (enzymm/utils.py:116-161: the 20 proteinogenic amino
+// acids + EnzyMM's "special" ones), as blank-stripped little-endian packed names.
+inline bool counted_residue(uint32_t resname)
+{
+    static const char *const names[] = {"ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU", "LYS",
+                                        "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL", "ASX", "GLX", "SEC", "PYL",
+                                        "UNK", "MSE", "SEP", "TPO", "PTR", "HYP", "CME", "CSO", "CSD", "PCA", "MLY", "DAL",
+                                        "DAR", "DSG", "ORN", "PTM"};
+    static uint32_t packed[40];
+    static const bool ready = [] {
+        for (int i = 0; i < 40; ++i)
+            packed[i] = (uint32_t)(unsigned char)names[i][0] | ((uint32_t)(unsigned char)names[i][1] << 8) |
+                        ((uint32_t)(unsigned char)names[i][2] << 16);
+        return true;
+    }();
+    (void)ready;
+    for (int i = 0; i < 40; ++i)
+        if (packed[i] == resname) return true;
+    return false;
+}
+
+// distinct residue NUMBERS among atoms of counted residues, chain ignored (jess_run.py:487-496)
+inline int32_t distinct_count(std::vector<int32_t> &v)
+{
+    std::sort(v.begin(), v.end());
+    return (int32_t)(std::unique(v.begin(), v.end()) - v.begin());
+}
+
 // One file into the packed columns at [base, base+capacity).  kind[] receives file-local kind
 // indices; *split is set when a residue key reappears after another residue (the caller then
 // regroups the file).  Returns atoms parsed or -1 (t_error set).
 int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t base, int64_t capacity,
-                  KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5])
+                  KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5],
+                  int32_t *residue_count)
 {
+    std::vector<int32_t> counted;
     int64_t n = 0, pos = 0;
     bool have_header = false;
     memset(header_id, 0, 5);
@@ -321,10 +351,11 @@ int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t ba
             const uint32_t name = strip_field(line + 12, 4), resname = strip_field(line + 17, 3);
             const uint16_t chain = (uint16_t)strip_field(line + 20, 2);
             const uint64_t kkey = (uint64_t)resname | ((uint64_t)name << 32);
+            const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum;
+            if ((kkey != prev_kind || rkey != prev_res) && counted_residue(resname)) counted.push_back(resnum);
             if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
             c.kind[i] = prev_kind_idx;
             c.chain[i] = chain;
-            const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum;
             if (rkey != prev_res || run < 0) {
                 prev_res = rkey;
                 ++run;
@@ -348,17 +379,22 @@ int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t ba
         std::sort(sorted.begin(), sorted.end());
         *split = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
     }
+    *residue_count = distinct_count(counted);
     return n;
 }
 
 // A file with a split residue: number residues by first appearance of their key and make every
 // residue's atoms contiguous with a stable sort (packing.py residue_ordinals does the same).
-void regroup_file(const PackedCols &c, int64_t base, int64_t n, const std::vector<uint64_t> &run_keys, int32_t *atom_id)
+void regroup_file(const PackedCols &c, int64_t base, int64_t n, std::vector<uint64_t> &run_keys, int32_t *atom_id)
 {
     std::unordered_map<uint64_t, int32_t> rank_of;
     std::vector<int32_t> rank_of_run(run_keys.size());
-    for (size_t r = 0; r < run_keys.size(); ++r)
-        rank_of_run[r] = rank_of.emplace(run_keys[r], (int32_t)rank_of.size()).first->second;
+    std::vector<uint64_t> by_rank;                 // residue key of every ordinal, first appearance order
+    for (size_t r = 0; r < run_keys.size(); ++r) {
+        const auto ins = rank_of.emplace(run_keys[r], (int32_t)rank_of.size());
+        if (ins.second) by_rank.push_back(run_keys[r]);
+        rank_of_run[r] = ins.first->second;
+    }
     std::vector<int32_t> ordinal((size_t)n), order((size_t)n);
     for (int64_t j = 0; j < n; ++j) {
         ordinal[(size_t)j] = rank_of_run[(size_t)c.residue[base + j]];
@@ -381,6 +417,7 @@ void regroup_file(const PackedCols &c, int64_t base, int64_t n, const std::vecto
         c.residue[dst] = ordinal[(size_t)order[(size_t)j]];
         atom_id[dst] = order[(size_t)j];
     }
+    run_keys.swap(by_rank);
 }
 
 bool read_file(const char *path, std::string &out, int *err)
@@ -427,6 +464,8 @@ struct FileBlock {
     double *xyz = nullptr; uint32_t *kind = nullptr; int32_t *residue = nullptr; float *bfactor = nullptr;
     uint16_t *chain = nullptr;
     std::vector<uint64_t> kinds;
+    std::vector<uint64_t> res_keys;      // (chain << 32 | residue number) of every residue ordinal
+    int32_t residue_count = 0;           // Match.query_residue_count of this structure
     bool split = false;
     void allocate(int64_t count)
     {
@@ -441,7 +480,7 @@ struct FileBlock {
         bfactor = reinterpret_cast<float *>(p); p += c * 4;
         chain = reinterpret_cast<uint16_t *>(p);
     }
-    void release() { mem.reset(); atom_id.reset(); std::vector<uint64_t>().swap(kinds); }
+    void release() { mem.reset(); atom_id.reset(); std::vector<uint64_t>().swap(kinds); std::vector<uint64_t>().swap(res_keys); }
 };
 
 }  // namespace
@@ -462,10 +501,12 @@ struct emm_pdb_batch {
     int32_t n_files = 0;
     int64_t n_atoms = 0;
     std::vector<int64_t> atom_off;
-    std::vector<int32_t> serial, resnum;
-    std::vector<char> name, altloc, resname, chain, icode, segment, element, header_id;
-    std::vector<double> xyz, occupancy, bfactor;
-    std::vector<int8_t> charge;
+    // Molecule columns (emm_pdb_load_files): not value-initialised, every entry is written by the parser
+    RawArray<int32_t> serial, resnum;
+    RawArray<char> name, altloc, resname, chain, icode, segment, element;
+    std::vector<char> header_id;
+    RawArray<double> xyz, occupancy, bfactor;
+    RawArray<int8_t> charge;
     // packed form (emm_pdb_pack_files)
     bool packed = false, has_atom_id = false, has_klass = false;
     int n_threads = 1;
@@ -476,6 +517,9 @@ struct emm_pdb_batch {
     RawArray<float> bfactor32;
     RawArray<uint16_t> chain16;
     std::vector<char> kind_names;
+    std::vector<int64_t> res_off;        // [n_files+1] into res_key
+    std::vector<uint64_t> res_key;       // per residue ordinal: chain << 32 | residue number
+    std::vector<int32_t> residue_count;  // per file
 };
 
 extern "C" {
@@ -611,6 +655,15 @@ static void finish_packed(emm_pdb_batch *b, std::vector<FileBlock> &blocks, int 
     }
     b->kind_names.assign(8 * global.keys.size(), 0);
     for (size_t j = 0; j < global.keys.size(); ++j) memcpy(&b->kind_names[8 * j], &global.keys[j], 8);
+    b->res_off.assign(nf + 1, 0);
+    b->residue_count.assign(nf, 0);
+    for (size_t f = 0; f < nf; ++f) {
+        b->res_off[f + 1] = b->res_off[f] + (int64_t)blocks[f].res_keys.size();
+        b->residue_count[f] = blocks[f].residue_count;
+    }
+    b->res_key.resize((size_t)b->res_off[nf]);
+    for (size_t f = 0; f < nf; ++f)
+        std::copy(blocks[f].res_keys.begin(), blocks[f].res_keys.end(), b->res_key.begin() + b->res_off[f]);
     // pass 2: blocks -> their place in the batch columns (first touch of those pages, in parallel)
     {
         std::atomic<int> next(0);
@@ -678,13 +731,15 @@ int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_thre
                 blk.allocate(count);
                 kinds.clear();
                 const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
-                const int64_t got = pack_into(text.data(), len, c, 0, count, kinds, run_keys, &blk.split, &b->header_id[5 * f]);
+                const int64_t got = pack_into(text.data(), len, c, 0, count, kinds, run_keys, &blk.split, &b->header_id[5 * f],
+                                              &blk.residue_count);
                 if (got != count) { messages[f] = t_error; errs[f] = 3; continue; }
                 blk.kinds = kinds.keys;
                 if (blk.split) {
                     blk.atom_id.reset(new int32_t[(size_t)std::max<int64_t>(count, 1)]);
                     regroup_file(c, 0, count, run_keys, blk.atom_id.get());
                 }
+                blk.res_keys = run_keys;
             }
         });
     }
@@ -732,6 +787,7 @@ int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *
                 uint32_t prev_kind_idx = 0;
                 int32_t run = -1;
                 const uint8_t *nm = name4[f], *rn = resname4[f], *ch = chain2[f];
+                std::vector<int32_t> counted;
                 for (int64_t a = 0; a < n; ++a) {
                     uint32_t name, res;
                     uint16_t chain;
@@ -739,10 +795,11 @@ int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *
                     memcpy(&res, rn + 4 * a, 4);
                     memcpy(&chain, ch + 2 * a, 2);
                     const uint64_t kkey = (uint64_t)res | ((uint64_t)name << 32);
+                    const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum[f][a];
+                    if ((kkey != prev_kind || rkey != prev_res) && counted_residue(res)) counted.push_back(resnum[f][a]);
                     if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
                     blk.kind[a] = prev_kind_idx;
                     blk.chain[a] = chain;
-                    const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum[f][a];
                     if (rkey != prev_res || run < 0) { prev_res = rkey; ++run; run_keys.push_back(rkey); }
                     blk.residue[a] = run;
                     blk.bfactor[a] = (float)bfactor[f][a];
@@ -757,6 +814,8 @@ int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *
                     const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
                     regroup_file(c, 0, n, run_keys, blk.atom_id.get());
                 }
+                blk.res_keys = run_keys;
+                blk.residue_count = distinct_count(counted);
             }
         };
         std::vector<std::thread> pool;
@@ -803,6 +862,9 @@ int emm_pdb_batch_packed(const emm_pdb_batch *b, emm_pdb_packed *out)
     out->n_kinds = (int32_t)(b->kind_names.size() / 8);
     out->kind_names = b->kind_names.data();
     out->header_id = b->header_id.data();
+    out->res_off = b->res_off.data();
+    out->res_key = b->res_key.data();
+    out->residue_count = b->residue_count.data();
     return EMM_OK;
 }
 

@@ -71,7 +71,58 @@ struct WarpState {
     int best_valid;
     int overflow;
     uint32_t best_asg[kMaxAtoms];
+    int donated;                 // this warp gave parts of its own pair away
+    int for_owner;               // searching a donated subtree on behalf of this warp, or -1
 };
+
+// ---- splitting one (template, structure) pair across the warps of its CTA -------------------------
+// Pair cost is heavy-tailed (a 21-atom template at cutoff 2.0 can take 100 ms of warp time against
+// one structure while the median pair takes 10 us).  A warp whose pair has run for a while gives
+// untouched partial assignments of the chunk it is entering -- whole subtrees of the search -- to
+// warps that have run out of templates: a donation is the chain of atoms placed so far; the helper
+// rebuilds that chain as one-entry queues and runs the ordinary search below it; results meet in
+// the owner's PairSlot (minimum RMSD with the lexicographic tie-break, summed complete-assignment
+// counts), and the owner writes the hit once every donation has come back.
+constexpr int kDonationRing = 32;
+
+struct Donation {
+    int owner;                   // warp whose pair this subtree belongs to
+    int depth;                   // atoms placed: plan positions 0 .. depth-1
+    int t;                       // template
+    int pad;
+    uint32_t chain[kMaxAtoms];   // chain[j] = atom at plan position j
+};
+
+struct PairSlot {
+    int lock;                    // spin lock (lane 0 of the merging warp)
+    int pending;                 // donations handed out and not merged back yet
+    int best_valid, overflow;
+    unsigned long long n_complete;
+    double best_rmsd;
+    uint32_t best_asg[kMaxAtoms];
+};
+
+struct CtaShare {
+    int ring_lock, ring_count;
+    int idle;                    // warps out of templates, waiting for donations
+    int in_loop;                 // warps that still own (or may still take) a template of this item
+    Donation ring[kDonationRing];
+    PairSlot slot[kSearchWarps];
+};
+
+__device__ __forceinline__ int peek(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+
+__device__ __forceinline__ void spin_lock(int *lock)
+{
+    while (atomicCAS(lock, 0, 1) != 0) __nanosleep(20);
+    __threadfence_block();
+}
+
+__device__ __forceinline__ void spin_unlock(int *lock)
+{
+    __threadfence_block();
+    atomicExch(lock, 0);
+}
 
 // Dynamic shared memory: [staged blob][per-warp queues][per-warp state].
 extern __shared__ __align__(16) unsigned char g_smem[];
@@ -506,6 +557,88 @@ __device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S
     __syncwarp();
 }
 
+// Lane 0: fold this warp's result of (a part of) a pair into the pair's slot.
+__device__ __noinline__ void merge_into_slot(PairSlot *ps, const WarpState *ws, int m)
+{
+    spin_lock(&ps->lock);
+    ps->n_complete += ws->n_complete;
+    ps->overflow |= ws->overflow;
+    if (ws->best_valid) {
+        bool better = !ps->best_valid || ws->best_rmsd < ps->best_rmsd;
+        if (!better && ws->best_rmsd == ps->best_rmsd) {
+            for (int i = 0; i < m; ++i)
+                if (ws->best_asg[i] != ps->best_asg[i]) { better = ws->best_asg[i] < ps->best_asg[i]; break; }
+        }
+        if (better) {
+            ps->best_valid = 1;
+            ps->best_rmsd = ws->best_rmsd;
+            for (int i = 0; i < m; ++i) ps->best_asg[i] = ws->best_asg[i];
+        }
+    }
+    spin_unlock(&ps->lock);
+}
+
+// Lane 0: the merged result of a split pair back into the owner's warp state, for emit_hit.
+__device__ __noinline__ void load_from_slot(const PairSlot *ps, WarpState *ws, int m, long long max_candidates)
+{
+    ws->best_valid = ps->best_valid;
+    ws->best_rmsd = ps->best_rmsd;
+    ws->n_complete = ps->n_complete;
+    ws->overflow = ps->overflow || (max_candidates > 0 && ps->n_complete >= (unsigned long long)max_candidates);
+    for (int i = 0; i < m; ++i) ws->best_asg[i] = ps->best_asg[i];
+}
+
+// Give the untouched tail of the chunk just entered at level k (valid = its live slots, anchors
+// compacted in ws) to idle warps, one partial per donation.  `first_free` = first compacted partial
+// no expansion has touched.  Returns the remaining valid mask.
+__device__ __noinline__ unsigned donate_tail(CtaShare *sh, uint32_t *Q, WarpState *ws, int wid, int t,
+                                             int k, int base, unsigned valid, int first_free, int idle, int lane)
+{
+    const int owner = ws->for_owner >= 0 ? ws->for_owner : wid;     // a helper donates on its owner's behalf
+    const bool fresh = ws->for_owner < 0 && !ws->donated;
+    const int P = __popc(valid);
+    int give = min(P - first_free, idle);          // warp-uniform: idle was read by one lane
+    if (give <= 0) return valid;
+    int at = 0;
+    if (lane == 0) {
+        spin_lock(&sh->ring_lock);
+        at = sh->ring_count;
+        give = min(give, kDonationRing - at);
+        if (give <= 0) spin_unlock(&sh->ring_lock);
+    }
+    give = __shfl_sync(kFull, give, 0);
+    at = __shfl_sync(kFull, at, 0);
+    if (give <= 0) return valid;
+    if (fresh && lane == 0) {        // first donation of this pair: an empty slot
+        PairSlot *ps = &sh->slot[owner];
+        ps->pending = 0; ps->best_valid = 0; ps->overflow = 0; ps->n_complete = 0ull; ps->best_rmsd = CUDART_INF;
+    }
+    unsigned gone = 0u;
+    if (lane < give) {
+        const int slot = (int)ws->vslot[P - give + lane];
+        gone = 1u << slot;
+        Donation *d = &sh->ring[at + lane];
+        d->owner = owner; d->depth = k; d->t = t;
+        uint32_t w = Q[queue_off(k) + base + slot];
+        Q[queue_off(k) + base + slot] = w | kEntryDead;          // the owner will not look at it again
+        for (int pos = k - 1; pos >= 0; --pos) {
+            d->chain[pos] = (uint32_t)entry_atom(w);
+            if (pos > 0) w = Q[queue_off(pos) + entry_parent(w)];
+        }
+    }
+    gone = __reduce_or_sync(kFull, gone);
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        atomicAdd(&sh->slot[owner].pending, give);
+        sh->ring_count = at + give;
+        ws->donated = 1;
+        spin_unlock(&sh->ring_lock);
+    }
+    __syncwarp();
+    return valid & ~gone;
+}
+
 // Guard band: decide one entry of level k (new atom at plan position k-1) with the oracle's FP64
 // expressions against every placed atom.
 __device__ __noinline__ bool exact_validate(const DevLibrary &L, const Blob &S, const uint32_t *Q, int a0,
@@ -596,6 +729,8 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
     return full;
 }
 
+__device__ __forceinline__ int L_atoms(const DevLibrary &L, int t) { return L.atom_off[t + 1] - L.atom_off[t]; }
+
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
@@ -676,22 +811,27 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     return valid;
 }
 
+// Search template t against the staged structure, or -- don_depth > 0 -- only the subtree below a
+// donated partial assignment of don_depth atoms (lane j holds the atom of plan position j in
+// don_atom) on behalf of warp don_owner.  Returns true when this warp gave parts of ITS pair away:
+// its own part is merged into its PairSlot and the caller writes the hit once all parts are back.
 template <bool kStats, bool kStaged, bool kCells>
-__device__ __forceinline__ void search_template(const SearchArgs &A, const Blob &S, const View<kStaged> &V, int s,
-                                                int t, uint32_t *Q, WarpState *ws, int lane, LaneStats &st)
+__device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob &S, const View<kStaged> &V, int s,
+                                                int t, uint32_t *Q, WarpState *ws, int lane, LaneStats &st,
+                                                CtaShare *sh, int wid, int don_depth, int don_owner, uint32_t don_atom)
 {
     const DevLibrary &L = A.L;
     const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
     const int64_t p0 = L.pair_off[t];
 
     // a template with an empty leader list cannot match this structure
-    {
+    if (don_depth == 0) {
         bool empty = false;
         if (lane < m) {
             const int src = L.plan_src[a0 + lane];
             if (src < 0) empty = V.lead_off(-src) == V.lead_off(-1 - src);
         }
-        if (__any_sync(kFull, empty)) return;
+        if (__any_sync(kFull, empty)) return false;
     }
 
     const double cut64 = L.dist_cut[t], dyn64 = L.max_dyn[t];
@@ -701,12 +841,27 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
     const unsigned lt_mask = (1u << lane) - 1u;
 
     if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0ull; if (kCells) { ws->cellrow[lane] = 0; ws->celli[lane] = -1; } }
-    if (lane == 0) { ws->best_valid = 0; ws->overflow = 0; ws->n_complete = 0ull; ws->best_rmsd = CUDART_INF; }
+    if (lane == 0) {
+        ws->best_valid = 0; ws->overflow = 0; ws->n_complete = 0ull; ws->best_rmsd = CUDART_INF;
+        ws->donated = 0; ws->for_owner = don_depth > 0 ? don_owner : -1;
+    }
     __syncwarp();
 
     int k = 0, base = 0;
     unsigned valid = 1u;          // level 0: the empty partial
     bool entered = true;
+    int visits = 0;               // level entries so far: a pair may donate once it has run for a while
+    if (don_depth > 0) {
+        // A donated subtree: the chain of placed atoms becomes one validated entry per level, every
+        // ancestor marked as fully expanded, so the walk below never leaves the subtree.
+        if (lane < don_depth) Q[queue_off(lane + 1)] = don_atom | kEntryValid;          // parent: slot 0
+        if (lane >= 1 && lane <= don_depth) { ws->n[lane] = 1; ws->chunk[lane] = 1; ws->cur[lane] = lane < don_depth ? -1 : 0; }
+        if (lane == 0) ws->cur[0] = -1;
+        __syncwarp();
+        k = don_depth;
+        entered = false;
+        valid = 0u;
+    } else
     // Fast start.  Level 0 has nothing to test: its expansion copies the first leader list into
     // queue 1 and entering level 1 only derives anchors.  When the list fits one chunk (the usual
     // case: plans start with the rarest type) do both here, without the level machinery.
@@ -753,6 +908,24 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
             if (kStats && lane == 0 && k > 0 && ws->cur[k] >= 0) {
                 atomicAdd(A.O.stats + 72 + k, (unsigned long long)__popc(valid));
                 atomicAdd(A.O.stats + 104 + k, 1ull);
+            }
+            // Split the pair: once it has run for a while and other warps of the CTA sit idle, give
+            // them the partials of this chunk that no expansion has touched yet (the tail of the
+            // compacted order, so the cursor of this level stays meaningful).
+            int idle = 0;
+            if (!kCells && A.P.donate_after >= 0 && k > 0 && k < m && valid && ++visits > A.P.donate_after) {
+                if (lane == 0) idle = peek(&sh->idle);         // one reader: the branch below must be warp-uniform
+                idle = __shfl_sync(kFull, idle, 0);
+            }
+            if (idle > 0) {
+                const int cur = ws->cur[k];
+                const int pend = ws->todo[k] != 0ull ? 1 : 0;
+                int first_free;
+                if ((int)L.plan_src[a0 + k] >= 0) first_free = (((cur + pend) << 5) + (1 << V.res_shift) - 1) >> V.res_shift;
+                else first_free = (cur >> 5) == 0 ? (cur & 31) + 1 : 32;       // leader level: during its first row pair only
+                const unsigned before = valid;
+                valid = donate_tail(sh, Q, ws, wid, t, k, base, valid, max(first_free, 1), idle, lane);
+                if (kStats && lane == 0 && valid != before) atomicAdd(A.O.stats + 12, (unsigned long long)__popc(before ^ valid));
             }
             if (k == m && valid) process_complete(A, S, t, Q, ws, base, valid, lane);
         }
@@ -971,8 +1144,24 @@ __device__ __forceinline__ void search_template(const SearchArgs &A, const Blob 
         entered = false;
     }
     if (kStats && lane == 0 && ws->n_complete) atomicAdd(A.O.stats + 4, ws->n_complete);
+    const int for_owner = ws->for_owner;
+    if (for_owner >= 0) {                    // a helper: the result goes to the owner's slot
+        if (lane == 0) {
+            merge_into_slot(&sh->slot[for_owner], ws, m);
+            __threadfence_block();
+            atomicSub(&sh->slot[for_owner].pending, 1);
+        }
+        __syncwarp();
+        return false;
+    }
+    if (ws->donated) {                       // the owner of a split pair: its own part joins the others
+        if (lane == 0) merge_into_slot(&sh->slot[wid], ws, m);
+        __syncwarp();
+        return true;
+    }
     if (ws->best_valid && lane == 0) emit_hit(A, S, s, t, ws);
     __syncwarp();
+    return false;
 }
 
 template <bool kStats, bool kStaged, bool kCells>
@@ -981,6 +1170,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
 {
     __shared__ int s_item, s_next_pos;
     __shared__ Blob s_blob;
+    __shared__ CtaShare s_share;                 // static: addressed by a constant, costs no register
     __shared__ __align__(8) uint64_t s_bar;      // mbarrier the TMA bulk copy of a blob completes on
 
     const int tid = threadIdx.x;
@@ -998,6 +1188,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
     const int qwords = queue_off(P.levels);      // queue words per warp
     uint32_t *Q = reinterpret_cast<uint32_t *>(g_smem + P.blob_cap) + (size_t)wid * qwords;
     WarpState *ws = reinterpret_cast<WarpState *>(g_smem + P.blob_cap + (size_t)kSearchWarps * qwords * 4) + wid;
+    CtaShare *const sh = &s_share;
 
     LaneStats st = {0ull, 0ull, 0ull};
     unsigned long long st_pairs = 0, st_staged = 0, st_global = 0;
@@ -1037,6 +1228,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             }
             if (tid == 0) {
                 s_next_pos = pos0;
+                sh->ring_lock = 0; sh->ring_count = 0; sh->idle = 0; sh->in_loop = kSearchWarps;
                 const int64_t abase = A.B.atom_off[s];
                 s_blob.orig = reinterpret_cast<const int32_t *>(gblob + hdr.off_orig);
                 s_blob.xyz64 = A.B.xyz + 3 * abase;
@@ -1058,21 +1250,82 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             V.off_atom = hdr.off_atom;
             V.off_resstart = hdr.off_resstart; V.off_leadoff = hdr.off_leadoff;
             V.off_lead = hdr.off_lead; V.res_shift = hdr.res_shift; V.eps = hdr.eps; V.wide = hdr.wide != 0;
+            // Per-warp work loop: take templates while there are any; a warp that split its pair helps
+            // with donated subtrees until all parts of the pair are back and then writes the hit; a
+            // warp out of templates helps until every warp of the CTA has left the loop.
+            if (lane == 0) sh->slot[wid].lock = 0;
+            bool fetching = true, counted_idle = false;
+            int owning = -1;
             for (;;) {
-                int t = -1;
-                if (lane == 0) {
-                    const int pos = atomicAdd(&s_next_pos, stride);
-                    if (pos < pos1) t = __ldg(A.sched + pos);
+                int t = -1, depth = 0, owner = 0;
+                uint32_t atom = 0u;
+                if (owning >= 0 || !fetching) {
+                    // lane 0 looks at the shared state and decides for the warp:
+                    // >= 0 take ring record idx | -1 write my split pair's hit | -2 leave | -3 wait
+                    int idx = -3;
+                    if (lane == 0) {
+                        if (peek(&sh->ring_count) > 0) {
+                            spin_lock(&sh->ring_lock);
+                            if (sh->ring_count > 0) idx = --sh->ring_count;      // the lock is kept until the record is copied
+                            else spin_unlock(&sh->ring_lock);
+                        }
+                        if (idx < 0) {
+                            if (owning >= 0) { if (peek(&sh->slot[wid].pending) == 0) idx = -1; }
+                            else if (peek(&sh->in_loop) == 0) idx = -2;
+                        }
+                    }
+                    idx = __shfl_sync(kFull, idx, 0);
+                    if (idx >= 0) {
+                        const Donation *d = &sh->ring[idx];
+                        t = d->t; depth = d->depth; owner = d->owner; atom = d->chain[lane];
+                        __syncwarp();
+                        if (lane == 0) {
+                            spin_unlock(&sh->ring_lock);
+                            if (counted_idle) atomicSub(&sh->idle, 1);
+                        }
+                        counted_idle = false;
+                    } else if (idx == -1) {
+                        // every part of my split pair is merged: write its hit, go back to the templates
+                        __threadfence_block();
+                        const int mo = L_atoms(A.L, owning);
+                        if (lane == 0) {
+                            if (counted_idle) atomicSub(&sh->idle, 1);
+                            load_from_slot(&sh->slot[wid], ws, mo, P.max_candidates);
+                            if (ws->best_valid) emit_hit(A, s_blob, s, owning, ws);
+                        }
+                        counted_idle = false;
+                        owning = -1;
+                        __syncwarp();
+                        continue;
+                    } else if (idx == -2) {
+                        if (lane == 0 && counted_idle) atomicSub(&sh->idle, 1);
+                        break;                       // every pair of this item is finished
+                    } else {
+                        if (!counted_idle) { if (lane == 0) atomicAdd(&sh->idle, 1); counted_idle = true; }
+                        __nanosleep(200);
+                        continue;
+                    }
+                } else {
+                    if (lane == 0) {
+                        const int pos = atomicAdd(&s_next_pos, stride);
+                        if (pos < pos1) t = __ldg(A.sched + pos);
+                    }
+                    t = __shfl_sync(kFull, t, 0);
+                    if (t < 0) {
+                        fetching = false;
+                        if (lane == 0) atomicSub(&sh->in_loop, 1);
+                        continue;
+                    }
                 }
-                t = __shfl_sync(kFull, t, 0);
-                if (t < 0) break;
                 unsigned long long pair_t0 = 0;
                 if (kStats) pair_t0 = global_ns();
-                search_template<kStats, kStaged, kCells>(A, s_blob, V, s, t, Q, ws, lane, st);
+                const bool split = search_template<kStats, kStaged, kCells>(A, s_blob, V, s, t, Q, ws, lane, st, sh, wid,
+                                                                            depth, owner, atom);
+                if (split) owning = t;
                 if (kStats && lane == 0) {
-                    ++st_pairs;
+                    if (depth == 0) ++st_pairs;
                     const unsigned long long dt = global_ns() - pair_t0;
-                    atomicMax(A.O.stats + 13, ((dt >> 10) << 24) | (unsigned long long)t);     // slowest pair: us, template
+                    atomicMax(A.O.stats + 13, ((dt >> 10) << 24) | (unsigned long long)t);     // slowest pair (or part of one): us, template
                     atomicAdd(A.O.stats + 28 + log2_bucket_us(dt, 12), 1ull);
                 }
             }
@@ -1121,7 +1374,8 @@ size_t search_smem_bytes(int blob_cap, int levels)
     return (size_t)blob_cap + (size_t)kSearchWarps * queue_off(levels) * 4 + (size_t)kSearchWarps * sizeof(WarpState);
 }
 
-size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels); }
+// shared memory a CTA needs besides the staged blob: the dynamic part above + the static CtaShare
+size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels) + sizeof(CtaShare); }
 
 cudaError_t configure_search(int smem_bytes)
 {

@@ -79,7 +79,7 @@ class _QueryParams(ctypes.Structure):
         ("conservation_cutoff", ctypes.c_float), ("template_begin", ctypes.c_int32),
         ("template_end", ctypes.c_int32), ("skip_mode", ctypes.c_int32),
         ("reset_structure_state", ctypes.c_int32), ("force_prepare", ctypes.c_int32),
-        ("cell_threshold", ctypes.c_int32),
+        ("cell_threshold", ctypes.c_int32), ("donate_after", ctypes.c_int32),
     ]
 
 
@@ -115,7 +115,7 @@ def load_cdll() -> ctypes.CDLL:
             getattr(lib, name).restype = ctypes.c_int
         lib.emm_library_destroy.restype = None
         lib.emm_session_destroy.restype = None
-        if lib.emm_abi_version() != 1:
+        if lib.emm_abi_version() != 2:
             raise ImportError("libenzymm_b200.so ABI version mismatch")
         assert ctypes.sizeof(_Stats) == 64
         if lib.emm_hit_size() != HIT_DTYPE.itemsize:
@@ -146,6 +146,7 @@ class PackedBatch:
         self.bfactor = None if bfactor is None else np.ascontiguousarray(bfactor, dtype=np.float32)
         self.chain = None if chain is None else np.ascontiguousarray(chain, dtype=np.uint16)
         self.atom_id = None if atom_id is None else np.ascontiguousarray(atom_id, dtype=np.int32)
+        self.table = None              # tsv.TableColumns when the batch came from a native packer
         n = int(self.atom_off[-1]) if len(self.atom_off) else 0
         for name in ("klass", "residue", "bfactor", "chain", "atom_id"):
             col = getattr(self, name)
@@ -262,10 +263,10 @@ class Session:
 
     def run(self, *, max_candidates: int = 10000, ignore_chain: bool = True, conservation_cutoff: float = 0.0,
             template_begin: int = 0, template_end: int = 0, skip_mode: int = 0, reset: bool = True,
-            force_prepare: bool = False, cell_threshold: int = 0, stream: int = 0):
+            force_prepare: bool = False, cell_threshold: int = 0, donate_after: int = 0, stream: int = 0):
         q = _QueryParams(int(max_candidates or 0), 1 if ignore_chain else 0, float(conservation_cutoff or 0.0),
                          int(template_begin), int(template_end), int(skip_mode), 1 if reset else 0,
-                         1 if force_prepare else 0, int(cell_threshold))
+                         1 if force_prepare else 0, int(cell_threshold), int(donate_after))
         _check(self._lib.emm_session_run(self.handle, ctypes.byref(q), ctypes.c_void_p(stream)))
 
     def download(self, stream: int = 0, with_stats: bool = False):

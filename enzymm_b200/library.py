@@ -41,8 +41,11 @@ LR_MODELS = 5
 _DATA = Path(__file__).resolve().parent / "data"
 
 
+MODE1_READINGS = ("N_or_O", "same_element", "exact_name", "N_O_or_S")
+
+
 def type_match(match_mode: int, residue_names: Sequence[str], atom_names: Sequence[str],
-               query_residue: str, query_atom: str) -> bool:
+               query_residue: str, query_atom: str, mode1: str = "N_or_O") -> bool:
     """May a template atom with this typing bind a query atom named ``query_atom`` in a residue
     named ``query_residue``?  (SURVEY.md 8c rules 2-3; names are whitespace-stripped.)
 
@@ -58,7 +61,17 @@ def type_match(match_mode: int, residue_names: Sequence[str], atom_names: Sequen
     if kind == 0:
         return query_atom in atom_names
     if kind == 1:
-        return query_atom[:1] in ("N", "O")
+        # the one reading no reference vector pins (4005 of the 7607 shipped templates carry such an
+        # atom); ``mode1`` selects an alternative so the exposure can be measured and a pin applied
+        if mode1 == "N_or_O":
+            return query_atom[:1] in ("N", "O")
+        if mode1 == "same_element":
+            return any(query_atom[:1] == n[:1] for n in atom_names)
+        if mode1 == "exact_name":
+            return query_atom in atom_names
+        if mode1 == "N_O_or_S":
+            return query_atom[:1] in ("N", "O", "S")
+        raise ValueError(f"unknown reading of match_mode 1: {mode1!r}")
     if kind == 3:
         return any(query_atom[:1] == n[:1] for n in atom_names)
     if kind == 8:
@@ -104,10 +117,14 @@ class CompiledLibrary:
     """
 
     def __init__(self, templates: Sequence[JessTemplate], rmsd_threshold, distance_cutoff,
-                 max_dynamic_distance, lr_models: Optional[dict] = None, plan_order: str = "leaders_first"):
+                 max_dynamic_distance, lr_models: Optional[dict] = None, plan_order: str = "leaders_first",
+                 mode1: str = "N_or_O"):
         if plan_order not in ("leaders_first", "leaders_first_greedy", "residue_major"):
             raise ValueError("plan_order must be 'leaders_first', 'leaders_first_greedy' or 'residue_major'")
+        if mode1 not in MODE1_READINGS:
+            raise ValueError(f"mode1 must be one of {MODE1_READINGS}")
         self.plan_order = plan_order
+        self.mode1 = mode1
         self.templates = list(templates)
         if not self.templates:
             raise ValueError("cannot compile an empty template list")
@@ -420,7 +437,7 @@ class CompiledLibrary:
         residue_name, atom_name = kind
         c = self._class_of_kind.get(kind)
         if c is None:
-            column = np.fromiter((type_match(k[0], k[1], k[2], residue_name, atom_name) for k in self.keys),
+            column = np.fromiter((type_match(k[0], k[1], k[2], residue_name, atom_name, self.mode1) for k in self.keys),
                                  dtype=bool, count=self.n_ttype)
             sig = column.tobytes()
             c = self._class_of_column.get(sig)

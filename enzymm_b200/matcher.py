@@ -468,7 +468,8 @@ class Matcher:
                 self.hits_per_structure = max(self.hits_per_structure, capacity // max(batch.n_structures, 1))
         raise EngineError(-4, "hit buffer kept overflowing")
 
-    def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0, queue=None):
+    def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0, queue=None,
+                   with_batch: bool = False, devices: Optional[Sequence[int]] = None, _with_span: bool = False):
         """Screen PDB files without building ``Molecule`` objects: a generator of
         ``(chunk_paths, header_ids, records)`` per chunk of ``chunk_size`` files, ``records`` being the
         hit records of the chunk (``structure`` indexes ``chunk_paths``; ``flags & 4`` = passes the
@@ -478,7 +479,15 @@ class Matcher:
         ``matches_for`` turns the records of one file into the ``Match`` objects ``run`` would have
         returned for it.  With ``queue`` (a ``sharding.ChunkQueue`` over ``len(paths)``) the chunks
         are not taken in order but pulled from the queue, which several ranks -- one per GPU --
-        share: each file is searched by exactly one of them."""
+        share: each file is searched by exactly one of them.
+
+        ``devices=[0, 1, ...]`` is the whole-box call from ONE process: a worker thread per listed GPU
+        (its own device library, sessions and streams; the compiled library is shared) pulls chunks
+        from one in-process counter and the generator hands the chunks back in input order -- the host
+        side merge of north_star; nothing crosses between the GPUs."""
+        if devices is not None and len(list(devices)) > 0 and not (len(list(devices)) == 1 and list(devices)[0] == self.device):
+            yield from self._scan_devices(paths, list(devices), chunk_size, threads, with_batch)
+            return
         import concurrent.futures
         from .engine import Session
         from .packing import pack_files
@@ -495,24 +504,29 @@ class Matcher:
             self._scan_lanes = [[None, engine.new_stream()], [None, engine.new_stream()]]
         lanes = self._scan_lanes
 
-        def collect(lane, chunk, ids, batch):
+        def collect(lane, span, chunk, ids, batch):
+            extra = ((batch,) if with_batch else ()) + ((span,) if _with_span else ())
             try:
-                return chunk, ids, lane[0].download(stream=lane[1])
+                return (chunk, ids, lane[0].download(stream=lane[1])) + extra
             except EngineError as exc:
+                if exc.status == -5 and exc.hits is not None:       # refused structures: keep the rest of the chunk
+                    warnings.warn(f"{len(exc.bad_structures)} structure(s) of a chunk were not searched: {exc}")
+                    return (chunk, ids, exc.hits) + extra
                 if exc.status != -4:
                     raise
-            return chunk, ids, self._search(batch)       # rare: rerun this chunk alone with a larger hit buffer
+            return (chunk, ids, self._search(batch)) + extra       # rare: rerun this chunk alone with a larger hit buffer
 
-        in_flight: collections.deque = collections.deque()      # (lane, chunk paths, ids, batch)
+        in_flight: collections.deque = collections.deque()      # (lane, span, chunk paths, ids, batch)
         try:
             with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
                 chunk = paths[first[0]:first[1]]
                 pending = pool.submit(pack_files, chunk, engine.compiled, True, threads)
                 ci = -1
+                span = first
                 while pending is not None:
                     ci += 1
                     batch, ids = pending.result()
-                    this_chunk = chunk
+                    this_chunk, this_span = chunk, span
                     span = next(spans, None)
                     if span is not None:
                         chunk = paths[span[0]:span[1]]
@@ -531,7 +545,7 @@ class Matcher:
                                                  grow(batch.n_atoms, sess.max_atoms if sess else 0),
                                                  grow(batch.n_structures, sess.max_structures if sess else 0), need_hits)
                     self._submit(sess, batch, stream=lane[1])
-                    in_flight.append((lane, this_chunk, ids, batch))
+                    in_flight.append((lane, this_span, this_chunk, ids, batch))
                     if len(in_flight) == 2:
                         yield collect(*in_flight.popleft())
                 while in_flight:
@@ -544,6 +558,114 @@ class Matcher:
                 except EngineError:
                     pass
 
+    def _scan_devices(self, paths, devices: List[int], chunk_size: int, threads: int, with_batch: bool):
+        """``scan_files`` over several GPUs of this host from one process (see ``scan_files``)."""
+        import queue as queue_module
+        import threading
+        paths = [os.fspath(p) for p in paths]
+        self._compile()
+        spans = iter([(i, min(i + chunk_size, len(paths))) for i in range(0, len(paths), chunk_size)])
+        lock = threading.Lock()
+
+        class Shared:                           # one counter for all workers: dynamic hand-out of chunks
+            def __iter__(self):
+                return self
+
+            def __next__(self):
+                with lock:
+                    return next(spans)
+
+        if not hasattr(self, "_device_workers"):
+            self._device_workers = {}
+        host = _available_cpus()
+        per_worker = threads or max(1, host // len(devices))
+        results: "queue_module.Queue" = queue_module.Queue(maxsize=4 * len(devices))
+
+        def work(slot, device):
+            try:
+                child = self._device_workers.get((slot, device))
+                if child is None:
+                    child = Matcher.__new__(Matcher)
+                    child.__dict__.update(self.__dict__)
+                    child.device, child._engine, child._scan_lanes, child._device_workers = device, None, None, {}
+                    self._device_workers[(slot, device)] = child
+                for item in child.scan_files(paths, chunk_size, per_worker, queue=Shared(), with_batch=with_batch,
+                                             _with_span=True):
+                    results.put(item)
+            except BaseException as exc:        # noqa: BLE001 -- surfaces in the consumer
+                results.put(exc)
+            finally:
+                results.put(None)
+
+        workers = [threading.Thread(target=work, args=(i, d), daemon=True) for i, d in enumerate(devices)]
+        for w in workers:
+            w.start()
+        waiting, finished, next_start = {}, 0, 0
+        while finished < len(workers):
+            item = results.get()
+            if item is None:
+                finished += 1
+                continue
+            if isinstance(item, BaseException):
+                raise item
+            waiting[item[-1][0]] = item[:-1]
+            while next_start in waiting:        # hand chunks back in input order
+                out = waiting.pop(next_start)
+                next_start += len(out[0])
+                yield out
+        for w in workers:
+            w.join()
+
+    def scan_to_tsv(self, paths: Sequence[os.PathLike], file: IO[str], chunk_size: int = 2048, threads: int = 0,
+                    queue=None, header: bool = True, predict_correctness: bool = True,
+                    devices: Optional[Sequence[int]] = None) -> int:
+        """PDB files -> the reference's results table, end to end: native ingest, GPU search, rows
+        formatted natively from the hit records (``tsv.TableWriter``) -- what ``_cli.py:217-316`` does
+        through ``load_molecules`` / ``Matcher.run`` / ``Match.dump``, without per-atom or per-match
+        Python objects.  Query ids are the file stems (repeats get ``_2``, ``_3`` ... as in
+        ``load_molecules``).  Rows are ordered as the reference orders them within each chunk of
+        ``chunk_size`` files, chunks in input order -- the order of the reference's own scale-out,
+        which splits the list and concatenates the tables (``nextflow/template_matcher.nf:43-62``).
+        Returns the number of rows written."""
+        from .tsv import TableWriter
+        writer = TableWriter(self, predict_correctness)
+        paths = [os.fspath(p) for p in paths]
+        seen: Dict[str, int] = collections.defaultdict(int)
+        stems = {}
+        for path in paths:
+            stem = Path(path).stem
+            seen[stem] += 1
+            stems[path] = stem if seen[stem] == 1 else f"{stem}_{seen[stem]}"
+        binary = not isinstance(file, io.TextIOBase) and hasattr(file, "write") and "b" in getattr(file, "mode", "")
+        emit = (lambda b: file.write(b)) if binary else (lambda b: file.write(b.decode("utf-8")))
+        if header:
+            emit(writer.header().encode())
+        n_rows = 0
+        for chunk, _, records, batch in self.scan_files(paths, chunk_size, threads, queue, with_batch=True, devices=devices):
+            selection = writer.select(records)
+            n_rows += len(selection[0])
+            emit(writer.format(records, batch.table, [stems[p] for p in chunk], selection))
+        return n_rows
+
+    def run_to_tsv(self, molecules: List[Molecule], file: IO[str], header: bool = True,
+                   predict_correctness: bool = True) -> int:
+        """``Matcher.run`` + ``Match.dump`` of every match (``_cli.py:248-316``) in one call, rows
+        formatted natively.  Returns the number of rows written."""
+        from .tsv import TableWriter
+        writer = TableWriter(self, predict_correctness)
+        if header:
+            file.write(writer.header())
+        if not self._active_sizes() or not molecules:
+            return 0
+        engine = self._ensure_engine()
+        batch = pack_molecules(molecules, engine.compiled)
+        if batch.table is None:
+            raise ValueError("run_to_tsv needs molecules read by Molecule.load / load_molecules")
+        records = self._search(batch)
+        selection = writer.select(records)
+        file.write(writer.format(records, batch.table, [m.id for m in molecules], selection).decode("utf-8"))
+        return len(selection[0])
+
     def close(self) -> None:
         """Release the device sessions, streams and library of this matcher."""
         engine = self._engine
@@ -553,6 +675,9 @@ class Matcher:
                     sess.close()
                 engine.free_stream(stream)
         self._scan_lanes = None
+        for child in getattr(self, "_device_workers", {}).values():
+            child.close()
+        self._device_workers = {}
         if engine is not None:
             engine.close()
             self._engine = None
@@ -578,40 +703,100 @@ class Matcher:
         engine = self._ensure_engine()
         return self._assemble(self._search(pack_molecules(molecules, engine.compiled)), molecules)
 
+    def _template_identity(self):
+        """Per compiled template: (completeness group code or -1, cluster member, cluster size) --
+        ``Match.get_identifying_attributes`` / ``_check_completeness`` (``jess_run.py:286-296, 738-783``)
+        evaluated once per template instead of once per hit."""
+        cached = getattr(self, "_identity", None)
+        if cached is None or len(cached[0]) != len(self._ordered):
+            codes: Dict[tuple, int] = {}
+            ident, member, size = [], [], []
+            for t in self._ordered:
+                if t.mcsa_id is not None and t.cluster is not None:
+                    ident.append(codes.setdefault((t.mcsa_id, t.cluster.id, t.dimension), len(codes)))
+                    member.append(t.cluster.member)
+                    size.append(t.cluster.size)
+                else:
+                    ident.append(-1)
+                    member.append(0)
+                    size.append(0)
+            cached = self._identity = (ident, member, size)
+        return cached
+
     def _assemble(self, records: np.ndarray, molecules: Sequence[Molecule]) -> Dict[Molecule, List[Match]]:
         """Hit records -> ``{molecule: [Match]}`` with the reference's per-size-group completeness
-        check and filtering (``jess_run.py:845-894``)."""
+        check and filtering (``jess_run.py:845-894``).  Columns are converted to Python numbers once,
+        records are grouped by (size group, molecule) with one sort, and a ``Hit`` decodes its atoms
+        and transform only when asked."""
         processed: Dict[Molecule, List[Match]] = collections.defaultdict(list)
-        by_cell: Dict[Tuple[int, int], List[np.void]] = collections.defaultdict(list)
+        n = len(records)
         bounds = np.asarray([hi for _, _, hi in self._groups])
-        for rec in records:
-            gi = int(np.searchsorted(bounds, int(rec["template_index"]), side="right"))
-            by_cell[(gi, int(rec["structure"]))].append(rec)
-
-        for gi, (size, lo, hi) in enumerate(self._groups):
-            rmsd, distance, max_dyn = self._get_jess_parameters(size)
-            self.verbose_print(f"Now matching query structure(s) to template of size {size}")
+        tidx = records["template_index"]
+        sidx = records["structure"]
+        group_of = np.searchsorted(bounds, tidx, side="right")
+        order = np.lexsort((tidx, sidx, group_of)) if n else np.zeros(0, dtype=np.int64)
+        cell_key = (group_of[order].astype(np.int64) * max(len(molecules), 1) + sidx[order]) if n else order
+        starts = np.flatnonzero(np.r_[True, cell_key[1:] != cell_key[:-1]]) if n else order
+        ends = np.r_[starts[1:], n] if n else order
+        cols = list(zip(records["rmsd"].tolist(), records["orientation"].tolist(), records["flags"].tolist(),
+                        records["n_complete"].tolist(), tidx.tolist(), sidx.tolist()))
+        ident, member, size = self._template_identity()
+        order_l, group_l = order.tolist(), group_of[order].tolist() if n else []
+        ordered, filtering = self._ordered, self.filter_matches
+        overflowed = 0
+        cell = 0
+        n_cells = len(starts)
+        starts_l, ends_l = starts.tolist(), ends.tolist()
+        for gi, (gsize, lo, hi) in enumerate(self._groups):
+            rmsd, distance, max_dyn = self._get_jess_parameters(gsize)
+            self.verbose_print(f"Now matching query structure(s) to template of size {gsize}")
             self.verbose_print(f"jess parameters are: {rmsd} {distance} {max_dyn}")
             total = 0
-            for mi, molecule in enumerate(molecules):
-                recs = by_cell.get((gi, mi))
-                if not recs:
-                    continue
-                matches = [Match(hit=Hit(r, self._ordered[int(r["template_index"])], molecule),
-                                 pairwise_distance=distance) for r in recs]
-                self._check_completeness(matches)
-                if self.filter_matches:
+            while cell < n_cells and group_l[starts_l[cell]] == gi:
+                rows = order_l[starts_l[cell]:ends_l[cell]]
+                cell += 1
+                molecule = molecules[cols[rows[0]][5]]
+                matches = []
+                for i in rows:
+                    sc = cols[i]
+                    matches.append(Match(hit=Hit(records[i], ordered[sc[4]], molecule, sc), pairwise_distance=distance))
+                # completeness of the raw hits of this (molecule, size group), before filtering
+                if len(matches) == 1:
+                    ti = cols[rows[0]][4]
+                    matches[0].complete = ident[ti] < 0 or (size[ti] == 1 and member[ti] == 1)
+                else:
+                    grouped: Dict[int, List[int]] = {}
+                    for j, i in enumerate(rows):
+                        ti = cols[i][4]
+                        if ident[ti] < 0:
+                            matches[j].complete = True
+                        else:
+                            grouped.setdefault(ident[ti], []).append(j)
+                    for js in grouped.values():
+                        ti0 = cols[rows[js[0]]][4]
+                        if sorted(member[cols[rows[j]][4]] for j in js) == list(range(1, size[ti0] + 1)):
+                            for j in js:
+                                matches[j].complete = True
+                if filtering:
                     for match in matches:
-                        if match.hit.missing_model:
-                            match.predicted_correct   # raises the reference's KeyError
-                        if match.hit.device_pass:
+                        flags = match.hit.flags
+                        if flags & 0x08:                       # EMM_HIT_NO_MODEL
+                            match.predicted_correct            # raises the reference's KeyError
+                        if flags & 0x04:                       # EMM_HIT_PASS
                             processed[molecule].append(match)
                             total += 1
+                            overflowed += flags & 0x01
                 else:
                     processed[molecule].extend(matches)
                     total += len(matches)
+                    overflowed += sum(m.hit.flags & 0x01 for m in matches)
             self.verbose_print(f"{total} matches found!")
             self.verbose_print(f"{len(processed)} target structures processed!")
+        if overflowed and self.warn:
+            # ADVICE r1: at the cap the best hit comes from the candidates examined so far, in this
+            # engine's enumeration order -- not reproducible against Jess; Match.hit.overflow marks them
+            warnings.warn(f"{overflowed} match(es) reached max_candidates={self.max_candidates}: their template has more "
+                          "candidate assignments than were examined, so a better one may exist (Match.hit.overflow)")
         return processed
 
     def run_single(self, molecule: Molecule) -> List[Match]:

@@ -179,7 +179,8 @@ def _pack_block_per_molecule(mols, b0, atom_off, sizes, library, xyz, klass, res
 class _PdbPacked(ctypes.Structure):       # struct emm_pdb_packed
     _fields_ = [("n_files", ctypes.c_int32), ("n_atoms", ctypes.c_int64)] + \
                [(k, ctypes.c_void_p) for k in ("atom_off", "xyz", "kind", "residue", "bfactor", "chain", "atom_id", "klass")] + \
-               [("n_kinds", ctypes.c_int32), ("kind_names", ctypes.c_void_p), ("header_id", ctypes.c_void_p)]
+               [("n_kinds", ctypes.c_int32), ("kind_names", ctypes.c_void_p), ("header_id", ctypes.c_void_p),
+                ("res_off", ctypes.c_void_p), ("res_key", ctypes.c_void_p), ("residue_count", ctypes.c_void_p)]
 
 
 def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrary, with_chain: bool = True,
@@ -233,4 +234,11 @@ def _packed_from_handle(lib, handle, library: CompiledLibrary, with_chain: bool)
     atom_id = grab(c.atom_id, np.int32, n) if c.atom_id else None
     headers = grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5)
     ids = [bytes(h).split(b"\0")[0].decode() or None for h in headers]
-    return PackedBatch(atom_off, xyz, klass, residue, bfactor, chain, atom_id), ids
+    batch = PackedBatch(atom_off, xyz, klass, residue, bfactor, chain, atom_id)
+    # what the results table needs about these structures (tsv.TableWriter), as views of the same buffers
+    from .tsv import TableColumns
+    res_off = grab(c.res_off, np.int64, nf + 1)
+    batch.table = TableColumns(atom_off, grab(c.kind, np.uint32, n), names, residue, res_off,
+                               grab(c.res_key, np.uint64, int(res_off[-1])), grab(c.residue_count, np.int32, nf),
+                               atom_id, owner)
+    return batch, ids

@@ -35,24 +35,50 @@ class Hit:
     are pinned by the reference tests and it feeds no decision (SURVEY.md 8c "parity unpinned").
     """
 
-    __slots__ = ("rmsd", "log_evalue", "template", "_molecule", "_atom_idx", "_rot", "_qbar", "_tbar",
+    __slots__ = ("rmsd", "log_evalue", "template", "_molecule", "_record", "_decoded",
                  "orientation", "flags", "n_complete", "template_index", "structure_index")
 
-    def __init__(self, record: np.void, template, molecule: Molecule):
-        n = int(record["n_atoms"])
-        self.rmsd = float(record["rmsd"])
+    def __init__(self, record: np.void, template, molecule: Molecule, scalars=None):
+        """``record``: one ``emm_hit`` row.  ``scalars`` (optional) = that row's (rmsd, orientation,
+        flags, n_complete, template_index, structure) as Python numbers, for callers that convert
+        whole columns at once (``Matcher._assemble``); the matched atoms and the transform are
+        decoded from the record when first asked for."""
+        if scalars is None:
+            scalars = (float(record["rmsd"]), float(record["orientation"]), int(record["flags"]),
+                       int(record["n_complete"]), int(record["template_index"]), int(record["structure"]))
+        self.rmsd, self.orientation, self.flags, self.n_complete, self.template_index, self.structure_index = scalars
         self.log_evalue = math.nan
         self.template = template
         self._molecule = molecule
-        self._atom_idx = np.asarray(record["atoms"][:n], dtype=np.int64)
-        self._rot = np.asarray(record["rot"], dtype=np.float64).reshape(3, 3).copy()
-        self._qbar = np.asarray(record["qbar"], dtype=np.float64).copy()
-        self._tbar = np.asarray(record["tbar"], dtype=np.float64).copy()
-        self.orientation = float(record["orientation"])
-        self.flags = int(record["flags"])
-        self.n_complete = int(record["n_complete"])
-        self.template_index = int(record["template_index"])
-        self.structure_index = int(record["structure"])
+        self._record = record
+        self._decoded = None
+
+    def _decode(self):
+        d = self._decoded
+        if d is None:
+            r = self._record
+            n = int(r["n_atoms"])
+            d = self._decoded = (np.asarray(r["atoms"][:n], dtype=np.int64),
+                                 np.asarray(r["rot"], dtype=np.float64).reshape(3, 3).copy(),
+                                 np.asarray(r["qbar"], dtype=np.float64).copy(),
+                                 np.asarray(r["tbar"], dtype=np.float64).copy())
+        return d
+
+    @property
+    def _atom_idx(self):
+        return self._decode()[0]
+
+    @property
+    def _rot(self):
+        return self._decode()[1]
+
+    @property
+    def _qbar(self):
+        return self._decode()[2]
+
+    @property
+    def _tbar(self):
+        return self._decode()[3]
 
     # device-side verdicts ----------------------------------------------------------------------
     @property

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "merge_hits", "gather_hits", "ChunkQueue"]
+__all__ = ["shard_bounds", "merge_hits", "gather_hits", "gather_hit_blocks", "place_blocks", "ChunkQueue"]
 
 
 def shard_bounds(n_items: int, world_size: int, rank: int, align: int = 1) -> Tuple[int, int]:
@@ -99,3 +99,54 @@ def gather_hits(first: int, hits: np.ndarray, dst: int = 0) -> Optional[np.ndarr
     if dist.get_rank() != dst:
         return None
     return merge_hits(gathered)
+
+
+def place_blocks(blocks: Sequence[Tuple[int, np.ndarray]]) -> np.ndarray:
+    """Hit lists of disjoint structure ranges -> one list in input order.  ``blocks`` = (first structure
+    of the range, its hits with range-local structure indices, already sorted by (structure,
+    template)); ranges are placed by their first structure, so no global sort is needed."""
+    blocks = sorted(blocks, key=lambda b: b[0])
+    total = sum(len(h) for _, h in blocks)
+    if not blocks:
+        raise ValueError("no blocks")
+    out = np.empty(total, dtype=blocks[0][1].dtype)
+    at = 0
+    for first, hits in blocks:
+        out[at:at + len(hits)] = hits
+        out["structure"][at:at + len(hits)] += first
+        at += len(hits)
+    return out
+
+
+def gather_hit_blocks(blocks: Sequence[Tuple[int, np.ndarray]], dtype, dst: int = 0, device=None) -> Optional[np.ndarray]:
+    """The host-side merge of a run in which every rank searched some chunks of ONE input list
+    (``ChunkQueue``): all hit records travel to ``dst`` as raw bytes in one padded ``gather`` (NCCL when
+    ``device`` is a CUDA device, else the group's CPU backend), the small (first, count) lists through
+    ``all_gather_object``; ``dst`` places every block at its position in input order
+    (``place_blocks``).  Other ranks get None.  Single process: just ``place_blocks``."""
+    dist = sys.modules.get("torch.distributed")
+    if dist is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return place_blocks(blocks) if blocks else np.zeros(0, dtype=dtype)
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    meta = [(int(first), int(len(hits))) for first, hits in blocks]
+    every = [None] * world
+    dist.all_gather_object(every, meta)
+    counts = [sum(n for _, n in m) for m in every]
+    width = max(max(counts), 1) * np.dtype(dtype).itemsize
+    mine = np.concatenate([h for _, h in blocks]) if blocks else np.zeros(0, dtype=dtype)
+    send = torch.zeros(width, dtype=torch.uint8, device=device)
+    if len(mine):
+        send[:mine.nbytes] = torch.from_numpy(mine.view(np.uint8).reshape(-1)).to(send.device)
+    recv = [torch.empty(width, dtype=torch.uint8, device=device) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst)
+    if rank != dst:
+        return None
+    placed = []
+    for r in range(world):
+        raw = recv[r][:counts[r] * np.dtype(dtype).itemsize].cpu().numpy().view(dtype)
+        at = 0
+        for first, n in every[r]:
+            placed.append((first, raw[at:at + n]))
+            at += n
+    return place_blocks(placed) if placed else np.zeros(0, dtype=dtype)

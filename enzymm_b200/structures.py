@@ -233,7 +233,8 @@ def _native_lib():
     """libenzymm_b200.so for its host-only PDB entry points (they need no GPU)."""
     global _native
     if _native is None:
-        path = Path(__file__).resolve().parent / "libenzymm_b200.so"
+        override = os.environ.get("EMM_LIBRARY")          # development: another build of the same ABI
+        path = Path(override) if override else Path(__file__).resolve().parent / "libenzymm_b200.so"
         if not path.exists():
             raise ImportError(f"{path} is missing: build it with `make -C enzymm_b200/csrc`")
         lib = ctypes.CDLL(str(path))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EMM_ABI_VERSION 1
+#define EMM_ABI_VERSION 2
 #define EMM_MAX_TEMPLATE_ATOMS 32   /* shipped library: 6..24 atoms per template            */
 #define EMM_MAX_RESIDUES 10         /* orientation residues (atom triplets) per template     */
 #define EMM_LR_MODELS 5             /* logistic models per (size, distance) cell             */
@@ -156,6 +156,9 @@ typedef struct emm_query_params {
     int32_t force_prepare;        /* 1: run the prepare kernel even if this batch is already prepared */
     int32_t cell_threshold;       /* > 0: leader candidate lists at least this long are searched through  */
                                   /* the uniform-grid cell list instead of scanned; <= 0: never (default) */
+    int32_t donate_after;         /* splitting of one expensive (template, structure) pair over the warps */
+                                  /* of its CTA: 0 default (after 48 level visits, when warps sit idle);  */
+                                  /* n > 0 after n level visits; < 0 never.  Results do not depend on it. */
 } emm_query_params;
 
 typedef struct emm_hit {
@@ -282,6 +285,10 @@ typedef struct emm_pdb_packed {
     int32_t n_kinds;
     const char *kind_names;       /* [n_kinds][8]: resname[4] name[4], blank-stripped, NUL padded */
     const char *header_id;        /* [n_files][5] */
+    /* what the results table needs besides the hits (Match.dump, jess_run.py:185-284) */
+    const int64_t *res_off;       /* [n_files+1] CSR into res_key */
+    const uint64_t *res_key;      /* per residue ordinal: chain id code << 32 | (uint32) residue number */
+    const int32_t *residue_count; /* [n_files] Match.query_residue_count (jess_run.py:487-496) */
 } emm_pdb_packed;
 int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
 int emm_pdb_batch_packed(const emm_pdb_batch *batch, emm_pdb_packed *out);
@@ -293,6 +300,42 @@ int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *
                      const double *const *xyz, const double *const *bfactor, int32_t n_threads, emm_pdb_batch **out);
 /* klass[a] = class_of_kind[kind[a]] for every atom, on the batch's thread pool */
 int emm_pdb_batch_classify(emm_pdb_batch *batch, const uint16_t *class_of_kind, int32_t n_kinds);
+
+/*
+ * Native writer for the rows of the results table (host only).  Replaces Match.dump per match
+ * (jess_run.py:185-284) when whole batches are written: the caller chooses and orders the rows
+ * (Matcher semantics: size groups, completeness, filter verdict, match indices) and gathers, per row,
+ * the residue name / chain / residue number of the matched atoms; this formats them byte for byte as
+ * Python does -- str(round(x, 5)), str(bool), csv QUOTE_MINIMAL with tabs.
+ */
+typedef struct emm_tsv_rows {
+    int64_t n_rows;
+    const int32_t *n_atoms;            /* [n_rows] matched atoms, three per template residue            */
+    const char *resname4;              /* [n_rows][EMM_MAX_TEMPLATE_ATOMS][4] blank-stripped, NUL padded */
+    const char *chain2;                /* [n_rows][EMM_MAX_TEMPLATE_ATOMS][2]                            */
+    const int32_t *resnum;             /* [n_rows][EMM_MAX_TEMPLATE_ATOMS]                               */
+    const double *rmsd;                /* [n_rows] Hit.rmsd                                              */
+    const double *log_evalue;          /* [n_rows] Hit.log_evalue (NaN: not reproducible)     */
+    const double *orientation;         /* [n_rows] Match.orientation                                     */
+    const int32_t *match_index;        /* [n_rows] Match.index                                           */
+    const uint8_t *complete;           /* [n_rows] Match.complete                                        */
+    const uint8_t *predicted;          /* [n_rows] Match.predicted_correct: 0 False, 1 True, 2 left empty */
+    const int32_t *template_index;     /* [n_rows] */
+    const int32_t *structure;          /* [n_rows] */
+    const char *const *query_id;       /* [n_structures] Molecule.id                                     */
+    const int32_t *query_atom_count;   /* [n_structures] */
+    const int32_t *query_residue_count;/* [n_structures] */
+    const char *const *tpl_distance;   /* [n_templates] str(pairwise_distance)                           */
+    const char *const *tpl_static;     /* [n_templates] columns template_pdb_id .. template_cath, tabbed  */
+    const uint8_t *tpl_multimeric;     /* [n_templates] Template.multimeric                              */
+    const int32_t *tpl_order_off;      /* [n_templates+1] CSR into tpl_order                             */
+    const int32_t *tpl_order;          /* Template.relative_order                                        */
+    const char *const *tpl_annotation; /* [n_templates] the trailing annotation columns, tabbed          */
+} emm_tsv_rows;
+int emm_tsv_format(const emm_tsv_rows *rows, char **text, int64_t *len);   /* *text: free with emm_tsv_free */
+void emm_tsv_free(char *text);
+/* str(round(v, 5)) as Python prints it (exposed for the formatter's own tests) */
+int emm_tsv_repr_round5(double v, char *out, int32_t capacity);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,9 @@ def _load():
         lib.jo_batch_query.restype = ctypes.c_int
         lib.jo_kabsch.restype = ctypes.c_double
         _lib = lib
+        reading = os.environ.get("EMM_ORACLE_MODE1")      # exposure studies only; the default is "N_or_O"
+        if reading:
+            lib.jo_set_mode1_reading(ctypes.c_int(MODE1_READINGS.index(reading)))
     return _lib
 
 
@@ -159,6 +162,15 @@ class OracleHit:
     def transform(self, xyz: np.ndarray) -> np.ndarray:
         """q' = R (q - qbar) + tbar  (SURVEY 8c rule 9)."""
         return (np.asarray(xyz, dtype=np.float64) - self.qbar) @ self.rot.T + self.tbar
+
+
+MODE1_READINGS = ("N_or_O", "same_element", "exact_name", "N_O_or_S")
+
+
+def set_mode1_reading(reading: str = "N_or_O") -> None:
+    """Reading of ``match_mode 1`` (unpinned upstream): the default is "N_or_O"; the others
+    exist to measure how much of the result depends on the choice (``tools/mode1_exposure.py``)."""
+    _load().jo_set_mode1_reading(ctypes.c_int(MODE1_READINGS.index(reading)))
 
 
 def _per_template(value, n: int) -> np.ndarray:

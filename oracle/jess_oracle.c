@@ -223,6 +223,10 @@ static double jo_superpose(int m, const double *t, const double *q, double rot[9
 
 static int jo_name_eq(const char *a, const char *b) { return memcmp(a, b, 4) == 0; }
 
+/* reading of match_mode 1: 0 "N or O" (default), 1 same element, 2 exact name, 3 "N, O or S" */
+static int jo_mode1_reading = 0;
+void jo_set_mode1_reading(int reading) { jo_mode1_reading = reading; }
+
 /* returns 1 match, 0 no match, -1 unknown match mode */
 static int jo_type_match(const jo_tpl *T, int i, const char *qname, const char *qres)
 {
@@ -241,7 +245,22 @@ static int jo_type_match(const jo_tpl *T, int i, const char *qname, const char *
             if (jo_name_eq(T->an_pool + 4 * k, qname)) return 1;
         return 0;
     case 1:
-        return qname[0] == 'N' || qname[0] == 'O';
+        /* UNPINNED: no reference vector exercises match_mode 1.  Reading 0 ("N or O") is the
+         * default; the alternatives exist so that the exposure can be measured (tools/mode1_exposure.py). */
+        switch (jo_mode1_reading) {
+        case 1:                                   /* same element as a template atom name (= mode 3) */
+            for (k = T->an_off[i]; k < T->an_off[i + 1]; ++k)
+                if (T->an_pool[4 * k] == qname[0]) return 1;
+            return 0;
+        case 2:                                   /* exact atom name (= mode 0) */
+            for (k = T->an_off[i]; k < T->an_off[i + 1]; ++k)
+                if (jo_name_eq(T->an_pool + 4 * k, qname)) return 1;
+            return 0;
+        case 3:                                   /* N, O or S */
+            return qname[0] == 'N' || qname[0] == 'O' || qname[0] == 'S';
+        default:
+            return qname[0] == 'N' || qname[0] == 'O';
+        }
     case 3:
         for (k = T->an_off[i]; k < T->an_off[i + 1]; ++k)
             if (T->an_pool[4 * k] == qname[0]) return 1;

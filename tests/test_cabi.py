@@ -27,7 +27,7 @@ def test_exports_every_declared_symbol():
 
 def test_abi_constants():
     lib = load_cdll()
-    assert lib.emm_abi_version() == 1
+    assert lib.emm_abi_version() == 2
     assert lib.emm_hit_size() == HIT_DTYPE.itemsize == 280
 
 

@@ -28,11 +28,11 @@ RMSD_TOL = 1e-4      # stated tolerance of north_star (Angstrom / radians)
 
 
 def compare_with_oracle(engine, templates, molecules, dist, *, rmsd=2.0, max_candidates=10000,
-                        ignore_chain=True, cutoff=0.0, oracle_molecules=None, atom_maps=None):
+                        ignore_chain=True, cutoff=0.0, oracle_molecules=None, atom_maps=None, donate_after=0):
     """Run both sides on the same inputs and assert the north_star bar.  Returns the GPU hits."""
     batch = pack_molecules(molecules, engine.compiled)
     hits = engine.query(batch, max_candidates=max_candidates, ignore_chain=ignore_chain,
-                        conservation_cutoff=cutoff)
+                        conservation_cutoff=cutoff, donate_after=donate_after)
     dist = np.broadcast_to(np.asarray(dist, dtype=np.float64), (len(templates),)).copy()
     omols = oracle_molecules if oracle_molecules is not None else molecules
     raw = oracle.query_raw(omols, oracle.OracleTemplates(templates), rmsd, dist, dist,
@@ -462,7 +462,7 @@ def test_query_batch_entry_point(active_templates, mol_1amy):
         hits = np.zeros(256, dtype=HIT_DTYPE)
         n = ctypes.c_int64(0)
         stats = _Stats()
-        params = _QueryParams(10000, 1, 0.0, 0, 0, 0, 1, 0, 0)
+        params = _QueryParams(10000, 1, 0.0, 0, 0, 0, 1, 0, 0, 0)
         st = batch.as_struct()
         rc = lib.emm_query_batch(dev.handle, ctypes.byref(st), ctypes.byref(params),
                                  hits.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(hits)), ctypes.byref(n),
@@ -779,3 +779,75 @@ def test_refused_structure_does_not_cost_the_batch(full_engine, active_templates
     with pytest.raises(EngineError) as info:
         full_engine.query(blob)
     assert info.value.bad_structures == {0: 3} and len(info.value.hits) == 0
+
+
+def test_pair_splitting_changes_nothing(full_engine, active_templates, mol_1amy, mol_af):
+    """One (template, structure) pair may be split over the warps of its CTA (subtrees donated to idle
+    warps, merged by minimum RMSD / lexicographic tie-break / summed counts).  ``donate_after=1`` makes
+    every pair donate whenever a warp is idle -- far more splitting than the default -- and nothing in
+    the results may move: against the oracle, and bit for bit against the unsplit search."""
+    dist = default_distances(active_templates)
+    split = compare_with_oracle(full_engine, active_templates, [mol_1amy, mol_af], dist, donate_after=1)
+    plain = full_engine.query(pack_molecules([mol_1amy, mol_af], full_engine.compiled), donate_after=-1)
+    assert split.tobytes() == plain.tobytes() and len(plain) == 24
+    # few templates: most warps idle from the start; loose cutoff: deep, wide trees; exhaustive counts
+    subset = [t for t in active_templates if t.effective_size in (3, 4)][::150] + \
+             [t for t in active_templates if t.effective_size >= 6][::40]
+    chunk = generate_chunk(2, SynthConfig(), active_templates, 6)
+    mols = [chunk.to_molecule(i) for i in range(chunk.n_structures)] + [mol_1amy]
+    eng = Engine(CompiledLibrary(subset, 2.0, 3.0, 3.0))
+    try:
+        for after in (1, 7):
+            hits = compare_with_oracle(eng, subset, mols, 3.0, max_candidates=10 ** 7, donate_after=after)
+            assert len(hits) > 20 and int(hits["n_complete"].max()) > 1000
+        unsplit = eng.query(pack_molecules(mols, eng.compiled), max_candidates=10 ** 7, donate_after=-1)
+        assert hits.tobytes() == unsplit.tobytes()
+        capped = compare_with_oracle(eng, subset, mols, 3.0, max_candidates=50, donate_after=1)
+        assert (capped["flags"] & HIT_OVERFLOW).any()
+    finally:
+        eng.close()
+    # a 4-chain assembly searched in place, split
+    big = generate_chunk(0, SynthConfig(n_chains=4), active_templates, 1).to_molecule(0)
+    few = active_templates[::300]
+    eng = Engine(CompiledLibrary(few, 2.0, default_distances(few), default_distances(few)))
+    try:
+        compare_with_oracle(eng, few, [big], default_distances(few), donate_after=1)
+    finally:
+        eng.close()
+
+
+def test_scan_files_over_several_devices_from_one_process(tmp_path, active_templates):
+    """The whole-box call: ``scan_files(paths, devices=[...])`` runs one worker per listed GPU in this
+    process, chunks handed out dynamically, results back in input order.  On a one-GPU box the two
+    workers share device 0 -- the threading, hand-out and re-ordering are what is under test; the
+    records must equal the single-worker scan, and the table written through it must not change."""
+    import io
+    chunk = generate_chunk(4, SynthConfig(n_residues=150), active_templates, 40)
+    paths = []
+    for i in range(chunk.n_structures):
+        path = tmp_path / f"s{i:03d}.pdb"
+        path.write_text(chunk.to_pdb(i))
+        paths.append(path)
+    matcher = jess_run.Matcher(active_templates)
+    try:
+        single = list(matcher.scan_files(paths, chunk_size=7))
+        multi = list(matcher.scan_files(paths, chunk_size=7, devices=[0, 0]))
+        assert [c for c, _, _ in multi] == [c for c, _, _ in single]
+        assert all(a[2].tobytes() == b[2].tobytes() for a, b in zip(single, multi)) and sum(len(r) for _, _, r in multi) > 10
+        one, two = io.StringIO(), io.StringIO()
+        rows = matcher.scan_to_tsv(paths, one, chunk_size=7)
+        assert matcher.scan_to_tsv(paths, two, chunk_size=7, devices=[0, 0]) == rows > 5
+        assert one.getvalue() == two.getvalue()
+        # and the table equals the reference-shaped route: Match objects, one dump per match, per chunk
+        want = io.StringIO()
+        first = True
+        for lo in range(0, len(paths), 7):
+            molecules = jess_run.load_molecules(paths[lo:lo + 7])
+            for matches in matcher.run(molecules).values():
+                for j, match in enumerate(matches):
+                    match.index = j + 1
+                    match.dump(want, header=first)
+                    first = False
+        assert one.getvalue() == want.getvalue()
+    finally:
+        matcher.close()

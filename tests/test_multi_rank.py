@@ -98,9 +98,15 @@ def _queue_worker(rank: int, world: int, port: int, queue):
         merged = gather_hits(0, mine)                           # already rebased to corpus indices
         spans = [None] * world
         dist.all_gather_object(spans, [p[0] for p in parts])
+        # the block-wise merge of the strong-scaling path: raw bytes in one gather, placed by range
+        from enzymm_b200.sharding import gather_hit_blocks
+        placed = gather_hit_blocks(parts, HIT_DTYPE)
         dist.barrier()
         if rank == 0:
+            assert placed.tobytes() == merged.tobytes()
             queue.put((merged.tobytes(), spans))
+        else:
+            assert placed is None
     finally:
         dist.destroy_process_group()
 

@@ -41,6 +41,12 @@ def main():
     sess.run(template_begin=0, template_end=half, skip_mode=2, reset=True, force_prepare=True)
     sess.run(template_begin=half, template_end=len(templates), skip_mode=2, reset=False)
     print("skip mode", len(sess.download()), "hits")
+    # pair splitting: few templates (idle warps from the start), donation at every level entry
+    few = Engine(CompiledLibrary(templates[:20], 2.0, 3.0, 3.0))
+    for chunk in (small, big):
+        hits = few.query(chunk.to_packed(few.compiled), max_candidates=10 ** 6, donate_after=1)
+        print("split pairs", len(hits), "hits")
+    few.close()
     engine.close()
     loose = [t for t in templates if t.effective_size <= 4][:40]
     engine = Engine(CompiledLibrary(loose, 2.0, 3.0, 3.0))
