@@ -18,12 +18,12 @@
 namespace emm {
 void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff, bool build_cells,
                     unsigned long long *stats, unsigned long long *bad, int sm_count, cudaStream_t stream);
-size_t search_smem_bytes(int blob_cap, int levels);
+size_t search_smem_bytes(int blob_cap, int levels, bool cells);
 size_t search_fixed_smem(int levels);
 cudaError_t configure_search(int smem_bytes);
 void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream);
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, const int *sched, const int *ids, bool stats, bool staged, int grid,
+                   const unsigned char *skip, const int4 *sched, const int *ids, bool stats, bool staged, int grid,
                    size_t smem, cudaStream_t stream);
 }  // namespace emm
 
@@ -67,8 +67,9 @@ struct emm_library {
     int32_t *d_lr_index = nullptr;
     int lr_capacity = 0;
     // visiting order of the templates of a range [tb, te): most expensive first
-    struct Sched { int *d_ids = nullptr; int n = 0, n_heavy = 0; };
-    std::vector<int> h_tpl_atoms;
+    struct Sched { int4 *d_ids = nullptr; int n = 0, n_heavy = 0; };
+    std::vector<int> h_tpl_atoms, h_atom_off;
+    std::vector<int64_t> h_pair_off;
     std::vector<double> h_cut;
     std::map<std::pair<int, int>, Sched> sched;
     std::mutex sched_mutex;
@@ -257,6 +258,8 @@ int emm_library_create(int device, const emm_library_desc *desc, emm_library **o
     lib->h_leader_ttype.assign(desc->leader_ttype, desc->leader_ttype + desc->n_leader);
     lib->h_tpl_atoms.resize((size_t)desc->n_templates);
     for (int t = 0; t < desc->n_templates; ++t) lib->h_tpl_atoms[(size_t)t] = desc->atom_off[t + 1] - desc->atom_off[t];
+    lib->h_atom_off.assign(desc->atom_off, desc->atom_off + desc->n_templates + 1);
+    lib->h_pair_off.assign(desc->pair_off, desc->pair_off + desc->n_templates + 1);
     lib->h_cut.assign(desc->distance_cutoff, desc->distance_cutoff + desc->n_templates);
 
     DevLibrary &d = lib->d;
@@ -388,8 +391,14 @@ static int get_sched(emm_library *lib, int tb, int te, emm_library::Sched *out)
         int heavy_atoms = kHeavyAtoms;
         if (const char *env = getenv("EMM_HEAVY_ATOMS")) heavy_atoms = atoi(env);                  // tuning knob
         for (int id : ids) sc.n_heavy += lib->h_tpl_atoms[(size_t)id] >= heavy_atoms;
-        CUDA_TRY(cudaMalloc(&sc.d_ids, sizeof(int) * (size_t)std::max(sc.n, 1)));
-        if (sc.n) CUDA_TRY(cudaMemcpy(sc.d_ids, ids.data(), sizeof(int) * (size_t)sc.n, cudaMemcpyHostToDevice));
+        // one 16-byte record per entry: template, first atom, atoms, first pair (pair table < 2^31 entries, checked at creation)
+        std::vector<int4> recs((size_t)std::max(sc.n, 1));
+        for (int i = 0; i < sc.n; ++i) {
+            const size_t t = (size_t)ids[(size_t)i];
+            recs[(size_t)i] = make_int4((int)t, lib->h_atom_off[t], lib->h_tpl_atoms[t], (int)lib->h_pair_off[t]);
+        }
+        CUDA_TRY(cudaMalloc(&sc.d_ids, sizeof(int4) * (size_t)std::max(sc.n, 1)));
+        if (sc.n) CUDA_TRY(cudaMemcpy(sc.d_ids, recs.data(), sizeof(int4) * (size_t)sc.n, cudaMemcpyHostToDevice));
         it = lib->sched.emplace(std::make_pair(tb, te), sc).first;
     }
     *out = it->second;
@@ -676,7 +685,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
         // stage no more than the batch needs: every KB not claimed here stays L1 for the template tables
         const int cap = staged ? (int)((s->max_staged + 1023) & ~int64_t(1023)) : 0;
         P.blob_cap = cap;
-        const size_t smem = search_smem_bytes(cap, P.levels);
+        const size_t smem = search_smem_bytes(cap, P.levels, P.cell_threshold > 0);
         {
             std::lock_guard<std::mutex> guard(g_config_mutex);
             if (lib->device >= 64 || smem > g_configured_smem[lib->device]) {   // raise only; never per launch

@@ -57,23 +57,34 @@ __device__ __forceinline__ uint32_t make_entry(int parent, int atom) { return ((
 // same-residue payload of an anchor: first atom of the residue | atoms in it << 22
 __device__ __forceinline__ int span_payload(int first, int count) { return first | (count << kAtomBits); }
 
-struct WarpState {
-    int n[kMaxAtoms + 1];        // entries queued per level
-    int chunk[kMaxAtoms + 1];    // size of the level's current chunk (its last `chunk` entries)
-    int cur[kMaxAtoms + 1];      // expansion cursor inside the chunk
-    unsigned long long todo[kMaxAtoms + 1];   // lanes (two candidate rows) of iteration `cur` still to be pushed
-    int cellrow[kMaxAtoms + 1];  // cell-list expansion: row of the anchor's cell box being scanned ...
-    int celli[kMaxAtoms + 1];    // ... and next position inside that row (-1 = row not started)
+// Resume point of a cell-list expansion (opt-in path): kept outside WarpState so that the default
+// kernels do not pay shared memory for it.
+struct CellState {
+    int row[kMaxAtoms + 1];      // row of the anchor's cell box being scanned ...
+    int pos[kMaxAtoms + 1];      // ... and next position inside that row (-1 = row not started)
+};
+
+// Per-warp search state.  Every byte here is shared memory taken from the L1 carve-out: with the
+// staged blob (~86 KB for 400-residue structures) and the queues (66 KB) the CTA must stay below
+// 196 KB, or the SM's L1 shrinks from 60 KB to 28 KB and every template-table read pays for it
+// (measured: 1.35x on the whole kernel).  Hence bytes for the small counters and no padding.
+struct alignas(16) WarpState {
     float4 anchor[32];           // per valid partial (compacted): anchor atom xyz, w = payload bits
-    unsigned char vslot[32];     // compacted list of valid chunk slots
+    unsigned long long todo[kMaxAtoms + 1];   // lanes (two candidate rows) of iteration `cur` still to be pushed
     double best_rmsd;
     unsigned long long n_complete;
+    CellState *cell;             // this warp's cell-list resume state (kCells kernels only)
+    int cur[kMaxAtoms + 1];      // expansion cursor inside the chunk
+    uint32_t best_asg[kMaxAtoms];
     int best_valid;
     int overflow;
-    uint32_t best_asg[kMaxAtoms];
     int donated;                 // this warp gave parts of its own pair away
     int for_owner;               // searching a donated subtree on behalf of this warp, or -1
+    uint8_t n[kMaxAtoms + 1];    // entries queued per level (<= kQueueCap)
+    uint8_t chunk[kMaxAtoms + 1];   // size of the level's current chunk (its last `chunk` entries)
+    unsigned char vslot[32];     // compacted list of valid chunk slots
 };
+static_assert(kQueueCap < 256, "queue counters are bytes");
 
 // ---- splitting one (template, structure) pair across the warps of its CTA -------------------------
 // Pair cost is heavy-tailed (a 21-atom template at cutoff 2.0 can take 100 ms of warp time against
@@ -83,7 +94,7 @@ struct WarpState {
 // rebuilds that chain as one-entry queues and runs the ordinary search below it; results meet in
 // the owner's PairSlot (minimum RMSD with the lexicographic tie-break, summed complete-assignment
 // counts), and the owner writes the hit once every donation has come back.
-constexpr int kDonationRing = 32;
+constexpr int kDonationRing = 16;
 
 struct Donation {
     int owner;                   // warp whose pair this subtree belongs to
@@ -183,7 +194,8 @@ struct SearchArgs {
     SearchParams P;
     SearchOut O;
     const unsigned char *skip;
-    const int *sched;          // [P.n_sched] template ids in visiting order
+    const int4 *sched;         // [P.n_sched] visiting order: (template, atom_off, atoms, pair_off) per entry, so a
+                               // warp learns all it needs to start a template from one (mostly L1-resident) load
     const int *ids;            // [P.n_structures] structures of this launch, or null for 0..n-1
 };
 
@@ -670,7 +682,7 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
     const unsigned lt_mask = (1u << lane) - 1u;
     const float hi = sqrtf(hi2) + 1e-3f;
     int n_next = *n_next_io;
-    int pidx = ws->cur[k], row = ws->cellrow[k], ipos = ws->celli[k];
+    int pidx = ws->cur[k], row = ws->cell->row[k], ipos = ws->cell->pos[k];
     unsigned todo = (unsigned)ws->todo[k];
     bool full = false;
     for (; pidx < P && !full; ++pidx, row = 0, ipos = -1) {
@@ -723,7 +735,7 @@ __device__ __noinline__ bool expand_cells(const View<kStaged> V, const Blob &S, 
         if (full) break;
     }
     __syncwarp();          // every lane has read the resume point above before lane 0 replaces it
-    if (lane == 0) { ws->cur[k] = pidx; ws->cellrow[k] = row; ws->celli[k] = ipos; ws->todo[k] = todo; }
+    if (lane == 0) { ws->cur[k] = pidx; ws->cell->row[k] = row; ws->cell->pos[k] = ipos; ws->todo[k] = todo; }
     *n_next_io = n_next;
     *done = !full && pidx >= P;
     return full;
@@ -817,12 +829,12 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
 // its own part is merged into its PairSlot and the caller writes the hit once all parts are back.
 template <bool kStats, bool kStaged, bool kCells>
 __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob &S, const View<kStaged> &V, int s,
-                                                int t, uint32_t *Q, WarpState *ws, int lane, LaneStats &st,
+                                                const int4 rec, uint32_t *Q, WarpState *ws, int lane, LaneStats &st,
                                                 CtaShare *sh, int wid, int don_depth, int don_owner, uint32_t don_atom)
 {
     const DevLibrary &L = A.L;
-    const int a0 = L.atom_off[t], m = L.atom_off[t + 1] - a0;
-    const int64_t p0 = L.pair_off[t];
+    const int t = rec.x, a0 = rec.y, m = rec.z;
+    const int64_t p0 = rec.w;
 
     // a template with an empty leader list cannot match this structure
     if (don_depth == 0) {
@@ -840,7 +852,7 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
     const float eps = V.eps;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0ull; if (kCells) { ws->cellrow[lane] = 0; ws->celli[lane] = -1; } }
+    if (lane <= m) { ws->n[lane] = 0; ws->chunk[lane] = 0; ws->cur[lane] = 0; ws->todo[lane] = 0ull; if (kCells) { ws->cell->row[lane] = 0; ws->cell->pos[lane] = -1; } }
     if (lane == 0) {
         ws->best_valid = 0; ws->overflow = 0; ws->n_complete = 0ull; ws->best_rmsd = CUDART_INF;
         ws->donated = 0; ws->for_owner = don_depth > 0 ? don_owner : -1;
@@ -1113,7 +1125,7 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
             if (full || (done && n_next > 0)) {
                 // descend: the last <= 32 entries of the next level form its chunk
                 ++k;
-                if (lane == 0) { ws->chunk[k] = min(32, n_next); ws->cur[k] = 0; ws->todo[k] = 0ull; if (kCells) { ws->cellrow[k] = 0; ws->celli[k] = -1; } }
+                if (lane == 0) { ws->chunk[k] = min(32, n_next); ws->cur[k] = 0; ws->todo[k] = 0ull; if (kCells) { ws->cell->row[k] = 0; ws->cell->pos[k] = -1; } }
                 __syncwarp();
                 entered = false;
                 continue;
@@ -1130,7 +1142,7 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
                 ws->chunk[k] = min(32, base);
                 ws->cur[k] = 0;
                 ws->todo[k] = 0ull;
-                if (kCells) { ws->cellrow[k] = 0; ws->celli[k] = -1; }
+                if (kCells) { ws->cell->row[k] = 0; ws->cell->pos[k] = -1; }
             }
             __syncwarp();
             if (base != 0) break;                 // more entries at this level: enter its next chunk
@@ -1189,6 +1201,12 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
     uint32_t *Q = reinterpret_cast<uint32_t *>(g_smem + P.blob_cap) + (size_t)wid * qwords;
     WarpState *ws = reinterpret_cast<WarpState *>(g_smem + P.blob_cap + (size_t)kSearchWarps * qwords * 4) + wid;
     CtaShare *const sh = &s_share;
+    if (kCells) {
+        if (lane == 0)
+            ws->cell = reinterpret_cast<CellState *>(g_smem + P.blob_cap + (size_t)kSearchWarps * qwords * 4 +
+                                                     (size_t)kSearchWarps * sizeof(WarpState)) + wid;
+        __syncwarp();
+    }
 
     LaneStats st = {0ull, 0ull, 0ull};
     unsigned long long st_pairs = 0, st_staged = 0, st_global = 0;
@@ -1256,8 +1274,10 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             if (lane == 0) sh->slot[wid].lock = 0;
             bool fetching = true, counted_idle = false;
             int owning = -1;
+            unsigned nap = 500u;              // ns between two looks at the shared state while waiting; backs off
             for (;;) {
                 int t = -1, depth = 0, owner = 0;
+                int4 rec = make_int4(-1, 0, 0, 0);
                 uint32_t atom = 0u;
                 if (owning >= 0 || !fetching) {
                     // lane 0 looks at the shared state and decides for the warp:
@@ -1278,12 +1298,14 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                     if (idx >= 0) {
                         const Donation *d = &sh->ring[idx];
                         t = d->t; depth = d->depth; owner = d->owner; atom = d->chain[lane];
+                        rec = make_int4(t, A.L.atom_off[t], L_atoms(A.L, t), (int)A.L.pair_off[t]);
                         __syncwarp();
                         if (lane == 0) {
                             spin_unlock(&sh->ring_lock);
                             if (counted_idle) atomicSub(&sh->idle, 1);
                         }
                         counted_idle = false;
+                        nap = 500u;
                     } else if (idx == -1) {
                         // every part of my split pair is merged: write its hit, go back to the templates
                         __threadfence_block();
@@ -1301,17 +1323,26 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                         if (lane == 0 && counted_idle) atomicSub(&sh->idle, 1);
                         break;                       // every pair of this item is finished
                     } else {
+                        // Waiting costs issue slots the searching warps need: sleep, and sleep longer the
+                        // longer nothing happens (a donation waits at most a few microseconds; it is only
+                        // made by pairs that have already run for tens of microseconds).
                         if (!counted_idle) { if (lane == 0) atomicAdd(&sh->idle, 1); counted_idle = true; }
-                        __nanosleep(200);
+                        if (kStats && lane == 0) atomicAdd(A.O.stats + 14, (unsigned long long)nap);    // warp-ns spent waiting
+                        __nanosleep(nap);
+                        nap = min(nap * 2u, 8000u);
                         continue;
                     }
                 } else {
-                    if (lane == 0) {
-                        const int pos = atomicAdd(&s_next_pos, stride);
-                        if (pos < pos1) t = __ldg(A.sched + pos);
-                    }
-                    t = __shfl_sync(kFull, t, 0);
+                    int pos = pos1;
+                    if (lane == 0) pos = atomicAdd(&s_next_pos, stride);
+                    pos = __shfl_sync(kFull, pos, 0);
+                    if (pos < pos1) rec = __ldg(A.sched + pos);        // same address in every lane: one broadcast load
+                    t = rec.x;
                     if (t < 0) {
+                        // No splitting in this launch: nobody will ever need help, so park at the barrier
+                        // below like a plain loop would (a waiting warp must not compete for issue slots
+                        // with the warps that are still searching).
+                        if (P.donate_after < 0) break;
                         fetching = false;
                         if (lane == 0) atomicSub(&sh->in_loop, 1);
                         continue;
@@ -1319,7 +1350,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                 }
                 unsigned long long pair_t0 = 0;
                 if (kStats) pair_t0 = global_ns();
-                const bool split = search_template<kStats, kStaged, kCells>(A, s_blob, V, s, t, Q, ws, lane, st, sh, wid,
+                const bool split = search_template<kStats, kStaged, kCells>(A, s_blob, V, s, rec, Q, ws, lane, st, sh, wid,
                                                                             depth, owner, atom);
                 if (split) owning = t;
                 if (kStats && lane == 0) {
@@ -1369,13 +1400,15 @@ __global__ void emm_skip_snapshot_kernel(int n, int mode, const int *any, const 
     if (i < n) skip[i] = (mode == 1 ? pass[i] : any[i]) > 0;
 }
 
-size_t search_smem_bytes(int blob_cap, int levels)
+size_t search_smem_bytes(int blob_cap, int levels, bool cells)
 {
-    return (size_t)blob_cap + (size_t)kSearchWarps * queue_off(levels) * 4 + (size_t)kSearchWarps * sizeof(WarpState);
+    return (size_t)blob_cap + (size_t)kSearchWarps * queue_off(levels) * 4 + (size_t)kSearchWarps * sizeof(WarpState) +
+           (cells ? (size_t)kSearchWarps * sizeof(CellState) : 0);
 }
 
-// shared memory a CTA needs besides the staged blob: the dynamic part above + the static CtaShare
-size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels) + sizeof(CtaShare); }
+// shared memory a CTA needs besides the staged blob, whichever kernel runs: the dynamic part above
+// (with the cell-list state) + the static CtaShare
+size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels, true) + sizeof(CtaShare); }
 
 cudaError_t configure_search(int smem_bytes)
 {
@@ -1395,7 +1428,7 @@ void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsi
 }
 
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
-                   const unsigned char *skip, const int *sched, const int *ids, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream)
+                   const unsigned char *skip, const int4 *sched, const int *ids, bool stats, bool staged, int grid, size_t smem, cudaStream_t stream)
 {
     if (P.n_items <= 0) return;
     SearchArgs A;
