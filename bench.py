@@ -244,7 +244,7 @@ def parity_against_oracle(hits, raw, molecules, templates):
             "checked": "hit set, atoms, rmsd ==, n_complete ==, orientation <= 1e-4, filter verdict"}
 
 
-def api_legs(workload, n_files: int, chunk: int = 2048):
+def api_legs(workload, n_files: int, chunk: int = 1024):
     """What a user of the Python-facing API gets, from PDB FILES on local disk (page cache) to results,
     on one GPU -- three entry points, each timed end to end on its second call (the first one allocates
     the device sessions):

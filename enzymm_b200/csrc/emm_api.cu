@@ -20,6 +20,7 @@ void launch_prepare(const DevLibrary &L, const DevBatch &B, float cutoff, bool b
                     unsigned long long *stats, unsigned long long *bad, int sm_count, cudaStream_t stream);
 size_t search_smem_bytes(int blob_cap, int levels, bool cells);
 size_t search_fixed_smem(int levels);
+size_t search_soft_cap(int levels);
 cudaError_t configure_search(int smem_bytes);
 void launch_skip_snapshot(int n, int mode, const int *any, const int *pass, unsigned char *skip, cudaStream_t stream);
 void launch_search(const DevLibrary &L, const DevBatch &B, const SearchParams &P, const SearchOut &O,
@@ -98,6 +99,8 @@ struct emm_session {
     unsigned char *d_skip = nullptr;
     int *d_ids = nullptr;          // structures that can be staged first, then the ones too large for shared memory
     int32_t *d_status = nullptr;   // per structure: BlobHeader.status written by the prepare kernel
+    int32_t *d_kept_bound = nullptr;   // per structure: atoms of a class other than 0 (blob sizing)
+    std::vector<int32_t> h_kept_bound;
     unsigned long long *d_stats = nullptr;
     // current batch
     int32_t n_structures = 0;
@@ -458,6 +461,7 @@ int emm_session_create(emm_library *lib, int64_t max_atoms, int32_t max_structur
     ALLOC(s->d_skip, (size_t)max_structures);
     ALLOC(s->d_ids, 4 * (size_t)max_structures);
     ALLOC(s->d_status, 4 * (size_t)max_structures);
+    ALLOC(s->d_kept_bound, 4 * (size_t)max_structures);
     ALLOC(s->d_stats, 8 * 136);
     s->blob_capacity = 64 * max_atoms + (1024 + 4 * (int64_t)lib->d.n_leader) * max_structures;   // grown on demand at upload
     ALLOC(s->d_blob, s->blob_capacity);
@@ -477,7 +481,7 @@ void emm_session_destroy(emm_session *s)
     cudaSetDevice(s->lib->device);
     void *ptrs[] = {s->d_atom_off, s->d_xyz, s->d_klass, s->d_residue, s->d_bfactor, s->d_chain, s->d_atom_id,
                     s->d_blob, s->d_blob_off, s->d_hits, s->d_hit_count, s->d_work, s->d_any, s->d_pass,
-                    s->d_skip, s->d_stats, s->d_ids, s->d_status};
+                    s->d_skip, s->d_stats, s->d_ids, s->d_status, s->d_kept_bound};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : s->ev_prepare) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : s->ev_search) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -507,19 +511,22 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     // exact size of every structure's leader lists (before masking): one table lookup per atom, on a
     // few threads for large batches (this loop is host time inside the end-to-end path)
     std::vector<int64_t> entries_of((size_t)n, 0);
+    s->h_kept_bound.assign((size_t)std::max(n, 1), 0);
     std::atomic<int> bad_input(0);
     {
         auto count = [&](int lo, int hi) {
             for (int i = lo; i < hi; ++i) {
                 const int64_t a0 = b->atom_off[i], a1 = b->atom_off[i + 1];
                 if (a1 < a0) { bad_input.store(1); return; }
-                int64_t entries = 0;
+                int64_t entries = 0, nonzero = 0;
                 for (int64_t a = a0; a < a1; ++a) {
                     const uint16_t k = b->klass[a];
                     if (k >= n_class) { bad_input.store(2); return; }
                     entries += cl[k];
+                    nonzero += k != 0;
                 }
                 entries_of[(size_t)i] = entries;
+                s->h_kept_bound[(size_t)i] = (int32_t)std::min<int64_t>(nonzero, 0x7fffffff);
             }
         };
         const int n_threads = b->n_atoms > (int64_t)2000000 ? std::min(4, std::max(1, (int)std::thread::hardware_concurrency())) : 1;
@@ -531,14 +538,30 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     }
     if (bad_input.load() == 1) return fail(EMM_ERR_INVALID, "atom_off must be non-decreasing");
     if (bad_input.load() == 2) return fail(EMM_ERR_INVALID, "typing class out of range");
+    // Staging policy.  A blob is staged when it fits next to the queues; but the CTA should also stay
+    // within 196 KB of shared memory, beyond which the SM's L1 shrinks from 60 to 28 KB and the whole
+    // launch runs ~1.35x slower.  So the few structures between that soft limit and the hard one are
+    // searched in place (4x slower for them) unless they are more than a tenth of the batch.
+    const int64_t soft_cap = (int64_t)search_soft_cap(lib->d.max_tpl_atoms + 1) & ~int64_t(1023);
+    std::vector<int64_t> staged_of((size_t)n, 0);
+    int64_t fits = 0, over_soft = 0;
     for (int i = 0; i < n; ++i) {
         const int64_t a0 = b->atom_off[i], a1 = b->atom_off[i + 1];
         int64_t staged = 0;
-        const int64_t bytes = blob_bytes(a1 - a0, lib->d.n_leader, entries_of[(size_t)i], &staged);
+        const int64_t bytes = blob_bytes(s->h_kept_bound[(size_t)i], is_wide(a1 - a0), lib->d.n_leader, entries_of[(size_t)i], &staged);
         if (bytes >= (int64_t)1 << 31) return fail(EMM_ERR_INPUT, "a structure is too large: its blob would exceed 2 GiB");
         s->h_blob_off[(size_t)i + 1] = s->h_blob_off[(size_t)i] + bytes;
-        if (!is_wide(a1 - a0) && ((staged + 1023) & ~int64_t(1023)) <= stage_cap) {
-            max_staged = std::max(max_staged, staged);
+        const int64_t rounded = (staged + 1023) & ~int64_t(1023);
+        const bool ok = !is_wide(a1 - a0) && rounded <= stage_cap;
+        staged_of[(size_t)i] = ok ? rounded : -1;
+        fits += ok;
+        over_soft += ok && rounded > soft_cap;
+    }
+    const bool keep_l1 = soft_cap > 0 && over_soft * 10 <= fits;
+    for (int i = 0; i < n; ++i) {
+        const int64_t rounded = staged_of[(size_t)i];
+        if (rounded >= 0 && !(keep_l1 && rounded > soft_cap)) {
+            max_staged = std::max(max_staged, rounded);
             s->h_ids.push_back(i);
         } else {
             large.push_back(i);      // searched in place from global memory, in a launch of their own
@@ -559,6 +582,7 @@ int emm_session_upload(emm_session *s, const emm_batch *b, void *stream_)
     if (n > 0) {
         CUDA_TRY(cudaMemcpyAsync(s->d_atom_off, b->atom_off, 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(s->d_blob_off, s->h_blob_off.data(), 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_kept_bound, s->h_kept_bound.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, stream));
         if (s->n_small != n) CUDA_TRY(cudaMemcpyAsync(s->d_ids, s->h_ids.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, stream));
     }
     if (na > 0) {
@@ -613,6 +637,7 @@ int emm_session_run(emm_session *s, const emm_query_params *q, void *stream_)
     B.blob = s->d_blob;
     B.blob_off = s->d_blob_off;
     B.status = s->d_status;
+    B.kept_bound = s->d_kept_bound;
 
     const float cutoff = q->conservation_cutoff > 0.f ? q->conservation_cutoff : 0.f;
     if (cutoff > 0.f && !s->has_bfactor) return fail(EMM_ERR_INVALID, "conservation_cutoff needs the bfactor column");

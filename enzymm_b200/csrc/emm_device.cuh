@@ -85,6 +85,8 @@ struct DevBatch {
     unsigned char *blob;     // all structure blobs
     const int64_t *blob_off; // [n_structures+1]
     int32_t *status;         // [n_structures] BlobHeader.status of every structure, written by prepare
+    const int32_t *kept_bound;  // [n_structures] atoms whose class is not 0: an upper bound of n_kept the
+                                // host sizes the blob with (class-0 atoms, ~17 % of a protein, never stay)
 };
 
 constexpr int kMaxCells = 4096;        // uniform-grid cells per structure (cell edge grows to fit)
@@ -163,12 +165,13 @@ struct SearchOut {
 
 inline __host__ __device__ int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
 
-// Size of a structure blob for n input atoms whose leader lists hold lead_entries entries in
-// total (the host computes this exactly at upload, so blobs are laid out without a size pass);
-// *staged_bound = upper bound of the prefix the search kernel stages (header .. leader lists).
-inline __host__ __device__ int64_t blob_bytes(int64_t n, int n_leader, int64_t lead_entries, int64_t *staged_bound = nullptr)
+// Size of a structure blob that keeps at most n atoms (n = atoms of a class other than 0; `wide` from
+// the INPUT atom count) whose leader lists hold lead_entries entries in total (the host computes this
+// exactly at upload, so blobs are laid out without a size pass); *staged_bound = upper bound of the
+// prefix the search kernel stages (header .. leader lists).
+inline __host__ __device__ int64_t blob_bytes(int64_t n, bool wide, int n_leader, int64_t lead_entries, int64_t *staged_bound = nullptr)
 {
-    const int64_t ib = is_wide(n) ? 4 : 2;   // bytes per index entry
+    const int64_t ib = wide ? 4 : 2;         // bytes per index entry
     int64_t b = sizeof(BlobHeader);
     b += 16 * n;                             // atom records (x, y, z, res_of | klass)
     b += align16(ib * (n + 1));              // res_start

@@ -87,10 +87,11 @@ emm_prepare_kernel(DevLibrary L, DevBatch B, float cutoff, int build_cells,
         const int N = (int)(B.atom_off[s + 1] - base);
         unsigned char *blob = B.blob + B.blob_off[s];
         const int64_t bound = B.blob_off[s + 1] - B.blob_off[s];
-        const int off_orig = (int)(bound - align16(4 * (int64_t)N));
+        const int Nb = B.kept_bound[s];          // atoms that can stay at all: what the host sized this blob for
+        const int off_orig = (int)(bound - align16(4 * (int64_t)Nb));
         int32_t *orig = reinterpret_cast<int32_t *>(blob + off_orig);
         // compact copy of the kept atoms' classes: pass D scans it once per leader type
-        uint16_t *bklass = reinterpret_cast<uint16_t *>(blob + off_orig - align16(2 * (int64_t)N));
+        uint16_t *bklass = reinterpret_cast<uint16_t *>(blob + off_orig - align16(2 * (int64_t)Nb));
         const uint16_t *klass_in = B.klass + base;
         const int32_t *res_in = B.residue + base;
         const double *xyz = B.xyz + 3 * base;

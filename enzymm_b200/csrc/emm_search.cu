@@ -95,6 +95,12 @@ static_assert(kQueueCap < 256, "queue counters are bytes");
 // the owner's PairSlot (minimum RMSD with the lexicographic tie-break, summed complete-assignment
 // counts), and the owner writes the hit once every donation has come back.
 constexpr int kDonationRing = 16;
+#ifndef EMM_DONATE_STRIDE
+#define EMM_DONATE_STRIDE 4
+#endif
+#ifndef EMM_NAP_NS
+#define EMM_NAP_NS 500u
+#endif
 
 struct Donation {
     int owner;                   // warp whose pair this subtree belongs to
@@ -925,10 +931,15 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
             // them the partials of this chunk that no expansion has touched yet (the tail of the
             // compacted order, so the cursor of this level stays meaningful).
             int idle = 0;
-            if (!kCells && A.P.donate_after >= 0 && k > 0 && k < m && valid && ++visits > A.P.donate_after) {
+#ifndef EMM_NO_DONATE
+            // looked at every EMM_DONATE_STRIDE-th level entry only: the look is a shared-memory load
+            // and a shuffle on the critical path of exactly the pairs that have many level entries
+            if (!kCells && A.P.donate_after >= 0 && k > 0 && k < m && valid && ++visits > A.P.donate_after &&
+                (visits & (EMM_DONATE_STRIDE - 1)) == 0) {
                 if (lane == 0) idle = peek(&sh->idle);         // one reader: the branch below must be warp-uniform
                 idle = __shfl_sync(kFull, idle, 0);
             }
+#endif
             if (idle > 0) {
                 const int cur = ws->cur[k];
                 const int pend = ws->todo[k] != 0ull ? 1 : 0;
@@ -1274,7 +1285,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             if (lane == 0) sh->slot[wid].lock = 0;
             bool fetching = true, counted_idle = false;
             int owning = -1;
-            unsigned nap = 500u;              // ns between two looks at the shared state while waiting; backs off
+            unsigned nap = EMM_NAP_NS;        // ns between two looks at the shared state while waiting; backs off
             for (;;) {
                 int t = -1, depth = 0, owner = 0;
                 int4 rec = make_int4(-1, 0, 0, 0);
@@ -1305,7 +1316,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                             if (counted_idle) atomicSub(&sh->idle, 1);
                         }
                         counted_idle = false;
-                        nap = 500u;
+                        nap = EMM_NAP_NS;
                     } else if (idx == -1) {
                         // every part of my split pair is merged: write its hit, go back to the templates
                         __threadfence_block();
@@ -1326,10 +1337,18 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                         // Waiting costs issue slots the searching warps need: sleep, and sleep longer the
                         // longer nothing happens (a donation waits at most a few microseconds; it is only
                         // made by pairs that have already run for tens of microseconds).
-                        if (!counted_idle) { if (lane == 0) atomicAdd(&sh->idle, 1); counted_idle = true; }
-                        if (kStats && lane == 0) atomicAdd(A.O.stats + 14, (unsigned long long)nap);    // warp-ns spent waiting
-                        __nanosleep(nap);
-                        nap = min(nap * 2u, 8000u);
+                        // Only a warp that is OUT of templates advertises itself as idle: an owner waiting
+                        // for the parts of its pair resumes in a moment, and counting it would make every
+                        // other long pair split as well (a cascade of one-partial searches for the rest of
+                        // the item: measured 5 % on the whole bench).  It still helps while it waits.
+                        if (!counted_idle && owning < 0) { if (lane == 0) atomicAdd(&sh->idle, 1); counted_idle = true; }
+                        if (kStats && lane == 0 && owning < 0) atomicAdd(A.O.stats + 14, (unsigned long long)nap);    // warp-ns spent waiting
+                        if (owning >= 0) {
+                            __nanosleep(200);            // the parts of my pair are short: look again soon
+                        } else {
+                            __nanosleep(nap);
+                            nap = min(nap * 2u, 8000u);
+                        }
                         continue;
                     }
                 } else {
@@ -1342,6 +1361,9 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                         // No splitting in this launch: nobody will ever need help, so park at the barrier
                         // below like a plain loop would (a waiting warp must not compete for issue slots
                         // with the warps that are still searching).
+#ifdef EMM_NO_DONATE
+                        break;
+#endif
                         if (P.donate_after < 0) break;
                         fetching = false;
                         if (lane == 0) atomicSub(&sh->in_loop, 1);
@@ -1409,6 +1431,14 @@ size_t search_smem_bytes(int blob_cap, int levels, bool cells)
 // shared memory a CTA needs besides the staged blob, whichever kernel runs: the dynamic part above
 // (with the cell-list state) + the static CtaShare
 size_t search_fixed_smem(int levels) { return search_smem_bytes(0, levels, true) + sizeof(CtaShare); }
+
+// largest staged blob that keeps a CTA of the default kernels within 196 KB of shared memory (the
+// carve-out step below which the SM keeps 60 KB of L1); 0 if the queues alone do not fit
+size_t search_soft_cap(int levels)
+{
+    const size_t keep = 196 * 1024, used = search_smem_bytes(0, levels, false) + sizeof(CtaShare) + 512;
+    return keep > used ? keep - used : 0;
+}
 
 cudaError_t configure_search(int smem_bytes)
 {

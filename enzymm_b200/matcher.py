@@ -725,73 +725,50 @@ class Matcher:
 
     def _assemble(self, records: np.ndarray, molecules: Sequence[Molecule]) -> Dict[Molecule, List[Match]]:
         """Hit records -> ``{molecule: [Match]}`` with the reference's per-size-group completeness
-        check and filtering (``jess_run.py:845-894``).  Columns are converted to Python numbers once,
-        records are grouped by (size group, molecule) with one sort, and a ``Hit`` decodes its atoms
-        and transform only when asked."""
+        check and filtering (``jess_run.py:845-894``).  Which records survive, their completeness and
+        their order are array operations (``tsv.RowSelector``, shared with the table writer); Python
+        objects are made for the surviving matches only, and a ``Hit`` decodes its atoms and
+        transform when asked."""
+        from .tsv import RowSelector
         processed: Dict[Molecule, List[Match]] = collections.defaultdict(list)
-        n = len(records)
-        bounds = np.asarray([hi for _, _, hi in self._groups])
-        tidx = records["template_index"]
-        sidx = records["structure"]
-        group_of = np.searchsorted(bounds, tidx, side="right")
-        order = np.lexsort((tidx, sidx, group_of)) if n else np.zeros(0, dtype=np.int64)
-        cell_key = (group_of[order].astype(np.int64) * max(len(molecules), 1) + sidx[order]) if n else order
-        starts = np.flatnonzero(np.r_[True, cell_key[1:] != cell_key[:-1]]) if n else order
-        ends = np.r_[starts[1:], n] if n else order
-        cols = list(zip(records["rmsd"].tolist(), records["orientation"].tolist(), records["flags"].tolist(),
-                        records["n_complete"].tolist(), tidx.tolist(), sidx.tolist()))
-        ident, member, size = self._template_identity()
-        order_l, group_l = order.tolist(), group_of[order].tolist() if n else []
-        ordered, filtering = self._ordered, self.filter_matches
+        selector = getattr(self, "_selector", None)
+        if selector is None or selector.bounds is None or len(selector.ident) != len(self._ordered):
+            selector = self._selector = RowSelector(self, predict_correctness=False)
+        try:
+            rows, _, complete, _ = selector.select(records)
+        except KeyError:
+            # a hit at a distance without logistic models: raise what the reference raises, from the
+            # reference's own formula (jess_run.py:339-342)
+            bad = records[(records["flags"] & 0x08) != 0][0]
+            template = self._ordered[int(bad["template_index"])]
+            distance = self._get_jess_parameters(template.effective_size)[1]
+            Match(hit=Hit(bad, template, molecules[int(bad["structure"])]), pairwise_distance=distance).predicted_correct
+            raise
+        rows_l = rows.tolist()
+        picked = records[rows] if len(rows) else records[:0]
+        cols = zip(picked["rmsd"].tolist(), picked["orientation"].tolist(), picked["flags"].tolist(),
+                   picked["n_complete"].tolist(), picked["template_index"].tolist(), picked["structure"].tolist())
+        ordered = self._ordered
+        distance_of = np.empty(len(ordered), dtype=object)
+        for gsize, lo, hi in self._groups:
+            distance_of[lo:hi] = self._get_jess_parameters(gsize)[1]
         overflowed = 0
-        cell = 0
-        n_cells = len(starts)
-        starts_l, ends_l = starts.tolist(), ends.tolist()
-        for gi, (gsize, lo, hi) in enumerate(self._groups):
-            rmsd, distance, max_dyn = self._get_jess_parameters(gsize)
-            self.verbose_print(f"Now matching query structure(s) to template of size {gsize}")
-            self.verbose_print(f"jess parameters are: {rmsd} {distance} {max_dyn}")
-            total = 0
-            while cell < n_cells and group_l[starts_l[cell]] == gi:
-                rows = order_l[starts_l[cell]:ends_l[cell]]
-                cell += 1
-                molecule = molecules[cols[rows[0]][5]]
-                matches = []
-                for i in rows:
-                    sc = cols[i]
-                    matches.append(Match(hit=Hit(records[i], ordered[sc[4]], molecule, sc), pairwise_distance=distance))
-                # completeness of the raw hits of this (molecule, size group), before filtering
-                if len(matches) == 1:
-                    ti = cols[rows[0]][4]
-                    matches[0].complete = ident[ti] < 0 or (size[ti] == 1 and member[ti] == 1)
-                else:
-                    grouped: Dict[int, List[int]] = {}
-                    for j, i in enumerate(rows):
-                        ti = cols[i][4]
-                        if ident[ti] < 0:
-                            matches[j].complete = True
-                        else:
-                            grouped.setdefault(ident[ti], []).append(j)
-                    for js in grouped.values():
-                        ti0 = cols[rows[js[0]]][4]
-                        if sorted(member[cols[rows[j]][4]] for j in js) == list(range(1, size[ti0] + 1)):
-                            for j in js:
-                                matches[j].complete = True
-                if filtering:
-                    for match in matches:
-                        flags = match.hit.flags
-                        if flags & 0x08:                       # EMM_HIT_NO_MODEL
-                            match.predicted_correct            # raises the reference's KeyError
-                        if flags & 0x04:                       # EMM_HIT_PASS
-                            processed[molecule].append(match)
-                            total += 1
-                            overflowed += flags & 0x01
-                else:
-                    processed[molecule].extend(matches)
-                    total += len(matches)
-                    overflowed += sum(m.hit.flags & 0x01 for m in matches)
-            self.verbose_print(f"{total} matches found!")
-            self.verbose_print(f"{len(processed)} target structures processed!")
+        for i, done, sc in zip(rows_l, complete.tolist(), cols):
+            molecule = molecules[sc[5]]
+            processed[molecule].append(Match(hit=Hit(records[i], ordered[sc[4]], molecule, sc), complete=bool(done),
+                                             pairwise_distance=distance_of[sc[4]]))
+            overflowed += sc[2] & 0x01
+        if self.verbose:
+            group_of = np.searchsorted(selector.bounds, picked["template_index"], side="right") if len(rows) else []
+            seen = 0
+            for gi, (gsize, lo, hi) in enumerate(self._groups):
+                rmsd, distance, max_dyn = self._get_jess_parameters(gsize)
+                self.verbose_print(f"Now matching query structure(s) to template of size {gsize}")
+                self.verbose_print(f"jess parameters are: {rmsd} {distance} {max_dyn}")
+                in_group = picked["structure"][np.asarray(group_of) == gi] if len(rows) else []
+                self.verbose_print(f"{len(in_group)} matches found!")
+                seen = len(set(picked["structure"][np.asarray(group_of) <= gi].tolist())) if len(rows) else 0
+                self.verbose_print(f"{seen} target structures processed!")
         if overflowed and self.warn:
             # ADVICE r1: at the cap the best hit comes from the candidates examined so far, in this
             # engine's enumeration order -- not reproducible against Jess; Match.hit.overflow marks them

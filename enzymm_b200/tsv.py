@@ -27,7 +27,7 @@ from .engine import HIT_NO_MODEL, HIT_PASS, load_cdll
 from .library import MAX_TEMPLATE_ATOMS
 from .templates import AnnotatedTemplate
 
-__all__ = ["TableColumns", "TableWriter", "TSV_HEADER"]
+__all__ = ["TableColumns", "RowSelector", "TableWriter", "TSV_HEADER"]
 
 TSV_HEADER = [
     "query_id", "pairwise_distance", "match_index", "template_pdb_id", "template_pdb_chains",
@@ -87,57 +87,21 @@ def _c_strings(values: Sequence[str]):
     return (ctypes.c_char_p * max(len(encoded), 1))(*encoded), encoded
 
 
-class TableWriter:
-    """Rows of the results table for the hit records of a ``Matcher``'s batches."""
+class RowSelector:
+    """Which hit records of a batch survive as matches, in which order, with which completeness flag:
+    ``Matcher.run``'s bookkeeping (``jess_run.py:738-783, 845-894``) as array operations."""
 
     def __init__(self, matcher, predict_correctness: bool = True):
         self.matcher = matcher
         matcher._compile()
         self.predict_correctness = predict_correctness
-        templates = matcher._ordered
         self.bounds = np.asarray([hi for _, _, hi in matcher._groups])
         ident, member, size = matcher._template_identity()
         self.ident = np.asarray(ident, dtype=np.int64)
         self.member = np.asarray(member, dtype=np.int64)
         self.size = np.asarray(size, dtype=np.int64)
         self.n_ident = int(self.ident.max()) + 2 if len(ident) else 1
-        distance, static, annotation, order_off, order = [], [], [], [0], []
-        for gsize, lo, hi in matcher._groups:
-            d = str(matcher._get_jess_parameters(gsize)[1])
-            distance.extend([d] * (hi - lo))
-        for t in templates:
-            c = t.cluster
-            static.append("\t".join([
-                str(t.pdb_id if t.pdb_id else ""), ",".join(set(r.chain_id for r in t.residues)),
-                str(c.id if c else ""), str(c.member if c else ""), str(c.size if c else ""),
-                str(t.effective_size), str(t.dimension), str(t.mcsa_id if t.mcsa_id else ""),
-                str(t.uniprot_id if t.uniprot_id else ""), ",".join(t.ec if t.ec is not None else ""),
-                ",".join(t.cath if t.cath else "")]))
-            if isinstance(t, AnnotatedTemplate) and hasattr(t, "number_of_mutated_residues"):
-                annotation.append("\t".join([
-                    str(t.number_of_mutated_residues), ",".join(str(i) for i in t.number_of_side_chain_residues),
-                    ",".join(str(i) for i in t.number_of_metal_ligands),
-                    ",".join(str(i) for i in t.number_of_ptm_residues), str(t.total_reference_residues)]))
-            else:
-                annotation.append("\t" * 5)                       # six empty columns, as the reference writes
-            order.extend(t.relative_order)
-            order_off.append(len(order))
-        self._distance, self._keep1 = _c_strings(distance)
-        self._static, self._keep2 = _c_strings(static)
-        self._annotation, self._keep3 = _c_strings(annotation)
-        self._multimeric = np.asarray([1 if t.multimeric else 0 for t in templates], dtype=np.uint8)
-        self._order_off = np.asarray(order_off, dtype=np.int32)
-        self._order = np.asarray(order if order else [0], dtype=np.int32)
-        self._lib = load_cdll()
-        self._lib.emm_tsv_format.restype = ctypes.c_int
-        self._lib.emm_tsv_free.restype = None
-        self._lib.emm_tsv_free.argtypes = [ctypes.c_void_p]
 
-    @staticmethod
-    def header() -> str:
-        return "\t".join(TSV_HEADER) + "\n"
-
-    # ---- which records become rows, in which order ---------------------------------------------------
     def select(self, records: np.ndarray):
         """``(rows, match_index, complete, predicted)``: indices into ``records`` in output order,
         ``Match.index``, ``Match.complete`` and the ``predicted_correct`` column (0 / 1 / 2 = empty)."""
@@ -187,6 +151,49 @@ class TableWriter:
         predicted = passing[rows].astype(np.uint8) if self.predict_correctness else np.full(len(rows), 2, dtype=np.uint8)
         return rows, match_index, complete[rows].astype(np.uint8), predicted
 
+
+class TableWriter(RowSelector):
+    """Rows of the results table for the hit records of a ``Matcher``'s batches."""
+
+    def __init__(self, matcher, predict_correctness: bool = True):
+        super().__init__(matcher, predict_correctness)
+        templates = matcher._ordered
+        distance, static, annotation, order_off, order = [], [], [], [0], []
+        for gsize, lo, hi in matcher._groups:
+            d = str(matcher._get_jess_parameters(gsize)[1])
+            distance.extend([d] * (hi - lo))
+        for t in templates:
+            c = t.cluster
+            static.append("\t".join([
+                str(t.pdb_id if t.pdb_id else ""), ",".join(set(r.chain_id for r in t.residues)),
+                str(c.id if c else ""), str(c.member if c else ""), str(c.size if c else ""),
+                str(t.effective_size), str(t.dimension), str(t.mcsa_id if t.mcsa_id else ""),
+                str(t.uniprot_id if t.uniprot_id else ""), ",".join(t.ec if t.ec is not None else ""),
+                ",".join(t.cath if t.cath else "")]))
+            if isinstance(t, AnnotatedTemplate) and hasattr(t, "number_of_mutated_residues"):
+                annotation.append("\t".join([
+                    str(t.number_of_mutated_residues), ",".join(str(i) for i in t.number_of_side_chain_residues),
+                    ",".join(str(i) for i in t.number_of_metal_ligands),
+                    ",".join(str(i) for i in t.number_of_ptm_residues), str(t.total_reference_residues)]))
+            else:
+                annotation.append("\t" * 5)                       # six empty columns, as the reference writes
+            order.extend(t.relative_order)
+            order_off.append(len(order))
+        self._distance, self._keep1 = _c_strings(distance)
+        self._static, self._keep2 = _c_strings(static)
+        self._annotation, self._keep3 = _c_strings(annotation)
+        self._multimeric = np.asarray([1 if t.multimeric else 0 for t in templates], dtype=np.uint8)
+        self._order_off = np.asarray(order_off, dtype=np.int32)
+        self._order = np.asarray(order if order else [0], dtype=np.int32)
+        self._lib = load_cdll()
+        self._lib.emm_tsv_format.restype = ctypes.c_int
+        self._lib.emm_tsv_free.restype = None
+        self._lib.emm_tsv_free.argtypes = [ctypes.c_void_p]
+
+    @staticmethod
+    def header() -> str:
+        return "\t".join(TSV_HEADER) + "\n"
+
     # ---- rows -> text ------------------------------------------------------------------------------------
     def format(self, records: np.ndarray, table: TableColumns, query_ids: Sequence[Optional[str]],
                selection=None) -> bytes:
@@ -235,3 +242,4 @@ class TableWriter:
         finally:
             self._lib.emm_tsv_free(text)
         del keep_ids
+

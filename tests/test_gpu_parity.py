@@ -851,3 +851,29 @@ def test_scan_files_over_several_devices_from_one_process(tmp_path, active_templ
         assert one.getvalue() == want.getvalue()
     finally:
         matcher.close()
+
+
+def test_staging_policy_keeps_the_l1_carveout(active_templates, monkeypatch):
+    """A staged blob beyond ~97 KB pushes the CTA past 196 KB of shared memory and the SM's L1 from 60
+    to 28 KB for the whole launch.  A lone structure of that size in a batch of ordinary ones is
+    therefore searched in place; when such structures are more than a tenth of the batch they are
+    staged after all.  Hits never depend on the route."""
+    monkeypatch.setenv("EMM_STATS", "1")
+    small = generate_chunk(5, SynthConfig(n_residues=200), active_templates, 20)
+    mid = generate_chunk(6, SynthConfig(n_residues=560), active_templates, 4)      # ~110 KB staged with the full library
+    dist = default_distances(active_templates)
+    eng = Engine(CompiledLibrary(active_templates, 2.0, dist, dist))
+    try:
+        lone = [small.to_molecule(i) for i in range(20)] + [mid.to_molecule(0)]
+        many = [small.to_molecule(i) for i in range(6)] + [mid.to_molecule(i) for i in range(4)]
+        for mols, in_place in ((lone, 1), (many, 0)):
+            hits, stats = eng.query(pack_molecules(mols, eng.compiled), with_stats=True)
+            assert (stats["global_blobs"] > 0) == bool(in_place), stats
+            alone = [eng.query(pack_molecules([m], eng.compiled)) for m in mols]
+            for i, part in enumerate(alone):
+                mine = hits[hits["structure"] == i]
+                assert mine["template_index"].tolist() == part["template_index"].tolist()
+                assert mine["rmsd"].tolist() == part["rmsd"].tolist() and np.array_equal(mine["atoms"], part["atoms"])
+        compare_with_oracle(eng, active_templates, lone[-2:], dist)
+    finally:
+        eng.close()
