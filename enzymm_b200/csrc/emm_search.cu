@@ -772,8 +772,8 @@ struct LaneStats {
 template <bool kStats, bool kStaged>
 __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob &S, const View<kStaged> &V,
                                                 uint32_t *Q, WarpState *ws,
-                                                int a0, int64_t p0, int m, int k, int base, int size,
-                                                float cut32, double cut64, double dyn64, int lane, LaneStats &st)
+                                                int a0, int p0, int m, int k, int base, int size,
+                                                float cut32, bool dynamic, int t, int lane, LaneStats &st)
 {
     const DevLibrary &L = A.L;
     const bool have = lane < size;
@@ -782,7 +782,6 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     const bool check = alive && !(e & kEntryValid);
     const int a = entry_atom(e);
     const int anchor_pos = k < m ? (int)L.plan_anchor[a0 + k] : -1;     // warp-uniform
-    const bool dynamic = dyn64 != cut64;
     const float eps = V.eps;
     const float4 pa = V.atom(a);
     const float xa = pa.x, ya = pa.y, za = pa.z;
@@ -802,7 +801,9 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
         if (check) {
             const float dx = xa - xb, dy = ya - yb, dz = za - zb;
             const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-            const float delta = dynamic ? (float)pair_delta(L, a0, k - 1, pos, cut64, dyn64) : cut32;
+            // (the FP64 thresholds are re-read where they are needed -- rare paths -- instead of
+            // living in four registers across the whole search)
+            const float delta = dynamic ? (float)pair_delta(L, a0, k - 1, pos, L.dist_cut[t], L.max_dyn[t]) : cut32;
             const float err = fabsf(d - __ldg(row + pos));
             if (err > delta + eps || b == a) alive = false;
             else if (err >= delta - eps) border = true;
@@ -811,7 +812,7 @@ __device__ __forceinline__ unsigned enter_level(const SearchArgs &A, const Blob 
     }
     if (check && alive && border) {
         if (kStats) ++st.exact;
-        alive = exact_validate(L, S, Q, a0, p0, k, e, cut64, dyn64);
+        alive = exact_validate(L, S, Q, a0, p0, k, e, L.dist_cut[t], L.max_dyn[t]);
     }
     if (check) Q[queue_off(k) + base + lane] = e | (alive ? kEntryValid : kEntryDead);
     const unsigned valid = __ballot_sync(kFull, alive);
@@ -840,7 +841,7 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
 {
     const DevLibrary &L = A.L;
     const int t = rec.x, a0 = rec.y, m = rec.z;
-    const int64_t p0 = rec.w;
+    const int p0 = rec.w;                // first pair of the template (the pair table holds < 2^31 entries)
 
     // a template with an empty leader list cannot match this structure
     if (don_depth == 0) {
@@ -852,8 +853,8 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
         if (__any_sync(kFull, empty)) return false;
     }
 
-    const double cut64 = L.dist_cut[t], dyn64 = L.max_dyn[t];
-    const bool dynamic = dyn64 != cut64;
+    const double cut64 = L.dist_cut[t];
+    const bool dynamic = L.max_dyn[t] != cut64;
     const float cut32 = (float)cut64;
     const float eps = V.eps;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -921,7 +922,7 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
                 // do with it, so do not re-derive its anchors -- fall through and pop it
                 valid = 0u;
             } else {
-                valid = k == 0 ? 1u : enter_level<kStats, kStaged>(A, S, V, Q, ws, a0, p0, m, k, base, size, cut32, cut64, dyn64, lane, st);
+                valid = k == 0 ? 1u : enter_level<kStats, kStaged>(A, S, V, Q, ws, a0, p0, m, k, base, size, cut32, dynamic, t, lane, st);
             }
             if (kStats && lane == 0 && k > 0 && ws->cur[k] >= 0) {
                 atomicAdd(A.O.stats + 72 + k, (unsigned long long)__popc(valid));
@@ -965,7 +966,7 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
             float lo2 = 0.f, hi2 = 3.0e38f;
             if (k > 0) {
                 const float dt = __ldg(L.anchor_dist32 + a0 + k);
-                const float rej = (dynamic ? (float)pair_delta(L, a0, k, (int)L.plan_anchor[a0 + k], cut64, dyn64) : cut32) + eps;
+                const float rej = (dynamic ? (float)pair_delta(L, a0, k, (int)L.plan_anchor[a0 + k], L.dist_cut[t], L.max_dyn[t]) : cut32) + eps;
                 const float lo = fmaxf(dt - rej, 0.f), hi = dt + rej;
                 lo2 = lo * lo * 0.999999f;
                 hi2 = hi * hi * 1.000001f;
@@ -1328,6 +1329,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                         }
                         counted_idle = false;
                         owning = -1;
+                        nap = EMM_NAP_NS;
                         __syncwarp();
                         continue;
                     } else if (idx == -2) {
@@ -1343,12 +1345,10 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                         // the item: measured 5 % on the whole bench).  It still helps while it waits.
                         if (!counted_idle && owning < 0) { if (lane == 0) atomicAdd(&sh->idle, 1); counted_idle = true; }
                         if (kStats && lane == 0 && owning < 0) atomicAdd(A.O.stats + 14, (unsigned long long)nap);    // warp-ns spent waiting
-                        if (owning >= 0) {
-                            __nanosleep(200);            // the parts of my pair are short: look again soon
-                        } else {
-                            __nanosleep(nap);
-                            nap = min(nap * 2u, 8000u);
-                        }
+                        // (ncu, round 2: with a fixed 200 ns nap the owners of split pairs alone issued 5 % of
+                        // the kernel's instructions while waiting for parts that run for milliseconds)
+                        __nanosleep(nap);
+                        nap = min(nap * 2u, owning >= 0 ? 4000u : 8000u);
                         continue;
                     }
                 } else {
@@ -1374,7 +1374,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                 if (kStats) pair_t0 = global_ns();
                 const bool split = search_template<kStats, kStaged, kCells>(A, s_blob, V, s, rec, Q, ws, lane, st, sh, wid,
                                                                             depth, owner, atom);
-                if (split) owning = t;
+                if (split) { owning = t; nap = 200u; }
                 if (kStats && lane == 0) {
                     if (depth == 0) ++st_pairs;
                     const unsigned long long dt = global_ns() - pair_t0;
