@@ -547,6 +547,7 @@ def run_strong(args, rank, local_rank, world):
     from enzymm_b200.engine import Engine, HIT_DTYPE, PackedBatch, Session
     from enzymm_b200.library import CompiledLibrary
     from enzymm_b200.sharding import ChunkQueue, gather_hit_blocks
+    from enzymm_b200.synth import kind_classes
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -568,8 +569,9 @@ def run_strong(args, rank, local_rank, world):
         src = c % world
         cols = None
         if rank == src:
-            packed = make_workload(c, chunk, args.residues, args.chains, workers).to_packed(engine.compiled)
-            cols = [packed.atom_off, packed.xyz, packed.klass, packed.residue, packed.bfactor]
+            made = make_workload(c, chunk, args.residues, args.chains, workers)
+            # atom KINDS travel, every rank classifies them through its own compiled library
+            cols = [made.atom_off, made.xyz, made.kind.astype(np.int16), made.residue, made.bfactor]
         if world > 1:
             shapes = [[(a.shape, str(a.dtype)) for a in cols]] if rank == src else [None]
             dist.broadcast_object_list(shapes, src=src)
@@ -582,11 +584,12 @@ def run_strong(args, rank, local_rank, world):
                 dist.broadcast(buf, src=src)
                 received.append(buf.cpu().numpy().view(dtype).reshape(shape))
             cols = received
-        host_chunks.append(PackedBatch(pinned(cols[0]), pinned(cols[1]), pinned(cols[2]), pinned(cols[3]), pinned(cols[4]),
-                                       None, None))
+        host_chunks.append(PackedBatch(pinned(cols[0]), pinned(cols[1]), pinned(kind_classes(engine.compiled)[cols[2]]),
+                                       pinned(cols[3]), pinned(cols[4]), None, None))
     t_gen = time.perf_counter() - t_gen
     max_atoms = max(b.n_atoms for b in host_chunks)
-    lanes = [(Session(engine.device_library, max_atoms, chunk, 64 * chunk), torch.cuda.Stream().cuda_stream) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]          # kept alive: the sessions only hold the raw handles
+    lanes = [(Session(engine.device_library, max_atoms, chunk, 64 * chunk), st.cuda_stream) for st in streams]
     kwargs = dict(max_candidates=10000, ignore_chain=True, reset=True, force_prepare=True)
 
     def sweep(n_total):

@@ -115,7 +115,7 @@ struct PairSlot {
     int pending;                 // donations handed out and not merged back yet
     int best_valid, overflow;
     unsigned long long n_complete;
-    double best_rmsd;
+    unsigned long long best_rmsd_bits;   // the double, as bits (all traffic through here is atomic, see sh_get)
     uint32_t best_asg[kMaxAtoms];
 };
 
@@ -127,7 +127,17 @@ struct CtaShare {
     PairSlot slot[kSearchWarps];
 };
 
-__device__ __forceinline__ int peek(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+// Everything warps tell each other through CtaShare goes through shared-memory atomics -- reads as
+// atomicAdd(p, 0), writes as atomicExch -- in addition to the locks and fences that order it: the
+// accesses are rare (a donation, a merge, a poll between two naps), and it keeps the protocol
+// visible to compute-sanitizer's racecheck, which knows barriers and atomics but not spin locks.
+__device__ __forceinline__ int sh_get(int *p) { return atomicAdd(p, 0); }
+__device__ __forceinline__ unsigned sh_get(unsigned *p) { return atomicAdd(p, 0u); }
+__device__ __forceinline__ unsigned long long sh_get(unsigned long long *p) { return atomicAdd(p, 0ull); }
+__device__ __forceinline__ void sh_set(int *p, int v) { atomicExch(p, v); }
+__device__ __forceinline__ void sh_set(unsigned *p, unsigned v) { atomicExch(p, v); }
+__device__ __forceinline__ void sh_set(unsigned long long *p, unsigned long long v) { atomicExch(p, v); }
+__device__ __forceinline__ int peek(int *p) { return sh_get(p); }
 
 __device__ __forceinline__ void spin_lock(int *lock)
 {
@@ -579,31 +589,35 @@ __device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S
 __device__ __noinline__ void merge_into_slot(PairSlot *ps, const WarpState *ws, int m)
 {
     spin_lock(&ps->lock);
-    ps->n_complete += ws->n_complete;
-    ps->overflow |= ws->overflow;
+    atomicAdd(&ps->n_complete, ws->n_complete);
+    if (ws->overflow) sh_set(&ps->overflow, 1);
     if (ws->best_valid) {
-        bool better = !ps->best_valid || ws->best_rmsd < ps->best_rmsd;
-        if (!better && ws->best_rmsd == ps->best_rmsd) {
-            for (int i = 0; i < m; ++i)
-                if (ws->best_asg[i] != ps->best_asg[i]) { better = ws->best_asg[i] < ps->best_asg[i]; break; }
+        const double have = __longlong_as_double((long long)sh_get(&ps->best_rmsd_bits));
+        bool better = !sh_get(&ps->best_valid) || ws->best_rmsd < have;
+        if (!better && ws->best_rmsd == have) {
+            for (int i = 0; i < m; ++i) {
+                const uint32_t theirs = sh_get(&ps->best_asg[i]);
+                if (ws->best_asg[i] != theirs) { better = ws->best_asg[i] < theirs; break; }
+            }
         }
         if (better) {
-            ps->best_valid = 1;
-            ps->best_rmsd = ws->best_rmsd;
-            for (int i = 0; i < m; ++i) ps->best_asg[i] = ws->best_asg[i];
+            sh_set(&ps->best_valid, 1);
+            sh_set(&ps->best_rmsd_bits, (unsigned long long)__double_as_longlong(ws->best_rmsd));
+            for (int i = 0; i < m; ++i) sh_set(&ps->best_asg[i], ws->best_asg[i]);
         }
     }
     spin_unlock(&ps->lock);
 }
 
 // Lane 0: the merged result of a split pair back into the owner's warp state, for emit_hit.
-__device__ __noinline__ void load_from_slot(const PairSlot *ps, WarpState *ws, int m, long long max_candidates)
+__device__ __noinline__ void load_from_slot(PairSlot *ps, WarpState *ws, int m, long long max_candidates)
 {
-    ws->best_valid = ps->best_valid;
-    ws->best_rmsd = ps->best_rmsd;
-    ws->n_complete = ps->n_complete;
-    ws->overflow = ps->overflow || (max_candidates > 0 && ps->n_complete >= (unsigned long long)max_candidates);
-    for (int i = 0; i < m; ++i) ws->best_asg[i] = ps->best_asg[i];
+    const unsigned long long n = sh_get(&ps->n_complete);
+    ws->best_valid = sh_get(&ps->best_valid);
+    ws->best_rmsd = __longlong_as_double((long long)sh_get(&ps->best_rmsd_bits));
+    ws->n_complete = n;
+    ws->overflow = sh_get(&ps->overflow) || (max_candidates > 0 && n >= (unsigned long long)max_candidates);
+    for (int i = 0; i < m; ++i) ws->best_asg[i] = sh_get(&ps->best_asg[i]);
 }
 
 // Give the untouched tail of the chunk just entered at level k (valid = its live slots, anchors
@@ -620,7 +634,7 @@ __device__ __noinline__ unsigned donate_tail(CtaShare *sh, uint32_t *Q, WarpStat
     int at = 0;
     if (lane == 0) {
         spin_lock(&sh->ring_lock);
-        at = sh->ring_count;
+        at = sh_get(&sh->ring_count);
         give = min(give, kDonationRing - at);
         if (give <= 0) spin_unlock(&sh->ring_lock);
     }
@@ -629,18 +643,19 @@ __device__ __noinline__ unsigned donate_tail(CtaShare *sh, uint32_t *Q, WarpStat
     if (give <= 0) return valid;
     if (fresh && lane == 0) {        // first donation of this pair: an empty slot
         PairSlot *ps = &sh->slot[owner];
-        ps->pending = 0; ps->best_valid = 0; ps->overflow = 0; ps->n_complete = 0ull; ps->best_rmsd = CUDART_INF;
+        sh_set(&ps->pending, 0); sh_set(&ps->best_valid, 0); sh_set(&ps->overflow, 0); sh_set(&ps->n_complete, 0ull);
+        sh_set(&ps->best_rmsd_bits, (unsigned long long)__double_as_longlong(CUDART_INF));
     }
     unsigned gone = 0u;
     if (lane < give) {
         const int slot = (int)ws->vslot[P - give + lane];
         gone = 1u << slot;
         Donation *d = &sh->ring[at + lane];
-        d->owner = owner; d->depth = k; d->t = t;
+        sh_set(&d->owner, owner); sh_set(&d->depth, k); sh_set(&d->t, t);
         uint32_t w = Q[queue_off(k) + base + slot];
         Q[queue_off(k) + base + slot] = w | kEntryDead;          // the owner will not look at it again
         for (int pos = k - 1; pos >= 0; --pos) {
-            d->chain[pos] = (uint32_t)entry_atom(w);
+            sh_set(&d->chain[pos], (uint32_t)entry_atom(w));
             if (pos > 0) w = Q[queue_off(pos) + entry_parent(w)];
         }
     }
@@ -649,7 +664,7 @@ __device__ __noinline__ unsigned donate_tail(CtaShare *sh, uint32_t *Q, WarpStat
     __syncwarp();
     if (lane == 0) {
         atomicAdd(&sh->slot[owner].pending, give);
-        sh->ring_count = at + give;
+        sh_set(&sh->ring_count, at + give);
         ws->donated = 1;
         spin_unlock(&sh->ring_lock);
     }
@@ -1259,6 +1274,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             if (tid == 0) {
                 s_next_pos = pos0;
                 sh->ring_lock = 0; sh->ring_count = 0; sh->idle = 0; sh->in_loop = kSearchWarps;
+                for (int w = 0; w < kSearchWarps; ++w) { sh->slot[w].lock = 0; sh->slot[w].pending = 0; }
                 const int64_t abase = A.B.atom_off[s];
                 s_blob.orig = reinterpret_cast<const int32_t *>(gblob + hdr.off_orig);
                 s_blob.xyz64 = A.B.xyz + 3 * abase;
@@ -1283,7 +1299,6 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
             // Per-warp work loop: take templates while there are any; a warp that split its pair helps
             // with donated subtrees until all parts of the pair are back and then writes the hit; a
             // warp out of templates helps until every warp of the CTA has left the loop.
-            if (lane == 0) sh->slot[wid].lock = 0;
             bool fetching = true, counted_idle = false;
             int owning = -1;
             unsigned nap = EMM_NAP_NS;        // ns between two looks at the shared state while waiting; backs off
@@ -1298,7 +1313,7 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                     if (lane == 0) {
                         if (peek(&sh->ring_count) > 0) {
                             spin_lock(&sh->ring_lock);
-                            if (sh->ring_count > 0) idx = --sh->ring_count;      // the lock is kept until the record is copied
+                            if (sh_get(&sh->ring_count) > 0) idx = atomicSub(&sh->ring_count, 1) - 1;   // the lock is kept until the record is copied
                             else spin_unlock(&sh->ring_lock);
                         }
                         if (idx < 0) {
@@ -1308,8 +1323,8 @@ emm_search_kernel(const __grid_constant__ SearchArgs A)
                     }
                     idx = __shfl_sync(kFull, idx, 0);
                     if (idx >= 0) {
-                        const Donation *d = &sh->ring[idx];
-                        t = d->t; depth = d->depth; owner = d->owner; atom = d->chain[lane];
+                        Donation *d = &sh->ring[idx];
+                        t = sh_get(&d->t); depth = sh_get(&d->depth); owner = sh_get(&d->owner); atom = sh_get(&d->chain[lane]);
                         rec = make_int4(t, A.L.atom_off[t], L_atoms(A.L, t), (int)A.L.pair_off[t]);
                         __syncwarp();
                         if (lane == 0) {

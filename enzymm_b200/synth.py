@@ -85,9 +85,7 @@ class SynthChunk:
         return int(self.atom_off[-1])
 
     def to_packed(self, library: CompiledLibrary, with_chain: bool = False) -> PackedBatch:
-        table = np.asarray([library.class_of(RESIDUE_ORDER[r], n) for r, n in zip(_KIND_RES, _KIND_NAME)],
-                           dtype=np.uint16)
-        return PackedBatch(self.atom_off, self.xyz, table[self.kind], self.residue, self.bfactor,
+        return PackedBatch(self.atom_off, self.xyz, kind_classes(library)[self.kind], self.residue, self.bfactor,
                            self.chain if with_chain else None, None)
 
     def to_molecule(self, i: int) -> Molecule:
@@ -119,6 +117,11 @@ class SynthChunk:
                          f"{a.temperature_factor:>6.2f}          {a.element:>2s}\n")
         lines.append("END\n")
         return "".join(lines)
+
+
+def kind_classes(library: CompiledLibrary) -> np.ndarray:
+    """Typing class (of ``library``) of every synthetic atom kind: ``klass = kind_classes(lib)[chunk.kind]``."""
+    return np.asarray([library.class_of(RESIDUE_ORDER[r], n) for r, n in zip(_KIND_RES, _KIND_NAME)], dtype=np.uint16)
 
 
 def _unit(v: np.ndarray) -> np.ndarray:

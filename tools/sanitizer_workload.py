@@ -22,6 +22,7 @@ from enzymm_b200.synth import SynthConfig, generate_chunk  # noqa: E402
 
 def main():
     step = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+    light = len(sys.argv) > 2 and sys.argv[2] == "light"      # racecheck is ~100x slower: bounded blow-ups
     templates = active_templates()[::step]
     dists = [DEFAULT_DIST[min(t.effective_size, 8)] for t in templates]
     small = generate_chunk(0, SynthConfig(), templates, 3)
@@ -44,13 +45,13 @@ def main():
     # pair splitting: few templates (idle warps from the start), donation at every level entry
     few = Engine(CompiledLibrary(templates[:20], 2.0, 3.0, 3.0))
     for chunk in (small, big):
-        hits = few.query(chunk.to_packed(few.compiled), max_candidates=10 ** 6, donate_after=1)
+        hits = few.query(chunk.to_packed(few.compiled), max_candidates=2000 if light else 10 ** 6, donate_after=1)
         print("split pairs", len(hits), "hits")
     few.close()
     engine.close()
-    loose = [t for t in templates if t.effective_size <= 4][:40]
+    loose = [t for t in templates if t.effective_size <= 4][:8 if light else 40]
     engine = Engine(CompiledLibrary(loose, 2.0, 3.0, 3.0))
-    for cap in (10 ** 7, 50):
+    for cap in ((2000, 50) if light else (10 ** 7, 50)):
         hits = engine.query(small.to_packed(engine.compiled), max_candidates=cap)
         print("loose cutoff, cap", cap, len(hits), "hits, most complete assignments", int(hits["n_complete"].max()))
     engine.close()
