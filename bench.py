@@ -535,7 +535,7 @@ def run_strong(args, rank, local_rank, world):
     a key in the process group's store: dynamic hand-out, no data-path collective), every chunk is
     uploaded from pinned host memory, prepared, searched and its hits read back (two sessions on two
     streams per rank, as the e2e leg of the weak-scaling bench), and at the end all hit records travel
-    to rank 0 in one NCCL gather and are placed in input order (``sharding.gather_hit_blocks``).
+    to rank 0 in one NCCL gather and are placed in input order (``sharding.gather_hit_buffer``).
     Wall clock from a barrier before the first chunk to the merged list on rank 0.
 
     Host memory: a 10^6-structure list is ~107 GB of SoA columns, so structure i of the list is
@@ -546,7 +546,7 @@ def run_strong(args, rank, local_rank, world):
     import torch.distributed as dist
     from enzymm_b200.engine import Engine, HIT_DTYPE, PackedBatch, Session
     from enzymm_b200.library import CompiledLibrary
-    from enzymm_b200.sharding import ChunkQueue, gather_hit_blocks
+    from enzymm_b200.sharding import ChunkQueue, gather_hit_buffer
     from enzymm_b200.synth import kind_classes
 
     torch.cuda.set_device(local_rank)
@@ -591,12 +591,19 @@ def run_strong(args, rank, local_rank, world):
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]          # kept alive: the sessions only hold the raw handles
     lanes = [(Session(engine.device_library, max_atoms, chunk, 64 * chunk), st.cuda_stream) for st in streams]
     kwargs = dict(max_candidates=10000, ignore_chain=True, reset=True, force_prepare=True)
+    # every chunk's hits are downloaded back to back into ONE pinned buffer (no per-chunk copies; the
+    # merge moves it with a single transfer): room for 12 hits per structure of this rank's share
+    hit_room = int(12 * (args.total / world) * 1.25) + 64 * chunk
+    hit_tensor = torch.empty(hit_room * HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    hit_records = hit_tensor.numpy().view(HIT_DTYPE)
 
     def sweep(n_total):
-        """Search chunks of an n_total-long list until the queue is empty; returns [(first, hits)]."""
+        """Search chunks of an n_total-long list until the queue is empty; returns the blocks
+        [(first structure, offset in hit_records, count)] (structure indices made global)."""
         queue = ChunkQueue(n_total, chunk)
         spans = iter(queue)
         blocks, flying = [], []
+        used = 0
 
         def submit(span, lane):
             sess, st = lanes[lane]
@@ -616,7 +623,10 @@ def run_strong(args, rank, local_rank, world):
                 span = next(spans, None)
             if len(flying) == 2 or span is None:
                 done, lane = flying.pop(0)
-                blocks.append((done[0], lanes[lane][0].download(stream=lanes[lane][1])))
+                got = lanes[lane][0].download(stream=lanes[lane][1], out=hit_records[used:])
+                got["structure"] += done[0]
+                blocks.append((done[0], used, len(got)))
+                used += len(got)
         return blocks
 
     def barrier():
@@ -624,8 +634,9 @@ def run_strong(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
 
+    merge = lambda blocks: gather_hit_buffer(hit_tensor, blocks, HIT_DTYPE.itemsize, device="cuda" if world > 1 else None)
     for _ in range(max(args.warmup, 1)):                       # warm-up: a short list through the same code
-        gather_hit_blocks(sweep(2 * world * chunk), HIT_DTYPE, device="cuda" if world > 1 else None)
+        merge(sweep(2 * world * chunk))
     sampler = ClockSampler(local_rank) if rank == 0 else None
     times, busy, n_hits = [], [], 0
     windows = []
@@ -635,12 +646,13 @@ def run_strong(args, rank, local_rank, world):
         t0 = time.perf_counter()
         blocks = sweep(args.total)
         t_search = time.perf_counter() - t0
-        merged = gather_hit_blocks(blocks, HIT_DTYPE, device="cuda" if world > 1 else None)
+        merged = merge(blocks)
         barrier()
         times.append(time.perf_counter() - t0)
         windows.append((w0, time.time()))
         busy.append(t_search)
         if rank == 0:
+            merged = merged.numpy().view(HIT_DTYPE)
             n_hits = len(merged)
             order_ok = bool(np.all(np.diff(merged["structure"].astype(np.int64)) >= 0))
             assert order_ok and int(merged["structure"].max()) < args.total

@@ -269,9 +269,18 @@ class Session:
                          1 if force_prepare else 0, int(cell_threshold), int(donate_after))
         _check(self._lib.emm_session_run(self.handle, ctypes.byref(q), ctypes.c_void_p(stream)))
 
-    def download(self, stream: int = 0, with_stats: bool = False):
+    def download(self, stream: int = 0, with_stats: bool = False, out: Optional[np.ndarray] = None):
+        """Hits of the last run(s), sorted by (structure, template).  ``out``: a HIT_DTYPE array to
+        receive them in place (e.g. a slice of one large pinned buffer) instead of a fresh copy."""
         n = ctypes.c_int64(0)
         stats = _Stats()
+        if out is not None:
+            if out.dtype != HIT_DTYPE or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a contiguous HIT_DTYPE array")
+            rc = self._lib.emm_session_download(self.handle, _p(out), ctypes.c_int64(len(out)), ctypes.byref(n),
+                                                ctypes.byref(stats), ctypes.c_void_p(stream))
+            _check(rc)
+            return (out[:n.value], {k: int(getattr(stats, k)) for k in STATS_FIELDS}) if with_stats else out[:n.value]
         rc = self._lib.emm_session_download(self.handle, _p(self._hits), ctypes.c_int64(self.hit_capacity),
                                             ctypes.byref(n), ctypes.byref(stats), ctypes.c_void_p(stream))
         if rc == -5:

@@ -13,7 +13,8 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "merge_hits", "gather_hits", "gather_hit_blocks", "place_blocks", "ChunkQueue"]
+__all__ = ["shard_bounds", "merge_hits", "gather_hits", "gather_hit_blocks", "gather_hit_buffer", "place_blocks",
+           "ChunkQueue"]
 
 
 def shard_bounds(n_items: int, world_size: int, rank: int, align: int = 1) -> Tuple[int, int]:
@@ -150,3 +151,54 @@ def gather_hit_blocks(blocks: Sequence[Tuple[int, np.ndarray]], dtype, dst: int 
             placed.append((first, raw[at:at + n]))
             at += n
     return place_blocks(placed) if placed else np.zeros(0, dtype=dtype)
+
+
+def gather_hit_buffer(buffer, blocks: Sequence[Tuple[int, int, int]], itemsize: int, dst: int = 0, device=None):
+    """The merge of ``gather_hit_blocks`` without host-side copies, for runs whose hit lists are large
+    (10^6 structures: ~1.8 GB of records).  ``buffer`` is this rank's ``torch.uint8`` host tensor
+    (pinned when CUDA is used) into which every chunk's hit records were downloaded back to back,
+    already carrying GLOBAL structure indices; ``blocks`` = (first structure of the chunk, offset in
+    records, count) per chunk.  One padded ``gather`` moves the bytes to ``dst``; there every block is
+    copied straight from the receive buffers to its place in the merged (pinned) tensor, in input
+    order.  Returns that tensor on ``dst`` (``.numpy().view(HIT_DTYPE)`` is the merged hit list),
+    None elsewhere.  Single process: the used prefix of ``buffer`` when the blocks are already in
+    input order, else a reordered copy."""
+    import torch
+    dist = sys.modules.get("torch.distributed")
+    multi = dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    meta = [(int(f), int(o), int(n)) for f, o, n in blocks]
+    if not multi:
+        used = sum(n for _, _, n in meta) * itemsize
+        if meta == sorted(meta) and all(a[1] + a[2] == b[1] for a, b in zip(meta, meta[1:])):
+            return buffer[:used]
+        out = torch.empty(used, dtype=torch.uint8)
+        at = 0
+        for _, off, n in sorted(meta):
+            out[at:at + n * itemsize] = buffer[off * itemsize:(off + n) * itemsize]
+            at += n * itemsize
+        return out
+    world, rank = dist.get_world_size(), dist.get_rank()
+    every = [None] * world
+    dist.all_gather_object(every, meta)
+    counts = [sum(n for _, _, n in m) for m in every]
+    width = max(max(counts), 1) * itemsize
+    send = torch.empty(width, dtype=torch.uint8, device=device)
+    mine = counts[rank] * itemsize
+    send[:mine].copy_(buffer[:mine], non_blocking=True)
+    recv = [torch.empty(width, dtype=torch.uint8, device=device) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst)
+    if rank != dst:
+        return None
+    total = sum(counts) * itemsize
+    merged = torch.empty(max(total, 1), dtype=torch.uint8)
+    if device is not None and str(device).startswith("cuda"):
+        merged = merged.pin_memory()
+    order = sorted((first, r, off, n) for r, m in enumerate(every) for first, off, n in m)
+    at = 0
+    for first, r, off, n in order:
+        nb = n * itemsize
+        merged[at:at + nb].copy_(recv[r][off * itemsize:off * itemsize + nb], non_blocking=True)
+        at += nb
+    if device is not None and str(device).startswith("cuda"):
+        torch.cuda.synchronize()
+    return merged[:total]

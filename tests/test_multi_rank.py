@@ -101,12 +101,24 @@ def _queue_worker(rank: int, world: int, port: int, queue):
         # the block-wise merge of the strong-scaling path: raw bytes in one gather, placed by range
         from enzymm_b200.sharding import gather_hit_blocks
         placed = gather_hit_blocks(parts, HIT_DTYPE)
+        # ... and its copy-free form: hits downloaded back to back into one buffer, global indices
+        import torch
+        from enzymm_b200.sharding import gather_hit_buffer
+        room = torch.zeros(64 * HIT_DTYPE.itemsize, dtype=torch.uint8)
+        records, blocks, used = room.numpy().view(HIT_DTYPE), [], 0
+        for lo, hits in parts:
+            records[used:used + len(hits)] = hits
+            records["structure"][used:used + len(hits)] += lo
+            blocks.append((lo, used, len(hits)))
+            used += len(hits)
+        buffered = gather_hit_buffer(room, blocks, HIT_DTYPE.itemsize)
         dist.barrier()
         if rank == 0:
             assert placed.tobytes() == merged.tobytes()
+            assert buffered.numpy().view(HIT_DTYPE).tobytes() == merged.tobytes()
             queue.put((merged.tobytes(), spans))
         else:
-            assert placed is None
+            assert placed is None and buffered is None
     finally:
         dist.destroy_process_group()
 
