@@ -634,7 +634,11 @@ def run_strong(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
 
-    merge = lambda blocks: gather_hit_buffer(hit_tensor, blocks, HIT_DTYPE.itemsize, device="cuda" if world > 1 else None)
+    merged_room = None
+    if world > 1 and rank == 0:                                # where the merged list lands; pinned once, up front
+        merged_room = torch.empty(int(12 * args.total * 1.25) * HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    merge = lambda blocks: gather_hit_buffer(hit_tensor, blocks, HIT_DTYPE.itemsize, device="cuda" if world > 1 else None,
+                                             out=merged_room)
     for _ in range(max(args.warmup, 1)):                       # warm-up: a short list through the same code
         merge(sweep(2 * world * chunk))
     sampler = ClockSampler(local_rank) if rank == 0 else None

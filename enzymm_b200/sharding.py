@@ -153,7 +153,8 @@ def gather_hit_blocks(blocks: Sequence[Tuple[int, np.ndarray]], dtype, dst: int 
     return place_blocks(placed) if placed else np.zeros(0, dtype=dtype)
 
 
-def gather_hit_buffer(buffer, blocks: Sequence[Tuple[int, int, int]], itemsize: int, dst: int = 0, device=None):
+def gather_hit_buffer(buffer, blocks: Sequence[Tuple[int, int, int]], itemsize: int, dst: int = 0, device=None,
+                      out=None):
     """The merge of ``gather_hit_blocks`` without host-side copies, for runs whose hit lists are large
     (10^6 structures: ~1.8 GB of records).  ``buffer`` is this rank's ``torch.uint8`` host tensor
     (pinned when CUDA is used) into which every chunk's hit records were downloaded back to back,
@@ -161,7 +162,8 @@ def gather_hit_buffer(buffer, blocks: Sequence[Tuple[int, int, int]], itemsize: 
     records, count) per chunk.  One padded ``gather`` moves the bytes to ``dst``; there every block is
     copied straight from the receive buffers to its place in the merged (pinned) tensor, in input
     order.  Returns that tensor on ``dst`` (``.numpy().view(HIT_DTYPE)`` is the merged hit list),
-    None elsewhere.  Single process: the used prefix of ``buffer`` when the blocks are already in
+    None elsewhere.  ``out``: a preallocated (pinned) ``torch.uint8`` tensor on ``dst`` to merge into --
+    pinning gigabytes takes longer than moving them.  Single process: the used prefix of ``buffer`` when the blocks are already in
     input order, else a reordered copy."""
     import torch
     dist = sys.modules.get("torch.distributed")
@@ -190,9 +192,12 @@ def gather_hit_buffer(buffer, blocks: Sequence[Tuple[int, int, int]], itemsize: 
     if rank != dst:
         return None
     total = sum(counts) * itemsize
-    merged = torch.empty(max(total, 1), dtype=torch.uint8)
-    if device is not None and str(device).startswith("cuda"):
-        merged = merged.pin_memory()
+    if out is not None and out.numel() >= total:
+        merged = out
+    else:
+        merged = torch.empty(max(total, 1), dtype=torch.uint8)
+        if device is not None and str(device).startswith("cuda"):
+            merged = merged.pin_memory()
     order = sorted((first, r, off, n) for r, m in enumerate(every) for first, off, n in m)
     at = 0
     for first, r, off, n in order:
