@@ -351,8 +351,9 @@ __device__ __forceinline__ void jacobi4(double (&a)[4][4], double (&v)[4][4])
 
 // Optimal proper rotation of the matched query atoms onto the template atoms; returns rmsd.
 // asg[i] = local atom id bound to template atom i (template order).
+template <typename AsgT>
 __device__ double superpose(int m, const double *__restrict__ txyz, const Blob &S,
-                            const uint32_t *asg, double (&rot)[9], double (&qbar)[3],
+                            const AsgT *asg, double (&rot)[9], double (&qbar)[3],
                             double (&tbar)[3])
 {
     const double inv_m = DDIV(1.0, (double)m);
@@ -515,6 +516,10 @@ __device__ __noinline__ void emit_hit(const SearchArgs &A, const Blob &S, int s,
 }
 
 // Superpose the validated complete assignments of one chunk of level m (one per lane), keep the best.
+// kNarrow: atom ids fit 16 bits (every staged structure).  The per-lane assignment is a local-memory
+// array; as 32-bit words it is 128 B per thread, 96 KB for the CTA's 768 threads -- more than the
+// SM's 60 KB of L1 -- and the superposition path thrashes (BASELINE config 4: -25 %).
+template <bool kNarrow>
 __device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S, int t, const uint32_t *Q,
                                               WarpState *ws, int base, unsigned valid, int lane)
 {
@@ -523,11 +528,12 @@ __device__ __noinline__ void process_complete(const SearchArgs &A, const Blob &S
     const double *txyz = L.xyz + 3 * (int64_t)a0;
     const double thr = L.rmsd_thr[t];
     bool have = (valid >> lane) & 1u;
-    uint32_t asg[kMaxAtoms];
+    using AsgT = typename std::conditional<kNarrow, uint16_t, uint32_t>::type;
+    AsgT asg[kMaxAtoms];
     if (have) {
         uint32_t w = Q[queue_off(m) + base + lane];
         for (int pos = m - 1; pos >= 0; --pos) {
-            asg[L.plan_atom[a0 + pos]] = (uint32_t)entry_atom(w);
+            asg[L.plan_atom[a0 + pos]] = (AsgT)entry_atom(w);
             if (pos > 0) w = Q[queue_off(pos) + entry_parent(w)];
         }
         if (!A.P.ignore_chain && S.chain) {
@@ -966,7 +972,7 @@ __device__ __forceinline__ bool search_template(const SearchArgs &A, const Blob 
                 valid = donate_tail(sh, Q, ws, wid, t, k, base, valid, max(first_free, 1), idle, lane);
                 if (kStats && lane == 0 && valid != before) atomicAdd(A.O.stats + 12, (unsigned long long)__popc(before ^ valid));
             }
-            if (k == m && valid) process_complete(A, S, t, Q, ws, base, valid, lane);
+            if (k == m && valid) process_complete<kStaged>(A, S, t, Q, ws, base, valid, lane);
         }
         if (k < m && valid) {
             // ---------------- expand the chunk of level k: a cheap dense filter ----------------

@@ -17,6 +17,10 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:emm_
 EMM_STATS=1 timeout 200 python tools/profile_workload.py 2048 2 > gpurun_out/${tag}_stats.log 2>&1
 timeout 300 python tools/stress_configs.py 296 256 > gpurun_out/${tag}_stress_configs.txt 2>&1
 EMM_DONATE_AFTER=-1 timeout 300 python tools/stress_configs.py 296 0 > gpurun_out/${tag}_stress_configs_unsplit.txt 2>&1
-timeout 700 compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitizer_workload.py 60 > gpurun_out/${tag}_racecheck.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_racecheck.log
-timeout 500 compute-sanitizer --tool memcheck python tools/sanitizer_workload.py 60 > gpurun_out/${tag}_memcheck.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_memcheck.log
-head -6 gpurun_out/${tag}_stats.log | cut -c1-200; cat gpurun_out/${tag}_stress_configs.txt; tail -2 gpurun_out/${tag}_racecheck.log; tail -2 gpurun_out/${tag}_memcheck.log
+if [ "${2:-}" = "sanitize" ]; then
+timeout 800 compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitizer_workload.py 60 light > gpurun_out/${tag}_racecheck.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_racecheck.log
+timeout 500 compute-sanitizer --tool memcheck python tools/sanitizer_workload.py 60 light > gpurun_out/${tag}_memcheck.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_memcheck.log
+tail -2 gpurun_out/${tag}_racecheck.log; tail -2 gpurun_out/${tag}_memcheck.log
+fi
+bash tools/gpu_strong.sh 1 1000000 1 4096 | tail -1 | cut -c1-200
+head -6 gpurun_out/${tag}_stats.log | cut -c1-200; cat gpurun_out/${tag}_stress_configs.txt
