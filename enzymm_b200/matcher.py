@@ -580,6 +580,16 @@ class Matcher:
         host = _available_cpus()
         per_worker = threads or max(1, host // len(devices))
         results: "queue_module.Queue" = queue_module.Queue(maxsize=4 * len(devices))
+        stop = threading.Event()                # set when the consumer goes away before the scan is over
+
+        def hand_over(item) -> bool:
+            while not stop.is_set():
+                try:
+                    results.put(item, timeout=0.2)
+                    return True
+                except queue_module.Full:
+                    continue
+            return False
 
         def work(slot, device):
             try:
@@ -591,30 +601,34 @@ class Matcher:
                     self._device_workers[(slot, device)] = child
                 for item in child.scan_files(paths, chunk_size, per_worker, queue=Shared(), with_batch=with_batch,
                                              _with_span=True):
-                    results.put(item)
+                    if not hand_over(item):
+                        break                   # closing the inner generator lets its device work finish
             except BaseException as exc:        # noqa: BLE001 -- surfaces in the consumer
-                results.put(exc)
+                hand_over(exc)
             finally:
-                results.put(None)
+                hand_over(None)
 
         workers = [threading.Thread(target=work, args=(i, d), daemon=True) for i, d in enumerate(devices)]
         for w in workers:
             w.start()
         waiting, finished, next_start = {}, 0, 0
-        while finished < len(workers):
-            item = results.get()
-            if item is None:
-                finished += 1
-                continue
-            if isinstance(item, BaseException):
-                raise item
-            waiting[item[-1][0]] = item[:-1]
-            while next_start in waiting:        # hand chunks back in input order
-                out = waiting.pop(next_start)
-                next_start += len(out[0])
-                yield out
-        for w in workers:
-            w.join()
+        try:
+            while finished < len(workers):
+                item = results.get()
+                if item is None:
+                    finished += 1
+                    continue
+                if isinstance(item, BaseException):
+                    raise item
+                waiting[item[-1][0]] = item[:-1]
+                while next_start in waiting:        # hand chunks back in input order
+                    out = waiting.pop(next_start)
+                    next_start += len(out[0])
+                    yield out
+        finally:
+            stop.set()                              # abandoned or failed: workers stop after their current chunk
+            for w in workers:
+                w.join()
 
     def scan_to_tsv(self, paths: Sequence[os.PathLike], file: IO[str], chunk_size: int = 2048, threads: int = 0,
                     queue=None, header: bool = True, predict_correctness: bool = True,

@@ -241,5 +241,5 @@ class TableWriter(RowSelector):
             return ctypes.string_at(text, length.value)
         finally:
             self._lib.emm_tsv_free(text)
-        del keep_ids
+            del keep_ids                         # the encoded ids had to outlive the call
 

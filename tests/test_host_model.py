@@ -794,3 +794,48 @@ def test_residue_ordinals_against_a_plain_python_reference():
             assert [want[i] for i in order.tolist()] == ordinal.tolist()    # the permutation realises it
             for a, b in zip(order.tolist(), order.tolist()[1:]):            # stable inside a residue
                 assert want[a] != want[b] or a < b
+
+
+def test_multi_device_scan_hands_chunks_back_in_input_order(monkeypatch, active_templates):
+    """``Matcher.scan_files(devices=[...])``: one worker thread per device pulls chunks from one counter;
+    the generator returns them in input order whatever order they finish in, propagates a worker's
+    exception, and lets the workers stop when it is abandoned early.  (Device work replaced by a stub:
+    this is the host-side hand-out and re-ordering; the GPU test runs the real thing.)"""
+    import random
+    import threading
+    import time
+    from enzymm_b200 import jess_run
+
+    matcher = jess_run.Matcher(active_templates[:50])
+    paths = [f"/nowhere/s{i:04d}.pdb" for i in range(103)]
+    seen_threads = set()
+    real = jess_run.Matcher.scan_files
+
+    def stub(self, paths, chunk_size=2048, threads=0, queue=None, with_batch=False, devices=None, _with_span=False):
+        if devices is not None:
+            yield from real(self, paths, chunk_size, threads, queue, with_batch, devices, _with_span)
+            return
+        seen_threads.add(threading.get_ident())
+        for span in queue:
+            time.sleep(random.random() * 0.01)
+            if getattr(self, "_explode_at", None) == span[0]:
+                raise RuntimeError("device lost")
+            yield (paths[span[0]:span[1]], [None] * (span[1] - span[0]), np.zeros(span[0], dtype=np.int8), span)
+
+    monkeypatch.setattr(jess_run.Matcher, "scan_files", stub)
+    monkeypatch.setattr(jess_run.Matcher, "close", lambda self: None)
+    chunks = list(matcher.scan_files(paths, chunk_size=10, devices=[0, 1, 2]))
+    assert [c[0] for c in chunks] == [paths[i:i + 10] for i in range(0, 103, 10)]
+    assert [len(c[2]) for c in chunks] == list(range(0, 103, 10)) and all(len(c) == 3 for c in chunks)
+    assert len(seen_threads) == 3
+    # abandoned after two chunks: the generator's close must not hang on workers blocked in the queue
+    gen = matcher.scan_files(paths * 20, chunk_size=5, devices=[0, 1])
+    assert [next(gen)[0][0], next(gen)[0][0]] == [paths[0], paths[5]]
+    t0 = time.time()
+    gen.close()
+    assert time.time() - t0 < 5
+    # a failing worker surfaces in the consumer
+    matcher._device_workers = {}
+    monkeypatch.setattr(jess_run.Matcher, "_explode_at", 40, raising=False)
+    with pytest.raises(RuntimeError, match="device lost"):
+        list(matcher.scan_files(paths, chunk_size=10, devices=[0, 1]))

@@ -144,3 +144,33 @@ def test_dynamic_chunk_queue_covers_every_structure_once():
     templates, mols = _inputs()
     want = merge_hits([(0, _oracle_hits(templates, mols))])
     assert got == want.tobytes()
+
+
+def test_hit_merges_in_a_single_process():
+    """Without a process group the merges are plain host operations: blocks in any order come out in
+    input order with global structure indices."""
+    import torch
+    from enzymm_b200.sharding import gather_hit_blocks, gather_hit_buffer, place_blocks
+    def block(first, structures):
+        h = np.zeros(len(structures), dtype=HIT_DTYPE)
+        h["structure"] = structures
+        h["template_index"] = np.arange(len(structures)) + first
+        return h
+    blocks = [(8, block(8, [0, 0, 3])), (0, block(0, [1, 2])), (4, block(4, [0]))]
+    merged = place_blocks(blocks)
+    assert merged["structure"].tolist() == [1, 2, 4, 8, 8, 11] and merged["template_index"].tolist() == [0, 1, 4, 8, 9, 10]
+    assert gather_hit_blocks(blocks, HIT_DTYPE).tobytes() == merged.tobytes()
+    assert len(gather_hit_blocks([], HIT_DTYPE)) == 0
+    # buffer form: records already carry global indices; blocks recorded out of input order
+    room = torch.zeros(16 * HIT_DTYPE.itemsize, dtype=torch.uint8)
+    records = room.numpy().view(HIT_DTYPE)
+    meta, used = [], 0
+    for first, hits in blocks:
+        records[used:used + len(hits)] = hits
+        records["structure"][used:used + len(hits)] += first
+        meta.append((first, used, len(hits)))
+        used += len(hits)
+    out = gather_hit_buffer(room, meta, HIT_DTYPE.itemsize).numpy().view(HIT_DTYPE)
+    assert out.tobytes() == merged.tobytes()
+    in_order = sorted(meta)
+    assert gather_hit_buffer(room, [(0, 0, 3)], HIT_DTYPE.itemsize).numel() == 3 * HIT_DTYPE.itemsize
