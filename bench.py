@@ -258,9 +258,16 @@ def api_legs(workload, n_files: int, chunk: int = 1024):
     import tempfile
     from enzymm_b200 import jess_run
     distinct = min(n_files, workload.n_structures, 1024)
-    root = tempfile.mkdtemp(prefix="emm_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    texts = [workload.to_pdb(i).encode() for i in range(distinct)]
+    need = 2 * sum(len(texts[i % distinct]) for i in range(n_files))
+    where = None                                  # RAM-backed if there is room, else the default temp directory
     try:
-        texts = [workload.to_pdb(i).encode() for i in range(distinct)]
+        if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need:
+            where = "/dev/shm"
+    except OSError:
+        pass
+    root = tempfile.mkdtemp(prefix="emm_bench_", dir=where)
+    try:
         paths = []
         for i in range(n_files):
             path = os.path.join(root, f"s{i:06d}.pdb")
@@ -520,7 +527,10 @@ def run_b200(args, rank, local_rank, world):
         line["parity"] = parity_against_oracle(hits, cpu_oracle_rate.raw, cpu_oracle_rate.molecules, templates)
     if world == 1 and args.api_files > 0:
         engine.close()              # the API legs bring their own Matcher (own device library and sessions)
-        line["e2e_api"] = api_legs(workload, args.api_files)
+        try:
+            line["e2e_api"] = api_legs(workload, args.api_files)
+        except Exception as exc:              # noqa: BLE001 -- an extra of the line, never a reason to lose it
+            line["e2e_api"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     print(json.dumps(line), flush=True)
     engine.close()
     if world > 1:
