@@ -352,7 +352,8 @@ int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t ba
             const uint16_t chain = (uint16_t)strip_field(line + 20, 2);
             const uint64_t kkey = (uint64_t)resname | ((uint64_t)name << 32);
             const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum;
-            if ((kkey != prev_kind || rkey != prev_res) && counted_residue(resname)) counted.push_back(resnum);
+            // once per run of equal (residue name, chain, number), not once per atom
+            if (((uint32_t)prev_kind != resname || rkey != prev_res) && counted_residue(resname)) counted.push_back(resnum);
             if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
             c.kind[i] = prev_kind_idx;
             c.chain[i] = chain;
@@ -796,7 +797,7 @@ int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *
                     memcpy(&chain, ch + 2 * a, 2);
                     const uint64_t kkey = (uint64_t)res | ((uint64_t)name << 32);
                     const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum[f][a];
-                    if ((kkey != prev_kind || rkey != prev_res) && counted_residue(res)) counted.push_back(resnum[f][a]);
+                    if (((uint32_t)prev_kind != res || rkey != prev_res) && counted_residue(res)) counted.push_back(resnum[f][a]);
                     if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
                     blk.kind[a] = prev_kind_idx;
                     blk.chain[a] = chain;
