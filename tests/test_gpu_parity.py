@@ -877,3 +877,27 @@ def test_staging_policy_keeps_the_l1_carveout(active_templates, monkeypatch):
         compare_with_oracle(eng, active_templates, lone[-2:], dist)
     finally:
         eng.close()
+
+
+def test_download_into_a_caller_buffer(full_engine, mol_1amy, mol_af):
+    """``Session.download(out=...)``: hits written straight into a slice of the caller's (pinned) buffer,
+    back to back over several batches -- what the strong-scaling merge is built on -- equal the copies
+    ``download()`` returns; a slice that is too small is the loud ``EMM_ERR_CAPACITY``."""
+    from enzymm_b200.engine import HIT_DTYPE
+    batches = [pack_molecules([m], full_engine.compiled) for m in (mol_1amy, mol_af, mol_1amy)]
+    room = np.zeros(64, dtype=HIT_DTYPE)
+    used, want = 0, []
+    sess = full_engine.session_for(max(b.n_atoms for b in batches), 1)
+    for batch in batches:
+        sess.upload(batch)
+        sess.run()
+        want.append(sess.download())
+        got = sess.download(out=room[used:])
+        assert got.base is not None and got.tobytes() == want[-1].tobytes()
+        used += len(got)
+    assert used == 13 + 11 + 13 and room[:used].tobytes() == np.concatenate(want).tobytes()
+    with pytest.raises(EngineError) as info:
+        sess.download(out=room[:5])
+    assert info.value.status == -4
+    with pytest.raises(ValueError):
+        sess.download(out=np.zeros(8, dtype=np.int32))
