@@ -157,8 +157,9 @@ typedef struct emm_query_params {
     int32_t cell_threshold;       /* > 0: leader candidate lists at least this long are searched through  */
                                   /* the uniform-grid cell list instead of scanned; <= 0: never (default) */
     int32_t donate_after;         /* splitting of one expensive (template, structure) pair over the warps */
-                                  /* of its CTA: 0 default (after 48 level visits, when warps sit idle);  */
-                                  /* n > 0 after n level visits; < 0 never.  Results do not depend on it. */
+                                  /* of its CTA: 0 default (launches below 8192 structures: after 48 level */
+                                  /* visits, when warps sit idle; larger launches: never); n > 0 after n   */
+                                  /* level visits; < 0 never.  Results do not depend on it.               */
 } emm_query_params;
 
 typedef struct emm_hit {
