@@ -297,7 +297,6 @@ def api_legs(workload, n_files: int, chunk: int = 1024):
             del molecules, matches
         for rep in range(2):
             sink = io.BytesIO()
-            sink.mode = "wb"
             t0 = time.perf_counter()
             rows = matcher.scan_to_tsv(paths, sink, chunk_size=chunk)
             out["files_to_tsv"] = n_files / (time.perf_counter() - t0)

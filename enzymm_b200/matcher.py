@@ -650,7 +650,8 @@ class Matcher:
             stem = Path(path).stem
             seen[stem] += 1
             stems[path] = stem if seen[stem] == 1 else f"{stem}_{seen[stem]}"
-        binary = not isinstance(file, io.TextIOBase) and hasattr(file, "write") and "b" in getattr(file, "mode", "")
+        # the rows arrive as UTF-8 bytes: written as they are to a binary file, decoded for a text file
+        binary = isinstance(file, (io.RawIOBase, io.BufferedIOBase)) or "b" in str(getattr(file, "mode", ""))
         emit = (lambda b: file.write(b)) if binary else (lambda b: file.write(b.decode("utf-8")))
         if header:
             emit(writer.header().encode())
