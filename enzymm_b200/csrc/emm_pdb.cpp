@@ -5,9 +5,17 @@
 // rule 1); coordinates go through strtod, i.e. they are exactly the doubles Python's float()
 // yields for the same text.  emm_pdb_load_files reads and parses many files on a thread pool into
 // one SoA batch, which is what the batched upload wants.
+//
+// mmCIF: a file whose first token is a data_ block header is read through its _atom_site category
+// instead (pyjess.Molecule.load(format="detect") accepts both): rows of the first model only, the
+// label_* identifiers unless EMM_PDB_CIF_AUTHOR asks for auth_*, numbers converted exactly as in the
+// PDB path.  No reference test holds a CIF file, so which identifiers PyJess would pick is unpinned.
+// gzip-compressed files (magic 1f 8b) are inflated on the worker that reads them.
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
@@ -24,15 +32,18 @@
 
 namespace {
 
+// hot helpers of the fixed-column reader: inlined into its loops whatever else calls them
+#define EMM_HOT inline __attribute__((always_inline))
+
 thread_local std::string t_error;
 
-inline bool is_coord_record(const char *p, int64_t n)
+EMM_HOT bool is_coord_record(const char *p, int64_t n)
 {
     return n >= 6 && (memcmp(p, "ATOM  ", 6) == 0 || memcmp(p, "HETATM", 6) == 0);
 }
 
 // copy columns [a, b) of a line (clipped to its length) stripped of blanks, NUL padded to width
-inline void field(const char *line, int64_t len, int a, int b, char *dst, int width)
+EMM_HOT void field(const char *line, int64_t len, int a, int b, char *dst, int width)
 {
     memset(dst, 0, (size_t)width);
     int lo = a, hi = std::min<int64_t>(b, len);
@@ -41,7 +52,7 @@ inline void field(const char *line, int64_t len, int a, int b, char *dst, int wi
     for (int i = 0; lo + i < hi && i < width; ++i) dst[i] = line[lo + i];
 }
 
-inline bool parse_int(const char *line, int64_t len, int a, int b, int32_t *out)
+EMM_HOT bool parse_int(const char *line, int64_t len, int a, int b, int32_t *out)
 {
     char buf[16];
     field(line, len, a, b, buf, 15);
@@ -57,7 +68,7 @@ inline bool parse_int(const char *line, int64_t len, int a, int b, int32_t *out)
 // Plain fixed-point decimals ("-12.345") are converted as mantissa / 10^k with one correctly
 // rounded division: mantissa < 2^53 and 10^k (k <= 18) are exact doubles, so the quotient is the
 // double nearest to the decimal -- bit-identical to strtod.  Anything else falls back to strtod.
-inline bool fast_real(const char *p, const char *end, double *out)
+EMM_HOT bool fast_real(const char *p, const char *end, double *out)
 {
     static const double pow10[19] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12,
                                      1e13, 1e14, 1e15, 1e16, 1e17, 1e18};
@@ -83,7 +94,7 @@ inline bool fast_real(const char *p, const char *end, double *out)
     return true;
 }
 
-inline bool parse_real(const char *line, int64_t len, int a, int b, double *out, bool optional)
+EMM_HOT bool parse_real(const char *line, int64_t len, int a, int b, double *out, bool optional)
 {
     {
         int lo = a, hi = (int)std::min<int64_t>(b, len);
@@ -101,7 +112,7 @@ inline bool parse_real(const char *line, int64_t len, int a, int b, double *out,
     return *end == 0;
 }
 
-inline bool fast_int(const char *p, const char *e, int32_t *out)
+EMM_HOT bool fast_int(const char *p, const char *e, int32_t *out)
 {
     while (p < e && *p == ' ') ++p;
     while (e > p && e[-1] == ' ') --e;
@@ -118,7 +129,7 @@ inline bool fast_int(const char *p, const char *e, int32_t *out)
     return true;
 }
 
-inline bool int_field(const char *line, int64_t ll, int a, int b, int32_t *out)
+EMM_HOT bool int_field(const char *line, int64_t ll, int a, int b, int32_t *out)
 {
     return fast_int(line + a, line + std::min<int64_t>(b, ll), out) || parse_int(line, ll, a, b, out);
 }
@@ -126,7 +137,7 @@ inline bool int_field(const char *line, int64_t ll, int a, int b, int32_t *out)
 // The canonical "%W.Ff" layout (blanks, optional '-', digits, '.', F digits) without the generic
 // scanner: same mantissa and the same single division as fast_real, so the same double.
 template <int W, int F>
-inline bool real_layout(const char *p, double *out)
+EMM_HOT bool real_layout(const char *p, double *out)
 {
     static_assert(F >= 1 && F <= 3 && W - F - 2 >= 0, "layout");
     if (p[W - F - 1] != '.') return false;
@@ -163,7 +174,7 @@ struct Columns {
     double *xyz; double *occupancy; double *bfactor; char *segment; char *element; int8_t *charge;
 };
 
-int64_t count_atoms(const char *text, int64_t len)
+int64_t pdb_count_atoms(const char *text, int64_t len)
 {
     int64_t n = 0, pos = 0;
     while (pos < len) {
@@ -179,7 +190,7 @@ int64_t count_atoms(const char *text, int64_t len)
 }
 
 // returns atoms parsed, or -1 (t_error set)
-int64_t parse_into(const char *text, int64_t len, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
+int64_t pdb_parse_into(const char *text, int64_t len, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
 {
     int64_t n = 0, pos = 0;
     bool have_header = false;
@@ -236,7 +247,7 @@ int64_t parse_into(const char *text, int64_t len, const Columns &c, int64_t base
 // ---- files -> emm_batch columns -------------------------------------------------------------------
 
 // blank-stripped field of width w (<= 4) as little-endian bytes, NUL padded: the same bytes field() yields
-inline uint32_t strip_field(const char *p, int w)
+EMM_HOT uint32_t strip_field(const char *p, int w)
 {
     int lo = 0, hi = w;
     while (lo < hi && (p[lo] == ' ' || p[lo] == '\t')) ++lo;
@@ -309,21 +320,61 @@ inline int32_t distinct_count(std::vector<int32_t> &v)
     return (int32_t)(std::unique(v.begin(), v.end()) - v.begin());
 }
 
-// One file into the packed columns at [base, base+capacity).  kind[] receives file-local kind
-// indices; *split is set when a residue key reappears after another residue (the caller then
-// regroups the file).  Returns atoms parsed or -1 (t_error set).
-int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t base, int64_t capacity,
-                  KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5],
-                  int32_t *residue_count)
-{
-    std::vector<int32_t> counted;
-    int64_t n = 0, pos = 0;
-    bool have_header = false;
-    memset(header_id, 0, 5);
+// The per-atom bookkeeping of the packed form, shared by the PDB reader, the mmCIF reader and
+// emm_pack_columns: file-local kind index, chain code, residue runs (a run = consecutive atoms with
+// one (chain, number) key), the residue numbers Match.query_residue_count counts.
+// (Everything the object owns is a scalar and every method is inlined, so that it lives in registers
+// inside the readers' loops; the vectors belong to the caller.)
+struct PackState {
+    const PackedCols c;
+    KindTable &kinds;
+    std::vector<uint64_t> &run_keys;
+    std::vector<int32_t> &counted;
     uint64_t prev_kind = ~0ull, prev_res = ~0ull;
     uint32_t prev_kind_idx = 0;
     int32_t run = -1;
-    run_keys.clear();
+    PackState(const PackedCols &cols, KindTable &k, std::vector<uint64_t> &r, std::vector<int32_t> &n)
+        : c(cols), kinds(k), run_keys(r), counted(n) { run_keys.clear(); counted.clear(); }
+    // name / resname: blank-stripped little-endian packed bytes (strip_field)
+    EMM_HOT void add(int64_t i, uint32_t name, uint32_t resname, uint16_t chain, int32_t resnum, float bf)
+    {
+        c.bfactor[i] = bf;
+        const uint64_t kkey = (uint64_t)resname | ((uint64_t)name << 32);
+        const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum;
+        // once per run of equal (residue name, chain, number), not once per atom
+        if (((uint32_t)prev_kind != resname || rkey != prev_res) && counted_residue(resname)) counted.push_back(resnum);
+        if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
+        c.kind[i] = prev_kind_idx;
+        c.chain[i] = chain;
+        if (rkey != prev_res || run < 0) {
+            prev_res = rkey;
+            ++run;
+            run_keys.push_back(rkey);
+        }
+        c.residue[i] = run;
+    }
+    // *split: a residue key reappears after another residue (the caller then regroups the file)
+    EMM_HOT void finish(bool *split, int32_t *residue_count)
+    {
+        std::vector<uint64_t> sorted(run_keys);
+        std::sort(sorted.begin(), sorted.end());
+        *split = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+        *residue_count = distinct_count(counted);
+    }
+};
+
+// One file into the packed columns at [base, base+capacity).  kind[] receives file-local kind
+// indices; *split is set when a residue key reappears after another residue (the caller then
+// regroups the file).  Returns atoms parsed or -1 (t_error set).
+int64_t pdb_pack_into(const char *text, int64_t len, const PackedCols &c, int64_t base, int64_t capacity,
+                      KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5],
+                      int32_t *residue_count)
+{
+    std::vector<int32_t> counted;
+    PackState state(c, kinds, run_keys, counted);
+    int64_t n = 0, pos = 0;
+    bool have_header = false;
+    memset(header_id, 0, 5);
     *split = false;
     while (pos < len) {
         const char *nl = (const char *)memchr(text + pos, '\n', (size_t)(len - pos));
@@ -347,22 +398,7 @@ int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t ba
                 return -1;
             }
             c.xyz[3 * i] = x; c.xyz[3 * i + 1] = y; c.xyz[3 * i + 2] = z;
-            c.bfactor[i] = (float)bf;
-            const uint32_t name = strip_field(line + 12, 4), resname = strip_field(line + 17, 3);
-            const uint16_t chain = (uint16_t)strip_field(line + 20, 2);
-            const uint64_t kkey = (uint64_t)resname | ((uint64_t)name << 32);
-            const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum;
-            // once per run of equal (residue name, chain, number), not once per atom
-            if (((uint32_t)prev_kind != resname || rkey != prev_res) && counted_residue(resname)) counted.push_back(resnum);
-            if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
-            c.kind[i] = prev_kind_idx;
-            c.chain[i] = chain;
-            if (rkey != prev_res || run < 0) {
-                prev_res = rkey;
-                ++run;
-                run_keys.push_back(rkey);
-            }
-            c.residue[i] = run;
+            state.add(i, strip_field(line + 12, 4), strip_field(line + 17, 3), (uint16_t)strip_field(line + 20, 2), resnum, (float)bf);
             ++n;
         } else if (ll >= 6 && memcmp(line, "ENDMDL", 6) == 0) {
             break;
@@ -375,12 +411,7 @@ int64_t pack_into(const char *text, int64_t len, const PackedCols &c, int64_t ba
         }
         pos = end + 1;
     }
-    {
-        std::vector<uint64_t> sorted(run_keys);
-        std::sort(sorted.begin(), sorted.end());
-        *split = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
-    }
-    *residue_count = distinct_count(counted);
+    state.finish(split, residue_count);
     return n;
 }
 
@@ -421,6 +452,356 @@ void regroup_file(const PackedCols &c, int64_t base, int64_t n, std::vector<uint
     run_keys.swap(by_rank);
 }
 
+// ---- mmCIF ----------------------------------------------------------------------------------------
+
+inline bool cif_space(char ch) { return ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n'; }
+
+// CIF 1.1 tokens: bare words, '...' / "..." (the closing quote is the one followed by white space),
+// ;-delimited text fields, # comments.
+struct CifTok {
+    const char *p;
+    int64_t len;
+    bool quoted;
+    bool is(const char *word) const
+    {
+        const size_t n = strlen(word);
+        return !quoted && (size_t)len == n && strncasecmp(p, word, n) == 0;
+    }
+    bool starts(const char *prefix) const
+    {
+        const size_t n = strlen(prefix);
+        return !quoted && (size_t)len >= n && strncasecmp(p, prefix, n) == 0;
+    }
+    bool null() const { return !quoted && len == 1 && (p[0] == '.' || p[0] == '?'); }
+};
+
+struct CifScanner {
+    const char *begin, *p, *end;
+    CifScanner(const char *text, int64_t len) : begin(text), p(text), end(text + len) {}
+    bool next(CifTok &t)
+    {
+        for (;;) {
+            while (p < end && cif_space(*p)) ++p;
+            if (p >= end) return false;
+            if (*p != '#') break;
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            p = nl ? nl + 1 : end;
+        }
+        if (*p == ';' && (p == begin || p[-1] == '\n')) {
+            const char *s = p + 1, *q = s;
+            for (;;) {
+                const char *nl = (const char *)memchr(q, '\n', (size_t)(end - q));
+                if (!nl) { q = end; break; }
+                if (nl + 1 < end && nl[1] == ';') { q = nl; break; }
+                q = nl + 1;
+            }
+            t.p = s; t.len = q - s; t.quoted = true;
+            p = q < end ? q + 2 : end;
+            return true;
+        }
+        if (*p == '\'' || *p == '"') {
+            const char quote = *p;
+            const char *s = p + 1, *q = s;
+            while (q < end && *q != '\n' && !(*q == quote && (q + 1 == end || cif_space(q[1])))) ++q;
+            t.p = s; t.len = q - s; t.quoted = true;
+            p = (q < end && *q == quote) ? q + 1 : q;
+            return true;
+        }
+        const char *s = p;
+        while (p < end && !cif_space(*p)) ++p;
+        t.p = s; t.len = p - s; t.quoted = false;
+        return true;
+    }
+};
+
+// The first token of the text (after white space and comments) is a data_ block header.
+bool looks_like_cif(const char *text, int64_t len)
+{
+    CifScanner scan(text, std::min<int64_t>(len, 65536));
+    CifTok t;
+    return scan.next(t) && t.starts("data_");
+}
+
+enum CifCol { C_GROUP, C_ID, C_SYMBOL, C_L_ATOM, C_A_ATOM, C_ALT, C_L_COMP, C_A_COMP, C_L_ASYM, C_A_ASYM, C_L_SEQ, C_A_SEQ,
+              C_INS, C_X, C_Y, C_Z, C_OCC, C_B, C_CHARGE, C_MODEL, C_N };
+const char *const kCifTags[C_N] = {"group_PDB", "id", "type_symbol", "label_atom_id", "auth_atom_id", "label_alt_id",
+                                   "label_comp_id", "auth_comp_id", "label_asym_id", "auth_asym_id", "label_seq_id",
+                                   "auth_seq_id", "pdbx_PDB_ins_code", "Cartn_x", "Cartn_y", "Cartn_z", "occupancy",
+                                   "B_iso_or_equiv", "pdbx_formal_charge", "pdbx_PDB_model_num"};
+
+inline int cif_column(const CifTok &tag)          // "_atom_site.<item>" -> CifCol or -1
+{
+    const int64_t skip = 11;
+    for (int k = 0; k < C_N; ++k) {
+        const size_t n = strlen(kCifTags[k]);
+        if ((size_t)(tag.len - skip) == n && strncasecmp(tag.p + skip, kCifTags[k], n) == 0) return k;
+    }
+    return -1;
+}
+
+struct AtomRec {
+    int32_t serial, resnum;
+    uint32_t name, resname;          // blank-stripped little-endian packed bytes, as strip_field
+    uint16_t chain, element;
+    char altloc, icode;
+    double x, y, z, occ, bf;
+    int8_t charge;
+};
+
+inline uint32_t cif_pack(const CifTok &t, int width)
+{
+    uint32_t v = 0;
+    if (t.p && !t.null())
+        for (int i = 0; i < width && i < t.len; ++i) v |= (uint32_t)(unsigned char)t.p[i] << (8 * i);
+    return v;
+}
+
+inline bool cif_real(const CifTok &t, double *out, bool optional)
+{
+    if (!t.p || t.null() || t.len == 0) { *out = 0.0; return optional; }
+    if (fast_real(t.p, t.p + t.len, out)) return true;
+    char buf[64];
+    if (t.len >= (int64_t)sizeof buf) return false;
+    memcpy(buf, t.p, (size_t)t.len);
+    buf[t.len] = 0;
+    if (char *paren = strchr(buf, '(')) *paren = 0;             // "1.234(5)": a standard uncertainty
+    char *stop = nullptr;
+    *out = strtod(buf, &stop);
+    return stop != buf && *stop == 0;
+}
+
+inline bool cif_int(const CifTok &t, int32_t *out)
+{
+    return t.p && !t.null() && t.len > 0 && fast_int(t.p, t.p + t.len, out);
+}
+
+// One _atom_site row -> AtomRec; false with t_error set when a required item is missing or malformed.
+bool cif_row(const CifTok *v, int64_t row, int flags, AtomRec &a)
+{
+    const bool author = (flags & EMM_PDB_CIF_AUTHOR) != 0;
+    auto pick = [&](int label, int auth) -> const CifTok & {
+        const CifTok &first = v[author ? auth : label], &second = v[author ? label : auth];
+        return (first.p && !first.null()) ? first : second;
+    };
+    if (!cif_real(v[C_X], &a.x, false) || !cif_real(v[C_Y], &a.y, false) || !cif_real(v[C_Z], &a.z, false) ||
+        !cif_real(v[C_OCC], &a.occ, true) || !cif_real(v[C_B], &a.bf, true)) {
+        t_error = "malformed _atom_site row " + std::to_string(row + 1) + ": coordinates, occupancy or B factor";
+        return false;
+    }
+    if (!cif_int(v[C_ID], &a.serial)) a.serial = (int32_t)(row + 1);
+    if (!cif_int(pick(C_L_SEQ, C_A_SEQ), &a.resnum)) a.resnum = 0;           // '.' for non-polymers without auth_seq_id
+    const CifTok &chain = pick(C_L_ASYM, C_A_ASYM);
+    if (chain.p && !chain.null() && chain.len > 2) {
+        t_error = "_atom_site row " + std::to_string(row + 1) + ": chain id '" + std::string(chain.p, (size_t)chain.len) +
+                  "' is longer than the two characters an Atom.chain_id holds";
+        return false;
+    }
+    a.chain = (uint16_t)cif_pack(chain, 2);
+    a.name = cif_pack(pick(C_L_ATOM, C_A_ATOM), 4);
+    a.resname = cif_pack(pick(C_L_COMP, C_A_COMP), 4);
+    a.element = (uint16_t)cif_pack(v[C_SYMBOL], 2);
+    a.altloc = (v[C_ALT].p && !v[C_ALT].null() && v[C_ALT].len > 0) ? v[C_ALT].p[0] : ' ';
+    a.icode = (v[C_INS].p && !v[C_INS].null() && v[C_INS].len > 0) ? v[C_INS].p[0] : ' ';
+    int32_t q = 0;
+    a.charge = (int8_t)(cif_int(v[C_CHARGE], &q) ? q : 0);
+    return true;
+}
+
+// Calls on_atom(rec) for every _atom_site row of the first model, in file order (the mmCIF counterpart
+// of "ATOM and HETATM records up to the first ENDMDL").  Returns the number of atoms delivered or -1
+// (t_error set).  header_id receives the data block name when it fits four characters.
+template <class F>
+int64_t cif_each_atom(const char *text, int64_t len, int flags, char header_id[5], F &&on_atom)
+{
+    memset(header_id, 0, 5);
+    CifScanner scan(text, len);
+    CifTok t;
+    if (!scan.next(t) || !t.starts("data_")) { t_error = "not an mmCIF text: no data_ block"; return -1; }
+    if (t.len - 5 >= 1 && t.len - 5 <= 4) memcpy(header_id, t.p + 5, (size_t)(t.len - 5));
+    CifTok row[C_N], pairs[C_N];
+    bool have_pairs = false;
+    for (int k = 0; k < C_N; ++k) pairs[k] = CifTok{nullptr, 0, false};
+    bool more = scan.next(t);
+    while (more) {
+        if (t.starts("data_")) break;                                  // a second block: not ours
+        if (t.is("loop_")) {
+            std::vector<int> cols;
+            bool ours = false;
+            while ((more = scan.next(t)) && !t.quoted && t.len > 0 && t.p[0] == '_') {
+                if (cols.empty()) ours = t.starts("_atom_site.");
+                cols.push_back(ours ? cif_column(t) : -1);
+            }
+            if (!ours) continue;                                       // its values are skipped by the main loop
+            if (cols.empty()) { t_error = "_atom_site loop without items"; return -1; }
+            bool have[C_N] = {false};
+            for (int c : cols) if (c >= 0) have[c] = true;
+            if (!have[C_X] || !have[C_Y] || !have[C_Z]) { t_error = "_atom_site loop without Cartn_x / Cartn_y / Cartn_z"; return -1; }
+            int64_t n = 0;
+            CifTok model0{nullptr, 0, false};
+            const size_t ncols = cols.size();
+            while (more) {
+                // a row starts unless the token ends the loop
+                if (!t.quoted && (t.is("loop_") || t.starts("data_") || t.starts("save_") || t.is("stop_") || t.is("global_") ||
+                                  (t.len > 0 && t.p[0] == '_')))
+                    break;
+                for (int k = 0; k < C_N; ++k) row[k] = CifTok{nullptr, 0, false};
+                for (size_t j = 0; j < ncols; ++j) {
+                    if (!more) { t_error = "_atom_site loop ends in the middle of a row"; return -1; }
+                    if (cols[j] >= 0) row[cols[j]] = t;
+                    more = scan.next(t);
+                }
+                if (row[C_MODEL].p) {
+                    if (!model0.p) model0 = row[C_MODEL];
+                    else if (model0.len != row[C_MODEL].len || memcmp(model0.p, row[C_MODEL].p, (size_t)model0.len) != 0) return n;
+                }
+                AtomRec a;
+                if (!cif_row(row, n, flags, a)) return -1;
+                if (!on_atom(a)) return -1;
+                ++n;
+            }
+            return n;
+        }
+        if (t.starts("_atom_site.")) {                                 // item-value pairs: a one-atom category
+            const int c = cif_column(t);
+            more = scan.next(t);
+            if (!more) break;
+            if (c >= 0) { pairs[c] = t; have_pairs = true; }
+        }
+        more = scan.next(t);
+    }
+    if (have_pairs) {
+        if (!pairs[C_X].p || !pairs[C_Y].p || !pairs[C_Z].p) { t_error = "_atom_site without Cartn_x / Cartn_y / Cartn_z"; return -1; }
+        AtomRec a;
+        if (!cif_row(pairs, 0, flags, a) || !on_atom(a)) return -1;
+        return 1;
+    }
+    return 0;
+}
+
+inline void unpack_field(uint32_t v, char *dst, int width)
+{
+    for (int i = 0; i < width; ++i) dst[i] = (char)((v >> (8 * i)) & 0xffu);
+}
+
+int64_t cif_parse_into(const char *text, int64_t len, int flags, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
+{
+    int64_t n = 0;
+    return cif_each_atom(text, len, flags, header_id, [&](const AtomRec &a) {
+        if (n >= capacity) { t_error = "atom capacity exceeded"; return false; }
+        const int64_t i = base + n++;
+        c.serial[i] = a.serial; c.resnum[i] = a.resnum;
+        c.xyz[3 * i] = a.x; c.xyz[3 * i + 1] = a.y; c.xyz[3 * i + 2] = a.z;
+        c.occupancy[i] = a.occ; c.bfactor[i] = a.bf;
+        unpack_field(a.name, c.name + 4 * i, 4);
+        unpack_field(a.resname, c.resname + 4 * i, 4);
+        unpack_field(a.chain, c.chain + 2 * i, 2);
+        unpack_field(a.element, c.element + 2 * i, 2);
+        memset(c.segment + 4 * i, 0, 4);
+        c.altloc[i] = a.altloc; c.icode[i] = a.icode; c.charge[i] = a.charge;
+        return true;
+    });
+}
+
+int64_t cif_pack_into(const char *text, int64_t len, int flags, const PackedCols &c, int64_t base, int64_t capacity,
+                      KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5], int32_t *residue_count)
+{
+    std::vector<int32_t> counted;
+    PackState state(c, kinds, run_keys, counted);
+    *split = false;
+    int64_t n = 0;
+    const int64_t got = cif_each_atom(text, len, flags, header_id, [&](const AtomRec &a) {
+        if (n >= capacity) { t_error = "atom capacity exceeded"; return false; }
+        const int64_t i = base + n++;
+        c.xyz[3 * i] = a.x; c.xyz[3 * i + 1] = a.y; c.xyz[3 * i + 2] = a.z;
+        state.add(i, a.name, a.resname, a.chain, a.resnum, (float)a.bf);
+        return true;
+    });
+    state.finish(split, residue_count);
+    return got;
+}
+
+// ---- either format --------------------------------------------------------------------------------
+
+int64_t count_atoms(const char *text, int64_t len, int flags)
+{
+    if (!looks_like_cif(text, len)) return pdb_count_atoms(text, len);
+    char id[5];
+    return cif_each_atom(text, len, flags, id, [](const AtomRec &) { return true; });
+}
+
+int64_t parse_into(const char *text, int64_t len, int flags, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
+{
+    return looks_like_cif(text, len) ? cif_parse_into(text, len, flags, c, base, capacity, header_id)
+                                     : pdb_parse_into(text, len, c, base, capacity, header_id);
+}
+
+int64_t pack_into(const char *text, int64_t len, int flags, const PackedCols &c, int64_t base, int64_t capacity,
+                  KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5], int32_t *residue_count)
+{
+    return looks_like_cif(text, len)
+               ? cif_pack_into(text, len, flags, c, base, capacity, kinds, run_keys, split, header_id, residue_count)
+               : pdb_pack_into(text, len, c, base, capacity, kinds, run_keys, split, header_id, residue_count);
+}
+
+// ---- gzip -----------------------------------------------------------------------------------------
+
+inline bool is_gzip(const char *p, int64_t len) { return len >= 2 && (unsigned char)p[0] == 0x1f && (unsigned char)p[1] == 0x8b; }
+
+// zlib is looked up at run time (the library does not link it: only gzip input needs it)
+struct Zlib {
+    int (*init2)(z_streamp, int, const char *, int) = nullptr;
+    int (*run)(z_streamp, int) = nullptr;
+    int (*reset)(z_streamp) = nullptr;
+    int (*end)(z_streamp) = nullptr;
+    bool ok = false;
+    Zlib()
+    {
+        void *h = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libz.so", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return;
+        init2 = reinterpret_cast<int (*)(z_streamp, int, const char *, int)>(dlsym(h, "inflateInit2_"));
+        run = reinterpret_cast<int (*)(z_streamp, int)>(dlsym(h, "inflate"));
+        reset = reinterpret_cast<int (*)(z_streamp)>(dlsym(h, "inflateReset"));
+        end = reinterpret_cast<int (*)(z_streamp)>(dlsym(h, "inflateEnd"));
+        ok = init2 && run && reset && end;
+    }
+};
+
+// inflate a (possibly multi-member) gzip image into a reusable buffer
+bool gunzip(const char *src, int64_t n, std::vector<char> &dst, int64_t *len)
+{
+    static const Zlib z;
+    if (!z.ok) return false;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (z.init2(&zs, 16 + MAX_WBITS, ZLIB_VERSION, (int)sizeof(z_stream)) != Z_OK) return false;
+    if (dst.size() < (size_t)n * 4 + 65536) dst.resize((size_t)n * 4 + 65536);
+    size_t got = 0, fed = 0;
+    int rc = Z_OK;
+    for (;;) {
+        if (got == dst.size()) dst.resize(dst.size() * 2);
+        const size_t in_now = std::min<size_t>((size_t)n - fed, 1u << 30), out_now = std::min<size_t>(dst.size() - got, 1u << 30);
+        zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(src)) + fed;
+        zs.avail_in = (uInt)in_now;
+        zs.next_out = reinterpret_cast<Bytef *>(dst.data()) + got;
+        zs.avail_out = (uInt)out_now;
+        rc = z.run(&zs, Z_NO_FLUSH);
+        fed += in_now - zs.avail_in;
+        got += out_now - zs.avail_out;
+        if (rc == Z_STREAM_END) {
+            if (fed >= (size_t)n || !is_gzip(src + fed, n - (int64_t)fed)) break;      // trailing garbage is ignored, as gzip does
+            if (z.reset(&zs) != Z_OK) { rc = Z_DATA_ERROR; break; }
+            continue;
+        }
+        if (rc != Z_OK && rc != Z_BUF_ERROR) break;
+        if (rc == Z_BUF_ERROR && fed >= (size_t)n && got < dst.size()) break;           // truncated stream
+    }
+    z.end(&zs);
+    if (rc != Z_STREAM_END) return false;
+    *len = (int64_t)got;
+    return true;
+}
+
 bool read_file(const char *path, std::string &out, int *err)
 {
     FILE *f = fopen(path, "rb");
@@ -433,6 +814,12 @@ bool read_file(const char *path, std::string &out, int *err)
     const size_t got = size ? fread(&out[0], 1, (size_t)size, f) : 0;
     fclose(f);
     if (got != (size_t)size) { *err = 2; return false; }
+    if (is_gzip(out.data(), (int64_t)out.size())) {
+        std::vector<char> plain;
+        int64_t len = 0;
+        if (!gunzip(out.data(), (int64_t)out.size(), plain, &len)) { *err = 4; return false; }
+        out.assign(plain.data(), (size_t)len);
+    }
     return true;
 }
 
@@ -484,6 +871,17 @@ struct FileBlock {
     void release() { mem.reset(); atom_id.reset(); std::vector<uint64_t>().swap(kinds); std::vector<uint64_t>().swap(res_keys); }
 };
 
+// message for a per-file error code: 1 open, 2 read, 3 parse (detail), 4 inflate
+std::string file_error(int code, const char *path, const std::string &detail)
+{
+    switch (code) {
+    case 1: return std::string("cannot open ") + path;
+    case 3: return std::string(path) + ": " + detail;
+    case 4: return std::string("cannot inflate ") + path + ": not a complete gzip stream (or zlib is not installed)";
+    default: return std::string("cannot read ") + path;
+    }
+}
+
 }  // namespace
 
 // array that is NOT value-initialised: its pages are first touched by the worker that fills them
@@ -530,7 +928,22 @@ const char *emm_pdb_last_error(void) { return t_error.c_str(); }
 int emm_pdb_count_atoms(const char *text, int64_t len, int64_t *n_atoms)
 {
     if (!text || !n_atoms || len < 0) return EMM_ERR_INVALID;
-    *n_atoms = count_atoms(text, len);
+    const int64_t n = count_atoms(text, len, 0);
+    if (n < 0) return EMM_ERR_INPUT;
+    *n_atoms = n;
+    return EMM_OK;
+}
+
+int emm_pdb_parse_ex(const char *text, int64_t len, int32_t flags, int64_t capacity, int32_t *serial, char *name,
+                     char *altloc, char *resname, char *chain, int32_t *resnum, char *icode, double *xyz,
+                     double *occupancy, double *bfactor, char *segment, char *element, int8_t *charge, char *header_id,
+                     int64_t *n_atoms)
+{
+    if (!text || !n_atoms || len < 0 || !header_id) return EMM_ERR_INVALID;
+    Columns c{serial, name, altloc, resname, chain, resnum, icode, xyz, occupancy, bfactor, segment, element, charge};
+    const int64_t n = parse_into(text, len, flags, c, 0, capacity, header_id);
+    if (n < 0) return EMM_ERR_INPUT;
+    *n_atoms = n;
     return EMM_OK;
 }
 
@@ -538,15 +951,16 @@ int emm_pdb_parse(const char *text, int64_t len, int64_t capacity, int32_t *seri
                   char *resname, char *chain, int32_t *resnum, char *icode, double *xyz, double *occupancy,
                   double *bfactor, char *segment, char *element, int8_t *charge, char *header_id, int64_t *n_atoms)
 {
-    if (!text || !n_atoms || len < 0 || !header_id) return EMM_ERR_INVALID;
-    Columns c{serial, name, altloc, resname, chain, resnum, icode, xyz, occupancy, bfactor, segment, element, charge};
-    const int64_t n = parse_into(text, len, c, 0, capacity, header_id);
-    if (n < 0) return EMM_ERR_INPUT;
-    *n_atoms = n;
-    return EMM_OK;
+    return emm_pdb_parse_ex(text, len, 0, capacity, serial, name, altloc, resname, chain, resnum, icode, xyz, occupancy,
+                            bfactor, segment, element, charge, header_id, n_atoms);
 }
 
 int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out)
+{
+    return emm_pdb_load_files_ex(paths, n_files, n_threads, 0, out);
+}
+
+int emm_pdb_load_files_ex(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t flags, emm_pdb_batch **out)
 {
     if (!paths || !out || n_files < 0) return EMM_ERR_INVALID;
     *out = nullptr;
@@ -555,14 +969,17 @@ int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_thre
     std::vector<std::string> texts((size_t)n_files);
     std::vector<int64_t> counts((size_t)n_files, 0);
     std::vector<int> errs((size_t)n_files, 0);
+    std::vector<std::string> messages((size_t)n_files);
     if (n_threads < 1) n_threads = 1;
     n_threads = std::min<int32_t>(n_threads, std::max(n_files, 1));
     {
         std::atomic<int> next(0);
         auto work = [&]() {
             for (int i; (i = next.fetch_add(1)) < n_files;) {
-                if (read_file(paths[i], texts[(size_t)i], &errs[(size_t)i]))
-                    counts[(size_t)i] = count_atoms(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size());
+                if (read_file(paths[i], texts[(size_t)i], &errs[(size_t)i])) {
+                    counts[(size_t)i] = count_atoms(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size(), flags);
+                    if (counts[(size_t)i] < 0) { counts[(size_t)i] = 0; errs[(size_t)i] = 3; messages[(size_t)i] = t_error; }
+                }
             }
         };
         std::vector<std::thread> pool;
@@ -572,7 +989,7 @@ int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_thre
     }
     for (int i = 0; i < n_files; ++i)
         if (errs[(size_t)i]) {
-            t_error = std::string(errs[(size_t)i] == 1 ? "cannot open " : "cannot read ") + paths[i];
+            t_error = file_error(errs[(size_t)i], paths[i], messages[(size_t)i]);
             const int rc = errs[(size_t)i] == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
             delete b;
             return rc;
@@ -589,10 +1006,9 @@ int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_thre
               b->icode.data(), b->xyz.data(), b->occupancy.data(), b->bfactor.data(), b->segment.data(),
               b->element.data(), b->charge.data()};
     std::atomic<int> next(0), failed(-1);
-    std::vector<std::string> messages((size_t)n_files);
     auto work = [&]() {
         for (int i; (i = next.fetch_add(1)) < n_files;) {
-            const int64_t got = parse_into(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size(), c,
+            const int64_t got = parse_into(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size(), flags, c,
                                            b->atom_off[(size_t)i], counts[(size_t)i], &b->header_id[5 * (size_t)i]);
             if (got != counts[(size_t)i]) { messages[(size_t)i] = t_error; failed.store(i); }
         }
@@ -696,6 +1112,11 @@ static void finish_packed(emm_pdb_batch *b, std::vector<FileBlock> &blocks, int 
 
 int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out)
 {
+    return emm_pdb_pack_files_ex(paths, n_files, n_threads, 0, out);
+}
+
+int emm_pdb_pack_files_ex(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t flags, emm_pdb_batch **out)
+{
     if (!paths || !out || n_files < 0) return EMM_ERR_INVALID;
     *out = nullptr;
     std::unique_ptr<emm_pdb_batch> b(new emm_pdb_batch());
@@ -722,17 +1143,23 @@ int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_thre
         run_pool([&]() {
             KindTable kinds;
             std::vector<uint64_t> run_keys;
-            std::vector<char> text;
+            std::vector<char> text, inflated;
             for (int i; (i = next.fetch_add(1)) < n_files;) {
                 const size_t f = (size_t)i;
                 int64_t len = 0;
                 if (!read_file_into(paths[i], text, &len, &errs[f])) continue;
+                const char *data = text.data();
+                if (is_gzip(data, len)) {
+                    if (!gunzip(data, len, inflated, &len)) { errs[f] = 4; continue; }
+                    data = inflated.data();
+                }
                 FileBlock &blk = blocks[f];
-                const int64_t count = count_atoms(text.data(), len);
+                const int64_t count = count_atoms(data, len, flags);
+                if (count < 0) { messages[f] = t_error; errs[f] = 3; continue; }
                 blk.allocate(count);
                 kinds.clear();
                 const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
-                const int64_t got = pack_into(text.data(), len, c, 0, count, kinds, run_keys, &blk.split, &b->header_id[5 * f],
+                const int64_t got = pack_into(data, len, flags, c, 0, count, kinds, run_keys, &blk.split, &b->header_id[5 * f],
                                               &blk.residue_count);
                 if (got != count) { messages[f] = t_error; errs[f] = 3; continue; }
                 blk.kinds = kinds.keys;
@@ -747,8 +1174,7 @@ int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_thre
     for (int i = 0; i < n_files; ++i)
         if (errs[(size_t)i]) {
             const int e = errs[(size_t)i];
-            if (e == 3) t_error = std::string(paths[i]) + ": " + messages[(size_t)i];
-            else t_error = std::string(e == 1 ? "cannot open " : "cannot read ") + paths[i];
+            t_error = file_error(e, paths[i], messages[(size_t)i]);
             return e == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
         }
     finish_packed(b.get(), blocks, n_threads);
@@ -783,40 +1209,26 @@ int emm_pack_columns(int32_t n_structures, const int64_t *sizes, const uint8_t *
                 FileBlock &blk = blocks[f];
                 blk.allocate(n);
                 kinds.clear();
-                run_keys.clear();
-                uint64_t prev_kind = ~0ull, prev_res = ~0ull;
-                uint32_t prev_kind_idx = 0;
-                int32_t run = -1;
-                const uint8_t *nm = name4[f], *rn = resname4[f], *ch = chain2[f];
+                const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
                 std::vector<int32_t> counted;
+                PackState state(c, kinds, run_keys, counted);
+                const uint8_t *nm = name4[f], *rn = resname4[f], *ch = chain2[f];
                 for (int64_t a = 0; a < n; ++a) {
                     uint32_t name, res;
                     uint16_t chain;
                     memcpy(&name, nm + 4 * a, 4);
                     memcpy(&res, rn + 4 * a, 4);
                     memcpy(&chain, ch + 2 * a, 2);
-                    const uint64_t kkey = (uint64_t)res | ((uint64_t)name << 32);
-                    const uint64_t rkey = ((uint64_t)chain << 32) | (uint32_t)resnum[f][a];
-                    if (((uint32_t)prev_kind != res || rkey != prev_res) && counted_residue(res)) counted.push_back(resnum[f][a]);
-                    if (kkey != prev_kind) { prev_kind = kkey; prev_kind_idx = kinds.lookup(kkey); }
-                    blk.kind[a] = prev_kind_idx;
-                    blk.chain[a] = chain;
-                    if (rkey != prev_res || run < 0) { prev_res = rkey; ++run; run_keys.push_back(rkey); }
-                    blk.residue[a] = run;
-                    blk.bfactor[a] = (float)bfactor[f][a];
+                    state.add(a, name, res, chain, resnum[f][a], (float)bfactor[f][a]);
                 }
                 if (n) memcpy(blk.xyz, xyz[f], (size_t)n * 3 * sizeof(double));
                 blk.kinds = kinds.keys;
-                std::vector<uint64_t> sorted(run_keys);
-                std::sort(sorted.begin(), sorted.end());
-                blk.split = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+                state.finish(&blk.split, &blk.residue_count);
                 if (blk.split) {
                     blk.atom_id.reset(new int32_t[(size_t)std::max<int64_t>(n, 1)]);
-                    const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
                     regroup_file(c, 0, n, run_keys, blk.atom_id.get());
                 }
                 blk.res_keys = run_keys;
-                blk.residue_count = distinct_count(counted);
             }
         };
         std::vector<std::thread> pool;

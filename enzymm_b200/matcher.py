@@ -267,8 +267,11 @@ def _install_lr_models():
 _install_lr_models()
 
 
-def load_molecules(molecule_paths: Sequence[Path], conservation_cutoff: float = 0, warn: bool = False) -> List[Molecule]:
+def load_molecules(molecule_paths: Sequence[Path], conservation_cutoff: float = 0, warn: bool = False,
+                   use_author: bool = False) -> List[Molecule]:
     """Load query structures; repeated file stems get ``_2``, ``_3`` ... ids (``jess_run.py:523-556``).
+    PDB and mmCIF files, gzip-compressed or not, are told apart by content (``Molecule.load``'s
+    ``format="detect"``); ``use_author`` picks the ``auth_*`` identifiers of mmCIF files.
 
     As upstream, ``conserved()`` is called and its RESULT DISCARDED (``jess_run.py:541-542``), so
     the cutoff does not mask anything on this path.  The intended masking
@@ -282,7 +285,7 @@ def load_molecules(molecule_paths: Sequence[Path], conservation_cutoff: float = 
         seen[stem] += 1
         ids.append(stem if seen[stem] == 1 else f"{stem}_{seen[stem]}")
     # native, multi-threaded ingest (emm_pdb_load_files); OS errors keep their Python types
-    for path, mol in zip(molecule_paths, load_many([str(p) for p in molecule_paths], ids=ids)):
+    for path, mol in zip(molecule_paths, load_many([str(p) for p in molecule_paths], ids=ids, use_author=use_author)):
         if conservation_cutoff:
             mol.conserved(conservation_cutoff)
         if mol:

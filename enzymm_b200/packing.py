@@ -184,8 +184,8 @@ class _PdbPacked(ctypes.Structure):       # struct emm_pdb_packed
 
 
 def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrary, with_chain: bool = True,
-               threads: int = 0) -> Tuple[PackedBatch, List[Optional[str]]]:
-    """PDB files -> ``PackedBatch`` on the native thread pool (``emm_pdb_pack_files``), without
+               threads: int = 0, use_author: bool = False) -> Tuple[PackedBatch, List[Optional[str]]]:
+    """PDB / mmCIF files (gzip-compressed or not) -> ``PackedBatch`` on the native thread pool (``emm_pdb_pack_files_ex``), without
     building ``Molecule`` objects: the same columns ``pack_molecules(load_many(paths), library)``
     gives, at parser speed.  Returns ``(batch, header_ids)``; what replaces the per-file
     ``Molecule.load`` of ``jess_run.py:538-548`` when only the hits are wanted."""
@@ -199,7 +199,8 @@ def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrar
     arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
     handle = ctypes.c_void_p()
     n_threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1)
-    rc = lib.emm_pdb_pack_files(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.byref(handle))
+    rc = lib.emm_pdb_pack_files_ex(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads),
+                                   ctypes.c_int32(1 if use_author else 0), ctypes.byref(handle))
     if rc != 0:
         raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
     return _packed_from_handle(lib, handle, library, with_chain)

@@ -286,11 +286,15 @@ def _columns_from_native(n, serial, name, altloc, resname, chain, resnum, icode,
                      "charge": charge}, raw)
 
 
-def _parse_pdb_native(data: bytes):
-    """One PDB text through emm_pdb_parse; same columns as ``_parse_pdb_text``."""
+CIF_AUTHOR = 1        # EMM_PDB_CIF_AUTHOR: read the auth_* identifiers of an mmCIF file before the label_* ones
+
+
+def _parse_pdb_native(data: bytes, flags: int = 0):
+    """One PDB or mmCIF text through emm_pdb_parse_ex; same columns as ``_parse_pdb_text``."""
     lib = _native_lib()
     n = ctypes.c_int64(0)
-    lib.emm_pdb_count_atoms(data, ctypes.c_int64(len(data)), ctypes.byref(n))
+    if lib.emm_pdb_count_atoms(data, ctypes.c_int64(len(data)), ctypes.byref(n)) != 0:
+        raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
     cap = max(n.value, 1)
     serial = np.zeros(cap, np.int32); resnum = np.zeros(cap, np.int32)
     name = np.zeros(4 * cap, np.uint8); resname = np.zeros(4 * cap, np.uint8); chain = np.zeros(2 * cap, np.uint8)
@@ -301,15 +305,32 @@ def _parse_pdb_native(data: bytes):
     header = ctypes.create_string_buffer(5)
     got = ctypes.c_int64(0)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = lib.emm_pdb_parse(data, ctypes.c_int64(len(data)), ctypes.c_int64(cap), p(serial), p(name), p(altloc),
-                           p(resname), p(chain), p(resnum), p(icode), p(xyz), p(occ), p(bfac), p(segment),
-                           p(element), p(charge), header, ctypes.byref(got))
+    rc = lib.emm_pdb_parse_ex(data, ctypes.c_int64(len(data)), ctypes.c_int32(flags), ctypes.c_int64(cap), p(serial),
+                              p(name), p(altloc), p(resname), p(chain), p(resnum), p(icode), p(xyz), p(occ), p(bfac),
+                              p(segment), p(element), p(charge), header, ctypes.byref(got))
     if rc != 0:
         raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
     k = got.value
     cols = _columns_from_native(k, serial[:k], name[:4 * k], altloc[:k], resname[:4 * k], chain[:2 * k], resnum[:k],
                                 icode[:k], occ[:k], bfac[:k], segment[:4 * k], element[:2 * k], charge[:k])
     return cols, xyz[:k], (header.value.decode() or None)
+
+
+def _first_cif_token(data: bytes) -> bytes:
+    """First token of a text after white space and ``#`` comments (where an mmCIF file has ``data_<name>``)."""
+    for line in data[:65536].splitlines():
+        line = line.strip()
+        if line and not line.startswith(b"#"):
+            return line.split()[0]
+    return b""
+
+
+def _looks_like_cif(data: bytes) -> bool:
+    return _first_cif_token(data)[:5].lower() == b"data_"
+
+
+def _cif_block_name(data: bytes) -> Optional[str]:
+    return _first_cif_token(data)[5:].decode("ascii", "replace") or None
 
 
 class Molecule:
@@ -345,9 +366,16 @@ class Molecule:
         return self
 
     @classmethod
-    def load(cls, file: Union[str, os.PathLike, IO[str]], id: Optional[str] = None) -> "Molecule":
-        """Read a PDB file (path or text file object).  OS errors propagate unchanged
-        (``FileNotFoundError`` / ``IsADirectoryError`` -> CLI errno, ``enzymm/_cli.py:318-328``)."""
+    def load(cls, file: Union[str, os.PathLike, IO[str]], format: str = "detect", id: Optional[str] = None,
+             use_author: bool = False) -> "Molecule":
+        """Read a PDB or mmCIF file (path, text or binary file object; gzip-compressed content is
+        inflated).  ``format``: ``"detect"`` (by content: a ``data_`` block header means mmCIF), ``"pdb"``
+        or ``"cif"``, as ``pyjess.Molecule.load``; ``use_author`` reads the ``auth_*`` identifiers of an
+        mmCIF file instead of the ``label_*`` ones.  The reference passes a path and an id only
+        (``jess_run.py:538``).  OS errors propagate unchanged (``FileNotFoundError`` /
+        ``IsADirectoryError`` -> CLI errno, ``enzymm/_cli.py:318-328``)."""
+        if format not in ("detect", "pdb", "cif"):
+            raise ValueError(f"invalid value for `format` argument: {format!r}")
         if isinstance(file, (str, os.PathLike)):
             with open(os.fspath(file), "rb") as handle:
                 data = handle.read()
@@ -355,12 +383,20 @@ class Molecule:
             data = file.read()
             if isinstance(data, str):
                 data = data.encode("ascii", "replace")
-        cols, xyz, header_id = _parse_pdb_native(data)
+        if data[:2] == b"\x1f\x8b":
+            import gzip
+            data = gzip.decompress(data)
+        is_cif = _looks_like_cif(data)
+        if format != "detect" and is_cif != (format == "cif"):
+            raise ValueError(f"the input is not in {format!r} format")
+        cols, xyz, header_id = _parse_pdb_native(data, CIF_AUTHOR if use_author else 0)
+        if is_cif and id is None:
+            header_id = _cif_block_name(data) or header_id        # the whole block name, not only four characters
         return cls._from_columns(cols, xyz, id if id is not None else header_id)
 
     @classmethod
-    def loads(cls, text: str, id: Optional[str] = None) -> "Molecule":
-        return cls.load(io.StringIO(text), id=id)
+    def loads(cls, text: str, format: str = "detect", id: Optional[str] = None, use_author: bool = False) -> "Molecule":
+        return cls.load(io.StringIO(text), format=format, id=id, use_author=use_author)
 
     # -- pyjess surface ---------------------------------------------------------------------
     def conserved(self, cutoff: float = 0.0) -> "Molecule":
@@ -449,9 +485,11 @@ class Molecule:
 
 
 def load_many(paths: Sequence[Union[str, os.PathLike]], ids: Optional[Sequence[Optional[str]]] = None,
-              threads: int = 0) -> List[Molecule]:
-    """Read and parse many PDB files on a native thread pool (``emm_pdb_load_files``); the returned
-    molecules are views into one SoA batch.  ``ids`` default to each file's HEADER idCode."""
+              threads: int = 0, use_author: bool = False) -> List[Molecule]:
+    """Read and parse many PDB / mmCIF files (gzip-compressed or not, told apart by content) on a native
+    thread pool (``emm_pdb_load_files_ex``); the returned molecules are views into one SoA batch.
+    ``ids`` default to each file's HEADER idCode (mmCIF: the data block name when it has at most four
+    characters)."""
     lib = _native_lib()
     paths = [os.fspath(p) for p in paths]
     if not paths:
@@ -464,7 +502,8 @@ def load_many(paths: Sequence[Union[str, os.PathLike]], ids: Optional[Sequence[O
     arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
     handle = ctypes.c_void_p()
     n_threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1)
-    rc = lib.emm_pdb_load_files(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.byref(handle))
+    rc = lib.emm_pdb_load_files_ex(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads),
+                                   ctypes.c_int32(CIF_AUTHOR if use_author else 0), ctypes.byref(handle))
     if rc != 0:
         raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
     owner = _NativeBatch(lib, handle)       # columns stay views of the native buffers: no copies

@@ -239,12 +239,28 @@ int emm_query_batch(emm_library *lib, const emm_batch *batch, const emm_query_pa
  * (jess_run.py:538): ATOM and HETATM records in file order up to the first ENDMDL; coordinates are
  * the doubles strtod / Python float() produce.  Strings are blank-stripped, NUL padded fixed-width
  * fields: name[4], resname[4], chain[2], segment[4], element[2]; altloc / icode are single chars.
+ *
+ * Every reader below takes PDB or mmCIF text and tells them apart by content, as
+ * pyjess.Molecule.load(format="detect") does: a text whose first token is a data_ block header is
+ * read through its _atom_site category -- the rows of the first pdbx_PDB_model_num, in file order,
+ * identifiers from the label_* items (label_atom_id, label_comp_id, label_asym_id, label_seq_id;
+ * an item that is absent or '.' / '?' falls back to its auth_* twin) unless EMM_PDB_CIF_AUTHOR asks
+ * for the auth_* items first (PyJess's use_author).  Names longer than the fields are cut; a chain
+ * id longer than two characters is EMM_ERR_INPUT.  header_id receives the data block name when it
+ * fits four characters.  The readers that take PATHS also accept gzip-compressed files (.gz by
+ * content, not by name).  No reference test holds an mmCIF or gzip input: this part is unpinned.
  */
+#define EMM_PDB_CIF_AUTHOR 1    /* flags of the _ex readers: prefer auth_* over label_* identifiers */
 int emm_pdb_count_atoms(const char *text, int64_t len, int64_t *n_atoms);
 int emm_pdb_parse(const char *text, int64_t len, int64_t capacity, int32_t *serial, char *name, char *altloc,
                   char *resname, char *chain, int32_t *resnum, char *icode, double *xyz, double *occupancy,
                   double *bfactor, char *segment, char *element, int8_t *charge, char *header_id /* [5] */,
                   int64_t *n_atoms);
+/* As emm_pdb_parse with reader flags (emm_pdb_parse = flags 0). */
+int emm_pdb_parse_ex(const char *text, int64_t len, int32_t flags, int64_t capacity, int32_t *serial, char *name,
+                     char *altloc, char *resname, char *chain, int32_t *resnum, char *icode, double *xyz,
+                     double *occupancy, double *bfactor, char *segment, char *element, int8_t *charge,
+                     char *header_id /* [5] */, int64_t *n_atoms);
 const char *emm_pdb_last_error(void);
 
 /* Many files at once on n_threads threads into one SoA batch owned by the library. */
@@ -259,6 +275,7 @@ typedef struct emm_pdb_columns {
     const char *header_id;        /* [n_files][5] HEADER idCode or empty */
 } emm_pdb_columns;
 int emm_pdb_load_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
+int emm_pdb_load_files_ex(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t flags, emm_pdb_batch **out);
 int emm_pdb_batch_columns(const emm_pdb_batch *batch, emm_pdb_columns *out);
 void emm_pdb_batch_free(emm_pdb_batch *batch);
 
@@ -292,6 +309,7 @@ typedef struct emm_pdb_packed {
     const int32_t *residue_count; /* [n_files] Match.query_residue_count (jess_run.py:487-496) */
 } emm_pdb_packed;
 int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
+int emm_pdb_pack_files_ex(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t flags, emm_pdb_batch **out);
 int emm_pdb_batch_packed(const emm_pdb_batch *batch, emm_pdb_packed *out);
 /* The same packing from per-structure columns that are already in memory (what Matcher.run has after
  * Molecule.load, jess_run.py:538-548): name4 / resname4 / chain2 are blank-stripped NUL-padded fixed

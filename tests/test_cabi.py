@@ -69,3 +69,21 @@ def test_library_is_sm100a_with_tma_staging():
     assert "arch = sm_100a" in sass and "arch = sm_90" not in sass
     assert "emm_search_kernel" in sass and "emm_prepare_kernel" in sass
     assert "UBLKCP.S.G" in sass and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64" in sass
+
+
+def test_c99_client_links_and_runs(tmp_path):
+    """The header is plain C (no C++ or torch types in any signature): a C99 translation unit
+    includes it with -pedantic, links the shared library and gets sane constants, the loud no-device
+    error (on a box without a GPU) and the host-only PDB reader's atom count for the 1AMY fixture."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    exe = tmp_path / "abi_client"
+    libdir = library_path().parent
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", "-o", str(exe),
+                    str(ROOT / "tests" / "c" / "abi_client.c"), f"-L{libdir}", "-lenzymm_b200", f"-Wl,-rpath,{libdir}"],
+                   check=True, capture_output=True, text=True, timeout=120)
+    run = subprocess.run([str(exe), str(ROOT / "tests" / "golden" / "1AMY.pdb")], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stderr
+    assert "abi=2 hit=280" in run.stdout and "atoms=3339" in run.stdout
