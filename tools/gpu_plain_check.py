@@ -8,6 +8,10 @@ with splitting on, checks that the hit records are identical byte for byte, and 
 times.  Then the small-launch cases: the two fixtures staged and a 4-chain assembly searched in
 place, ``donate_after=-1`` (plain instantiation) against ``donate_after=1`` (split at every chance).
 
+Meaningful with ``tools/patches/plain_instantiation.patch`` applied (``git apply`` it, ``make -C
+enzymm_b200/csrc``): the shipped kernel has one instantiation and ignores ``EMM_SPLIT_CAPABLE``.  The
+result of the round-2 run is ``profiles/r02_plain_instantiation.txt``.
+
 usage: python tools/gpu_plain_check.py [n_structures=10000] [out=gpurun_out/r02_plain_check.txt]
 """
 import os
