@@ -919,6 +919,9 @@ struct emm_pdb_batch {
     std::vector<int64_t> res_off;        // [n_files+1] into res_key
     std::vector<uint64_t> res_key;       // per residue ordinal: chain << 32 | residue number
     std::vector<int32_t> residue_count;  // per file
+    // EMM_PDB_SKIP_BAD: what went wrong with the files that were skipped (0 = fine; file_error codes)
+    std::vector<int32_t> file_status;
+    std::vector<std::string> file_message;
 };
 
 extern "C" {
@@ -1171,11 +1174,19 @@ int emm_pdb_pack_files_ex(const char *const *paths, int32_t n_files, int32_t n_t
             }
         });
     }
+    b->file_status.assign(nf, 0);
+    b->file_message.assign(nf, std::string());
     for (int i = 0; i < n_files; ++i)
         if (errs[(size_t)i]) {
             const int e = errs[(size_t)i];
             t_error = file_error(e, paths[i], messages[(size_t)i]);
-            return e == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
+            if (!(flags & EMM_PDB_SKIP_BAD)) return e == 1 ? EMM_ERR_INVALID : EMM_ERR_INPUT;
+            // skipped and named: the file stays in the batch as a structure without atoms
+            b->file_status[(size_t)i] = e;
+            b->file_message[(size_t)i] = t_error;
+            blocks[(size_t)i] = FileBlock();
+            blocks[(size_t)i].allocate(0);
+            memset(&b->header_id[5 * (size_t)i], 0, 5);
         }
     finish_packed(b.get(), blocks, n_threads);
     *out = b.release();
@@ -1279,6 +1290,19 @@ int emm_pdb_batch_packed(const emm_pdb_batch *b, emm_pdb_packed *out)
     out->res_key = b->res_key.data();
     out->residue_count = b->residue_count.data();
     return EMM_OK;
+}
+
+int emm_pdb_batch_file_status(const emm_pdb_batch *b, int32_t *status, int32_t capacity)
+{
+    if (!b || !status || capacity < b->n_files) return EMM_ERR_INVALID;
+    for (int32_t i = 0; i < b->n_files; ++i) status[i] = (size_t)i < b->file_status.size() ? b->file_status[(size_t)i] : 0;
+    return EMM_OK;
+}
+
+const char *emm_pdb_batch_file_message(const emm_pdb_batch *b, int32_t file)
+{
+    if (!b || file < 0 || (size_t)file >= b->file_message.size()) return "";
+    return b->file_message[(size_t)file].c_str();
 }
 
 void emm_pdb_batch_free(emm_pdb_batch *b) { delete b; }

@@ -472,8 +472,9 @@ class Matcher:
         raise EngineError(-4, "hit buffer kept overflowing")
 
     def scan_files(self, paths: Sequence[os.PathLike], chunk_size: int = 2048, threads: int = 0, queue=None,
-                   with_batch: bool = False, devices: Optional[Sequence[int]] = None, _with_span: bool = False):
-        """Screen PDB files without building ``Molecule`` objects: a generator of
+                   with_batch: bool = False, devices: Optional[Sequence[int]] = None, _with_span: bool = False,
+                   on_error: str = "raise"):
+        """Screen PDB / mmCIF files (gzip-compressed or not) without building ``Molecule`` objects: a generator of
         ``(chunk_paths, header_ids, records)`` per chunk of ``chunk_size`` files, ``records`` being the
         hit records of the chunk (``structure`` indexes ``chunk_paths``; ``flags & 4`` = passes the
         filter).  Three stages overlap: files are read, parsed and packed natively
@@ -487,9 +488,13 @@ class Matcher:
         ``devices=[0, 1, ...]`` is the whole-box call from ONE process: a worker thread per listed GPU
         (its own device library, sessions and streams; the compiled library is shared) pulls chunks
         from one in-process counter and the generator hands the chunks back in input order -- the host
-        side merge of north_star; nothing crosses between the GPUs."""
+        side merge of north_star; nothing crosses between the GPUs.
+
+        ``on_error="skip"``: a file that cannot be read or parsed is reported with a warning and has no
+        hits instead of ending the scan (``packing.pack_files``); the default raises, as the reference's
+        ``load_molecules`` would."""
         if devices is not None and len(list(devices)) > 0 and not (len(list(devices)) == 1 and list(devices)[0] == self.device):
-            yield from self._scan_devices(paths, list(devices), chunk_size, threads, with_batch)
+            yield from self._scan_devices(paths, list(devices), chunk_size, threads, with_batch, on_error)
             return
         import concurrent.futures
         from .engine import Session
@@ -523,7 +528,7 @@ class Matcher:
         try:
             with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
                 chunk = paths[first[0]:first[1]]
-                pending = pool.submit(pack_files, chunk, engine.compiled, True, threads)
+                pending = pool.submit(pack_files, chunk, engine.compiled, True, threads, False, on_error)
                 ci = -1
                 span = first
                 while pending is not None:
@@ -533,7 +538,7 @@ class Matcher:
                     span = next(spans, None)
                     if span is not None:
                         chunk = paths[span[0]:span[1]]
-                        pending = pool.submit(pack_files, chunk, engine.compiled, True, threads)
+                        pending = pool.submit(pack_files, chunk, engine.compiled, True, threads, False, on_error)
                     else:
                         pending = None
                     lane = lanes[ci % 2]
@@ -561,7 +566,8 @@ class Matcher:
                 except EngineError:
                     pass
 
-    def _scan_devices(self, paths, devices: List[int], chunk_size: int, threads: int, with_batch: bool):
+    def _scan_devices(self, paths, devices: List[int], chunk_size: int, threads: int, with_batch: bool,
+                      on_error: str = "raise"):
         """``scan_files`` over several GPUs of this host from one process (see ``scan_files``)."""
         import queue as queue_module
         import threading
@@ -603,7 +609,7 @@ class Matcher:
                     child.device, child._engine, child._scan_lanes, child._device_workers = device, None, None, {}
                     self._device_workers[(slot, device)] = child
                 for item in child.scan_files(paths, chunk_size, per_worker, queue=Shared(), with_batch=with_batch,
-                                             _with_span=True):
+                                             _with_span=True, on_error=on_error):
                     if not hand_over(item):
                         break                   # closing the inner generator lets its device work finish
             except BaseException as exc:        # noqa: BLE001 -- surfaces in the consumer
@@ -635,7 +641,7 @@ class Matcher:
 
     def scan_to_tsv(self, paths: Sequence[os.PathLike], file: IO[str], chunk_size: int = 2048, threads: int = 0,
                     queue=None, header: bool = True, predict_correctness: bool = True,
-                    devices: Optional[Sequence[int]] = None) -> int:
+                    devices: Optional[Sequence[int]] = None, on_error: str = "raise") -> int:
         """PDB files -> the reference's results table, end to end: native ingest, GPU search, rows
         formatted natively from the hit records (``tsv.TableWriter``) -- what ``_cli.py:217-316`` does
         through ``load_molecules`` / ``Matcher.run`` / ``Match.dump``, without per-atom or per-match
@@ -659,7 +665,8 @@ class Matcher:
         if header:
             emit(writer.header().encode())
         n_rows = 0
-        for chunk, _, records, batch in self.scan_files(paths, chunk_size, threads, queue, with_batch=True, devices=devices):
+        for chunk, _, records, batch in self.scan_files(paths, chunk_size, threads, queue, with_batch=True, devices=devices,
+                                                        on_error=on_error):
             selection = writer.select(records)
             n_rows += len(selection[0])
             emit(writer.format(records, batch.table, [stems[p] for p in chunk], selection))

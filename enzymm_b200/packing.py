@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import warnings
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -184,26 +185,48 @@ class _PdbPacked(ctypes.Structure):       # struct emm_pdb_packed
 
 
 def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrary, with_chain: bool = True,
-               threads: int = 0, use_author: bool = False) -> Tuple[PackedBatch, List[Optional[str]]]:
-    """PDB / mmCIF files (gzip-compressed or not) -> ``PackedBatch`` on the native thread pool (``emm_pdb_pack_files_ex``), without
-    building ``Molecule`` objects: the same columns ``pack_molecules(load_many(paths), library)``
-    gives, at parser speed.  Returns ``(batch, header_ids)``; what replaces the per-file
-    ``Molecule.load`` of ``jess_run.py:538-548`` when only the hits are wanted."""
+               threads: int = 0, use_author: bool = False, on_error: str = "raise") -> Tuple[PackedBatch, List[Optional[str]]]:
+    """PDB / mmCIF files (gzip-compressed or not) -> ``PackedBatch`` on the native thread pool
+    (``emm_pdb_pack_files_ex``), without building ``Molecule`` objects: the same columns
+    ``pack_molecules(load_many(paths), library)`` gives, at parser speed.  Returns ``(batch, header_ids)``;
+    what replaces the per-file ``Molecule.load`` of ``jess_run.py:538-548`` when only the hits are wanted.
+
+    ``on_error="raise"`` (default) keeps the reference's behaviour -- the first unreadable or malformed
+    file raises, OS errors with their Python types (``_cli.py:318-328`` maps them to exit codes).
+    ``on_error="skip"`` is for screening runs over very many files: such a file is reported with a
+    warning, stays in the batch as a structure without atoms (it can have no hits) and is listed in
+    ``batch.bad_files`` (index -> message); every other file is packed as usual."""
+    if on_error not in ("raise", "skip"):
+        raise ValueError(f"on_error must be 'raise' or 'skip', not {on_error!r}")
     lib = _native_lib()
     paths = [os.fspath(p) for p in paths]
-    for p in paths:
-        if os.path.isdir(p):
-            raise IsADirectoryError(21, "Is a directory", p)
-        if not os.path.exists(p):
-            raise FileNotFoundError(2, "No such file or directory", p)
+    skip = on_error == "skip"
+    if not skip:
+        for p in paths:
+            if os.path.isdir(p):
+                raise IsADirectoryError(21, "Is a directory", p)
+            if not os.path.exists(p):
+                raise FileNotFoundError(2, "No such file or directory", p)
     arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
     handle = ctypes.c_void_p()
     n_threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1)
-    rc = lib.emm_pdb_pack_files_ex(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads),
-                                   ctypes.c_int32(1 if use_author else 0), ctypes.byref(handle))
+    flags = (1 if use_author else 0) | (2 if skip else 0)          # EMM_PDB_CIF_AUTHOR | EMM_PDB_SKIP_BAD
+    rc = lib.emm_pdb_pack_files_ex(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.c_int32(flags),
+                                   ctypes.byref(handle))
     if rc != 0:
         raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
-    return _packed_from_handle(lib, handle, library, with_chain)
+    bad = {}
+    if skip and paths:
+        status = np.zeros(len(paths), dtype=np.int32)
+        lib.emm_pdb_batch_file_status(handle, status.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(len(status)))
+        lib.emm_pdb_batch_file_message.restype = ctypes.c_char_p
+        lib.emm_pdb_batch_file_message.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+        for i in np.nonzero(status)[0]:
+            bad[int(i)] = lib.emm_pdb_batch_file_message(handle, int(i)).decode(errors="replace")
+            warnings.warn(f"skipped: {bad[int(i)]}")
+    batch, ids = _packed_from_handle(lib, handle, library, with_chain)
+    batch.bad_files = bad
+    return batch, ids
 
 
 def _packed_from_handle(lib, handle, library: CompiledLibrary, with_chain: bool):

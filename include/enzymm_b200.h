@@ -251,6 +251,9 @@ int emm_query_batch(emm_library *lib, const emm_batch *batch, const emm_query_pa
  * content, not by name).  No reference test holds an mmCIF or gzip input: this part is unpinned.
  */
 #define EMM_PDB_CIF_AUTHOR 1    /* flags of the _ex readers: prefer auth_* over label_* identifiers */
+#define EMM_PDB_SKIP_BAD 2      /* emm_pdb_pack_files_ex: a file that cannot be opened, read, inflated or parsed
+                                 * does not fail the call; it stays in the batch as a structure without atoms
+                                 * and emm_pdb_batch_file_status / _file_message say what happened to it */
 int emm_pdb_count_atoms(const char *text, int64_t len, int64_t *n_atoms);
 int emm_pdb_parse(const char *text, int64_t len, int64_t capacity, int32_t *serial, char *name, char *altloc,
                   char *resname, char *chain, int32_t *resnum, char *icode, double *xyz, double *occupancy,
@@ -310,6 +313,11 @@ typedef struct emm_pdb_packed {
 } emm_pdb_packed;
 int emm_pdb_pack_files(const char *const *paths, int32_t n_files, int32_t n_threads, emm_pdb_batch **out);
 int emm_pdb_pack_files_ex(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t flags, emm_pdb_batch **out);
+/* Per file of a packed batch: 0 fine, 1 cannot open, 2 cannot read, 3 malformed, 4 cannot inflate (only
+ * EMM_PDB_SKIP_BAD leaves non-zero entries); the message is "" for a file that is fine and stays valid
+ * until the batch is freed. */
+int emm_pdb_batch_file_status(const emm_pdb_batch *batch, int32_t *status /* [n_files] */, int32_t capacity);
+const char *emm_pdb_batch_file_message(const emm_pdb_batch *batch, int32_t file);
 int emm_pdb_batch_packed(const emm_pdb_batch *batch, emm_pdb_packed *out);
 /* The same packing from per-structure columns that are already in memory (what Matcher.run has after
  * Molecule.load, jess_run.py:538-548): name4 / resname4 / chain2 are blank-stripped NUL-padded fixed

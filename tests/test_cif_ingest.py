@@ -221,3 +221,46 @@ def test_readers_survive_mutated_inputs_under_sanitizers(tmp_path, mol_1amy):
     seeds[2].write_text("".join((GOLDEN / "1AMY.pdb").read_text().splitlines(keepends=True)[:120]))
     run = subprocess.run([str(exe), "30000"] + [str(s) for s in seeds], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0 and "fuzzed 30000 inputs" in run.stdout, (run.stdout + run.stderr)[-2000:]
+
+
+def test_bad_files_can_be_skipped_and_named(tmp_path, active_templates, mol_1amy):
+    """``pack_files(on_error="skip")``: an unreadable or malformed file does not end a screening run -- it
+    is warned about, listed in ``batch.bad_files`` and stays in the batch as a structure without atoms;
+    the files around it are packed as if it were not there.  The default still raises, with Python's
+    exception types for OS errors (the reference's ``load_molecules`` + ``_cli.py:318-328``)."""
+    good = GOLDEN / "1AMY.pdb"
+    text = good.read_text()
+    broken = tmp_path / "broken.pdb"
+    broken.write_text(text.replace(text.splitlines()[700][30:38], "  abcdef", 1))
+    cut = tmp_path / "cut.cif.gz"
+    cut.write_bytes(gzip.compress(to_cif(mol_1amy, "X").encode())[:2000])
+    long_chain = tmp_path / "long_chain.cif"
+    small = mol_1amy.select(np.arange(len(mol_1amy)) < 4)
+    long_chain.write_text(to_cif(small, "X").replace(" A 1 ", " AAA 1 "))
+    folder = tmp_path / "folder.pdb"
+    folder.mkdir()
+    paths = [good, tmp_path / "missing.pdb", broken, good, cut, long_chain, folder, good]
+    lib = CompiledLibrary(active_templates[::40], 2.0, 1.5, 1.5)
+    with pytest.raises(FileNotFoundError):
+        pack_files(paths, lib)
+    with pytest.raises(IsADirectoryError):
+        pack_files([good, folder], lib)
+    with pytest.raises(ValueError, match="malformed"):
+        pack_files([good, broken], lib)
+    with pytest.raises(ValueError):
+        pack_files(paths, lib, on_error="ignore")
+    with pytest.warns(UserWarning) as caught:
+        batch, ids = pack_files(paths, lib, threads=3, on_error="skip")
+    assert sorted(batch.bad_files) == [1, 2, 4, 5, 6] and len(caught) == 5
+    assert "cannot open" in batch.bad_files[1] and "malformed" in batch.bad_files[2] and "inflate" in batch.bad_files[4]
+    assert "chain id" in batch.bad_files[5] and "cannot read" in batch.bad_files[6]
+    sizes = np.diff(batch.atom_off).tolist()
+    assert sizes == [3339, 0, 0, 3339, 0, 0, 0, 3339] and ids == ["1AMY", None, None, "1AMY", None, None, None, "1AMY"]
+    alone, _ = pack_files([good], lib)
+    for k in (0, 3, 7):
+        lo, hi = int(batch.atom_off[k]), int(batch.atom_off[k + 1])
+        assert batch.xyz[lo:hi].tobytes() == alone.xyz.tobytes() and batch.klass[lo:hi].tolist() == alone.klass.tolist()
+        assert batch.residue[lo:hi].tolist() == alone.residue.tolist()
+    assert batch.table.residue_count.tolist() == [alone.table.residue_count[0] if s else 0 for s in sizes]
+    clean, _ = pack_files([good, good], lib, on_error="skip")
+    assert clean.bad_files == {}

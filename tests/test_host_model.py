@@ -811,7 +811,8 @@ def test_multi_device_scan_hands_chunks_back_in_input_order(monkeypatch, active_
     seen_threads = set()
     real = jess_run.Matcher.scan_files
 
-    def stub(self, paths, chunk_size=2048, threads=0, queue=None, with_batch=False, devices=None, _with_span=False):
+    def stub(self, paths, chunk_size=2048, threads=0, queue=None, with_batch=False, devices=None, _with_span=False,
+             on_error="raise"):
         if devices is not None:
             yield from real(self, paths, chunk_size, threads, queue, with_batch, devices, _with_span)
             return
