@@ -492,7 +492,17 @@ class Matcher:
 
         ``on_error="skip"``: a file that cannot be read or parsed is reported with a warning and has no
         hits instead of ending the scan (``packing.pack_files``); the default raises, as the reference's
-        ``load_molecules`` would."""
+        ``load_molecules`` would.
+
+        Paths that all end in ``.emmpack`` are packed corpus files (``packing.write_corpus``) and go
+        through ``scan_corpus`` instead: no text is parsed."""
+        from .packing import is_corpus
+        paths = list(paths)
+        if paths and all(is_corpus(p) for p in paths):
+            if queue is not None or devices is not None:
+                raise ValueError("packed corpus files are scanned by one process on one device: shard the corpus files")
+            yield from self.scan_corpus(paths, chunk_size, with_batch=with_batch)
+            return
         if devices is not None and len(list(devices)) > 0 and not (len(list(devices)) == 1 and list(devices)[0] == self.device):
             yield from self._scan_devices(paths, list(devices), chunk_size, threads, with_batch, on_error)
             return
@@ -565,6 +575,36 @@ class Matcher:
                     lane[0].download(stream=lane[1])
                 except EngineError:
                     pass
+
+    def scan_corpus(self, corpus_paths: Sequence[os.PathLike], chunk_size: int = 4096, with_batch: bool = False):
+        """Screen packed corpus files (``packing.write_corpus``: structures parsed and packed once, kept
+        as the raw columns of the upload): a generator of ``(query_ids, header_ids, records)`` per chunk of
+        ``chunk_size`` structures, as ``scan_files`` yields them for text files.  The file is mapped and
+        its kinds classified for this matcher's library on a background thread while the previous chunk
+        is on the device; nothing is parsed (at > 10^4 structures/s the text parse is the
+        wall)."""
+        import concurrent.futures
+        from .packing import read_corpus, slice_batch
+        if not self._active_sizes():
+            return
+        engine = self._ensure_engine()
+        corpus_paths = [os.fspath(p) for p in corpus_paths]
+
+        def chunks():
+            with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
+                pending = pool.submit(read_corpus, corpus_paths[0], engine.compiled) if corpus_paths else None
+                for k in range(len(corpus_paths)):
+                    batch, ids = pending.result()
+                    pending = pool.submit(read_corpus, corpus_paths[k + 1], engine.compiled) if k + 1 < len(corpus_paths) else None
+                    headers = batch.header_ids
+                    for lo in range(0, batch.n_structures, chunk_size):
+                        hi = min(lo + chunk_size, batch.n_structures)
+                        whole = lo == 0 and hi == batch.n_structures
+                        yield (batch if whole else slice_batch(batch, lo, hi)), ids[lo:hi], headers[lo:hi]
+
+        for batch, ids, headers in chunks():
+            records = self._search(batch)
+            yield (ids, headers, records) + ((batch,) if with_batch else ())
 
     def _scan_devices(self, paths, devices: List[int], chunk_size: int, threads: int, with_batch: bool,
                       on_error: str = "raise"):
@@ -665,11 +705,13 @@ class Matcher:
         if header:
             emit(writer.header().encode())
         n_rows = 0
+        from .packing import is_corpus
+        stored_ids = bool(paths) and all(is_corpus(p) for p in paths)       # corpus files carry their query ids
         for chunk, _, records, batch in self.scan_files(paths, chunk_size, threads, queue, with_batch=True, devices=devices,
                                                         on_error=on_error):
             selection = writer.select(records)
             n_rows += len(selection[0])
-            emit(writer.format(records, batch.table, [stems[p] for p in chunk], selection))
+            emit(writer.format(records, batch.table, list(chunk) if stored_ids else [stems[p] for p in chunk], selection))
         return n_rows
 
     def run_to_tsv(self, molecules: List[Molecule], file: IO[str], header: bool = True,

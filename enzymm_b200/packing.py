@@ -17,7 +17,8 @@ from .engine import PackedBatch
 from .library import CompiledLibrary
 from .structures import Molecule, _Columns, _NativeBatch, _native_lib, _native_view
 
-__all__ = ["residue_ordinals", "pack_molecules", "pack_files", "chain_codes"]
+__all__ = ["residue_ordinals", "pack_molecules", "pack_files", "chain_codes", "write_corpus", "read_corpus",
+           "slice_batch", "is_corpus", "CORPUS_SUFFIX"]
 
 
 def chain_codes(col: np.ndarray) -> np.ndarray:
@@ -266,3 +267,185 @@ def _packed_from_handle(lib, handle, library: CompiledLibrary, with_chain: bool)
                                grab(c.res_key, np.uint64, int(res_off[-1])), grab(c.residue_count, np.int32, nf),
                                atom_id, owner)
     return batch, ids
+
+
+# ---- packed corpus files -------------------------------------------------------------------------
+# "at > 10^4 structures/s the text parse is the wall" -- a corpus that is screened more
+# than once (another template library, other thresholds) is parsed ONCE into the columns the upload
+# wants and kept in a file that is mapped, not read: one header, then the raw arrays of
+# ``emm_pdb_packed``.  What is stored is independent of any template library: per atom its KIND
+# (residue name, atom name), not its typing class; ``read_corpus`` classifies the few hundred kinds
+# through the library at hand and expands them with one array lookup.
+
+CORPUS_SUFFIX = ".emmpack"
+_CORPUS_MAGIC = b"EMMPACK1"
+_CORPUS_ARRAYS = ("atom_off", "xyz", "kind", "residue", "bfactor", "chain", "atom_id", "kind_names", "header_id",
+                  "res_off", "res_key", "residue_count", "name_off", "name_blob")
+
+
+def is_corpus(path) -> bool:
+    return os.fspath(path).endswith(CORPUS_SUFFIX)
+
+
+def _query_ids(paths: Sequence[str]) -> List[str]:
+    """File stems, repeats numbered ``_2``, ``_3`` ... (``load_molecules``, ``jess_run.py:523-536``)."""
+    import collections
+    from pathlib import Path
+    seen = collections.defaultdict(int)
+    out = []
+    for p in paths:
+        stem = Path(p).stem
+        seen[stem] += 1
+        out.append(stem if seen[stem] == 1 else f"{stem}_{seen[stem]}")
+    return out
+
+
+def write_corpus(paths: Sequence[Union[str, os.PathLike]], out: Union[str, os.PathLike], threads: int = 0,
+                 use_author: bool = False, on_error: str = "raise", ids: Optional[Sequence[str]] = None) -> int:
+    """Parse and pack ``paths`` (PDB / mmCIF, gzip-compressed or not) on the native thread pool and write
+    the packed columns to ``out`` (conventionally ``*.emmpack``).  ``ids``: the query id of every
+    structure (default: the file stems, as ``load_molecules`` names them).  Returns the number of
+    structures written; with ``on_error="skip"`` an unreadable file is written as a structure without
+    atoms (``pack_files``)."""
+    import json
+    if on_error not in ("raise", "skip"):
+        raise ValueError(f"on_error must be 'raise' or 'skip', not {on_error!r}")
+    lib = _native_lib()
+    paths = [os.fspath(p) for p in paths]
+    names = list(ids) if ids is not None else _query_ids(paths)
+    if len(names) != len(paths):
+        raise ValueError("ids must name every path")
+    skip = on_error == "skip"
+    if not skip:
+        for p in paths:
+            if os.path.isdir(p):
+                raise IsADirectoryError(21, "Is a directory", p)
+            if not os.path.exists(p):
+                raise FileNotFoundError(2, "No such file or directory", p)
+    arr = (ctypes.c_char_p * max(len(paths), 1))(*[p.encode() for p in paths])
+    handle = ctypes.c_void_p()
+    n_threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1)
+    flags = (1 if use_author else 0) | (2 if skip else 0)
+    rc = lib.emm_pdb_pack_files_ex(arr, ctypes.c_int32(len(paths)), ctypes.c_int32(n_threads), ctypes.c_int32(flags),
+                                   ctypes.byref(handle))
+    if rc != 0:
+        raise ValueError(lib.emm_pdb_last_error().decode(errors="replace"))
+    owner = _NativeBatch(lib, handle)
+    c = _PdbPacked()
+    if lib.emm_pdb_batch_packed(handle, ctypes.byref(c)) != 0:
+        raise RuntimeError("emm_pdb_batch_packed failed")
+    if skip and paths:
+        status = np.zeros(len(paths), dtype=np.int32)
+        lib.emm_pdb_batch_file_status(handle, status.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(len(status)))
+        lib.emm_pdb_batch_file_message.restype = ctypes.c_char_p
+        lib.emm_pdb_batch_file_message.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+        for i in np.nonzero(status)[0]:
+            warnings.warn(f"skipped: {lib.emm_pdb_batch_file_message(handle, int(i)).decode(errors='replace')}")
+    n, nf = c.n_atoms, c.n_files
+    grab = lambda ptr, dtype, count: _native_view(owner, ptr, dtype, count)
+    res_off = grab(c.res_off, np.int64, nf + 1)
+    encoded = [s.encode("utf-8") for s in names]
+    name_off = np.zeros(nf + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in encoded], out=name_off[1:])
+    arrays = {
+        "atom_off": grab(c.atom_off, np.int64, nf + 1), "xyz": grab(c.xyz, np.float64, 3 * n).reshape(n, 3),
+        "kind": grab(c.kind, np.uint32, n), "residue": grab(c.residue, np.int32, n),
+        "bfactor": grab(c.bfactor, np.float32, n), "chain": grab(c.chain, np.uint16, n),
+        "atom_id": grab(c.atom_id, np.int32, n) if c.atom_id else None,
+        "kind_names": grab(c.kind_names, np.uint8, 8 * c.n_kinds).reshape(-1, 8),
+        "header_id": grab(c.header_id, np.uint8, 5 * nf).reshape(nf, 5),
+        "res_off": res_off, "res_key": grab(c.res_key, np.uint64, int(res_off[-1]) if nf else 0),
+        "residue_count": grab(c.residue_count, np.int32, nf),
+        "name_off": name_off, "name_blob": np.frombuffer(b"".join(encoded), dtype=np.uint8),
+    }
+    layout, offset = {}, 0
+    for key in _CORPUS_ARRAYS:
+        a = arrays[key]
+        if a is None:
+            continue
+        a = arrays[key] = np.ascontiguousarray(a)
+        layout[key] = {"dtype": a.dtype.str, "shape": list(a.shape), "offset": offset}
+        offset += (a.nbytes + 63) & ~63
+    header = json.dumps({"version": 1, "n_structures": int(nf), "n_atoms": int(n), "arrays": layout}).encode()
+    data_start = (16 + len(header) + 63) & ~63
+    tmp = os.fspath(out) + f".{os.getpid()}.tmp"
+    with open(tmp, "wb") as f:
+        f.write(_CORPUS_MAGIC)
+        f.write(np.uint64(len(header)).tobytes())
+        f.write(header)
+        for key, spec in layout.items():
+            f.seek(data_start + spec["offset"])
+            f.write(arrays[key].tobytes() if arrays[key].nbytes < (1 << 20) else arrays[key].data)
+        f.truncate(data_start + offset)
+    os.replace(tmp, os.fspath(out))
+    return int(nf)
+
+
+def read_corpus(path: Union[str, os.PathLike], library: CompiledLibrary, with_chain: bool = True
+                ) -> Tuple[PackedBatch, List[str]]:
+    """A corpus file -> ``(PackedBatch, query ids)`` for ``library``: the big columns are views of the
+    mapped file (page cache, no parse, no copy); the typing class column is expanded here from the
+    stored kinds.  ``batch.table`` carries what the results table needs, ``batch.header_ids`` the
+    HEADER idCodes."""
+    import json
+    import mmap
+    path = os.fspath(path)
+    with open(path, "rb") as f:
+        head = f.read(16)
+        if len(head) < 16 or head[:8] != _CORPUS_MAGIC:
+            raise ValueError(f"{path} is not a packed corpus (no {_CORPUS_MAGIC.decode()} header)")
+        n_header = int(np.frombuffer(head[8:], dtype=np.uint64)[0])
+        meta = json.loads(f.read(n_header).decode())
+        if meta.get("version") != 1:
+            raise ValueError(f"{path}: unsupported corpus version {meta.get('version')!r}")
+        data_start = (16 + n_header + 63) & ~63
+        size = os.fstat(f.fileno()).st_size
+        mapped = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) if size > data_start else None
+
+    def view(key):
+        spec = meta["arrays"].get(key)
+        if spec is None:
+            return None
+        count = int(np.prod(spec["shape"])) if spec["shape"] else 1
+        if count == 0:
+            return np.zeros(spec["shape"], dtype=np.dtype(spec["dtype"]))
+        end = data_start + spec["offset"] + count * np.dtype(spec["dtype"]).itemsize
+        if mapped is None or end > size:
+            raise ValueError(f"{path}: truncated corpus file")
+        return np.frombuffer(mapped, dtype=np.dtype(spec["dtype"]), count=count,
+                             offset=data_start + spec["offset"]).reshape(spec["shape"])
+
+    a = {key: view(key) for key in _CORPUS_ARRAYS}
+    names = a["kind_names"]
+    class_of_kind = np.zeros(max(len(names), 1), dtype=np.uint16)
+    for i, row in enumerate(names):
+        res = bytes(row[:4]).split(b"\0")[0].decode("ascii", "replace")
+        name = bytes(row[4:]).split(b"\0")[0].decode("ascii", "replace")
+        class_of_kind[i] = library.class_of(res, name)
+    klass = class_of_kind[a["kind"]] if len(a["kind"]) else np.zeros(0, dtype=np.uint16)
+    batch = PackedBatch(a["atom_off"], a["xyz"], klass, a["residue"], a["bfactor"], a["chain"] if with_chain else None,
+                        a["atom_id"])
+    from .tsv import TableColumns
+    batch.table = TableColumns(batch.atom_off, a["kind"], names, a["residue"], a["res_off"], a["res_key"],
+                               a["residue_count"], a["atom_id"], mapped)
+    batch.header_ids = [bytes(h).split(b"\0")[0].decode() or None for h in a["header_id"]]
+    batch.bad_files = {}
+    blob, off = a["name_blob"].tobytes(), a["name_off"]
+    ids = [blob[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(len(off) - 1)]
+    return batch, ids
+
+
+def slice_batch(batch: PackedBatch, lo: int, hi: int) -> PackedBatch:
+    """Structures ``[lo, hi)`` of a packed batch as a batch of their own (views, offsets rebased)."""
+    a0, a1 = int(batch.atom_off[lo]), int(batch.atom_off[hi])
+    cut = lambda col: None if col is None else col[a0:a1]
+    out = PackedBatch(batch.atom_off[lo:hi + 1] - a0, batch.xyz[a0:a1], batch.klass[a0:a1], batch.residue[a0:a1],
+                      cut(batch.bfactor), cut(batch.chain), cut(batch.atom_id))
+    table = getattr(batch, "table", None)
+    if table is not None:
+        from .tsv import TableColumns
+        r0, r1 = int(table.res_off[lo]), int(table.res_off[hi])
+        out.table = TableColumns(out.atom_off, table.kind[a0:a1], table.kind_names, out.residue,
+                                 table.res_off[lo:hi + 1] - r0, table.res_key[r0:r1], table.residue_count[lo:hi],
+                                 out.atom_id, table._owner)
+    return out
