@@ -28,6 +28,7 @@ import subprocess
 import sys
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
@@ -91,3 +92,83 @@ def test_reference_test_files_with_placeholder_annotations(tmp_path):
         plus = [line[2:] for line in why.splitlines() if line.startswith("+ ")]
         assert len(minus) == len(plus) == 1, why
         assert minus[0].replace("\tnan\t", "\t-3.08424\t") == plus[0], why
+
+
+def test_reference_cli_over_the_shim_writes_the_native_table(tmp_path, mol_1amy, mol_af):
+    """The reference's unmodified command line (``enzymm._cli.main``, ``--skip-annotation``) over the shim -- device
+    call = oracle here -- writes, after its ``# Version`` line, exactly the table this repo's native writer
+    produces from the same hit records: files in, TSV out, two implementations of everything in between."""
+    import shutil
+    from conftest import GOLDEN
+    from enzymm_b200 import jess_run, template
+    from enzymm_b200.packing import pack_molecules
+    from enzymm_b200.tsv import TableWriter
+    from test_host_model import _oracle_records
+    ref = ROOT / "baseline" / "_ref" / "enzymm"
+    if not (ref / "jess_run.py").exists():
+        pytest.skip("baseline/_ref is absent: run __graft_entry__.build() where /root/reference exists")
+    tdir = tmp_path / "templates"
+    for size in ("3_residues", "4_residues", "5_residues"):
+        for entry in ("csa3d_0285", "csa3d_0045", "csa3d_0421", "csa3d_0415"):
+            src = ref / "jess_templates_20230210" / size / "results" / entry
+            if src.is_dir():
+                shutil.copytree(src, tdir / size / "results" / entry)
+    paths = [GOLDEN / "1AMY.pdb", GOLDEN / "AF-P0DUB6-F1-model_v4.pdb"]
+    for extra in ([], ["--unfiltered"], ["--skip-smaller-hits"]):
+        out = tmp_path / "cli.tsv"
+        run = subprocess.run([sys.executable, str(ROOT / "tools" / "run_reference_cli.py"), "--device", "oracle", "--",
+                              "-i", str(paths[0]), "-i", str(paths[1]), "-o", str(out), "-t", str(tdir), "--skip-annotation",
+                              "-n", "4"] + extra, capture_output=True, text=True, cwd=tmp_path, timeout=900)
+        assert run.returncode == 0, (run.stdout + run.stderr)[-2000:]
+        version, _, table = out.read_text().partition("\n")
+        assert version.startswith("# Version")
+        # the reference lists a template directory with an UNSORTED recursive glob (template.py:1490-1495: directory
+        # order), this repo's load_templates sorts; give both Matchers the same list
+        import glob
+        templates = [template.AnnotatedTemplate.load(Path(p), warn=False, with_annotations=False)
+                     for p in glob.glob(f"{tdir}/**/*.pdb", recursive=True)]
+        matcher = jess_run.Matcher(templates, filter_matches="--unfiltered" not in extra,
+                                   skip_smaller_hits="--skip-smaller-hits" in extra)
+        molecules = [mol_1amy, mol_af]
+        records = _oracle_records(matcher, molecules)
+        if "--skip-smaller-hits" in extra:
+            # what the device does with skip_mode (jess_run.py:951-958): size groups in descending order, a structure
+            # that holds a surviving hit is not searched with smaller templates -- the oracle records hold every group
+            from enzymm_b200.engine import HIT_PASS
+            keep, done = np.ones(len(records), dtype=bool), set()
+            for _, lo, hi in matcher._groups:
+                group = (records["template_index"] >= lo) & (records["template_index"] < hi)
+                keep &= ~(group & np.isin(records["structure"], list(done)))
+                done |= set(records["structure"][group & keep & ((records["flags"] & HIT_PASS) != 0)].tolist())
+            assert not keep.all()
+            records = records[keep]
+        writer = TableWriter(matcher, predict_correctness="--unfiltered" not in extra)
+        want = writer.header() + writer.format(records, pack_molecules(molecules, matcher._compile()).table,
+                                               ["1AMY", "AF-P0DUB6-F1-model_v4"]).decode()
+        assert table == want, extra
+        assert len(table.splitlines()) > 4
+
+
+
+def test_pythonpath_shim_resolves_pyjess_and_has_no_cpu_fallback(tmp_path):
+    """``shim/pyjess`` in front of ``PYTHONPATH`` is all it takes for the unmodified reference to import this
+    repo's stand-in; on a box without a GPU its command line then stops with the engine's loud error."""
+    import os
+    from conftest import GOLDEN
+    from enzymm_b200.engine import load_cdll
+    ref_root = ROOT / "baseline" / "_ref"
+    if not (ref_root / "enzymm" / "jess_run.py").exists():
+        pytest.skip("baseline/_ref is absent: run __graft_entry__.build() where /root/reference exists")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(ROOT / "shim"), str(ROOT), str(ref_root)]))
+    probe = subprocess.run([sys.executable, "-c", "import pyjess, enzymm.jess_run as j; "
+                            "print(pyjess.__file__); print(j.pyjess.Jess.__module__, j.pyjess.__version__)"],
+                           capture_output=True, text=True, cwd=tmp_path, env=env, timeout=300)
+    assert probe.returncode == 0, probe.stderr[-2000:]
+    assert str(ROOT / "shim" / "pyjess") in probe.stdout and "enzymm_b200.pyjess_api" in probe.stdout
+    if load_cdll().emm_device_count() > 0:
+        return
+    tdir = ref_root / "enzymm" / "jess_templates_20230210" / "5_residues" / "results" / "csa3d_0285"
+    run = subprocess.run([sys.executable, "-m", "enzymm", "-i", str(GOLDEN / "1AMY.pdb"), "-o", str(tmp_path / "o.tsv"),
+                          "-t", str(tdir), "--skip-annotation", "-n", "2"],
+                         capture_output=True, text=True, cwd=tmp_path, env=env, timeout=600)
+    assert run.returncode != 0 and "EMM_ERR_NO_DEVICE" in run.stderr and "no CPU fallback" in run.stderr
