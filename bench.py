@@ -252,6 +252,8 @@ def api_legs(workload, n_files: int, chunk: int = 1024):
       files_to_matches  load_molecules(paths) + Matcher.run(molecules): Molecule objects -> {Molecule: [Match]}
                         (the reference's own call sequence, _cli.py:217-248)
       files_to_tsv      Matcher.scan_to_tsv(paths, file): the reference's results table (_cli.py:270-316)
+    and, from the same files written once as a packed corpus (packing.write_corpus):
+      corpus_to_hits / corpus_to_tsv   the same two calls on the ``.emmpack`` file: no text is parsed
     """
     import io
     import shutil
@@ -302,6 +304,29 @@ def api_legs(workload, n_files: int, chunk: int = 1024):
             out["files_to_tsv"] = n_files / (time.perf_counter() - t0)
             out["tsv_rows"], out["tsv_bytes"] = rows, sink.tell()
         out["hits"] = hits
+        # the same files as a packed corpus (packing.write_corpus: parsed once, screened from the mapped columns);
+        # an extra of the extra -- a failure here costs only these keys
+        try:
+            from enzymm_b200.packing import write_corpus
+            table_from_text = sink.getvalue()
+            corpus = os.path.join(root, "all.emmpack")
+            t0 = time.perf_counter()
+            write_corpus(paths, corpus)
+            out["corpus_write"] = n_files / (time.perf_counter() - t0)
+            out["corpus_bytes"] = os.path.getsize(corpus)
+            corpus_hits = 0
+            for rep in range(2):
+                t0 = time.perf_counter()
+                corpus_hits = sum(len(records) for _, _, records in matcher.scan_files([corpus], chunk_size=4096))
+                out["corpus_to_hits"] = n_files / (time.perf_counter() - t0)
+            for rep in range(2):
+                sink = io.BytesIO()
+                t0 = time.perf_counter()
+                matcher.scan_to_tsv([corpus], sink, chunk_size=chunk)
+                out["corpus_to_tsv"] = n_files / (time.perf_counter() - t0)
+            out["corpus_equal"] = {"hits": corpus_hits == hits, "table": sink.getvalue() == table_from_text}
+        except Exception as exc:              # noqa: BLE001
+            out["corpus_error"] = f"{type(exc).__name__}: {exc}"[:300]
         matcher.close()
         return out
     finally:
