@@ -602,9 +602,51 @@ class Matcher:
                         whole = lo == 0 and hi == batch.n_structures
                         yield (batch if whole else slice_batch(batch, lo, hi)), ids[lo:hi], headers[lo:hi]
 
-        for batch, ids, headers in chunks():
-            records = self._search(batch)
-            yield (ids, headers, records) + ((batch,) if with_batch else ())
+        # two device sessions on two streams, as scan_files: chunk i+1 crosses PCIe while chunk i is searched
+        from .engine import Session
+        if self._scan_lanes is None:
+            self._scan_lanes = [[None, engine.new_stream()], [None, engine.new_stream()]]
+        lanes = self._scan_lanes
+
+        def collect(lane, batch, ids, headers):
+            extra = (batch,) if with_batch else ()
+            try:
+                return (ids, headers, lane[0].download(stream=lane[1])) + extra
+            except EngineError as exc:
+                if exc.status == -5 and exc.hits is not None:       # refused structures: keep the rest of the chunk
+                    warnings.warn(f"{len(exc.bad_structures)} structure(s) of a chunk were not searched: {exc}")
+                    return (ids, headers, exc.hits) + extra
+                if exc.status != -4:
+                    raise
+            return (ids, headers, self._search(batch)) + extra     # rare: rerun this chunk alone with a larger hit buffer
+
+        in_flight: collections.deque = collections.deque()          # (lane, batch, ids, headers)
+        try:
+            for ci, (batch, ids, headers) in enumerate(chunks()):
+                lane = lanes[ci % 2]
+                sess = lane[0]
+                need_hits = self._hit_capacity(batch.n_structures)
+                if sess is None or batch.n_atoms > sess.max_atoms or batch.n_structures > sess.max_structures \
+                        or need_hits > sess.hit_capacity:
+                    if sess is not None:
+                        sess.close()
+                    grow = lambda v, old: max(int(v * 1.1) + 1, old)
+                    sess = lane[0] = Session(engine.device_library,
+                                             grow(batch.n_atoms, sess.max_atoms if sess else 0),
+                                             grow(batch.n_structures, sess.max_structures if sess else 0), need_hits)
+                self._submit(sess, batch, stream=lane[1])
+                in_flight.append((lane, batch, ids, headers))
+                if len(in_flight) == 2:
+                    yield collect(*in_flight.popleft())
+            while in_flight:
+                yield collect(*in_flight.popleft())
+        finally:
+            while in_flight:                    # generator abandoned early: let the device finish, drop the hits
+                lane = in_flight.popleft()[0]
+                try:
+                    lane[0].download(stream=lane[1])
+                except EngineError:
+                    pass
 
     def _scan_devices(self, paths, devices: List[int], chunk_size: int, threads: int, with_batch: bool,
                       on_error: str = "raise"):

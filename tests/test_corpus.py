@@ -104,7 +104,7 @@ def test_scan_corpus_and_table_on_oracle_records(corpus, active_templates, monke
     matcher._compile()
     offsets = {}
 
-    def fake_search(self, batch):
+    def oracle_for(batch):
         # which structures of the corpus is this chunk? (by their first coordinates)
         sizes = np.diff(batch.atom_off).tolist()
         for start in range(len(molecules)):
@@ -113,17 +113,43 @@ def test_scan_corpus_and_table_on_oracle_records(corpus, active_templates, monke
                     np.array_equal(np.sort(m.xyz[:, 0]), np.sort(batch.xyz[int(batch.atom_off[k]):int(batch.atom_off[k + 1]), 0]))
                     for k, m in enumerate(window)):
                 offsets[len(offsets)] = start
-                return _oracle_records(self, window)
+                return _oracle_records(matcher, window)
         raise AssertionError("chunk does not match any window of the corpus")
 
-    monkeypatch.setattr(jess_run.Matcher, "_ensure_engine", lambda self: type("E", (), {"compiled": self._compile()})())
-    monkeypatch.setattr(jess_run.Matcher, "_search", fake_search)
+    class FakeSession:                                   # the device side of one lane: upload, run, download
+        created = []
+
+        def __init__(self, library, max_atoms, max_structures, hit_capacity):
+            self.max_atoms, self.max_structures, self.hit_capacity = max_atoms, max_structures, hit_capacity
+            self.batch, self.busy = None, False
+            FakeSession.created.append(self)
+
+        def upload(self, batch, stream=0):
+            assert not self.busy, "a lane was reused before its chunk was collected"
+            assert batch.n_atoms <= self.max_atoms and batch.n_structures <= self.max_structures
+            self.batch, self.busy = batch, True
+
+        def run(self, **params):
+            assert params["skip_mode"] == 0 and params["template_end"] == len(matcher._ordered)
+
+        def download(self, stream=0):
+            self.busy = False
+            return oracle_for(self.batch)
+
+        def close(self):
+            pass
+
+    import enzymm_b200.engine as engine_module
+    fake_engine = type("E", (), {"compiled": matcher._compile(), "device_library": None, "new_stream": lambda self: 7})()
+    monkeypatch.setattr(jess_run.Matcher, "_ensure_engine", lambda self: fake_engine)
+    monkeypatch.setattr(engine_module, "Session", FakeSession)
     seen_ids, all_records = [], []
     for ids, headers, records in matcher.scan_files([out], chunk_size=5):
         assert len(ids) == len(headers) <= 5
         seen_ids += ids
         all_records.append(records)
     assert seen_ids == [m.id for m in molecules] and list(offsets.values()) == [0, 5, 10]
+    assert 2 <= len(FakeSession.created) <= 3                      # two lanes (one may be re-created to grow)
     assert sum(len(r) for r in all_records) > 10
     text = io.StringIO()
     n_rows = matcher.scan_to_tsv([out], text, chunk_size=len(molecules))
