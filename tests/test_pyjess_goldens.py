@@ -41,3 +41,24 @@ def test_oracle_reproduces_harvested_pyjess_hits(active_templates):
             m = len(active_templates[ti])
             assert [int(serial[a]) for a in raw[si, ti]["atoms"][:m]] == [a[0] for a in h["atoms"]], (entry["id"], h["template"])
             assert float(raw[si, ti]["rmsd"]) == pytest.approx(h["rmsd"], abs=1e-6)
+
+
+@pytest.mark.skipif(not HARVEST.exists(), reason="no harvested PyJess goldens (tools/harvest_pyjess_goldens.py)")
+def test_mmcif_reader_reads_what_pyjess_reads(mol_1amy):
+    """The harvest holds how the real ``pyjess.Molecule.load`` read an mmCIF rendering of 1AMY (two models,
+    auth_* items that differ from the label_* items), with and without ``use_author``."""
+    from test_cif_ingest import to_cif
+    with gzip.open(HARVEST, "rt") as handle:
+        data = json.load(handle)
+    if "mmcif" not in data:
+        pytest.skip(f"the harvest has no mmCIF section ({data.get('mmcif_error', 'older tool')})")
+    text = to_cif(mol_1amy, "1AMY", models=(1, 2))
+    for key, use_author in (("label", False), ("auth", True)):
+        want = data["mmcif"][key]
+        got = Molecule.loads(text, use_author=use_author)
+        assert len(got) == want["n_atoms"]
+        for i, (serial, name, resname, chain, resnum, x, y, z) in enumerate(want["atoms"]):
+            atom = got.atom(i)
+            assert (atom.serial, atom.name, atom.residue_name, atom.chain_id, atom.residue_number) == \
+                   (serial, name, resname, chain, resnum), (key, i)
+            assert (atom.x, atom.y, atom.z) == (x, y, z)

@@ -12,6 +12,8 @@ best_match=True, ignore_chain=True)`` per effective-size group at the default th
 records every hit: template id, matched atoms in template order (serial, name, residue name, chain,
 residue number), ``rmsd`` and ``log_evalue``.  That pins what no vector in the reference's tests
 pins: the reading of ``match_mode 1``, ``<=`` at the thresholds, ``log_evalue``.
+It also records how the real ``Molecule.load`` reads an mmCIF rendering of 1AMY (``use_author`` both ways),
+which pins this repo's mmCIF reader (``tests/test_pyjess_goldens.py``).
 """
 import gzip
 import json
@@ -61,6 +63,28 @@ def main():
                                        for a in hit.atoms(transform=False)]})
         out["structures"].append({"id": path.stem, "n_atoms": len(molecule), "hits": hits})
         print(path.stem, len(hits), file=sys.stderr)
+    # how PyJess reads mmCIF (this repo's choices -- first model, label_* identifiers unless use_author, where
+    # '.' falls back to auth_* -- are unpinned: the reference holds no mmCIF input): an mmCIF rendering of
+    # 1AMY whose auth_* items differ from its label_* items, through the real Molecule.load both ways
+    sys.path.insert(0, str(ROOT / "tests"))
+    try:
+        from test_cif_ingest import to_cif
+        from enzymm_b200.structures import Molecule as OwnMolecule
+        own = OwnMolecule.load(ROOT / "tests" / "golden" / "1AMY.pdb")
+        cif_path = Path(work) / "1AMY.cif"
+        cif_path.write_text(to_cif(own, "1AMY", models=(1, 2)))
+        out["mmcif"] = {}
+        for use_author in (False, True):
+            try:
+                mol = pyjess.Molecule.load(str(cif_path), format="detect", use_author=use_author)
+            except TypeError:                        # a PyJess without the keyword
+                mol = pyjess.Molecule.load(str(cif_path))
+            out["mmcif"]["auth" if use_author else "label"] = {
+                "id": mol.id, "n_atoms": len(mol),
+                "atoms": [[a.serial, a.name, a.residue_name, a.chain_id, a.residue_number, a.x, a.y, a.z]
+                          for a in list(mol)[:200]]}
+    except Exception as exc:                        # noqa: BLE001 -- e.g. a PyJess built without gemmi
+        out["mmcif_error"] = f"{type(exc).__name__}: {exc}"
     target = ROOT / "tests" / "golden" / "pyjess_hits.json.gz"
     with gzip.open(target, "wt") as handle:
         json.dump(out, handle)
