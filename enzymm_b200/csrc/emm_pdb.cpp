@@ -454,7 +454,15 @@ void regroup_file(const PackedCols &c, int64_t base, int64_t n, std::vector<uint
 
 // ---- mmCIF ----------------------------------------------------------------------------------------
 
-inline bool cif_space(char ch) { return ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n'; }
+struct CifSpaceTable {
+    bool is[256];
+    constexpr CifSpaceTable() : is()
+    {
+        for (int i = 0; i < 256; ++i) is[i] = i == ' ' || i == '\t' || i == '\r' || i == '\n';
+    }
+};
+constexpr CifSpaceTable kCifSpace;
+EMM_HOT bool cif_space(char ch) { return kCifSpace.is[(unsigned char)ch]; }
 
 // CIF 1.1 tokens: bare words, '...' / "..." (the closing quote is the one followed by white space),
 // ;-delimited text fields, # comments.
@@ -478,7 +486,7 @@ struct CifTok {
 struct CifScanner {
     const char *begin, *p, *end;
     CifScanner(const char *text, int64_t len) : begin(text), p(text), end(text + len) {}
-    bool next(CifTok &t)
+    EMM_HOT bool next(CifTok &t)
     {
         for (;;) {
             while (p < end && cif_space(*p)) ++p;
@@ -639,12 +647,16 @@ int64_t cif_each_atom(const char *text, int64_t len, int flags, char header_id[5
             int64_t n = 0;
             CifTok model0{nullptr, 0, false};
             const size_t ncols = cols.size();
+            for (int k = 0; k < C_N; ++k) row[k] = CifTok{nullptr, 0, false};      // mapped entries are rewritten by every row
             while (more) {
-                // a row starts unless the token ends the loop
-                if (!t.quoted && (t.is("loop_") || t.starts("data_") || t.starts("save_") || t.is("stop_") || t.is("global_") ||
-                                  (t.len > 0 && t.p[0] == '_')))
-                    break;
-                for (int k = 0; k < C_N; ++k) row[k] = CifTok{nullptr, 0, false};
+                // a row starts unless the token ends the loop: a tag or one of the reserved words
+                if (!t.quoted && t.len > 0) {
+                    const char c0 = t.p[0];
+                    if (c0 == '_') break;
+                    if ((c0 == 'l' || c0 == 'L' || c0 == 'd' || c0 == 'D' || c0 == 's' || c0 == 'S' || c0 == 'g' || c0 == 'G') &&
+                        (t.is("loop_") || t.starts("data_") || t.starts("save_") || t.is("stop_") || t.is("global_")))
+                        break;
+                }
                 for (size_t j = 0; j < ncols; ++j) {
                     if (!more) { t_error = "_atom_site loop ends in the middle of a row"; return -1; }
                     if (cols[j] >= 0) row[cols[j]] = t;
@@ -683,41 +695,48 @@ inline void unpack_field(uint32_t v, char *dst, int width)
     for (int i = 0; i < width; ++i) dst[i] = (char)((v >> (8 * i)) & 0xffu);
 }
 
+inline void cif_store(const AtomRec &a, const Columns &c, int64_t i)
+{
+    c.serial[i] = a.serial; c.resnum[i] = a.resnum;
+    c.xyz[3 * i] = a.x; c.xyz[3 * i + 1] = a.y; c.xyz[3 * i + 2] = a.z;
+    c.occupancy[i] = a.occ; c.bfactor[i] = a.bf;
+    unpack_field(a.name, c.name + 4 * i, 4);
+    unpack_field(a.resname, c.resname + 4 * i, 4);
+    unpack_field(a.chain, c.chain + 2 * i, 2);
+    unpack_field(a.element, c.element + 2 * i, 2);
+    memset(c.segment + 4 * i, 0, 4);
+    c.altloc[i] = a.altloc; c.icode[i] = a.icode; c.charge[i] = a.charge;
+}
+
 int64_t cif_parse_into(const char *text, int64_t len, int flags, const Columns &c, int64_t base, int64_t capacity, char header_id[5])
 {
     int64_t n = 0;
     return cif_each_atom(text, len, flags, header_id, [&](const AtomRec &a) {
         if (n >= capacity) { t_error = "atom capacity exceeded"; return false; }
-        const int64_t i = base + n++;
-        c.serial[i] = a.serial; c.resnum[i] = a.resnum;
-        c.xyz[3 * i] = a.x; c.xyz[3 * i + 1] = a.y; c.xyz[3 * i + 2] = a.z;
-        c.occupancy[i] = a.occ; c.bfactor[i] = a.bf;
-        unpack_field(a.name, c.name + 4 * i, 4);
-        unpack_field(a.resname, c.resname + 4 * i, 4);
-        unpack_field(a.chain, c.chain + 2 * i, 2);
-        unpack_field(a.element, c.element + 2 * i, 2);
-        memset(c.segment + 4 * i, 0, 4);
-        c.altloc[i] = a.altloc; c.icode[i] = a.icode; c.charge[i] = a.charge;
+        cif_store(a, c, base + n++);
         return true;
     });
 }
 
-int64_t cif_pack_into(const char *text, int64_t len, int flags, const PackedCols &c, int64_t base, int64_t capacity,
-                      KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5], int32_t *residue_count)
+// The readers that take paths tokenise an mmCIF text ONCE: the rows are collected here, counted, and
+// the columns filled from the records (the text API counts and parses in two calls, so it reads twice).
+int64_t cif_collect(const char *text, int64_t len, int flags, char header_id[5], std::vector<AtomRec> &atoms)
+{
+    atoms.clear();
+    return cif_each_atom(text, len, flags, header_id, [&](const AtomRec &a) { atoms.push_back(a); return true; });
+}
+
+void cif_fill_packed(const std::vector<AtomRec> &atoms, const PackedCols &c, KindTable &kinds, std::vector<uint64_t> &run_keys,
+                     bool *split, int32_t *residue_count)
 {
     std::vector<int32_t> counted;
     PackState state(c, kinds, run_keys, counted);
-    *split = false;
-    int64_t n = 0;
-    const int64_t got = cif_each_atom(text, len, flags, header_id, [&](const AtomRec &a) {
-        if (n >= capacity) { t_error = "atom capacity exceeded"; return false; }
-        const int64_t i = base + n++;
+    for (size_t i = 0; i < atoms.size(); ++i) {
+        const AtomRec &a = atoms[i];
         c.xyz[3 * i] = a.x; c.xyz[3 * i + 1] = a.y; c.xyz[3 * i + 2] = a.z;
-        state.add(i, a.name, a.resname, a.chain, a.resnum, (float)a.bf);
-        return true;
-    });
+        state.add((int64_t)i, a.name, a.resname, a.chain, a.resnum, (float)a.bf);
+    }
     state.finish(split, residue_count);
-    return got;
 }
 
 // ---- either format --------------------------------------------------------------------------------
@@ -733,14 +752,6 @@ int64_t parse_into(const char *text, int64_t len, int flags, const Columns &c, i
 {
     return looks_like_cif(text, len) ? cif_parse_into(text, len, flags, c, base, capacity, header_id)
                                      : pdb_parse_into(text, len, c, base, capacity, header_id);
-}
-
-int64_t pack_into(const char *text, int64_t len, int flags, const PackedCols &c, int64_t base, int64_t capacity,
-                  KindTable &kinds, std::vector<uint64_t> &run_keys, bool *split, char header_id[5], int32_t *residue_count)
-{
-    return looks_like_cif(text, len)
-               ? cif_pack_into(text, len, flags, c, base, capacity, kinds, run_keys, split, header_id, residue_count)
-               : pdb_pack_into(text, len, c, base, capacity, kinds, run_keys, split, header_id, residue_count);
 }
 
 // ---- gzip -----------------------------------------------------------------------------------------
@@ -973,6 +984,9 @@ int emm_pdb_load_files_ex(const char *const *paths, int32_t n_files, int32_t n_t
     std::vector<int64_t> counts((size_t)n_files, 0);
     std::vector<int> errs((size_t)n_files, 0);
     std::vector<std::string> messages((size_t)n_files);
+    std::vector<char> is_cif((size_t)n_files, 0);
+    std::vector<std::vector<AtomRec>> cif_atoms((size_t)n_files);
+    b->header_id.assign(5 * (size_t)n_files, 0);
     if (n_threads < 1) n_threads = 1;
     n_threads = std::min<int32_t>(n_threads, std::max(n_files, 1));
     {
@@ -980,7 +994,15 @@ int emm_pdb_load_files_ex(const char *const *paths, int32_t n_files, int32_t n_t
         auto work = [&]() {
             for (int i; (i = next.fetch_add(1)) < n_files;) {
                 if (read_file(paths[i], texts[(size_t)i], &errs[(size_t)i])) {
-                    counts[(size_t)i] = count_atoms(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size(), flags);
+                    std::string &text = texts[(size_t)i];
+                    if (looks_like_cif(text.data(), (int64_t)text.size())) {
+                        is_cif[(size_t)i] = 1;
+                        counts[(size_t)i] = cif_collect(text.data(), (int64_t)text.size(), flags, &b->header_id[5 * (size_t)i],
+                                                        cif_atoms[(size_t)i]);
+                        std::string().swap(text);                       // the records are all pass 2 needs
+                    } else {
+                        counts[(size_t)i] = pdb_count_atoms(text.data(), (int64_t)text.size());
+                    }
                     if (counts[(size_t)i] < 0) { counts[(size_t)i] = 0; errs[(size_t)i] = 3; messages[(size_t)i] = t_error; }
                 }
             }
@@ -1004,15 +1026,20 @@ int emm_pdb_load_files_ex(const char *const *paths, int32_t n_files, int32_t n_t
     b->serial.resize(n); b->resnum.resize(n); b->name.resize(4 * n); b->altloc.resize(n); b->resname.resize(4 * n);
     b->chain.resize(2 * n); b->icode.resize(n); b->segment.resize(4 * n); b->element.resize(2 * n);
     b->xyz.resize(3 * n); b->occupancy.resize(n); b->bfactor.resize(n); b->charge.resize(n);
-    b->header_id.assign(5 * (size_t)n_files, 0);
     Columns c{b->serial.data(), b->name.data(), b->altloc.data(), b->resname.data(), b->chain.data(), b->resnum.data(),
               b->icode.data(), b->xyz.data(), b->occupancy.data(), b->bfactor.data(), b->segment.data(),
               b->element.data(), b->charge.data()};
     std::atomic<int> next(0), failed(-1);
     auto work = [&]() {
         for (int i; (i = next.fetch_add(1)) < n_files;) {
-            const int64_t got = parse_into(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size(), flags, c,
-                                           b->atom_off[(size_t)i], counts[(size_t)i], &b->header_id[5 * (size_t)i]);
+            if (is_cif[(size_t)i]) {
+                std::vector<AtomRec> &atoms = cif_atoms[(size_t)i];
+                for (size_t a = 0; a < atoms.size(); ++a) cif_store(atoms[a], c, b->atom_off[(size_t)i] + (int64_t)a);
+                std::vector<AtomRec>().swap(atoms);
+                continue;
+            }
+            const int64_t got = pdb_parse_into(texts[(size_t)i].data(), (int64_t)texts[(size_t)i].size(), c,
+                                               b->atom_off[(size_t)i], counts[(size_t)i], &b->header_id[5 * (size_t)i]);
             if (got != counts[(size_t)i]) { messages[(size_t)i] = t_error; failed.store(i); }
         }
     };
@@ -1147,6 +1174,7 @@ int emm_pdb_pack_files_ex(const char *const *paths, int32_t n_files, int32_t n_t
             KindTable kinds;
             std::vector<uint64_t> run_keys;
             std::vector<char> text, inflated;
+            std::vector<AtomRec> cif_atoms;
             for (int i; (i = next.fetch_add(1)) < n_files;) {
                 const size_t f = (size_t)i;
                 int64_t len = 0;
@@ -1157,14 +1185,19 @@ int emm_pdb_pack_files_ex(const char *const *paths, int32_t n_files, int32_t n_t
                     data = inflated.data();
                 }
                 FileBlock &blk = blocks[f];
-                const int64_t count = count_atoms(data, len, flags);
+                const bool cif = looks_like_cif(data, len);
+                const int64_t count = cif ? cif_collect(data, len, flags, &b->header_id[5 * f], cif_atoms) : pdb_count_atoms(data, len);
                 if (count < 0) { messages[f] = t_error; errs[f] = 3; continue; }
                 blk.allocate(count);
                 kinds.clear();
                 const PackedCols c{blk.xyz, blk.kind, blk.residue, blk.bfactor, blk.chain};
-                const int64_t got = pack_into(data, len, flags, c, 0, count, kinds, run_keys, &blk.split, &b->header_id[5 * f],
-                                              &blk.residue_count);
-                if (got != count) { messages[f] = t_error; errs[f] = 3; continue; }
+                if (cif) {
+                    cif_fill_packed(cif_atoms, c, kinds, run_keys, &blk.split, &blk.residue_count);
+                } else {
+                    const int64_t got = pdb_pack_into(data, len, c, 0, count, kinds, run_keys, &blk.split, &b->header_id[5 * f],
+                                                      &blk.residue_count);
+                    if (got != count) { messages[f] = t_error; errs[f] = 3; continue; }
+                }
                 blk.kinds = kinds.keys;
                 if (blk.split) {
                     blk.atom_id.reset(new int32_t[(size_t)std::max<int64_t>(count, 1)]);
