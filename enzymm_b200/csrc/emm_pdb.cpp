@@ -556,7 +556,7 @@ struct AtomRec {
     int8_t charge;
 };
 
-inline uint32_t cif_pack(const CifTok &t, int width)
+EMM_HOT uint32_t cif_pack(const CifTok &t, int width)
 {
     uint32_t v = 0;
     if (t.p && !t.null())
@@ -564,7 +564,7 @@ inline uint32_t cif_pack(const CifTok &t, int width)
     return v;
 }
 
-inline bool cif_real(const CifTok &t, double *out, bool optional)
+EMM_HOT bool cif_real(const CifTok &t, double *out, bool optional)
 {
     if (!t.p || t.null() || t.len == 0) { *out = 0.0; return optional; }
     if (fast_real(t.p, t.p + t.len, out)) return true;
@@ -578,7 +578,7 @@ inline bool cif_real(const CifTok &t, double *out, bool optional)
     return stop != buf && *stop == 0;
 }
 
-inline bool cif_int(const CifTok &t, int32_t *out)
+EMM_HOT bool cif_int(const CifTok &t, int32_t *out)
 {
     return t.p && !t.null() && t.len > 0 && fast_int(t.p, t.p + t.len, out);
 }
