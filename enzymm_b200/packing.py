@@ -220,8 +220,6 @@ def pack_files(paths: Sequence[Union[str, os.PathLike]], library: CompiledLibrar
     if skip and paths:
         status = np.zeros(len(paths), dtype=np.int32)
         lib.emm_pdb_batch_file_status(handle, status.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(len(status)))
-        lib.emm_pdb_batch_file_message.restype = ctypes.c_char_p
-        lib.emm_pdb_batch_file_message.argtypes = [ctypes.c_void_p, ctypes.c_int32]
         for i in np.nonzero(status)[0]:
             bad[int(i)] = lib.emm_pdb_batch_file_message(handle, int(i)).decode(errors="replace")
             warnings.warn(f"skipped: {bad[int(i)]}")
@@ -337,8 +335,6 @@ def write_corpus(paths: Sequence[Union[str, os.PathLike]], out: Union[str, os.Pa
     if skip and paths:
         status = np.zeros(len(paths), dtype=np.int32)
         lib.emm_pdb_batch_file_status(handle, status.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(len(status)))
-        lib.emm_pdb_batch_file_message.restype = ctypes.c_char_p
-        lib.emm_pdb_batch_file_message.argtypes = [ctypes.c_void_p, ctypes.c_int32]
         for i in np.nonzero(status)[0]:
             warnings.warn(f"skipped: {lib.emm_pdb_batch_file_message(handle, int(i)).decode(errors='replace')}")
     n, nf = c.n_atoms, c.n_files
@@ -369,15 +365,19 @@ def write_corpus(paths: Sequence[Union[str, os.PathLike]], out: Union[str, os.Pa
     header = json.dumps({"version": 1, "n_structures": int(nf), "n_atoms": int(n), "arrays": layout}).encode()
     data_start = (16 + len(header) + 63) & ~63
     tmp = os.fspath(out) + f".{os.getpid()}.tmp"
-    with open(tmp, "wb") as f:
-        f.write(_CORPUS_MAGIC)
-        f.write(np.uint64(len(header)).tobytes())
-        f.write(header)
-        for key, spec in layout.items():
-            f.seek(data_start + spec["offset"])
-            f.write(arrays[key].tobytes() if arrays[key].nbytes < (1 << 20) else arrays[key].data)
-        f.truncate(data_start + offset)
-    os.replace(tmp, os.fspath(out))
+    try:
+        with open(tmp, "wb") as f:
+            f.write(_CORPUS_MAGIC)
+            f.write(np.uint64(len(header)).tobytes())
+            f.write(header)
+            for key, spec in layout.items():
+                f.seek(data_start + spec["offset"])
+                f.write(arrays[key].tobytes() if arrays[key].nbytes < (1 << 20) else arrays[key].data)
+            f.truncate(data_start + offset)
+        os.replace(tmp, os.fspath(out))
+    finally:
+        if os.path.exists(tmp):                      # a write that failed half way leaves nothing behind
+            os.unlink(tmp)
     return int(nf)
 
 

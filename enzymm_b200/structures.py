@@ -241,6 +241,8 @@ def _native_lib():
         lib.emm_pdb_last_error.restype = ctypes.c_char_p
         lib.emm_pdb_batch_free.argtypes = [ctypes.c_void_p]
         lib.emm_pdb_batch_free.restype = None
+        lib.emm_pdb_batch_file_message.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+        lib.emm_pdb_batch_file_message.restype = ctypes.c_char_p
         _native = lib
     return _native
 
