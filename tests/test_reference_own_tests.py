@@ -147,6 +147,19 @@ def test_reference_cli_over_the_shim_writes_the_native_table(tmp_path, mol_1amy,
                                                ["1AMY", "AF-P0DUB6-F1-model_v4"]).decode()
         assert table == want, extra
         assert len(table.splitlines()) > 4
+    # and the same command line reads an mmCIF rendering of the structure through the shim's Molecule.load
+    from test_cif_ingest import to_cif
+    (tmp_path / "cif").mkdir()
+    (tmp_path / "cif" / "1AMY.cif").write_text(to_cif(mol_1amy, "1AMY"))
+    tables = []
+    for source in (paths[0], tmp_path / "cif" / "1AMY.cif"):
+        out = tmp_path / "one.tsv"
+        run = subprocess.run([sys.executable, str(ROOT / "tools" / "run_reference_cli.py"), "--device", "oracle", "--",
+                              "-i", str(source), "-o", str(out), "-t", str(tdir), "--skip-annotation", "-n", "2"],
+                             capture_output=True, text=True, cwd=tmp_path, timeout=900)
+        assert run.returncode == 0, (run.stdout + run.stderr)[-2000:]
+        tables.append(out.read_text())
+    assert tables[0] == tables[1] and len(tables[0].splitlines()) > 4
 
 
 
