@@ -499,9 +499,12 @@ class Matcher:
         from .packing import is_corpus
         paths = list(paths)
         if paths and all(is_corpus(p) for p in paths):
-            if queue is not None or devices is not None:
-                raise ValueError("packed corpus files are scanned by one process on one device: shard the corpus files")
-            yield from self.scan_corpus(paths, chunk_size, with_batch=with_batch)
+            if devices is not None and len(list(devices)) > 0 and not (len(list(devices)) == 1 and list(devices)[0] == self.device):
+                if queue is not None:
+                    raise ValueError("devices= and queue= are two ways to share one list: pass one of them")
+                yield from self._scan_devices(paths, list(devices), chunk_size, threads, with_batch, on_error, corpus=True)
+            else:
+                yield from self.scan_corpus(paths, chunk_size, with_batch=with_batch, queue=queue, _with_span=_with_span)
             return
         if devices is not None and len(list(devices)) > 0 and not (len(list(devices)) == 1 and list(devices)[0] == self.device):
             yield from self._scan_devices(paths, list(devices), chunk_size, threads, with_batch, on_error)
@@ -576,31 +579,57 @@ class Matcher:
                 except EngineError:
                     pass
 
-    def scan_corpus(self, corpus_paths: Sequence[os.PathLike], chunk_size: int = 4096, with_batch: bool = False):
+    @staticmethod
+    def corpus_plan(corpus_paths: Sequence[os.PathLike], chunk_size: int = 4096) -> List[Tuple[int, int, int, int]]:
+        """The chunks of a list of corpus files, in input order: ``(file index, first structure, one past the
+        last, position of the first structure in the whole list)`` -- what ``scan_corpus`` iterates over and
+        what a shared ``queue`` hands out (``ChunkQueue(len(plan), 1)``)."""
+        from .packing import Corpus
+        plan, start = [], 0
+        for k, path in enumerate(corpus_paths):
+            n = Corpus.size_of(path)
+            plan += [(k, lo, min(lo + chunk_size, n), start + lo) for lo in range(0, n, chunk_size)]
+            start += n
+        return plan
+
+    def scan_corpus(self, corpus_paths: Sequence[os.PathLike], chunk_size: int = 4096, with_batch: bool = False,
+                    queue=None, _with_span: bool = False):
         """Screen packed corpus files (``packing.write_corpus``: structures parsed and packed once, kept
         as the raw columns of the upload): a generator of ``(query_ids, header_ids, records)`` per chunk of
-        ``chunk_size`` structures, as ``scan_files`` yields them for text files.  The file is mapped and
-        its kinds classified for this matcher's library on a background thread while the previous chunk
-        is on the device; nothing is parsed (at > 10^4 structures/s the text parse is the
-        wall)."""
+        ``chunk_size`` structures, as ``scan_files`` yields them for text files.  The files are mapped;
+        a chunk's typing classes are expanded from the stored kinds for this matcher's library on a
+        background thread while the previous chunk is on the device; nothing is parsed (SURVEY.md 8f-2:
+        at > 10^4 structures/s the text parse is the wall).  ``queue``: an iterable of ``(i, j)`` index
+        ranges into ``corpus_plan(corpus_paths, chunk_size)`` shared by several workers or ranks
+        (``sharding.ChunkQueue(len(plan), 1)``), instead of the whole plan in order."""
         import concurrent.futures
-        from .packing import read_corpus, slice_batch
+        from .packing import Corpus
         if not self._active_sizes():
             return
         engine = self._ensure_engine()
         corpus_paths = [os.fspath(p) for p in corpus_paths]
+        plan = self.corpus_plan(corpus_paths, chunk_size)
+        order = (k for i, j in queue for k in range(i, j)) if queue is not None else iter(range(len(plan)))
+        opened: Dict[int, Corpus] = {}                    # at most two files stay mapped: this one and the next
+
+        def produce(index):
+            k, lo, hi, start = plan[index]
+            corpus = opened.get(k)
+            if corpus is None:
+                for stale in [f for f in opened if f < k - 1]:
+                    del opened[stale]
+                corpus = opened[k] = Corpus(corpus_paths[k])
+            return corpus.chunk(lo, hi, engine.compiled), corpus.ids(lo, hi), (start, start + hi - lo)
 
         def chunks():
             with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-                pending = pool.submit(read_corpus, corpus_paths[0], engine.compiled) if corpus_paths else None
-                for k in range(len(corpus_paths)):
-                    batch, ids = pending.result()
-                    pending = pool.submit(read_corpus, corpus_paths[k + 1], engine.compiled) if k + 1 < len(corpus_paths) else None
-                    headers = batch.header_ids
-                    for lo in range(0, batch.n_structures, chunk_size):
-                        hi = min(lo + chunk_size, batch.n_structures)
-                        whole = lo == 0 and hi == batch.n_structures
-                        yield (batch if whole else slice_batch(batch, lo, hi)), ids[lo:hi], headers[lo:hi]
+                first = next(order, None)
+                pending = pool.submit(produce, first) if first is not None else None
+                while pending is not None:
+                    batch, ids, span = pending.result()
+                    following = next(order, None)
+                    pending = pool.submit(produce, following) if following is not None else None
+                    yield batch, ids, span
 
         # two device sessions on two streams, as scan_files: chunk i+1 crosses PCIe while chunk i is searched
         from .engine import Session
@@ -608,8 +637,9 @@ class Matcher:
             self._scan_lanes = [[None, engine.new_stream()], [None, engine.new_stream()]]
         lanes = self._scan_lanes
 
-        def collect(lane, batch, ids, headers):
-            extra = (batch,) if with_batch else ()
+        def collect(lane, batch, ids, span):
+            headers = batch.header_ids
+            extra = ((batch,) if with_batch else ()) + ((span,) if _with_span else ())
             try:
                 return (ids, headers, lane[0].download(stream=lane[1])) + extra
             except EngineError as exc:
@@ -620,9 +650,9 @@ class Matcher:
                     raise
             return (ids, headers, self._search(batch)) + extra     # rare: rerun this chunk alone with a larger hit buffer
 
-        in_flight: collections.deque = collections.deque()          # (lane, batch, ids, headers)
+        in_flight: collections.deque = collections.deque()          # (lane, batch, ids, span)
         try:
-            for ci, (batch, ids, headers) in enumerate(chunks()):
+            for ci, (batch, ids, span) in enumerate(chunks()):
                 lane = lanes[ci % 2]
                 sess = lane[0]
                 need_hits = self._hit_capacity(batch.n_structures)
@@ -635,7 +665,7 @@ class Matcher:
                                              grow(batch.n_atoms, sess.max_atoms if sess else 0),
                                              grow(batch.n_structures, sess.max_structures if sess else 0), need_hits)
                 self._submit(sess, batch, stream=lane[1])
-                in_flight.append((lane, batch, ids, headers))
+                in_flight.append((lane, batch, ids, span))
                 if len(in_flight) == 2:
                     yield collect(*in_flight.popleft())
             while in_flight:
@@ -649,13 +679,18 @@ class Matcher:
                     pass
 
     def _scan_devices(self, paths, devices: List[int], chunk_size: int, threads: int, with_batch: bool,
-                      on_error: str = "raise"):
-        """``scan_files`` over several GPUs of this host from one process (see ``scan_files``)."""
+                      on_error: str = "raise", corpus: bool = False):
+        """``scan_files`` over several GPUs of this host from one process (see ``scan_files``).  ``corpus``:
+        the paths are packed corpus files and the workers share the chunk plan instead of the path list --
+        no text is parsed, so one process can keep every GPU of the box busy."""
         import queue as queue_module
         import threading
         paths = [os.fspath(p) for p in paths]
         self._compile()
-        spans = iter([(i, min(i + chunk_size, len(paths))) for i in range(0, len(paths), chunk_size)])
+        if corpus:
+            spans = iter([(i, i + 1) for i in range(len(self.corpus_plan(paths, chunk_size)))])
+        else:
+            spans = iter([(i, min(i + chunk_size, len(paths))) for i in range(0, len(paths), chunk_size)])
         lock = threading.Lock()
 
         class Shared:                           # one counter for all workers: dynamic hand-out of chunks
@@ -690,8 +725,10 @@ class Matcher:
                     child.__dict__.update(self.__dict__)
                     child.device, child._engine, child._scan_lanes, child._device_workers = device, None, None, {}
                     self._device_workers[(slot, device)] = child
-                for item in child.scan_files(paths, chunk_size, per_worker, queue=Shared(), with_batch=with_batch,
-                                             _with_span=True, on_error=on_error):
+                scan = child.scan_corpus(paths, chunk_size, with_batch=with_batch, queue=Shared(), _with_span=True) if corpus \
+                    else child.scan_files(paths, chunk_size, per_worker, queue=Shared(), with_batch=with_batch,
+                                          _with_span=True, on_error=on_error)
+                for item in scan:
                     if not hand_over(item):
                         break                   # closing the inner generator lets its device work finish
             except BaseException as exc:        # noqa: BLE001 -- surfaces in the consumer

@@ -18,7 +18,7 @@ from .library import CompiledLibrary
 from .structures import Molecule, _Columns, _NativeBatch, _native_lib, _native_view
 
 __all__ = ["residue_ordinals", "pack_molecules", "pack_files", "chain_codes", "write_corpus", "read_corpus",
-           "slice_batch", "is_corpus", "CORPUS_SUFFIX"]
+           "Corpus", "slice_batch", "is_corpus", "CORPUS_SUFFIX"]
 
 
 def chain_codes(col: np.ndarray) -> np.ndarray:
@@ -381,16 +381,41 @@ def write_corpus(paths: Sequence[Union[str, os.PathLike]], out: Union[str, os.Pa
     return int(nf)
 
 
-def read_corpus(path: Union[str, os.PathLike], library: CompiledLibrary, with_chain: bool = True
-                ) -> Tuple[PackedBatch, List[str]]:
-    """A corpus file -> ``(PackedBatch, query ids)`` for ``library``: the big columns are views of the
-    mapped file (page cache, no parse, no copy); the typing class column is expanded here from the
-    stored kinds.  ``batch.table`` carries what the results table needs, ``batch.header_ids`` the
-    HEADER idCodes."""
-    import json
-    import mmap
-    path = os.fspath(path)
-    with open(path, "rb") as f:
+class Corpus:
+    """One mapped corpus file.  ``chunk(lo, hi, library)`` gives the structures ``[lo, hi)`` as a
+    ``PackedBatch`` of their own -- views of the mapped columns with offsets rebased, the typing class
+    column expanded from the stored kinds for ``library`` -- so a large corpus is handed to the device
+    chunk by chunk without ever being classified, copied or even touched as a whole."""
+
+    def __init__(self, path: Union[str, os.PathLike]):
+        import mmap
+        self.path = path = os.fspath(path)
+        with open(path, "rb") as f:
+            meta, data_start = self._header(f, path)
+            size = os.fstat(f.fileno()).st_size
+            mapped = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) if size > data_start else None
+        self._mapped = mapped
+
+        def view(key):
+            spec = meta["arrays"].get(key)
+            if spec is None:
+                return None
+            count = int(np.prod(spec["shape"])) if spec["shape"] else 1
+            if count == 0:
+                return np.zeros(spec["shape"], dtype=np.dtype(spec["dtype"]))
+            end = data_start + spec["offset"] + count * np.dtype(spec["dtype"]).itemsize
+            if mapped is None or end > size:
+                raise ValueError(f"{path}: truncated corpus file")
+            return np.frombuffer(mapped, dtype=np.dtype(spec["dtype"]), count=count,
+                                 offset=data_start + spec["offset"]).reshape(spec["shape"])
+
+        self._a = {key: view(key) for key in _CORPUS_ARRAYS}
+        self.n_structures = len(self._a["atom_off"]) - 1
+        self._classes = {}                       # id(library) -> (library, class of every stored kind)
+
+    @staticmethod
+    def _header(f, path):
+        import json
         head = f.read(16)
         if len(head) < 16 or head[:8] != _CORPUS_MAGIC:
             raise ValueError(f"{path} is not a packed corpus (no {_CORPUS_MAGIC.decode()} header)")
@@ -398,41 +423,60 @@ def read_corpus(path: Union[str, os.PathLike], library: CompiledLibrary, with_ch
         meta = json.loads(f.read(n_header).decode())
         if meta.get("version") != 1:
             raise ValueError(f"{path}: unsupported corpus version {meta.get('version')!r}")
-        data_start = (16 + n_header + 63) & ~63
-        size = os.fstat(f.fileno()).st_size
-        mapped = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) if size > data_start else None
+        return meta, (16 + n_header + 63) & ~63
 
-    def view(key):
-        spec = meta["arrays"].get(key)
-        if spec is None:
-            return None
-        count = int(np.prod(spec["shape"])) if spec["shape"] else 1
-        if count == 0:
-            return np.zeros(spec["shape"], dtype=np.dtype(spec["dtype"]))
-        end = data_start + spec["offset"] + count * np.dtype(spec["dtype"]).itemsize
-        if mapped is None or end > size:
-            raise ValueError(f"{path}: truncated corpus file")
-        return np.frombuffer(mapped, dtype=np.dtype(spec["dtype"]), count=count,
-                             offset=data_start + spec["offset"]).reshape(spec["shape"])
+    @classmethod
+    def size_of(cls, path: Union[str, os.PathLike]) -> int:
+        """Number of structures in a corpus file (reads its header only)."""
+        with open(os.fspath(path), "rb") as f:
+            return int(cls._header(f, os.fspath(path))[0]["n_structures"])
 
-    a = {key: view(key) for key in _CORPUS_ARRAYS}
-    names = a["kind_names"]
-    class_of_kind = np.zeros(max(len(names), 1), dtype=np.uint16)
-    for i, row in enumerate(names):
-        res = bytes(row[:4]).split(b"\0")[0].decode("ascii", "replace")
-        name = bytes(row[4:]).split(b"\0")[0].decode("ascii", "replace")
-        class_of_kind[i] = library.class_of(res, name)
-    klass = class_of_kind[a["kind"]] if len(a["kind"]) else np.zeros(0, dtype=np.uint16)
-    batch = PackedBatch(a["atom_off"], a["xyz"], klass, a["residue"], a["bfactor"], a["chain"] if with_chain else None,
-                        a["atom_id"])
-    from .tsv import TableColumns
-    batch.table = TableColumns(batch.atom_off, a["kind"], names, a["residue"], a["res_off"], a["res_key"],
-                               a["residue_count"], a["atom_id"], mapped)
-    batch.header_ids = [bytes(h).split(b"\0")[0].decode() or None for h in a["header_id"]]
-    batch.bad_files = {}
-    blob, off = a["name_blob"].tobytes(), a["name_off"]
-    ids = [blob[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(len(off) - 1)]
-    return batch, ids
+    def classes(self, library: CompiledLibrary) -> np.ndarray:
+        """Typing class of every stored kind for ``library`` (a few hundred look-ups, kept per library)."""
+        hit = self._classes.get(id(library))
+        if hit is not None and hit[0] is library:
+            return hit[1]
+        names = self._a["kind_names"]
+        class_of_kind = np.zeros(max(len(names), 1), dtype=np.uint16)
+        for i, row in enumerate(names):
+            res = bytes(row[:4]).split(b"\0")[0].decode("ascii", "replace")
+            name = bytes(row[4:]).split(b"\0")[0].decode("ascii", "replace")
+            class_of_kind[i] = library.class_of(res, name)
+        self._classes[id(library)] = (library, class_of_kind)
+        return class_of_kind
+
+    def ids(self, lo: int = 0, hi: Optional[int] = None) -> List[str]:
+        hi = self.n_structures if hi is None else hi
+        off = self._a["name_off"]
+        blob = self._a["name_blob"][int(off[lo]):int(off[hi])].tobytes()
+        base = int(off[lo])
+        return [blob[int(off[i]) - base:int(off[i + 1]) - base].decode("utf-8") for i in range(lo, hi)]
+
+    def chunk(self, lo: int, hi: int, library: CompiledLibrary, with_chain: bool = True) -> PackedBatch:
+        from .tsv import TableColumns
+        a = self._a
+        a0, a1 = int(a["atom_off"][lo]), int(a["atom_off"][hi])
+        kind = a["kind"][a0:a1]
+        klass = self.classes(library)[kind] if a1 > a0 else np.zeros(0, dtype=np.uint16)
+        atom_id = None if a["atom_id"] is None else a["atom_id"][a0:a1]
+        batch = PackedBatch(a["atom_off"][lo:hi + 1] - a0, a["xyz"][a0:a1], klass, a["residue"][a0:a1], a["bfactor"][a0:a1],
+                            a["chain"][a0:a1] if with_chain else None, atom_id)
+        r0, r1 = int(a["res_off"][lo]), int(a["res_off"][hi])
+        batch.table = TableColumns(batch.atom_off, kind, a["kind_names"], batch.residue, a["res_off"][lo:hi + 1] - r0,
+                                   a["res_key"][r0:r1], a["residue_count"][lo:hi], batch.atom_id, self._mapped)
+        batch.header_ids = [bytes(h).split(b"\0")[0].decode() or None for h in a["header_id"][lo:hi]]
+        batch.bad_files = {}
+        return batch
+
+
+def read_corpus(path: Union[str, os.PathLike], library: CompiledLibrary, with_chain: bool = True
+                ) -> Tuple[PackedBatch, List[str]]:
+    """A whole corpus file -> ``(PackedBatch, query ids)`` for ``library``: the big columns are views of the
+    mapped file (page cache, no parse, no copy); the typing class column is expanded here from the
+    stored kinds.  ``batch.table`` carries what the results table needs, ``batch.header_ids`` the
+    HEADER idCodes.  (``Corpus`` hands out chunks instead.)"""
+    corpus = Corpus(path)
+    return corpus.chunk(0, corpus.n_structures, library, with_chain), corpus.ids()
 
 
 def slice_batch(batch: PackedBatch, lo: int, hi: int) -> PackedBatch:

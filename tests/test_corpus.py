@@ -155,5 +155,22 @@ def test_scan_corpus_and_table_on_oracle_records(corpus, active_templates, monke
     n_rows = matcher.scan_to_tsv([out], text, chunk_size=len(molecules))
     want = _reference_rows(matcher, _oracle_records(matcher, molecules), molecules)
     assert text.getvalue() == want and n_rows == len(want.splitlines()) - 1 > 5
+    # the whole-box call on corpus files: one worker per device shares the chunk plan, chunks come back in input order
+    single = list(matcher.scan_files([out], chunk_size=2))
+    assert [len(c[0]) for c in single] == [2] * 6
+    monkeypatch.setattr(jess_run.Matcher, "close", lambda self: None)
+    multi = list(matcher.scan_files([out], chunk_size=2, devices=[0, 1, 2]))
+    assert [c[0] for c in multi] == [c[0] for c in single] and all(len(c) == 3 for c in multi)
+    assert all(a[2].tobytes() == b[2].tobytes() for a, b in zip(multi, single))
+    # two corpus files, a shared queue over the chunk plan (what ranks of a torchrun job would share)
+    from enzymm_b200.packing import write_corpus
+    second = out.parent / "second.emmpack"
+    write_corpus(paths[:5], second, threads=2)
+    plan = jess_run.Matcher.corpus_plan([out, second], 4)
+    assert plan == [(0, 0, 4, 0), (0, 4, 8, 4), (0, 8, 12, 8), (1, 0, 4, 12), (1, 4, 5, 16)]
+    both = list(matcher.scan_files([out, second], chunk_size=4))
+    assert [i for c in both for i in c[0]] == [m.id for m in molecules] + [m.id for m in molecules[:5]]
+    mine = list(matcher.scan_files([out, second], chunk_size=4, queue=iter([(1, 2), (3, 5)])))
+    assert [c[0] for c in mine] == [both[1][0], both[3][0], both[4][0]]
     with pytest.raises(ValueError):
-        list(matcher.scan_files([out], devices=[0, 1]))
+        list(matcher.scan_files([out], devices=[0, 1], queue=iter([(0, 1)])))

@@ -37,5 +37,9 @@ def test_scan_corpus_equals_scan_files(tmp_path, active_templates):
             a, b = io.StringIO(), io.StringIO()
             assert matcher.scan_to_tsv(paths, a, chunk_size=4, threads=2) == matcher.scan_to_tsv([corpus], b, chunk_size=4) > 0
             assert a.getvalue() == b.getvalue()
+            # the whole-box call on the corpus: two workers (sharing device 0 on a one-GPU box) pull from one chunk plan
+            shared = list(matcher.scan_files([corpus], chunk_size=3, devices=[0, 0]))
+            assert [c[0] for c in shared] == [c[0] for c in from_corpus]
+            assert all(x[2].tobytes() == y[2].tobytes() for x, y in zip(shared, from_corpus))
         finally:
             matcher.close()
