@@ -44,17 +44,44 @@ static void run_one(const std::string &text, int flags)
     free(copy);
 }
 
+// the path-taking readers (one tokenisation for mmCIF, gzip inflation): the same text through a file
+static void run_file(const std::string &text, int flags, const char *scratch)
+{
+    FILE *f = fopen(scratch, "wb");
+    if (!f) return;
+    fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+    const char *paths[2] = {scratch, scratch};
+    emm_pdb_batch *b = nullptr;
+    if (emm_pdb_pack_files_ex(paths, 2, 2, flags | EMM_PDB_SKIP_BAD, &b) == 0) {
+        emm_pdb_packed view;
+        emm_pdb_batch_packed(b, &view);
+        int32_t status[2];
+        emm_pdb_batch_file_status(b, status, 2);
+        (void)emm_pdb_batch_file_message(b, 0);
+        emm_pdb_batch_free(b);
+    }
+    b = nullptr;
+    if (emm_pdb_load_files_ex(paths, 2, 1, flags, &b) == 0) {
+        emm_pdb_columns cols;
+        emm_pdb_batch_columns(b, &cols);
+        emm_pdb_batch_free(b);
+    }
+}
+
 int main(int argc, char **argv)
 {
     std::mt19937_64 rng(12345);
     const int iters = atoi(argv[1]);
     std::vector<std::string> seeds;
     for (int i = 2; i < argc; ++i) seeds.push_back(slurp(argv[i]));
+    const std::string scratch = std::string(argv[2]) + ".fuzz.tmp";      // next to the first seed; gzip seeds are mutated as bytes
     long done = 0;
     for (int it = 0; it < iters; ++it) {
         std::string t = seeds[rng() % seeds.size()];
         // keep it small: a random window that includes the start (so the format is detected) or not
-        if (t.size() > 6000) {
+        const bool gz = t.size() > 2 && (unsigned char)t[0] == 0x1f && (unsigned char)t[1] == 0x8b;
+        if (!gz && t.size() > 6000) {
             const size_t keep = 500 + rng() % 5500;
             if (rng() % 3) t = t.substr(0, keep);
             else { const size_t off = rng() % (t.size() - keep); t = t.substr(0, 200) + t.substr(off, keep); }
@@ -73,8 +100,10 @@ int main(int argc, char **argv)
             }
         }
         run_one(t, (int)(rng() % 2));
+        if (it % 8 == 0) run_file(t, (int)(rng() % 2), scratch.c_str());
         ++done;
     }
+    remove(scratch.c_str());
     printf("fuzzed %ld inputs\n", done);
     return 0;
 }

@@ -199,8 +199,9 @@ def test_broken_gzip_is_an_error(tmp_path):
 
 def test_readers_survive_mutated_inputs_under_sanitizers(tmp_path, mol_1amy):
     """``tests/c/fuzz_readers.cpp`` + ``csrc/emm_pdb.cpp`` under AddressSanitizer / UBSan: 30 000 mutated
-    mmCIF and PDB texts (truncations, stray quotes / semicolons / keywords, random bytes) through
-    ``emm_pdb_count_atoms`` and ``emm_pdb_parse_ex`` -- no over-read, no overflow, no crash."""
+    mmCIF and PDB texts and gzip images (truncations, stray quotes / semicolons / keywords, random bytes)
+    through ``emm_pdb_count_atoms`` / ``emm_pdb_parse_ex`` and, every eighth one as a file, through
+    ``emm_pdb_pack_files_ex`` / ``emm_pdb_load_files_ex`` -- no over-read, no overflow, no crash."""
     import shutil
     import subprocess
     from conftest import ROOT
@@ -219,6 +220,8 @@ def test_readers_survive_mutated_inputs_under_sanitizers(tmp_path, mol_1amy):
     seeds[0].write_text(to_cif(small, "X"))
     seeds[1].write_text(to_cif(small, "NMR", models=(1, 2), with_auth=False, decimals=5))
     seeds[2].write_text("".join((GOLDEN / "1AMY.pdb").read_text().splitlines(keepends=True)[:120]))
+    seeds.append(tmp_path / "d.cif.gz")
+    seeds[3].write_bytes(gzip.compress(to_cif(small, "Z").encode()))
     run = subprocess.run([str(exe), "30000"] + [str(s) for s in seeds], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0 and "fuzzed 30000 inputs" in run.stdout, (run.stdout + run.stderr)[-2000:]
 
